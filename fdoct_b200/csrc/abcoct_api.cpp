@@ -1,0 +1,731 @@
+// C ABI of the B200-native ABC-OCT reconstruction path (see include/abcoct.h for the reference citations).
+// Host side only: parameter / .ini handling, the bit-exact lambda->k tables, calibration state, device
+// buffers, the pinned ingest ring on CUDA streams and the multi-GPU sharding by B-scan.
+#include "../../include/abcoct.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+
+using namespace abcoct;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+constexpr int kSlots = 3;  // pinned-ring depth per GPU (>= 3 streams per GPU)
+
+struct GpuState {
+  int dev = 0;
+  int sm_count = 0;
+  cudaStream_t stream[kSlots] = {};
+  cudaEvent_t slot_done[kSlots] = {};
+  cudaEvent_t ev[4] = {};
+  unsigned char* d_tables = nullptr;
+  float* d_gain = nullptr;
+  float* d_subg = nullptr;
+  // per-slot device + pinned staging for the host-buffer API
+  uint8_t* d_in[kSlots] = {};
+  uint8_t* d_out8[kSlots] = {};
+  float* d_outdb[kSlots] = {};
+  uint8_t* h_in[kSlots] = {};
+  uint8_t* h_out8[kSlots] = {};
+  float* h_outdb[kSlots] = {};
+  float* d_scratch[kSlots] = {};
+  int* d_minmax[kSlots] = {};
+  size_t scratch_bscans[kSlots] = {};
+  size_t slot_bscans = 0;  // capacity of the per-slot staging buffers, in B-scans
+  bool slot_db = false;
+};
+
+}  // namespace
+
+struct abcoct_ctx {
+  abcoct_params p{};
+  int opw = 0, oph = 0, M = 0, N = 0, D = 0, A = 1;
+  std::vector<int32_t> nk;
+  std::vector<double> frac, win;
+  std::vector<double> yb, yp, yd;
+  bool have_yb = false, have_yp = false, have_yd = false, cal_dirty = true, has_sub = false;
+  const PlanEntry* plan = nullptr;
+  int G = 1, smem = 0, regs = 0;
+  std::vector<GpuState> gpus;
+  std::string err;
+  uint64_t launches = 0;
+  double last_recon_ms = 0, last_norm_ms = 0;
+};
+
+namespace {
+
+int fail(abcoct_ctx* c, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (c)
+    c->err = buf;
+  else
+    g_create_error = buf;
+  return code;
+}
+
+#define CU(c, call)                                                                                      \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess) return fail(c, ABCOCT_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------ reference tables
+// BscanFFT.cpp:615-698, same expression order, plain IEEE doubles (this file is built with -ffp-contract=off).
+void build_ref_tables(int opw, int m, int N, double lmin, double lmax, std::vector<int32_t>& nk, std::vector<double>& frac) {
+  const double pi = 3.141592653589793;  // BscanFFT.cpp:609
+  const int M = m * opw;
+  const double deltalambda = (lmax - lmin) / opw;  // :615
+  std::vector<double> lambdas(M), k(M), klinear(N), diffk(M);
+  for (unsigned i = 0; i < (unsigned)M; ++i) lambdas[i] = lmin + i * deltalambda / (unsigned)m;  // :641
+  for (int i = 0; i < M; ++i) k[i] = (2 * pi) / lambdas[i];                                       // :644
+  const double kmin = 2 * pi / (lmax - deltalambda);                                              // :645
+  const double kmax = 2 * pi / lmin;                                                              // :646
+  const double deltak = (kmax - kmin) / N;                                                        // :647
+  for (unsigned f = 0; f < (unsigned)N; ++f) klinear[f] = kmin + (f + 1) * deltak;                // :652
+  for (int i = 1; i < M; ++i) diffk[i] = k[i - 1] - k[i];                                         // :667
+  diffk[0] = diffk[1];                                                                            // :671
+  nk.assign(N, 0);
+  frac.assign(N, 0.0);
+  for (int f = 0; f < N; ++f)  // :673-690
+    for (int i = 0; i < M; ++i)
+      if (k[i] < klinear[f]) {
+        nk[f] = i;
+        break;
+      }
+  for (int f = 0; f < N; ++f) frac[f] = (klinear[f] - k[nk[f]]) / diffk[nk[f]];  // :695
+}
+
+// BscanFFT.cpp:936-944: x = float(p)/float(opw-1) in f32, everything else in f64.
+void build_window(int opw, std::vector<double>& win) {
+  const double pi = 3.141592653589793;
+  win.resize(opw);
+  for (unsigned p = 0; p < (unsigned)opw; ++p) {
+    float nn = p;
+    float NN = opw - 1;
+    win[p] = 0.62 - 0.48 * std::abs(nn / NN - 0.5) + 0.38 * std::cos(2 * pi * (nn / NN - 0.5));
+  }
+}
+
+int validate(const abcoct_params& p, std::string& why, int& code) {
+  code = ABCOCT_ERR_INVALID;
+  auto bad = [&](const char* s) {
+    why = s;
+    return 1;
+  };
+  if (p.w == 0 || p.h == 0) return bad("w and h must be positive");
+  if (p.binx == 0 || p.biny == 0) return bad("binning factors must be >= 1");
+  if (p.bpp != 8 && p.bpp != 16) return bad("bpp must be 8 or 16");
+  if (p.averages == 0) return bad("averages must be >= 1");
+  if (p.fft_multiplier == 0) return bad("fft_multiplier must be >= 1");
+  if (!(p.lambdamax > p.lambdamin) || !(p.lambdamin > 0)) return bad("need 0 < lambdamin < lambdamax");
+  const unsigned opw = p.w / p.binx, oph = p.h / p.biny;
+  if (opw < 8 || oph < 1) return bad("binned frame too small");
+  if (p.numfftpoints < p.fft_multiplier * opw)
+    return bad("numfftpoints < fft_multiplier * (w / binx): the reference reads past fractionalk (BscanFFT.cpp:1170)");
+  if (p.numdisplaypoints > p.numfftpoints / 2) return bad("numdisplaypoints > numfftpoints / 2 (bins above N/2 mirror the lower half)");
+  if (p.numdisplaypoints < 6) return bad("numdisplaypoints < 6 (rows 4 and 5 are addressed, BscanFFT.cpp:1239, 1252)");
+  if (p.clampupper && oph < 6) return bad("clampupper needs at least 6 A-scans (element (5,5), BscanFFT.cpp:1252)");
+  if (p.variant > 1 || p.weight_mode > 1) return bad("variant / weight_mode out of range");
+  code = ABCOCT_ERR_UNSUPPORTED;
+  if (p.bpp != 16) return bad("bpp == 8 frames are not built yet (SURVEY.md section 8f rank 4)");
+  if (p.binx != 1 || p.biny != 1) return bad("input binning > 1 is not built yet (SURVEY.md section 7 step 6)");
+  if (p.mediann > 0) return bad("medianBlur pre-filter is not built yet (SURVEY.md section 8f rank 4)");
+  if (p.movavgn > 0) return bad("smoothmovavg is not built yet (SURVEY.md section 8f rank 4)");
+  if (p.fft_multiplier != 1) return bad("increasefftpointsmultiplier > 1 is not built yet (SURVEY.md section 7 step 5)");
+  if (p.rowwisenormalize || !p.donotnormalize) return bad("rowwisenormalize / !donotnormalize are not built yet (SURVEY.md section 7 step 6)");
+  if (opw % 8) return bad("w / binx must be a multiple of 8");
+  if (!find_plan((int)p.numfftpoints)) {
+    why = "numfftpoints has no compiled FFT plan; available:";
+    int ns[64];
+    int n = list_plans(ns, 64);
+    for (int i = 0; i < n && i < 64; ++i) why += " " + std::to_string(ns[i]);
+    return 1;
+  }
+  code = 0;
+  return 0;
+}
+
+int upload_calibration(abcoct_ctx* c) {
+  if (!c->have_yb) return fail(c, ABCOCT_ERR_STATE, "no background set: data_yb is all zeros in the reference until key 'b' (BscanFFT.cpp:562)");
+  const size_t n = (size_t)c->oph * c->opw;
+  std::vector<float> gain(n), subg(n);
+  bool has_sub = false;
+  const bool dark = c->p.variant == 1 && c->have_yd;
+  for (size_t i = 0; i < n; ++i) {
+    const double sub = (dark ? c->yd[i] : 0.0) + (c->have_yp ? c->yp[i] : 0.0);
+    gain[i] = (float)(1.0 / c->yb[i]);
+    subg[i] = (float)(sub / c->yb[i]);
+    has_sub |= (sub != 0.0);
+  }
+  c->has_sub = has_sub;
+  for (GpuState& g : c->gpus) {
+    CU(c, cudaSetDevice(g.dev));
+    if (!g.d_gain) CU(c, cudaMalloc(&g.d_gain, n * 4));
+    if (!g.d_subg) CU(c, cudaMalloc(&g.d_subg, n * 4));
+    CU(c, cudaMemcpy(g.d_gain, gain.data(), n * 4, cudaMemcpyHostToDevice));
+    CU(c, cudaMemcpy(g.d_subg, subg.data(), n * 4, cudaMemcpyHostToDevice));
+  }
+  // occupancy: the most groups per CTA that fit in shared memory
+  int G = c->plan->gmax;
+  while (G > 1 && c->plan->smem_bytes(c->opw, has_sub, G) > 227 * 1024) --G;
+  c->G = G;
+  c->smem = c->plan->smem_bytes(c->opw, has_sub, G);
+  if (c->smem > 227 * 1024) return fail(c, ABCOCT_ERR_UNSUPPORTED, "shared memory budget exceeded (%d bytes)", c->smem);
+  for (GpuState& g : c->gpus) {
+    CU(c, cudaSetDevice(g.dev));
+    CU(c, c->plan->attrs(has_sub, c->smem, &c->regs));
+  }
+  c->cal_dirty = false;
+  return ABCOCT_OK;
+}
+
+int ensure_scratch(abcoct_ctx* c, GpuState& g, int slot, size_t nB) {
+  if (g.scratch_bscans[slot] >= nB) return ABCOCT_OK;
+  if (g.d_scratch[slot]) cudaFree(g.d_scratch[slot]);
+  if (g.d_minmax[slot]) cudaFree(g.d_minmax[slot]);
+  g.d_scratch[slot] = nullptr;
+  g.d_minmax[slot] = nullptr;
+  g.scratch_bscans[slot] = 0;
+  CU(c, cudaMalloc(&g.d_scratch[slot], nB * c->oph * c->D * sizeof(float)));
+  CU(c, cudaMalloc(&g.d_minmax[slot], nB * 2 * sizeof(int)));
+  g.scratch_bscans[slot] = nB;
+  return ABCOCT_OK;
+}
+
+size_t scratch_chunk_bscans(const abcoct_ctx* c) {
+  size_t mb = 1024;
+  if (const char* e = getenv("ABCOCT_SCRATCH_MB")) mb = (size_t)std::max(1L, atol(e));
+  const size_t per = (size_t)c->oph * c->D * sizeof(float);
+  return std::max<size_t>(1, mb * 1024 * 1024 / per);
+}
+
+// Enqueue the two kernels for nB B-scans resident on device g; everything on `st`.
+int enqueue_device(abcoct_ctx* c, GpuState& g, int slot, const uint8_t* d_frames, size_t nB, size_t row_stride, size_t frame_stride,
+                   uint8_t* d_out8, float* d_outdb, cudaStream_t st, bool time_it) {
+  const size_t chunkB = std::min(nB, scratch_chunk_bscans(c));
+  int rc = ensure_scratch(c, g, slot, chunkB);
+  if (rc) return rc;
+  const int groups_total = g.sm_count * c->G;
+  for (size_t b0 = 0; b0 < nB; b0 += chunkB) {
+    const size_t nb = std::min(chunkB, nB - b0);
+    ReconArgs a{};
+    a.frames = d_frames + b0 * c->A * frame_stride;
+    a.frame_stride = frame_stride;
+    a.row_stride = row_stride;
+    a.W = c->opw;
+    a.oph = c->oph;
+    a.D = c->D;
+    a.A = c->A;
+    a.nB = (int)nb;
+    a.npairs = (c->oph + 1) / 2;
+    int Gb = std::max(1, 8 / c->A);
+    while (Gb > 1 && (size_t)a.npairs * ((nb + Gb - 1) / Gb) < (size_t)4 * groups_total) Gb >>= 1;
+    a.Gb = Gb;
+    a.nitems = a.npairs * (int)((nb + Gb - 1) / Gb);
+    a.gain = g.d_gain;
+    a.subg = g.d_subg;
+    a.idxT = reinterpret_cast<const uint16_t*>(g.d_tables);
+    a.scratch = g.d_scratch[slot];
+    a.minmax = g.d_minmax[slot];
+    a.inv_W = 1.0f / (float)c->opw;
+    a.out_scale = 0.5f / (float)c->A;
+    a.db_scale = (float)(0.6931471805599453 * (20.0 * (1.0 / 2.303)));
+    a.thr = (float)c->p.bscanthreshold;
+    a.clamp55 = c->p.clampupper ? 1 : 0;
+    const int grid = std::min(g.sm_count, (a.nitems + c->G - 1) / c->G);
+    CU(c, launch_minmax_init(a.minmax, (int)nb, st));
+    if (time_it) CU(c, cudaEventRecord(g.ev[0], st));
+    CU(c, c->plan->launch(a, c->has_sub, c->G, grid, st));
+    if (time_it) CU(c, cudaEventRecord(g.ev[1], st));
+    CU(c, launch_normalise(a.scratch, a.minmax, d_out8 + b0 * c->D * c->oph, d_outdb ? d_outdb + b0 * c->D * c->oph : nullptr, (int)nb,
+                           c->oph, c->D, a.thr, a.clamp55, (float)c->p.clamp_db, st));
+    if (time_it) CU(c, cudaEventRecord(g.ev[2], st));
+    c->launches += 3;
+  }
+  return ABCOCT_OK;
+}
+
+int ensure_slots(abcoct_ctx* c, GpuState& g, size_t slotB, bool want_db) {
+  if (g.slot_bscans >= slotB && (g.slot_db || !want_db)) return ABCOCT_OK;
+  CU(c, cudaSetDevice(g.dev));
+  const size_t in_bytes = slotB * c->A * (size_t)c->p.h * c->p.w * 2;
+  const size_t out_px = slotB * (size_t)c->D * c->oph;
+  for (int s = 0; s < kSlots; ++s) {
+    if (g.d_in[s]) cudaFree(g.d_in[s]);
+    if (g.d_out8[s]) cudaFree(g.d_out8[s]);
+    if (g.d_outdb[s]) cudaFree(g.d_outdb[s]);
+    if (g.h_in[s]) cudaFreeHost(g.h_in[s]);
+    if (g.h_out8[s]) cudaFreeHost(g.h_out8[s]);
+    if (g.h_outdb[s]) cudaFreeHost(g.h_outdb[s]);
+    g.d_in[s] = g.d_out8[s] = nullptr;
+    g.d_outdb[s] = nullptr;
+    g.h_in[s] = g.h_out8[s] = nullptr;
+    g.h_outdb[s] = nullptr;
+    CU(c, cudaMalloc(&g.d_in[s], in_bytes));
+    CU(c, cudaMalloc(&g.d_out8[s], out_px));
+    CU(c, cudaMallocHost(&g.h_in[s], in_bytes));
+    CU(c, cudaMallocHost(&g.h_out8[s], out_px));
+    if (want_db) {
+      CU(c, cudaMalloc(&g.d_outdb[s], out_px * 4));
+      CU(c, cudaMallocHost(&g.h_outdb[s], out_px * 4));
+    }
+  }
+  g.slot_bscans = slotB;
+  g.slot_db = want_db;
+  return ABCOCT_OK;
+}
+
+bool is_pinned(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeHost;
+}
+
+}  // namespace
+
+// ================================================================================================ C ABI
+extern "C" {
+
+void abcoct_params_default(abcoct_params* o) {
+  if (!o) return;
+  memset(o, 0, sizeof *o);
+  o->w = 640;  // BscanFFT.cpp:389
+  o->h = 480;  // :390
+  o->bpp = 8;  // :357
+  o->binx = o->biny = 1;
+  o->averages = 1;
+  o->numfftpoints = 1024;     // :368
+  o->numdisplaypoints = 512;  // :369
+  o->lambdamin = 816e-9;      // :381
+  o->lambdamax = 884e-9;      // :382
+  o->mediann = 5;             // :383
+  o->movavgn = 0;             // :373
+  o->fft_multiplier = 1;      // :384
+  o->rowwisenormalize = 0;    // :386
+  o->donotnormalize = 1;      // :387
+  o->variant = 0;
+  o->weight_mode = 0;
+  o->bscanthreshold = -30.0;  // :385
+  o->clampupper = 0;          // :374
+  o->clamp_db = 50.0;         // :1252
+}
+
+int abcoct_params_from_ini(const char* path, int flavour, abcoct_params* o) {
+  if (!o || !path) return ABCOCT_ERR_INVALID;
+  if (flavour < ABCOCT_INI_BSCANFFT || flavour > ABCOCT_INI_SIM) return ABCOCT_ERR_INVALID;
+  abcoct_params_default(o);
+  if (flavour == ABCOCT_INI_DARK) o->variant = 1;
+  if (flavour == ABCOCT_INI_SPINJNT) o->clamp_db = 30.0;  // BscanFFTspinjnt.cpp:1886
+  std::ifstream in(path);
+  if (!in.is_open()) return ABCOCT_ERR_IO;  // "Unable to open ini file, using defaults." BscanFFT.cpp:484
+  enum F { SKIP, BPP, W, H, BIN, BINX, BINY, AVG, NFFT, MOVAVG, NDISP, LMIN, LMAX, MEDIAN, MULT, ROWNORM, NONORM, BANDPASS };
+  std::vector<F> order = {SKIP /*camgain*/, SKIP /*camtime*/, BPP, W, H};
+  const bool offsets = flavour == ABCOCT_INI_BSCANFFT || flavour == ABCOCT_INI_SPINJ || flavour == ABCOCT_INI_SPINJNT;
+  if (offsets) {
+    order.push_back(SKIP);  // offsetx
+    order.push_back(SKIP);  // offsety
+  }
+  for (int i = 0; i < 4; ++i) order.push_back(SKIP);  // camspeed cambinx cambiny usbtraffic
+  if (flavour == ABCOCT_INI_SPINJNT) {
+    order.insert(order.end(), {BINX, BINY, SKIP /*bscanbinx*/, SKIP /*bscanbiny*/});
+  } else {
+    order.push_back(BIN);
+  }
+  order.insert(order.end(), {SKIP /*dirdescr*/, AVG, NFFT, SKIP /*saveframes*/, SKIP /*manualaveraging*/, SKIP /*manualaverages*/,
+                             SKIP /*saveinterferograms*/, MOVAVG, NDISP, LMIN, LMAX, MEDIAN, MULT});
+  if (flavour != ABCOCT_INI_SIM) order.insert(order.end(), {ROWNORM, NONORM});
+  if (flavour == ABCOCT_INI_DARK) order.insert(order.end(), {BANDPASS, SKIP /*lowpassfilter*/});
+  std::string tok;
+  for (int i = 0; i < 3; ++i)  // "first three lines of ini file are comments" BscanFFT.cpp:420-423
+    if (!(in >> tok)) return ABCOCT_OK;
+  bool first = true;
+  for (F f : order) {
+    if (!first && !(in >> tok)) break;  // the comment token between values
+    first = false;
+    if (!(in >> tok)) break;            // the value token
+    char* end = nullptr;
+    const long iv = strtol(tok.c_str(), &end, 10);
+    const bool numeric = end != tok.c_str();
+    const double dv = atof(tok.c_str());  // BscanFFT.cpp:479-480 (atof on the lambda strings)
+    bool stop = false;
+    switch (f) {
+      case SKIP: break;
+      case BPP: o->bpp = (uint32_t)iv; stop = !numeric; break;
+      case W: o->w = (uint32_t)iv; stop = !numeric; break;
+      case H: o->h = (uint32_t)iv; stop = !numeric; break;
+      case BIN: o->binx = o->biny = (uint32_t)iv; stop = !numeric; break;
+      case BINX: o->binx = (uint32_t)iv; stop = !numeric; break;
+      case BINY: o->biny = (uint32_t)iv; stop = !numeric; break;
+      case AVG: o->averages = (uint32_t)iv; stop = !numeric; break;
+      case NFFT: o->numfftpoints = (uint32_t)iv; stop = !numeric; break;
+      case MOVAVG: o->movavgn = (int32_t)iv; stop = !numeric; break;
+      case NDISP: o->numdisplaypoints = (uint32_t)iv; stop = !numeric; break;
+      case LMIN: o->lambdamin = dv; break;
+      case LMAX: o->lambdamax = dv; break;
+      case MEDIAN: o->mediann = (int32_t)iv; stop = !numeric; break;
+      case MULT: o->fft_multiplier = (uint32_t)iv; stop = !numeric; break;
+      case ROWNORM: o->rowwisenormalize = iv != 0; stop = !numeric; break;
+      case NONORM: o->donotnormalize = iv != 0; stop = !numeric; break;
+      case BANDPASS: o->bandpassfilter = iv != 0; stop = !numeric; break;
+    }
+    if (stop) break;  // an istream in the fail state ignores every later extraction
+  }
+  return ABCOCT_OK;
+}
+
+const char* abcoct_last_error(const abcoct_ctx* c) { return c ? c->err.c_str() : g_create_error.c_str(); }
+
+int abcoct_create(const abcoct_params* params, const int* gpu_ids, int ngpu, abcoct_ctx** out) {
+  if (!params || !out) return fail(nullptr, ABCOCT_ERR_INVALID, "null argument");
+  *out = nullptr;
+  std::string why;
+  int code = 0;
+  if (validate(*params, why, code)) return fail(nullptr, code, "%s", why.c_str());
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(nullptr, ABCOCT_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+  }
+  if (ngpu < 1) ngpu = 1;
+  if (ngpu > ndev && !gpu_ids) return fail(nullptr, ABCOCT_ERR_INVALID, "ngpu = %d but only %d devices are visible", ngpu, ndev);
+  abcoct_ctx* c = new abcoct_ctx();
+  c->p = *params;
+  c->opw = params->w / params->binx;
+  c->oph = params->h / params->biny;
+  c->M = params->fft_multiplier * c->opw;
+  c->N = params->numfftpoints;
+  c->D = params->numdisplaypoints;
+  c->A = params->averages;
+  c->plan = find_plan(c->N);
+  build_ref_tables(c->opw, params->fft_multiplier, c->N, params->lambdamin, params->lambdamax, c->nk, c->frac);
+  build_window(c->opw, c->win);
+  // gather tables for the kernel: end points q = 0, N-1 are never written in the reference (BscanFFT.cpp:1164)
+  std::vector<int> idx(c->N);
+  std::vector<float> wq(c->N), winf(c->opw);
+  for (int q = 0; q < c->N; ++q) {
+    int i = c->nk[q];
+    double w = params->weight_mode == 0 ? c->frac[c->nk[q]] : c->frac[q];  // :1170 quirk vs corrected
+    if (q == 0 || q == c->N - 1) {
+      i = c->M;  // sentinel slot holding zero
+      w = 0.0;
+    } else if (i == 0) {  // slopes[0] = slopes[1] (:1161): y0 + w (y1 - y0) == y1 + (w - 1)(y1 - y0)
+      i = 1;
+      w = w - 1.0;
+    }
+    idx[q] = i;
+    wq[q] = (float)w;
+  }
+  for (int i = 0; i < c->opw; ++i) winf[i] = (float)c->win[i];
+  std::vector<unsigned char> blob;
+  c->plan->build_blob(c->opw, idx.data(), wq.data(), winf.data(), blob);
+
+  c->gpus.resize(ngpu);
+  for (int i = 0; i < ngpu; ++i) {
+    GpuState& g = c->gpus[i];
+    g.dev = gpu_ids ? gpu_ids[i] : i;
+    cudaError_t e = cudaSetDevice(g.dev);
+    cudaDeviceProp prop{};
+    if (e == cudaSuccess) e = cudaGetDeviceProperties(&prop, g.dev);
+    if (e != cudaSuccess) {
+      fail(nullptr, ABCOCT_ERR_CUDA, "cudaSetDevice(%d): %s", g.dev, cudaGetErrorString(e));
+      abcoct_destroy(c);
+      return ABCOCT_ERR_CUDA;
+    }
+    if (prop.major != 10) {
+      fail(nullptr, ABCOCT_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", g.dev, prop.major, prop.minor);
+      abcoct_destroy(c);
+      return ABCOCT_ERR_CUDA;
+    }
+    g.sm_count = prop.multiProcessorCount;
+    bool ok = true;
+    for (int s = 0; s < kSlots && ok; ++s) {
+      ok = ok && cudaStreamCreateWithFlags(&g.stream[s], cudaStreamNonBlocking) == cudaSuccess;
+      ok = ok && cudaEventCreateWithFlags(&g.slot_done[s], cudaEventDisableTiming) == cudaSuccess;
+    }
+    for (int k = 0; k < 4 && ok; ++k) ok = ok && cudaEventCreate(&g.ev[k]) == cudaSuccess;
+    ok = ok && cudaMalloc(&g.d_tables, blob.size()) == cudaSuccess;
+    ok = ok && cudaMemcpy(g.d_tables, blob.data(), blob.size(), cudaMemcpyHostToDevice) == cudaSuccess;
+    if (!ok) {
+      fail(nullptr, ABCOCT_ERR_CUDA, "device %d setup failed: %s", g.dev, cudaGetErrorString(cudaGetLastError()));
+      abcoct_destroy(c);
+      return ABCOCT_ERR_CUDA;
+    }
+  }
+  *out = c;
+  return ABCOCT_OK;
+}
+
+void abcoct_destroy(abcoct_ctx* c) {
+  if (!c) return;
+  for (GpuState& g : c->gpus) {
+    cudaSetDevice(g.dev);
+    cudaDeviceSynchronize();
+    for (int s = 0; s < kSlots; ++s) {
+      if (g.stream[s]) cudaStreamDestroy(g.stream[s]);
+      if (g.slot_done[s]) cudaEventDestroy(g.slot_done[s]);
+      cudaFree(g.d_in[s]);
+      cudaFree(g.d_out8[s]);
+      cudaFree(g.d_outdb[s]);
+      cudaFree(g.d_scratch[s]);
+      cudaFree(g.d_minmax[s]);
+      if (g.h_in[s]) cudaFreeHost(g.h_in[s]);
+      if (g.h_out8[s]) cudaFreeHost(g.h_out8[s]);
+      if (g.h_outdb[s]) cudaFreeHost(g.h_outdb[s]);
+    }
+    for (int k = 0; k < 4; ++k)
+      if (g.ev[k]) cudaEventDestroy(g.ev[k]);
+    cudaFree(g.d_tables);
+    cudaFree(g.d_gain);
+    cudaFree(g.d_subg);
+  }
+  cudaGetLastError();
+  delete c;
+}
+
+static int set_cal(abcoct_ctx* c, std::vector<double>& dst, bool& have, const double* src, size_t ld) {
+  if (!c) return ABCOCT_ERR_INVALID;
+  const size_t n = (size_t)c->oph * c->opw;
+  if (!src) {
+    dst.clear();
+    have = false;
+  } else {
+    if (ld == 0) ld = c->opw;
+    if (ld < (size_t)c->opw) return fail(c, ABCOCT_ERR_INVALID, "ld < opw");
+    dst.resize(n);
+    for (int r = 0; r < c->oph; ++r) memcpy(&dst[(size_t)r * c->opw], src + (size_t)r * ld, (size_t)c->opw * sizeof(double));
+    have = true;
+  }
+  c->cal_dirty = true;
+  return ABCOCT_OK;
+}
+int abcoct_set_background(abcoct_ctx* c, const double* yb, size_t ld) {
+  if (c && !yb) return fail(c, ABCOCT_ERR_INVALID, "background must not be NULL");
+  return c ? set_cal(c, c->yb, c->have_yb, yb, ld) : ABCOCT_ERR_INVALID;
+}
+int abcoct_set_pishift(abcoct_ctx* c, const double* yp, size_t ld) { return c ? set_cal(c, c->yp, c->have_yp, yp, ld) : ABCOCT_ERR_INVALID; }
+int abcoct_set_dark(abcoct_ctx* c, const double* yd, size_t ld) { return c ? set_cal(c, c->yd, c->have_yd, yd, ld) : ABCOCT_ERR_INVALID; }
+
+int abcoct_set_calibration_from_frames(abcoct_ctx* c, int which, const void* frames, size_t nframes, size_t stride_bytes) {
+  if (!c || !frames || nframes == 0 || which < 0 || which > 2) return c ? fail(c, ABCOCT_ERR_INVALID, "bad argument") : ABCOCT_ERR_INVALID;
+  if (stride_bytes == 0) stride_bytes = (size_t)c->p.w * 2;
+  const size_t n = (size_t)c->oph * c->opw;
+  std::vector<double> acc(n, 0.0);  // accumulate(data_y, baccum), BscanFFT.cpp:1043
+  const uint8_t* base = static_cast<const uint8_t*>(frames);
+  for (size_t f = 0; f < nframes; ++f)
+    for (int r = 0; r < c->oph; ++r) {
+      const uint16_t* row = reinterpret_cast<const uint16_t*>(base + (f * c->p.h + r) * stride_bytes);
+      double* a = &acc[(size_t)r * c->opw];
+      for (int x = 0; x < c->opw; ++x) a[x] += (double)row[x];
+    }
+  const double s = 1.0 / (double)nframes;  // Mat / double multiplies by the reciprocal, BscanFFT.cpp:1057
+  for (double& v : acc) v *= s;
+  std::vector<double>& dst = which == 0 ? c->yb : which == 1 ? c->yp : c->yd;
+  bool& have = which == 0 ? c->have_yb : which == 1 ? c->have_yp : c->have_yd;
+  dst.swap(acc);
+  have = true;
+  c->cal_dirty = true;
+  return ABCOCT_OK;
+}
+
+int abcoct_build_tables(const abcoct_params* p, int32_t* nk, double* frac, double* win) {
+  if (!p || p->binx == 0 || p->w / p->binx == 0 || p->fft_multiplier == 0 || p->numfftpoints == 0) return ABCOCT_ERR_INVALID;
+  const int opw = p->w / p->binx;
+  if (p->numfftpoints < p->fft_multiplier * (uint32_t)opw) return ABCOCT_ERR_INVALID;
+  std::vector<int32_t> vnk;
+  std::vector<double> vfrac, vwin;
+  build_ref_tables(opw, p->fft_multiplier, p->numfftpoints, p->lambdamin, p->lambdamax, vnk, vfrac);
+  build_window(opw, vwin);
+  if (nk) memcpy(nk, vnk.data(), vnk.size() * sizeof(int32_t));
+  if (frac) memcpy(frac, vfrac.data(), vfrac.size() * sizeof(double));
+  if (win) memcpy(win, vwin.data(), vwin.size() * sizeof(double));
+  return ABCOCT_OK;
+}
+
+int abcoct_get_tables(const abcoct_ctx* c, int32_t* nk, double* frac) {
+  if (!c) return ABCOCT_ERR_INVALID;
+  if (nk) memcpy(nk, c->nk.data(), c->nk.size() * sizeof(int32_t));
+  if (frac) memcpy(frac, c->frac.data(), c->frac.size() * sizeof(double));
+  return ABCOCT_OK;
+}
+int abcoct_get_window(const abcoct_ctx* c, double* w) {
+  if (!c || !w) return ABCOCT_ERR_INVALID;
+  memcpy(w, c->win.data(), c->win.size() * sizeof(double));
+  return ABCOCT_OK;
+}
+
+int abcoct_process_bscans_device(abcoct_ctx* c, int gi, const void* d_frames, size_t nframes, size_t stride_bytes, uint8_t* d_u8,
+                                 float* d_db, void* cuda_stream) {
+  if (!c) return ABCOCT_ERR_INVALID;
+  if (gi < 0 || gi >= (int)c->gpus.size()) return fail(c, ABCOCT_ERR_INVALID, "gpu_index out of range");
+  if (!d_frames || !d_u8) return fail(c, ABCOCT_ERR_INVALID, "null buffer");
+  if (nframes == 0 || nframes % c->A) return fail(c, ABCOCT_ERR_INVALID, "nframes must be a positive multiple of averages (%d)", c->A);
+  if (stride_bytes == 0) stride_bytes = (size_t)c->p.w * 2;
+  if (stride_bytes % 16 || (reinterpret_cast<uintptr_t>(d_frames) & 15)) return fail(c, ABCOCT_ERR_INVALID, "device frames must be 16-byte aligned with a 16-byte multiple row stride");
+  if (c->cal_dirty) {
+    int rc = upload_calibration(c);
+    if (rc) return rc;
+  }
+  GpuState& g = c->gpus[gi];
+  CU(c, cudaSetDevice(g.dev));
+  cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : g.stream[0];
+  int rc = enqueue_device(c, g, 0, static_cast<const uint8_t*>(d_frames), nframes / c->A, stride_bytes, stride_bytes * c->p.h, d_u8, d_db, st,
+                          true);
+  if (rc) return rc;
+  if (!cuda_stream) {
+    CU(c, cudaStreamSynchronize(st));
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, g.ev[0], g.ev[1]) == cudaSuccess) c->last_recon_ms = ms;
+    if (cudaEventElapsedTime(&ms, g.ev[1], g.ev[2]) == cudaSuccess) c->last_norm_ms = ms;
+    cudaGetLastError();
+  }
+  return ABCOCT_OK;
+}
+
+int abcoct_process_bscans(abcoct_ctx* c, const void* frames, size_t nframes, size_t stride_bytes, uint8_t* out8, float* outdb) {
+  if (!c) return ABCOCT_ERR_INVALID;
+  if (!frames || !out8) return fail(c, ABCOCT_ERR_INVALID, "null buffer");
+  if (nframes == 0 || nframes % c->A) return fail(c, ABCOCT_ERR_INVALID, "nframes must be a positive multiple of averages (%d)", c->A);
+  const size_t dense = (size_t)c->p.w * 2;
+  if (stride_bytes == 0) stride_bytes = dense;
+  if (stride_bytes < dense) return fail(c, ABCOCT_ERR_INVALID, "stride_bytes < w * bytes per pixel");
+  if (c->cal_dirty) {
+    int rc = upload_calibration(c);
+    if (rc) return rc;
+  }
+  const size_t nB = nframes / c->A;
+  const size_t ngpu = c->gpus.size();
+  const size_t frame_in = stride_bytes * c->p.h;          // caller layout
+  const size_t frame_dev = dense * c->p.h;                // dense on the device
+  const size_t bscan_in_dev = frame_dev * c->A;
+  const size_t out_px = (size_t)c->D * c->oph;
+  // slot size: about 64 MiB of input per slot, at least one B-scan, and enough slots to cover all GPUs
+  size_t slotB = std::max<size_t>(1, (64u << 20) / bscan_in_dev);
+  slotB = std::min(slotB, std::max<size_t>(1, (nB + ngpu * kSlots - 1) / (ngpu * kSlots)));
+  for (GpuState& g : c->gpus) {
+    int rc = ensure_slots(c, g, slotB, outdb != nullptr);
+    if (rc) return rc;
+  }
+  const bool in_pinned = is_pinned(frames) && stride_bytes == dense;
+  const bool out_pinned = is_pinned(out8) && (!outdb || is_pinned(outdb));
+  struct Pending {
+    size_t b0 = 0, nb = 0;
+    bool busy = false;
+  };
+  std::vector<Pending> pend(ngpu * kSlots);
+  auto drain = [&](size_t gi, int s) -> int {
+    Pending& pd = pend[gi * kSlots + s];
+    if (!pd.busy) return ABCOCT_OK;
+    GpuState& g = c->gpus[gi];
+    CU(c, cudaSetDevice(g.dev));
+    CU(c, cudaEventSynchronize(g.slot_done[s]));
+    if (!out_pinned) {
+      memcpy(out8 + pd.b0 * out_px, g.h_out8[s], pd.nb * out_px);
+      if (outdb) memcpy(outdb + pd.b0 * out_px, g.h_outdb[s], pd.nb * out_px * 4);
+    }
+    pd.busy = false;
+    return ABCOCT_OK;
+  };
+  size_t chunk = 0;
+  for (size_t b0 = 0; b0 < nB; b0 += slotB, ++chunk) {
+    const size_t nb = std::min(slotB, nB - b0);
+    const size_t gi = chunk % ngpu;
+    const int s = (int)((chunk / ngpu) % kSlots);
+    int rc = drain(gi, s);
+    if (rc) return rc;
+    GpuState& g = c->gpus[gi];
+    CU(c, cudaSetDevice(g.dev));
+    cudaStream_t st = g.stream[s];
+    const uint8_t* src = static_cast<const uint8_t*>(frames) + b0 * c->A * frame_in;
+    const size_t nfr = nb * c->A;
+    if (in_pinned) {
+      CU(c, cudaMemcpyAsync(g.d_in[s], src, nfr * frame_dev, cudaMemcpyHostToDevice, st));
+    } else {
+      // pageable (or pitched) caller memory: stage through the pinned ring
+      if (stride_bytes == dense) {
+        memcpy(g.h_in[s], src, nfr * frame_dev);
+      } else {
+        for (size_t r = 0; r < nfr * c->p.h; ++r) memcpy(g.h_in[s] + r * dense, src + r * stride_bytes, dense);
+      }
+      CU(c, cudaMemcpyAsync(g.d_in[s], g.h_in[s], nfr * frame_dev, cudaMemcpyHostToDevice, st));
+    }
+    rc = enqueue_device(c, g, s, g.d_in[s], nb, dense, frame_dev, g.d_out8[s], outdb ? g.d_outdb[s] : nullptr, st, false);
+    if (rc) return rc;
+    uint8_t* dst8 = out_pinned ? out8 + b0 * out_px : g.h_out8[s];
+    CU(c, cudaMemcpyAsync(dst8, g.d_out8[s], nb * out_px, cudaMemcpyDeviceToHost, st));
+    if (outdb) {
+      float* dstdb = out_pinned ? outdb + b0 * out_px : g.h_outdb[s];
+      CU(c, cudaMemcpyAsync(dstdb, g.d_outdb[s], nb * out_px * 4, cudaMemcpyDeviceToHost, st));
+    }
+    CU(c, cudaEventRecord(g.slot_done[s], st));
+    pend[gi * kSlots + s] = Pending{b0, nb, true};
+  }
+  for (size_t gi = 0; gi < ngpu; ++gi)
+    for (int s = 0; s < kSlots; ++s) {
+      int rc = drain(gi, s);
+      if (rc) return rc;
+    }
+  return ABCOCT_OK;
+}
+
+int abcoct_debug_linearised(abcoct_ctx* c, const void*, size_t, float*) {
+  return c ? fail(c, ABCOCT_ERR_UNSUPPORTED, "debug tap not built yet") : ABCOCT_ERR_INVALID;
+}
+
+void* abcoct_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaMallocHost(&p, bytes) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+void abcoct_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
+int abcoct_get_info(const abcoct_ctx* c, abcoct_info* o) {
+  if (!c || !o) return ABCOCT_ERR_INVALID;
+  memset(o, 0, sizeof *o);
+  o->opw = c->opw;
+  o->oph = c->oph;
+  o->M = c->M;
+  o->N = c->N;
+  o->D = c->D;
+  o->averages = c->A;
+  o->fft_threads = c->plan->d.T;
+  o->fft_radix[0] = c->plan->d.R0;
+  o->fft_radix[1] = c->plan->d.R1;
+  o->fft_radix[2] = c->plan->d.RL;
+  o->groups_per_cta = c->G;
+  o->ctas_per_sm = 1;
+  o->smem_bytes = c->smem;
+  o->regs_per_thread = c->regs;
+  o->ngpu = (uint32_t)c->gpus.size();
+  o->sm_count = c->gpus.empty() ? 0 : c->gpus[0].sm_count;
+  o->kernel_launches = c->launches;
+  o->last_recon_ms = c->last_recon_ms;
+  o->last_norm_ms = c->last_norm_ms;
+  return ABCOCT_OK;
+}
+
+}  // extern "C"

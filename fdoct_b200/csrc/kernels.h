@@ -1,0 +1,33 @@
+// Host-visible interface of the CUDA translation units (plan registry + launchers).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <vector>
+
+#include "plan.h"
+#include "recon_kernel.cuh"
+
+namespace abcoct {
+
+// One compiled FFT plan: how to build its table blob and how to launch it.
+struct PlanEntry {
+  PlanDesc d;
+  int gmax;  // most groups (packed A-scan pairs in flight) one CTA may hold
+  // bytes of dynamic shared memory for G groups
+  int (*smem_bytes)(int W, bool has_sub, int G);
+  int (*table_bytes)(int W);
+  // pack idx (N entries, already sentinel-remapped, values in [1, M]), weights (N), window (W) and the
+  // inter-pass twiddles into the blob the kernel copies to shared memory
+  void (*build_blob)(int W, const int* idx, const float* wq, const float* win, std::vector<unsigned char>& blob);
+  cudaError_t (*launch)(const ReconArgs& a, bool has_sub, int G, int grid, cudaStream_t st);
+  cudaError_t (*attrs)(bool has_sub, int smem, int* regs);  // opt in to large smem, report registers/thread
+};
+
+const PlanEntry* find_plan(int N);
+int list_plans(int* out, int cap);
+
+cudaError_t launch_minmax_init(int* minmax, int nB, cudaStream_t st);
+cudaError_t launch_normalise(const float* scratch, const int* minmax, uint8_t* out8, float* outdb, int nB, int oph, int D,
+                             float thr, int clamp55, float clamp_db, cudaStream_t st);
+}  // namespace abcoct

@@ -1,0 +1,152 @@
+/*
+ * abcoct.h - C ABI of the B200-native ABC-OCT B-scan reconstruction path.
+ *
+ * The reference (hn-88/FDOCT) has NO function / plugin / FFI boundary on this path: the
+ * reconstruction is an inline block of main() (BscanFFT.cpp:953-958, 987-991, 1125-1255;
+ * identical copies in BscanFFTspin.cpp:1095-1399, BscanFFTspinj.cpp:1635-1982,
+ * BscanFFTpeak.cpp:1557-1873, BscanFFTwebcam.cpp:1044-1349; dark-frame variant
+ * BscanDark.cpp:946-951, 1268-1393).  The "signature" of that block is the set of locals it
+ * reads and writes; every entry point below cites the reference statements it replaces, so a
+ * host app can delete those lines and make one call instead.
+ *
+ * Conventions: plain C, no C++ exceptions cross the ABI, `int` status with 0 == success
+ * (like QHYCCD_SUCCESS, BscanFFT.cpp:730) and negative == error; abcoct_last_error() gives the
+ * text.  A context is not thread-safe (the reference block is single-threaded).  There is no
+ * CPU fallback: every compute entry point fails with ABCOCT_ERR_CUDA when no sm_100 device
+ * is present.
+ */
+#ifndef ABCOCT_H
+#define ABCOCT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ABCOCT_VERSION 100
+
+enum {
+  ABCOCT_OK = 0,
+  ABCOCT_ERR_INVALID = -1,     /* bad argument / parameter combination the reference cannot run either */
+  ABCOCT_ERR_UNSUPPORTED = -2, /* valid in the reference but not built yet (listed in DESIGN.md)        */
+  ABCOCT_ERR_CUDA = -3,        /* CUDA runtime error, no device, wrong architecture                     */
+  ABCOCT_ERR_STATE = -4,       /* e.g. process called before a background was set                       */
+  ABCOCT_ERR_IO = -5           /* ini file could not be opened                                          */
+};
+
+/* Which positional .ini layout to parse (the parser is BscanFFT.cpp:395-484). */
+enum {
+  ABCOCT_INI_BSCANFFT = 0, /* BscanFFT.cpp:424-476, BscanFFTspin.cpp:439-491                      */
+  ABCOCT_INI_SPINJ = 1,    /* BscanFFTspinj.cpp:864-918   (+ offlinetoolpath)                     */
+  ABCOCT_INI_SPINJNT = 2,  /* BscanFFTspinjnt.cpp:769-829 (binvaluex/y, bscanbinx/y)              */
+  ABCOCT_INI_DARK = 3,     /* BscanDark.cpp:434-486       (no offsets, + bandpass/lowpass)        */
+  ABCOCT_INI_PEAK = 4,     /* BscanFFTpeak.cpp:1030-1080  (no offsets, + peakholdnumframes)       */
+  ABCOCT_INI_WEBCAM = 5,   /* BscanFFTwebcam.cpp:458-508  (no offsets, + channelnum)              */
+  ABCOCT_INI_SIM = 6       /* BscanFFTsim.cpp:316-360     (no offsets, stops after multiplier)    */
+};
+
+/* Mirrors the locals the block reads (BscanFFT.cpp:357-387 defaults, filled by the .ini parser). */
+typedef struct abcoct_params {
+  uint32_t w, h;             /* raw frame width / height in pixels (BscanFFT.cpp:430-432)                  */
+  uint32_t bpp;              /* 8 or 16 (BscanFFT.cpp:428); 16-bit frames may hold 12-bit data              */
+  uint32_t binx, biny;       /* binvalue (BscanFFT.cpp:446) or binvaluex/y (BscanFFTspinjnt.cpp:1553)       */
+  uint32_t averages;         /* averagestoggle: frames averaged per B-scan (BscanFFT.cpp:450, 481, 1193)   */
+  uint32_t numfftpoints;     /* N (BscanFFT.cpp:452)                                                       */
+  uint32_t numdisplaypoints; /* D (BscanFFT.cpp:464)                                                       */
+  double lambdamin, lambdamax; /* BscanFFT.cpp:479-480                                                     */
+  int32_t mediann;           /* BscanFFT.cpp:470, 953                                                      */
+  int32_t movavgn;           /* BscanFFT.cpp:462, 990                                                      */
+  uint32_t fft_multiplier;   /* increasefftpointsmultiplier (BscanFFT.cpp:472, 1146)                       */
+  uint8_t rowwisenormalize;  /* BscanFFT.cpp:474, 1126                                                     */
+  uint8_t donotnormalize;    /* BscanFFT.cpp:476, 1128                                                     */
+  uint8_t variant;           /* 0 = FFT (BscanFFT.cpp), 1 = DARK (BscanDark.cpp:1269 subtracts data_yd)    */
+  uint8_t weight_mode;       /* 0 = reference quirk fractionalk[nearestkindex[q]] (BscanFFT.cpp:1170),
+                                1 = corrected fractionalk[q]                                               */
+  double bscanthreshold;     /* BscanFFT.cpp:385, 1247 (default -30.0)                                     */
+  uint8_t clampupper;        /* BscanFFT.cpp:374, 1248                                                     */
+  uint8_t bandpassfilter;    /* BscanDark.cpp:218-236 (inside the Fourier upsample only)                   */
+  uint8_t reserved[6];
+  double clamp_db;           /* 50.0 (BscanFFT.cpp:1252), 30.0 in BscanFFTspinjnt.cpp:1886                 */
+} abcoct_params;
+
+typedef struct abcoct_ctx abcoct_ctx; /* opaque; one per caller thread; may span 1..8 GPUs */
+
+/* Fill *out with the reference's compile-time defaults (BscanFFT.cpp:357-390). */
+void abcoct_params_default(abcoct_params* out);
+
+/* Positional whitespace-token .ini parser: skips three tokens, then alternating comment / value
+ * (BscanFFT.cpp:417-482).  A missing file is ABCOCT_ERR_IO and leaves the defaults in *out, like
+ * "Unable to open ini file, using defaults." (BscanFFT.cpp:484). */
+int abcoct_params_from_ini(const char* path, int ini_flavour, abcoct_params* out);
+
+/* Replaces the one-time precompute BscanFFT.cpp:545-546, 615-698, 932-944 and owns the state the
+ * block keeps between frames (data_yb/yp/yd, bscantransposed, indextemp).  gpu_ids == NULL means
+ * device 0..ngpu-1.  Rejects what is undefined behaviour in the reference: numfftpoints <
+ * fft_multiplier * (w / binx) (BscanFFT.cpp:1170 reads past fractionalk), numdisplaypoints >
+ * numfftpoints / 2 or < 6 (rows 4 and 5 are addressed at :1239, :1252). */
+int abcoct_create(const abcoct_params* params, const int* gpu_ids, int ngpu, abcoct_ctx** out);
+void abcoct_destroy(abcoct_ctx* ctx);
+const char* abcoct_last_error(const abcoct_ctx* ctx); /* ctx may be NULL: error of the last failed create */
+
+/* Calibration state, oph x opw doubles with a row stride of `ld` elements.
+ *   background = data_yb (BscanFFT.cpp:1050-1057; BscanDark.cpp:996), required before processing;
+ *   pishift    = data_yp (BscanFFT.cpp:1081), NULL -> zeros (BscanFFT.cpp:563);
+ *   dark       = data_yd (BscanDark.cpp:1045-1067), used by the DARK variant only.               */
+int abcoct_set_background(abcoct_ctx* ctx, const double* yb, size_t ld);
+int abcoct_set_pishift(abcoct_ctx* ctx, const double* yp, size_t ld);
+int abcoct_set_dark(abcoct_ctx* ctx, const double* yd, size_t ld);
+/* Mean of nframes raw frames after median + binning, the capture done on keys b / o / r / t
+ * (BscanFFT.cpp:1041-1062; BscanDark.cpp:1045-1225).  which: 0 background, 1 pishift (nframes==1), 2 dark. */
+int abcoct_set_calibration_from_frames(abcoct_ctx* ctx, int which, const void* frames, size_t nframes,
+                                       size_t stride_bytes);
+
+/* Host-only (no GPU needed): the one-time precompute of BscanFFT.cpp:615-698 and :936-944 for `params`.
+ * nearestkindex / fractionalk have numfftpoints entries, barthannwin has w / binx; any may be NULL. */
+int abcoct_build_tables(const abcoct_params* params, int32_t* nearestkindex, double* fractionalk, double* barthannwin);
+
+/* The bit-exact tables of BscanFFT.cpp:673-698 (N entries each) and the window of :936-944 (opw). */
+int abcoct_get_tables(const abcoct_ctx* ctx, int32_t* nearestkindex, double* fractionalk);
+int abcoct_get_window(const abcoct_ctx* ctx, double* barthannwin);
+
+/* THE HOT PATH.  Replaces BscanFFT.cpp:953-958, 987-991, 1125-1255 for `nframes` consecutive frames.
+ *   frames       nframes x h x w pixels (uint8 when bpp == 8, else uint16), HOST memory, rows
+ *                `stride_bytes` apart (0 -> dense); pinned memory from abcoct_host_alloc is copied
+ *                straight to the device, other memory goes through the internal pinned ring.
+ *   nframes      must be a multiple of `averages`; nB = nframes / averages B-scans come out.
+ *   bscan_u8     nB x D x oph, the display image bscandisp (BscanFFT.cpp:1254-1255).
+ *   bscan_db     nullable, nB x D x oph float, bscandb after the DC-row mask (BscanFFT.cpp:1237-1240).
+ * Synchronous: inputs may be freed and outputs are valid on return. */
+int abcoct_process_bscans(abcoct_ctx* ctx, const void* frames, size_t nframes, size_t stride_bytes,
+                          uint8_t* bscan_u8, float* bscan_db);
+
+/* Same computation with every buffer already resident on GPU `gpu_index` (index into gpu_ids).
+ * Asynchronous on `cuda_stream` (a cudaStream_t; NULL = the context's own stream, then the call
+ * synchronises before returning). */
+int abcoct_process_bscans_device(abcoct_ctx* ctx, int gpu_index, const void* d_frames, size_t nframes,
+                                 size_t stride_bytes, uint8_t* d_bscan_u8, float* d_bscan_db,
+                                 void* cuda_stream);
+
+/* Linear (pre-log) averaged magnitude `bscan` (BscanFFT.cpp:1220-1222) of the LAST device/host call's
+ * first B-scan and per-stage debug taps are exposed for the parity tests only. */
+int abcoct_debug_linearised(abcoct_ctx* ctx, const void* frame, size_t stride_bytes, float* ylin /* oph x N */);
+
+/* Pinned host memory for zero-staging ingest (the caller's ring buffer). */
+void* abcoct_host_alloc(size_t bytes);
+void abcoct_host_free(void* p);
+
+/* Introspection used by bench.py / tests: derived sizes and launch accounting. */
+typedef struct abcoct_info {
+  uint32_t opw, oph, M, N, D, averages;
+  uint32_t fft_threads, fft_radix[3], groups_per_cta, ctas_per_sm, smem_bytes, regs_per_thread;
+  uint32_t ngpu, sm_count;
+  uint64_t kernel_launches;        /* kernels launched by this ctx so far                     */
+  double last_recon_ms, last_norm_ms; /* CUDA-event time of the last device call's two kernels   */
+} abcoct_info;
+int abcoct_get_info(const abcoct_ctx* ctx, abcoct_info* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ABCOCT_H */
