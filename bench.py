@@ -1,0 +1,360 @@
+#!/usr/bin/env python
+"""bench.py - throughput of the ABC-OCT B-scan reconstruction path (BASELINE.json metric: A-scans/s, B-scans/s,
+HBM GB/s vs peak at 1/2/4/8 B200).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c5-2048] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+A "step" is one pass of the hot path over one batch of synthetic frames (fdoct_b200.synth, after the reference's
+generator Matlab files/wangOCTimg2.m).  One JSON line is printed by rank 0:
+
+  value        device-resident A-scans/s, whole job (frames already in HBM, larger than L2, CUDA-event timed,
+               max over ranks), `ms_per_step` the matching time
+  e2e          the same metric through the host-buffer C-ABI call abcoct_process_bscans (pinned host frames in,
+               host display B-scans out, H2D + D2H inside the timed region)
+  roofline     fused reconstruction kernel: algorithmic bytes per launch / mean launch duration (CUDA events on the
+               launching stream, inside the timed region) against the measured HBM peak (MEASURED_PEAKS.json)
+  cpu_baseline the oracle (the reference's OpenCV arithmetic via cv2) timed on this box's host cores on a bounded sample
+
+`--impl reference` times that CPU implementation only (all host cores, one process per core, disjoint B-scans).
+The oracle is used here ONLY as the thing timed in those two legs; the product path never touches it.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+LMIN, LMAX = 840.5e-9, 859.5e-9
+
+# name -> parameters; `frames` = frames per step and per GPU (weak scaling)
+WORKLOADS = {
+    "c1": dict(w=1280, h=960, N=1280, D=640, A=1, variant=0, frames=384, seed=1001,
+               desc="C1 1280x960 u16, N=1280, D=640, averages=1, FFT variant"),
+    "c2": dict(w=1280, h=960, N=1280, D=640, A=8, variant=1, frames=384, seed=1002,
+               desc="C2 1280x960 u16, N=1280, D=640, averages=8, DARK variant"),
+    "c4": dict(w=1920, h=1200, N=1920, D=960, A=1, variant=0, frames=125, seed=1004,
+               desc="C4 1920x1200 u16 (12-bit), N=1920, D=960, 125 B-scans per GPU"),
+    "c5-1024": dict(w=1024, h=1024, N=1024, D=512, A=1, variant=0, frames=512, seed=1005,
+                    desc="C5 1024-sample u16 spectra, 1024 A-scans/frame, D=512"),
+    "c5-2048": dict(w=2048, h=1024, N=2048, D=1024, A=1, variant=0, frames=256, seed=1005,
+                    desc="C5 2048-sample u16 spectra, 1024 A-scans/frame, D=1024 (north_star target config)"),
+    "c5-4096": dict(w=4096, h=1024, N=4096, D=2048, A=1, variant=0, frames=128, seed=1005,
+                    desc="C5 4096-sample u16 spectra, 1024 A-scans/frame, D=2048"),
+}
+DEFAULT_WORKLOAD = "c5-2048"
+
+
+def oracle_params(wl):
+    from oracle.abcoct_oracle import Params
+
+    return Params(w=wl["w"], h=wl["h"], numfftpoints=wl["N"], numdisplaypoints=wl["D"], averages=wl["A"],
+                  variant=wl["variant"], lambdamin=LMIN, lambdamax=LMAX)
+
+
+def abi_params(api, wl):
+    return api.default_params(w=wl["w"], h=wl["h"], bpp=16, binx=1, biny=1, averages=wl["A"], numfftpoints=wl["N"],
+                              numdisplaypoints=wl["D"], lambdamin=LMIN, lambdamax=LMAX, mediann=0, movavgn=0, fft_multiplier=1,
+                              rowwisenormalize=0, donotnormalize=1, variant=wl["variant"], weight_mode=0)
+
+
+def make_inputs(wl, nframes, n_unique=4):
+    """Synthetic frames + calibration for one rank. Few unique interferograms, tiled to the batch size."""
+    from fdoct_b200 import synth
+
+    w, h, A, seed = wl["w"], wl["h"], wl["A"], wl["seed"]
+    dark = wl["variant"] == 1
+    fs = 4095 if wl.get("twelve_bit") else 65535
+    nu = max(A, n_unique) if nframes >= max(A, n_unique) else nframes
+    uniq = synth.make_frames(nu, w, h, seed=seed, dark=dark, full_scale=fs)
+    frames = uniq[np.arange(nframes) % nu]
+    yd = None
+    if dark:
+        yd = synth.make_dark_frames(2, w, h, seed=seed + 2).mean(axis=0)
+        yr = synth.make_background_frames(2, w, h, seed=seed + 1, dark=True, full_scale=fs).mean(axis=0)
+        ys = yd + 0.02 * (yr - yd)
+        yb = (yr - yd) + (ys - yd)  # BscanDark.cpp:996
+    else:
+        yb = synth.make_background_frames(2, w, h, seed=seed + 1, full_scale=fs).mean(axis=0)
+    return frames, uniq, yb, yd
+
+
+# --------------------------------------------------------------------------------------------- CPU reference leg
+def _cpu_worker(args):
+    """One worker process: oracle over its own B-scans. Returns A-scans processed."""
+    import cv2
+
+    from oracle.abcoct_oracle import Oracle
+
+    wl, frames, yb, yd = args
+    cv2.setNumThreads(1)
+    o = Oracle(oracle_params(wl))
+    o.set_background(yb)
+    if yd is not None:
+        o.set_dark(yd)
+    o.process_bscans(frames)
+    return frames.shape[0] * wl["h"]
+
+
+def time_cpu_reference(wl, uniq, yb, yd, cores, bscans_per_core):
+    """All host cores, one oracle process per core over disjoint B-scans; returns (A-scans/s, sample description)."""
+    import multiprocessing as mp
+
+    A = wl["A"]
+    per = np.concatenate([uniq] * ((bscans_per_core * A + len(uniq) - 1) // len(uniq)))[: bscans_per_core * A]
+    jobs = [(wl, per, yb, yd)] * cores
+    ctx = mp.get_context("fork")
+    with ctx.Pool(cores) as pool:
+        pool.map(_cpu_worker, [(wl, per[:A], yb, yd)] * cores)  # warm the workers (imports, cv2 init)
+        t0 = time.perf_counter()
+        n = sum(pool.map(_cpu_worker, jobs))
+        dt = time.perf_counter() - t0
+    return n / dt, dt, f"{cores} processes x {bscans_per_core} B-scans ({per.shape[0]} frames of {wl['h']} A-scans each)"
+
+
+def calibrate_cpu_sample(wl, uniq, yb, yd, target_s):
+    """Pick how many B-scans per core make about `target_s` seconds of CPU work (one timed B-scan on this host)."""
+    t0 = time.perf_counter()
+    _cpu_worker((wl, uniq[: wl["A"]], yb, yd))
+    one = max(time.perf_counter() - t0, 1e-3)
+    return int(max(1, min(64, round(target_s / one))))
+
+
+# --------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, pw, reasons = [], [], [], set()
+        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for _, r in self.rows]
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def measured_hbm_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# --------------------------------------------------------------------------------------------- main arms
+def run_reference(args, wl, rank):
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    _, uniq, yb, yd = make_inputs(wl, max(wl["A"], 4))
+    per_core = calibrate_cpu_sample(wl, uniq, yb, yd, target_s=args.cpu_seconds / max(1, args.steps + args.warmup))
+    vals = []
+    for i in range(args.warmup + args.steps):
+        v, dt, sample = time_cpu_reference(wl, uniq, yb, yd, cores, per_core)
+        if i >= args.warmup:
+            vals.append((v, dt))
+    value = float(np.mean([v for v, _ in vals]))
+    ms = float(np.mean([dt for _, dt in vals]) * 1e3)
+    import cv2
+
+    line = {
+        "impl": "reference", "metric": "A-scans/s", "value": value, "unit": "A-scans/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64/f32 (OpenCV)", "data": "synthetic",
+        "config": {"workload": wl["desc"], "name": args.workload, "sample_per_step": sample},
+        "bscans_per_s": value / (wl["h"] * wl["A"]),
+        "cpu_baseline": {"value": value, "unit": "A-scans/s", "cores": cores, "kind": "port",
+                         "sample": sample + f"; oracle = Python restatement calling OpenCV {cv2.__version__} kernels"},
+        "e2e": {"value": value, "unit": "A-scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args, wl, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+
+    from fdoct_b200 import api
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    w, h, N, D, A = wl["w"], wl["h"], wl["N"], wl["D"], wl["A"]
+    nframes = args.frames or wl["frames"]
+    nframes = max(A, nframes // A * A)
+    nB = nframes // A
+    frames, uniq, yb, yd = make_inputs(wl, nframes)
+    ctx = api.Context(abi_params(api, wl), gpu_ids=[local_rank])
+    ctx.set_background(yb)
+    if yd is not None:
+        ctx.set_dark(yd)
+
+    # ---- device-resident leg
+    d_in = torch.from_numpy(frames.view(np.int16)).to(dev)
+    d_out = torch.empty((nB, D, h), dtype=torch.uint8, device=dev)
+    stream = torch.cuda.current_stream()
+
+    def step_dev():
+        ctx.process_bscans_device(d_in.data_ptr(), nframes, d_out.data_ptr(), None, stream=stream.cuda_stream)
+
+    for _ in range(max(3, args.warmup)):
+        step_dev()
+    barrier()
+    ctx.timing_reset()
+    l0 = ctx.info().kernel_launches
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record(stream)
+    for _ in range(args.steps):
+        step_dev()
+    e1.record(stream)
+    barrier()
+    t1 = time.perf_counter()
+    dev_ms = e0.elapsed_time(e1)
+    launches = ctx.info().kernel_launches - l0
+    nchunks, recon_ms, norm_ms = ctx.timing_read(0)
+    clocks = sampler.stop(t0, t1) if sampler else None
+
+    # ---- end-to-end leg: pinned host frames -> abcoct_process_bscans -> host display B-scans
+    pin_in = api.PinnedArray(frames.shape, np.uint16)
+    pin_in.array[...] = frames
+    pin_out = api.PinnedArray((nB, D, h), np.uint8)
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    ctx.process_bscans(pin_in.array, out8=pin_out.array)  # warm-up (allocates the ring)
+    barrier()
+    t2 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ctx.process_bscans(pin_in.array, out8=pin_out.array)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t2
+    ok = bool(np.array_equal(pin_out.array, d_out.cpu().numpy()))
+
+    # ---- max over ranks
+    t = torch.tensor([dev_ms, e2e_s * 1e3, recon_ms / max(nchunks, 1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms, recon_launch_ms = [float(x) for x in t.cpu()]
+    info = ctx.info()
+
+    if rank == 0:
+        ascans_step = nframes * h * world
+        value = ascans_step * args.steps / (dev_ms * 1e-3)
+        e2e_value = ascans_step * e2e_steps / (e2e_ms * 1e-3)
+        peak, peak_src = measured_hbm_peak()
+        bytes_per_ascan = 2 * w + D / A  # u16 pixels in + u8 display pixels out, dB output off
+        ascans_per_launch = nframes * h / max(nchunks // max(args.steps, 1), 1)
+        achieved = bytes_per_ascan * ascans_per_launch / (recon_launch_ms * 1e-3) / 1e9 if recon_launch_ms > 0 else None
+        line = {
+            "metric": "A-scans/s", "value": value, "unit": "A-scans/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": dev_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": wl["desc"], "name": args.workload, "frames_per_step_per_gpu": nframes,
+                       "ascans_per_step": ascans_step, "input_bytes_per_step_per_gpu": int(frames.nbytes),
+                       "l2": "inputs larger than L2 (no flush needed)" if frames.nbytes > 256e6 else "inputs SMALLER than 2x L2",
+                       "parallelism": f"{world} GPU(s), B-scans sharded by rank, no collective on the data path"},
+            "bscans_per_s": value / (h * A),
+            "gpu_launches": int(launches),
+            "kernel_ms_per_step": {"recon": recon_ms / args.steps, "normalise": norm_ms / args.steps},
+            "e2e": {"value": e2e_value, "unit": "A-scans/s", "h2d_bytes_per_step": int(frames.nbytes) * world,
+                    "d2h_bytes_per_step": int(nB * D * h) * world, "steps": e2e_steps, "matches_device_leg": ok},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "kernel": "recon_kernel (fused reconstruction)", "bytes_per_ascan": bytes_per_ascan,
+                         "ascans_per_launch": ascans_per_launch, "launch_ms": recon_launch_ms, "peak_source": peak_src,
+                         "whole_step_frac": bytes_per_ascan * value / world / 1e9 / peak},
+            "plan": {"fft_threads": info.fft_threads, "radix": list(info.fft_radix), "groups_per_cta": info.groups_per_cta,
+                     "smem_bytes": info.smem_bytes, "regs_per_thread": info.regs_per_thread, "sm_count": info.sm_count},
+            "clocks": clocks,
+        }
+        if not args.no_cpu and world >= 1:
+            cores = os.cpu_count() or 1
+            per_core = calibrate_cpu_sample(wl, uniq, yb, yd, target_s=args.cpu_seconds)
+            v, dt, sample = time_cpu_reference(wl, uniq, yb, yd, cores, per_core)
+            line["cpu_baseline"] = {"value": v, "unit": "A-scans/s", "cores": cores, "kind": "port",
+                                    "sample": sample + f"; {dt:.1f} s; oracle = Python restatement calling the reference's OpenCV kernels (cv2)"}
+        print(json.dumps(line), flush=True)
+    pin_in.free()
+    pin_out.free()
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--frames", type=int, default=0, help="frames per step per GPU (default: the workload's)")
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work per timed CPU sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world and world == 1 and args.gpus > 1:
+        # convenience: relaunch under torchrun when started as plain `python bench.py --gpus N`
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}", "--master-addr", "127.0.0.1",
+               "--master-port", str(29500 + os.getpid() % 1000), os.path.abspath(__file__)] + sys.argv[1:]
+        raise SystemExit(subprocess.call(cmd))
+    wl = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, wl, rank)
+    else:
+        run_ours(args, wl, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -54,7 +54,7 @@ EXPORTS = [
     "abcoct_params_default", "abcoct_params_from_ini", "abcoct_create", "abcoct_destroy", "abcoct_last_error",
     "abcoct_set_background", "abcoct_set_pishift", "abcoct_set_dark", "abcoct_set_calibration_from_frames",
     "abcoct_build_tables", "abcoct_get_tables", "abcoct_get_window", "abcoct_process_bscans",
-    "abcoct_process_bscans_device", "abcoct_debug_linearised", "abcoct_host_alloc", "abcoct_host_free", "abcoct_get_info",
+    "abcoct_process_bscans_device", "abcoct_timing_reset", "abcoct_timing_read", "abcoct_debug_linearised", "abcoct_host_alloc", "abcoct_host_free", "abcoct_get_info",
 ]
 
 _lib = None
@@ -90,6 +90,8 @@ def lib() -> C.CDLL:
     L.abcoct_get_window.argtypes = [vp, vp]
     L.abcoct_process_bscans.argtypes = [vp, vp, sz, sz, vp, vp]
     L.abcoct_process_bscans_device.argtypes = [vp, i32, vp, sz, sz, vp, vp, vp]
+    L.abcoct_timing_reset.argtypes = [vp]
+    L.abcoct_timing_read.argtypes = [vp, i32, C.POINTER(C.c_uint32), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.abcoct_debug_linearised.argtypes = [vp, vp, sz, vp]
     L.abcoct_host_alloc.argtypes = [sz]
     L.abcoct_host_alloc.restype = vp
@@ -244,6 +246,15 @@ class Context:
         """Device-pointer call (abcoct_process_bscans_device); pointers are raw integers (e.g. tensor.data_ptr())."""
         self._check(lib().abcoct_process_bscans_device(self._h, gpu_index, d_frames, nframes, stride_bytes, d_out8,
                                                        d_outdb, stream))
+
+    def timing_reset(self):
+        self._check(lib().abcoct_timing_reset(self._h))
+
+    def timing_read(self, gpu_index: int = 0):
+        """(chunks timed, summed recon-kernel ms, summed normalise-kernel ms) since timing_reset."""
+        n, r, m = C.c_uint32(), C.c_double(), C.c_double()
+        self._check(lib().abcoct_timing_read(self._h, gpu_index, C.byref(n), C.byref(r), C.byref(m)))
+        return n.value, r.value, m.value
 
     def info(self) -> Info:
         i = Info()

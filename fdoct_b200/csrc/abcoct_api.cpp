@@ -23,6 +23,7 @@ namespace {
 
 thread_local std::string g_create_error;
 
+constexpr int kTimedChunks = 512;  // timing-event pool size (chunks timed between two abcoct_timing_reset calls)
 constexpr int kSlots = 3;  // pinned-ring depth per GPU (>= 3 streams per GPU)
 
 struct GpuState {
@@ -30,7 +31,8 @@ struct GpuState {
   int sm_count = 0;
   cudaStream_t stream[kSlots] = {};
   cudaEvent_t slot_done[kSlots] = {};
-  cudaEvent_t ev[4] = {};
+  std::vector<cudaEvent_t> tev;  // timing-event pool: 3 events per timed chunk (before recon, between, after normalise)
+  size_t tev_used = 0;
   unsigned char* d_tables = nullptr;
   float* d_gain = nullptr;
   float* d_subg = nullptr;
@@ -251,12 +253,16 @@ int enqueue_device(abcoct_ctx* c, GpuState& g, int slot, const uint8_t* d_frames
     a.clamp55 = c->p.clampupper ? 1 : 0;
     const int grid = std::min(g.sm_count, (a.nitems + c->G - 1) / c->G);
     CU(c, launch_minmax_init(a.minmax, (int)nb, st));
-    if (time_it) CU(c, cudaEventRecord(g.ev[0], st));
+    const bool timed = time_it && g.tev_used + 3 <= g.tev.size();
+    if (timed) CU(c, cudaEventRecord(g.tev[g.tev_used], st));
     CU(c, c->plan->launch(a, c->has_sub, c->G, grid, st));
-    if (time_it) CU(c, cudaEventRecord(g.ev[1], st));
+    if (timed) CU(c, cudaEventRecord(g.tev[g.tev_used + 1], st));
     CU(c, launch_normalise(a.scratch, a.minmax, d_out8 + b0 * c->D * c->oph, d_outdb ? d_outdb + b0 * c->D * c->oph : nullptr, (int)nb,
                            c->oph, c->D, a.thr, a.clamp55, (float)c->p.clamp_db, st));
-    if (time_it) CU(c, cudaEventRecord(g.ev[2], st));
+    if (timed) {
+      CU(c, cudaEventRecord(g.tev[g.tev_used + 2], st));
+      g.tev_used += 3;
+    }
     c->launches += 3;
   }
   return ABCOCT_OK;
@@ -462,7 +468,8 @@ int abcoct_create(const abcoct_params* params, const int* gpu_ids, int ngpu, abc
       ok = ok && cudaStreamCreateWithFlags(&g.stream[s], cudaStreamNonBlocking) == cudaSuccess;
       ok = ok && cudaEventCreateWithFlags(&g.slot_done[s], cudaEventDisableTiming) == cudaSuccess;
     }
-    for (int k = 0; k < 4 && ok; ++k) ok = ok && cudaEventCreate(&g.ev[k]) == cudaSuccess;
+    g.tev.assign(3 * kTimedChunks, nullptr);
+    for (size_t k = 0; k < g.tev.size() && ok; ++k) ok = ok && cudaEventCreate(&g.tev[k]) == cudaSuccess;
     ok = ok && cudaMalloc(&g.d_tables, blob.size()) == cudaSuccess;
     ok = ok && cudaMemcpy(g.d_tables, blob.data(), blob.size(), cudaMemcpyHostToDevice) == cudaSuccess;
     if (!ok) {
@@ -492,8 +499,8 @@ void abcoct_destroy(abcoct_ctx* c) {
       if (g.h_out8[s]) cudaFreeHost(g.h_out8[s]);
       if (g.h_outdb[s]) cudaFreeHost(g.h_outdb[s]);
     }
-    for (int k = 0; k < 4; ++k)
-      if (g.ev[k]) cudaEventDestroy(g.ev[k]);
+    for (cudaEvent_t e : g.tev)
+      if (e) cudaEventDestroy(e);
     cudaFree(g.d_tables);
     cudaFree(g.d_gain);
     cudaFree(g.d_subg);
@@ -591,12 +598,36 @@ int abcoct_process_bscans_device(abcoct_ctx* c, int gi, const void* d_frames, si
   int rc = enqueue_device(c, g, 0, static_cast<const uint8_t*>(d_frames), nframes / c->A, stride_bytes, stride_bytes * c->p.h, d_u8, d_db, st,
                           true);
   if (rc) return rc;
-  if (!cuda_stream) {
-    CU(c, cudaStreamSynchronize(st));
-    float ms = 0;
-    if (cudaEventElapsedTime(&ms, g.ev[0], g.ev[1]) == cudaSuccess) c->last_recon_ms = ms;
-    if (cudaEventElapsedTime(&ms, g.ev[1], g.ev[2]) == cudaSuccess) c->last_norm_ms = ms;
-    cudaGetLastError();
+  if (!cuda_stream) CU(c, cudaStreamSynchronize(st));
+  return ABCOCT_OK;
+}
+
+int abcoct_timing_reset(abcoct_ctx* c) {
+  if (!c) return ABCOCT_ERR_INVALID;
+  for (GpuState& g : c->gpus) g.tev_used = 0;
+  return ABCOCT_OK;
+}
+
+int abcoct_timing_read(abcoct_ctx* c, int gi, uint32_t* nchunks, double* recon_ms, double* norm_ms) {
+  if (!c) return ABCOCT_ERR_INVALID;
+  if (gi < 0 || gi >= (int)c->gpus.size()) return fail(c, ABCOCT_ERR_INVALID, "gpu_index out of range");
+  GpuState& g = c->gpus[gi];
+  CU(c, cudaSetDevice(g.dev));
+  double r = 0, n = 0;
+  for (size_t k = 0; k + 3 <= g.tev_used; k += 3) {
+    float a = 0, b = 0;
+    CU(c, cudaEventSynchronize(g.tev[k + 2]));
+    CU(c, cudaEventElapsedTime(&a, g.tev[k], g.tev[k + 1]));
+    CU(c, cudaEventElapsedTime(&b, g.tev[k + 1], g.tev[k + 2]));
+    r += a;
+    n += b;
+  }
+  if (nchunks) *nchunks = (uint32_t)(g.tev_used / 3);
+  if (recon_ms) *recon_ms = r;
+  if (norm_ms) *norm_ms = n;
+  if (g.tev_used) {
+    c->last_recon_ms = r / (g.tev_used / 3);
+    c->last_norm_ms = n / (g.tev_used / 3);
   }
   return ABCOCT_OK;
 }

@@ -128,6 +128,13 @@ int abcoct_process_bscans_device(abcoct_ctx* ctx, int gpu_index, const void* d_f
                                  size_t stride_bytes, uint8_t* d_bscan_u8, float* d_bscan_db,
                                  void* cuda_stream);
 
+/* Kernel timing of the device entry point (bench.py's roofline): every chunk enqueued by
+ * abcoct_process_bscans_device after abcoct_timing_reset is bracketed by CUDA events ON THE LAUNCHING STREAM
+ * (up to 512 chunks); abcoct_timing_read waits for them and returns the summed durations of the fused
+ * reconstruction kernel and of the display-normalisation kernel, and how many chunks were timed. */
+int abcoct_timing_reset(abcoct_ctx* ctx);
+int abcoct_timing_read(abcoct_ctx* ctx, int gpu_index, uint32_t* nchunks, double* recon_ms, double* norm_ms);
+
 /* Linear (pre-log) averaged magnitude `bscan` (BscanFFT.cpp:1220-1222) of the LAST device/host call's
  * first B-scan and per-stage debug taps are exposed for the parity tests only. */
 int abcoct_debug_linearised(abcoct_ctx* ctx, const void* frame, size_t stride_bytes, float* ylin /* oph x N */);
@@ -142,7 +149,7 @@ typedef struct abcoct_info {
   uint32_t fft_threads, fft_radix[3], groups_per_cta, ctas_per_sm, smem_bytes, regs_per_thread;
   uint32_t ngpu, sm_count;
   uint64_t kernel_launches;        /* kernels launched by this ctx so far                     */
-  double last_recon_ms, last_norm_ms; /* CUDA-event time of the last device call's two kernels   */
+  double last_recon_ms, last_norm_ms; /* mean per-chunk kernel times of the last abcoct_timing_read */
 } abcoct_info;
 int abcoct_get_info(const abcoct_ctx* ctx, abcoct_info* out);
 

@@ -1,0 +1,231 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI, against the oracle and the committed
+golden fixtures.  Everything here needs a B200 (`-m gpu`)."""
+import os
+
+import numpy as np
+import pytest
+
+from util import GOLDEN, MAG_RTOL, abi_params, assert_display_parity, mag_rel_err, oracle_params
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_abi(op, frames, yb, yp=None, yd=None, **kw):
+    from fdoct_b200 import api
+
+    with api.Context(abi_params(op), **kw) as ctx:
+        ctx.set_background(yb)
+        if yp is not None:
+            ctx.set_pishift(yp)
+        if yd is not None:
+            ctx.set_dark(yd)
+        out8, outdb = ctx.process_bscans(np.ascontiguousarray(frames), want_db=True)
+        info = ctx.info()
+    assert info.kernel_launches >= 3
+    return out8, outdb
+
+
+def _check(out8, outdb, ref8, refdb, what):
+    assert out8.shape == ref8.shape and outdb.shape == refdb.shape
+    assert np.isfinite(outdb).all(), what
+    err = mag_rel_err(outdb, refdb)
+    assert err <= MAG_RTOL, f"{what}: magnitude error {err:.3g} > {MAG_RTOL}"
+    frac = assert_display_parity(out8, ref8, what)
+    return err, frac
+
+
+# ------------------------------------------------------------------------------------------- golden fixtures
+def test_golden_wang128():
+    """The reference's own fixture frames (Matlab files/imgi.png, backg.png) through the CUDA path."""
+    z = np.load(os.path.join(GOLDEN, "wang128.npz"))
+    op = oracle_params(w=128, h=96, numfftpoints=128, numdisplaypoints=64, lambdamin=816e-9, lambdamax=884e-9)
+    out8, outdb = _run_abi(op, z["img"][None], z["bg"].astype(np.float64))
+    _check(out8, outdb, z["disp"][None], z["db"][None], "wang128")
+
+
+@pytest.mark.parametrize("name", ["synth_fft_1280x32", "synth_dark_1280x16_a4", "synth_fft_1024x17_n2048_clamp"])
+def test_golden_synth(name):
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    w, h, N, D, A, variant, seed, clamp, wm = [int(x) for x in z["params"]]
+    op = oracle_params(w=w, h=h, numfftpoints=N, numdisplaypoints=D, averages=A, variant=variant, lambdamin=840.5e-9,
+                       lambdamax=859.5e-9, bscanthreshold=float(z["thr"]), clampupper=bool(clamp), weight_mode=wm)
+    out8, outdb = _run_abi(op, z["frames"], z["yb"], yd=z["yd"] if "yd" in z.files else None)
+    _check(out8, outdb, z["out8"], z["outdb"], name)
+
+
+# ------------------------------------------------------------------------------------------- live oracle
+CASES = [
+    # w,    h,  N,    D,    A, nB, variant, extras
+    (128, 7, 128, 64, 1, 3, 0, {}),
+    (96, 8, 128, 33, 2, 2, 0, {}),
+    (256, 9, 256, 128, 1, 2, 0, {}),
+    (512, 6, 512, 200, 3, 1, 1, {}),
+    (640, 5, 640, 320, 1, 2, 0, {"weight_mode": 1}),
+    (1024, 12, 1024, 512, 1, 2, 0, {}),
+    (1000, 6, 1024, 300, 1, 1, 0, {}),
+    (1280, 10, 1280, 640, 2, 2, 1, {}),
+    (1280, 6, 2048, 1024, 1, 1, 0, {"pishift": True}),
+    (1920, 5, 1920, 960, 1, 2, 0, {}),
+    (2048, 11, 2048, 1024, 1, 2, 0, {}),
+    (2048, 4, 2048, 700, 4, 1, 0, {"clampupper": True, "bscanthreshold": 10.0}),
+    (2560, 4, 2560, 320, 1, 1, 0, {}),
+    (2880, 4, 2880, 360, 1, 1, 0, {}),
+    (1920, 4, 3840, 1024, 1, 1, 0, {}),
+    (3840, 3, 3840, 1024, 1, 1, 0, {}),
+    (4096, 6, 4096, 2048, 1, 1, 0, {}),
+    (4096, 3, 4096, 2048, 2, 2, 1, {"pishift": True}),
+]
+
+
+@pytest.mark.parametrize("w,h,N,D,A,nB,variant,extra", CASES)
+def test_against_oracle(w, h, N, D, A, nB, variant, extra):
+    from fdoct_b200 import synth
+    from oracle.abcoct_oracle import Oracle, dark_background
+
+    extra = dict(extra)
+    pishift = extra.pop("pishift", False)
+    if extra.get("clampupper"):
+        h = max(h, 6)
+    op = oracle_params(w=w, h=h, numfftpoints=N, numdisplaypoints=D, averages=A, variant=variant, lambdamin=840.5e-9,
+                       lambdamax=859.5e-9, **extra)
+    seed = 7000 + w + 3 * N + A
+    dark = variant == 1
+    frames = synth.make_frames(nB * A, w, h, seed=seed, dark=dark)
+    o = Oracle(op)
+    yd = yp = None
+    if dark:
+        yd = o.calib_mean_of_frames(synth.make_dark_frames(2, w, h, seed=seed + 2))
+        yr = o.calib_mean_of_frames(synth.make_background_frames(2, w, h, seed=seed + 1, dark=True))
+        ys = yd + 0.02 * (yr - yd)
+        yb = dark_background(yr, yd, ys)
+        o.set_dark(yd)
+    else:
+        yb = o.calib_mean_of_frames(synth.make_background_frames(2, w, h, seed=seed + 1))
+    if pishift:
+        yp = 0.05 * synth.make_frames(1, w, h, seed=seed + 5)[0].astype(np.float64)
+        o.set_pishift(yp)
+    o.set_background(yb)
+    ref8, refdb = o.process_bscans(frames)
+    out8, outdb = _run_abi(op, frames, yb, yp=yp, yd=yd)
+    _check(out8, outdb, ref8, refdb, f"w{w} N{N} A{A}")
+
+
+def test_tables_bit_exact_through_ctx():
+    from fdoct_b200 import api
+    from oracle.abcoct_oracle import barthann_window, build_tables
+
+    op = oracle_params(w=1280, h=8, numfftpoints=2048, numdisplaypoints=512, lambdamin=840.5e-9, lambdamax=859.5e-9)
+    with api.Context(abi_params(op)) as ctx:
+        nk, fr, win = ctx.tables()
+    t = build_tables(op)
+    assert np.array_equal(nk, t["nearestkindex"])
+    assert np.array_equal(fr, t["fractionalk"])
+    assert np.array_equal(win, barthann_window(op.opw))
+
+
+# ------------------------------------------------------------------------------------------- API behaviour
+def _ctx(op):
+    from fdoct_b200 import api
+
+    return api.Context(abi_params(op))
+
+
+def test_state_and_argument_errors():
+    from fdoct_b200 import api
+
+    op = oracle_params(w=256, h=4, numfftpoints=256, numdisplaypoints=64, averages=2)
+    frames = np.full((2, 4, 256), 1000, np.uint16)
+    with _ctx(op) as ctx:
+        with pytest.raises(api.AbcoctError) as e:  # no background yet: data_yb is zeros in the reference
+            ctx.process_bscans(frames)
+        assert e.value.code == api.ERR_STATE
+        ctx.set_background(np.full((4, 256), 500.0))
+        with pytest.raises(api.AbcoctError) as e:  # nframes not a multiple of averages
+            ctx.process_bscans(frames[:1])
+        assert e.value.code == api.ERR_INVALID
+        out = ctx.process_bscans(frames)
+        assert out.shape == (1, 64, 4)
+
+
+def test_host_device_and_batching_bitwise_identical():
+    """Same frames through (a) one host call, (b) one call per B-scan, (c) the device-pointer entry: same bits."""
+    import torch
+
+    from fdoct_b200 import api, synth
+
+    w, h, N, D, A, nB = 1024, 33, 1024, 512, 2, 5
+    op = oracle_params(w=w, h=h, numfftpoints=N, numdisplaypoints=D, averages=A, lambdamin=840.5e-9, lambdamax=859.5e-9)
+    frames = synth.make_frames(nB * A, w, h, seed=11)
+    yb = synth.make_background_frames(2, w, h, seed=12).mean(axis=0)
+    with api.Context(abi_params(op)) as ctx:
+        ctx.set_background(yb)
+        a8, adb = ctx.process_bscans(frames, want_db=True)
+        for b in range(nB):
+            b8, bdb = ctx.process_bscans(frames[b * A:(b + 1) * A], want_db=True)
+            assert np.array_equal(b8[0], a8[b]) and np.array_equal(bdb[0], adb[b])
+        d_in = torch.from_numpy(frames.view(np.int16)).cuda()
+        d8 = torch.empty((nB, D, h), dtype=torch.uint8, device="cuda")
+        ddb = torch.empty((nB, D, h), dtype=torch.float32, device="cuda")
+        torch.cuda.synchronize()
+        ctx.process_bscans_device(d_in.data_ptr(), nB * A, d8.data_ptr(), ddb.data_ptr())
+        assert np.array_equal(d8.cpu().numpy(), a8) and np.array_equal(ddb.cpu().numpy(), adb)
+        # pinned caller buffers take the zero-staging path
+        pin = api.PinnedArray(frames.shape, np.uint16)
+        pin.array[...] = frames
+        p8 = ctx.process_bscans(pin.array)
+        assert np.array_equal(p8, a8)
+        pin.free()
+
+
+def test_averaging_identical_frames_equals_single():
+    """A copies of one frame averaged == that frame alone (mean of equal magnitudes), up to f32 rounding."""
+    from fdoct_b200 import synth
+
+    w, h, N, D = 1280, 16, 1280, 640
+    f = synth.make_frames(1, w, h, seed=21)
+    yb = synth.make_background_frames(2, w, h, seed=22).mean(axis=0)
+    one = oracle_params(w=w, h=h, numfftpoints=N, numdisplaypoints=D, averages=1, lambdamin=840.5e-9, lambdamax=859.5e-9)
+    four = oracle_params(w=w, h=h, numfftpoints=N, numdisplaypoints=D, averages=4, lambdamin=840.5e-9, lambdamax=859.5e-9)
+    a8, adb = _run_abi(one, f, yb)
+    b8, bdb = _run_abi(four, np.repeat(f, 4, axis=0), yb)
+    assert mag_rel_err(bdb, adb) < 1e-6
+    assert np.abs(a8.astype(int) - b8.astype(int)).max() <= 1
+
+
+def test_full_size_properties_c5():
+    """BASELINE config C5 at full size (N = 2048, 1024 A-scans per frame, 64 frames): properties that need no oracle
+    run - duplicated frames give identical B-scans, every B-scan spans 0..255, rows 0/1 mirror row 4 - plus an
+    oracle check of a few sampled B-scans."""
+    from fdoct_b200 import synth
+    from oracle.abcoct_oracle import Oracle
+
+    w, h, N, D, nB = 2048, 1024, 2048, 1024, 64
+    op = oracle_params(w=w, h=h, numfftpoints=N, numdisplaypoints=D, lambdamin=840.5e-9, lambdamax=859.5e-9)
+    uniq = synth.make_frames(4, w, h, seed=1005)
+    frames = uniq[np.arange(nB) % 4]
+    yb = synth.make_background_frames(2, w, h, seed=1006).mean(axis=0)
+    out8, outdb = _run_abi(op, frames, yb)
+    for b in range(4, nB):
+        assert np.array_equal(out8[b], out8[b % 4]) and np.array_equal(outdb[b], outdb[b % 4])
+    assert (out8.reshape(nB, -1).min(axis=1) == 0).all() and (out8.reshape(nB, -1).max(axis=1) == 255).all()
+    assert np.array_equal(outdb[:, 0], outdb[:, 4]) and np.array_equal(outdb[:, 1], outdb[:, 4])
+    o = Oracle(op)
+    o.set_background(yb)
+    ref8, refdb = o.process_bscans(uniq[:2])
+    _check(out8[:2], outdb[:2], ref8, refdb, "C5 full size")
+
+
+def test_multi_gpu_context_matches_single():
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from fdoct_b200 import synth
+
+    w, h, N, D, nB = 1024, 64, 1024, 512, 13
+    op = oracle_params(w=w, h=h, numfftpoints=N, numdisplaypoints=D, lambdamin=840.5e-9, lambdamax=859.5e-9)
+    frames = synth.make_frames(nB, w, h, seed=31, n_unique=3)
+    yb = synth.make_background_frames(2, w, h, seed=32).mean(axis=0)
+    a8, adb = _run_abi(op, frames, yb)
+    b8, bdb = _run_abi(op, frames, yb, ngpu=2)
+    assert np.array_equal(a8, b8) and np.array_equal(adb, bdb)

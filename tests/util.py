@@ -1,0 +1,65 @@
+"""Shared helpers for the parity tests: oracle <-> C-ABI parameter mapping and the tolerance definitions.
+
+Tolerances (BASELINE.json north_star):
+  * index / weight tables ............ bit-exact (int32 equal, f64 equal)
+  * magnitude ........................ <= 1e-4 relative to max(|ref|, 1e-3 * A-scan max)
+  * 8-bit display image .............. +-1 LSB; exact 0 / 255 present like the reference's min-max normalise
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+MAG_RTOL = 1e-4
+MAG_FLOOR = 1e-3
+DB_PER_NEPER = 20.0 * (1.0 / 2.303)  # BscanFFT.cpp:1237
+
+
+def oracle_params(**kw):
+    from oracle.abcoct_oracle import Params
+
+    return Params(**kw)
+
+
+def abi_params(op):
+    """oracle Params -> ctypes abcoct_params (same field names)."""
+    from fdoct_b200 import api
+
+    return api.default_params(
+        w=op.w, h=op.h, bpp=op.bpp, binx=op.binx, biny=op.biny, averages=op.averages, numfftpoints=op.numfftpoints,
+        numdisplaypoints=op.numdisplaypoints, lambdamin=op.lambdamin, lambdamax=op.lambdamax, mediann=op.mediann,
+        movavgn=op.movavgn, fft_multiplier=op.fft_multiplier, rowwisenormalize=int(op.rowwisenormalize),
+        donotnormalize=int(op.donotnormalize), variant=op.variant, weight_mode=op.weight_mode,
+        bscanthreshold=op.bscanthreshold, clampupper=int(op.clampupper), clamp_db=op.clamp_db,
+        bandpassfilter=int(op.bandpassfilter))
+
+
+def db_to_mag(db):
+    """Invert bscandb = ln(bscan + 1e-5) * 20/2.303 (BscanFFT.cpp:1222-1237) back to the averaged magnitude."""
+    return np.exp(np.asarray(db, dtype=np.float64) / DB_PER_NEPER) - 1e-5
+
+
+def mag_rel_err(db_got, db_ref):
+    """Worst |mag_got - mag_ref| / max(|mag_ref|, 1e-3 * max over the A-scan); arrays are [nB, D, oph]."""
+    g, r = db_to_mag(db_got), db_to_mag(db_ref)
+    # rows 0,1 are copies of row 4 (DC mask) - they take part like any other row
+    colmax = np.abs(r).max(axis=-2, keepdims=True)
+    den = np.maximum(np.abs(r), MAG_FLOOR * colmax)
+    return float((np.abs(g - r) / den).max())
+
+
+def assert_display_parity(got8, ref8, what=""):
+    d = np.abs(got8.astype(np.int16) - ref8.astype(np.int16))
+    assert d.max() <= 1, f"{what}: display differs by {d.max()} LSB at {np.argwhere(d > 1)[:5]}"
+    # the reference's min-max normalise puts exact 0 and 255 in every B-scan; so must we, at the same places
+    for b in range(ref8.shape[0]):
+        assert got8[b].min() == ref8[b].min() and got8[b].max() == ref8[b].max(), what
+        assert (got8[b][ref8[b] == 255] >= 254).all() and (got8[b][ref8[b] == 0] <= 1).all(), what
+    return float((d > 0).mean())
