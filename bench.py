@@ -132,43 +132,56 @@ def calibrate_cpu_sample(wl, uniq, yb, yd, target_s):
 
 # --------------------------------------------------------------------------------------------- clocks
 class ClockSampler:
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """Samples SM clock, power and throttle reasons of one GPU through NVML every ~2 ms from a thread, so that even a
+    timed region of a few tens of milliseconds holds samples (nvidia-smi -lms is too coarse for that)."""
 
     def __init__(self, gpu_index):
-        self.rows = []
-        self.proc = None
+        self.rows, self.stop_flag, self.h, self.nv = [], False, None, None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={gpu_index}", f"--query-gpu={self.QUERY}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
-            self.th.start()
-        except Exception:
-            self.proc = None
+            import pynvml as nv
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), line.strip()))
+            nv.nvmlInit()
+            self.nv = nv
+            self.h = nv.nvmlDeviceGetHandleByIndex(gpu_index)
+            self.max_sm = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+            self.th = threading.Thread(target=self._loop, daemon=True)
+            self.th.start()
+        except Exception as e:  # pragma: no cover
+            self.err = repr(e)
+            self.h = None
+
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                self.rows.append((time.perf_counter(), sm, pw, rs))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def stop(self, t0, t1):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, pw, reasons = [], [], [], set()
-        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.15] or [r for _, r in self.rows]
-        for r in rows:
-            f = [x.strip() for x in r.split(",")]
-            try:
-                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
-            except Exception:
-                continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
+        if self.h is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + getattr(self, "err", "?")]}
+        self.stop_flag = True
+        self.th.join(timeout=1.0)
+        nv = self.nv
+        rows = [r for r in self.rows if t0 <= r[0] <= t1]
+        in_region = len(rows)
+        if not rows:
+            rows = self.rows[-3:]
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        reasons = sorted(n for n, bit in names.items() if any(r[3] & bit for r in rows))
+        return {"sm_mhz": float(np.median([r[1] for r in rows])) if rows else None, "sm_max_mhz": float(self.max_sm),
+                "power_w_max": max(r[2] for r in rows) if rows else None, "samples": in_region, "reasons": reasons}
 
 
 def measured_hbm_peak():

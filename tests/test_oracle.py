@@ -1,0 +1,104 @@
+"""CPU tests of the oracle itself (the checker): committed golden vectors, the reference's literal loops vs the
+vectorised forms, and a physics known-answer test on the reference's own fixture frames."""
+import os
+
+import numpy as np
+import pytest
+
+from util import GOLDEN, oracle_params
+
+from oracle.abcoct_oracle import (Oracle, barthann_window, build_tables, build_tables_linear_scan, smoothmovavg,
+                                  zeropadrowwise)
+
+
+def test_tables_match_literal_linear_scan():
+    """searchsorted form == the reference's O(N*M) first-k[i]<klinear[f] scan (BscanFFT.cpp:673-690)."""
+    for w, m, N in [(128, 1, 128), (160, 4, 640), (320, 2, 700), (96, 1, 128)]:
+        p = oracle_params(w=w, h=4, numfftpoints=N, fft_multiplier=m, lambdamin=840.5e-9, lambdamax=859.5e-9)
+        t = build_tables(p)
+        assert np.array_equal(t["nearestkindex"], build_tables_linear_scan(p))
+        nk, fr = t["nearestkindex"], t["fractionalk"]
+        assert (np.diff(nk) <= 0).all() and nk.min() >= 1 and nk.max() <= p.M - 1
+        assert (fr > 0).all() and (fr <= 1.0 + 1e-9).all()
+
+
+def test_golden_wang128_regression_and_physics():
+    """The committed vectors for the reference's fixture frames reproduce, and the two reflectors of
+    Matlab files/wangOCTimg.m (50 um apart) appear as two peaks whose bin spacing matches z = n*pi/(kmax-kmin)."""
+    z = np.load(os.path.join(GOLDEN, "wang128.npz"))
+    p = oracle_params(w=128, h=96, numfftpoints=128, numdisplaypoints=64, lambdamin=816e-9, lambdamax=884e-9)
+    o = Oracle(p, strict=True)
+    o.set_background(z["bg"].astype(np.float64))
+    d = {}
+    db, disp = o.push_frame(z["img"], d)
+    assert np.array_equal(disp, z["disp"])
+    assert np.allclose(db, z["db"], rtol=0, atol=2e-5)
+    assert np.array_equal(o.t["nearestkindex"], z["nk"]) and np.array_equal(o.t["fractionalk"], z["frac"])
+    # physics: a reflector at depth ls in a sample of index ns = 1.38 (wangOCTimg.m:14, 43-46: phase 2 k ns ls) lands in
+    # bin ns * ls * (kmax - kmin) / pi (depth per bin pi / (kmax - kmin), wangOCTrec4.m:200-202); row ii holds reflectors
+    # at ii um (reflectivity 0.5) and ii + 50 um (0.25).
+    t = o.t
+    bins_per_m = 1.38 * (t["kmax"] - t["kmin"]) / np.pi
+    for row in (30, 40, 70):
+        col = db[6:, row]  # one A-scan, skip the masked DC rows
+        pk = np.argsort(col)[::-1]
+        first = int(pk[0])
+        second = int(next(i for i in pk[1:] if abs(i - first) > 3))
+        lo, hi = sorted((first + 6, second + 6))
+        assert abs(lo - (row + 1) * 1e-6 * bins_per_m) <= 1.5, (row, lo, (row + 1) * 1e-6 * bins_per_m)
+        assert abs(hi - (row + 51) * 1e-6 * bins_per_m) <= 1.5, (row, hi, (row + 51) * 1e-6 * bins_per_m)
+
+
+@pytest.mark.parametrize("name", ["synth_fft_1280x32", "synth_dark_1280x16_a4", "synth_fft_1024x17_n2048_clamp"])
+def test_golden_synth_regression(name):
+    """Vectorised oracle == the committed outputs (generated with the strict per-row form)."""
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    w, h, N, D, A, variant, seed, clamp, wm = [int(x) for x in z["params"]]
+    p = oracle_params(w=w, h=h, numfftpoints=N, numdisplaypoints=D, averages=A, variant=variant, lambdamin=840.5e-9,
+                      lambdamax=859.5e-9, bscanthreshold=float(z["thr"]), clampupper=bool(clamp), weight_mode=wm)
+    o = Oracle(p, strict=False)
+    if "yd" in z.files:
+        o.set_dark(z["yd"])
+    o.set_background(z["yb"])
+    out8, outdb = o.process_bscans(z["frames"])
+    assert np.abs(out8.astype(int) - z["out8"].astype(int)).max() <= 1
+    assert (out8 != z["out8"]).mean() < 1e-3
+    assert np.allclose(outdb, z["outdb"], rtol=0, atol=2e-4)
+    if clamp:
+        # element (5,5) is forced to clamp_db before the min-max normalise (BscanFFT.cpp:1248-1254)
+        v = np.maximum(outdb[0], p.bscanthreshold)
+        v[5, 5] = p.clamp_db
+        assert abs(int(out8[0, 5, 5]) - round(255 * (p.clamp_db - v.min()) / (v.max() - v.min()))) <= 1
+
+
+def test_strict_and_vectorised_agree():
+    from fdoct_b200 import synth
+
+    p = oracle_params(w=256, h=6, numfftpoints=512, numdisplaypoints=128, averages=2, fft_multiplier=2, lambdamin=840.5e-9,
+                      lambdamax=859.5e-9)
+    frames = synth.make_frames(4, 256, 6, seed=5)
+    yb = synth.make_background_frames(2, 256, 6, seed=6).mean(axis=0)
+    outs = []
+    for strict in (True, False):
+        o = Oracle(p, strict=strict)
+        o.set_background(yb)
+        outs.append(o.process_bscans(frames))
+    assert np.abs(outs[0][0].astype(int) - outs[1][0].astype(int)).max() <= 1
+    assert np.allclose(outs[0][1], outs[1][1], rtol=0, atol=1e-6)
+
+
+def test_window_and_helpers():
+    w = barthann_window(640)
+    assert w.shape == (640,) and abs(w[0]) < 1e-6 and abs(w[-1]) < 1e-6 and abs(w.max() - 1.0) < 1e-3
+    a = np.arange(12, dtype=np.float64).reshape(2, 6)
+    s = smoothmovavg(a, 1)  # 3 taps + centre again, /4; edge taps replaced by the centre sample
+    assert np.allclose(s[0, 1:-1], a[0, 1:-1]) and np.isclose(s[0, 0], (0 + 0 + 1 + 0) / 4) and np.isclose(s[0, -1], (4 + 5 + 5 + 5) / 4)
+    # Fourier upsample of a band-limited row: result = m * irfft(padded rfft)
+    x = np.cos(2 * np.pi * 3 * np.arange(32) / 32)[None, :]
+    up = zeropadrowwise(x, 2)
+    assert up.shape == (1, 64) and np.allclose(up[0, ::2], x[0], atol=1e-5)
+
+
+def test_oracle_rejects_undefined_reference_behaviour():
+    with pytest.raises(ValueError):
+        Oracle(oracle_params(w=256, h=4, numfftpoints=128))  # N < M reads past fractionalk (BscanFFT.cpp:1170)
