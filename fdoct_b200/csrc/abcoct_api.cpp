@@ -44,7 +44,7 @@ struct GpuState {
   uint8_t* h_out8[kSlots] = {};
   float* h_outdb[kSlots] = {};
   float* d_scratch[kSlots] = {};
-  int* d_minmax[kSlots] = {};
+  int* d_sched[kSlots] = {};
   size_t scratch_bscans[kSlots] = {};
   size_t slot_bscans = 0;  // capacity of the per-slot staging buffers, in B-scans
   bool slot_db = false;
@@ -177,6 +177,15 @@ int upload_calibration(abcoct_ctx* c) {
     has_sub |= (sub != 0.0);
   }
   c->has_sub = has_sub;
+  {  // the kernel reads calibration rows in the bank-conflict-free layout (cal_phys in recon_kernel.cuh)
+    std::vector<float> tmp(c->opw);
+    for (int r = 0; r < c->oph; ++r) {
+      cal_swizzle_row(&gain[(size_t)r * c->opw], tmp.data(), c->opw);
+      std::copy(tmp.begin(), tmp.end(), gain.begin() + (size_t)r * c->opw);
+      cal_swizzle_row(&subg[(size_t)r * c->opw], tmp.data(), c->opw);
+      std::copy(tmp.begin(), tmp.end(), subg.begin() + (size_t)r * c->opw);
+    }
+  }
   for (GpuState& g : c->gpus) {
     CU(c, cudaSetDevice(g.dev));
     if (!g.d_gain) CU(c, cudaMalloc(&g.d_gain, n * 4));
@@ -198,15 +207,17 @@ int upload_calibration(abcoct_ctx* c) {
   return ABCOCT_OK;
 }
 
+int scratch_pitch(const abcoct_ctx* c) { return (c->D + 31) / 32 * 32; }  // whole 128-byte lines per A-scan
+
 int ensure_scratch(abcoct_ctx* c, GpuState& g, int slot, size_t nB) {
   if (g.scratch_bscans[slot] >= nB) return ABCOCT_OK;
   if (g.d_scratch[slot]) cudaFree(g.d_scratch[slot]);
-  if (g.d_minmax[slot]) cudaFree(g.d_minmax[slot]);
+  if (g.d_sched[slot]) cudaFree(g.d_sched[slot]);
   g.d_scratch[slot] = nullptr;
-  g.d_minmax[slot] = nullptr;
+  g.d_sched[slot] = nullptr;
   g.scratch_bscans[slot] = 0;
-  CU(c, cudaMalloc(&g.d_scratch[slot], nB * c->oph * c->D * sizeof(float)));
-  CU(c, cudaMalloc(&g.d_minmax[slot], nB * 2 * sizeof(int)));
+  CU(c, cudaMalloc(&g.d_scratch[slot], nB * c->oph * (size_t)scratch_pitch(c) * sizeof(float)));
+  CU(c, cudaMalloc(&g.d_sched[slot], sched_ints((int)nB) * sizeof(int)));
   g.scratch_bscans[slot] = nB;
   return ABCOCT_OK;
 }
@@ -214,7 +225,7 @@ int ensure_scratch(abcoct_ctx* c, GpuState& g, int slot, size_t nB) {
 size_t scratch_chunk_bscans(const abcoct_ctx* c) {
   size_t mb = 1024;
   if (const char* e = getenv("ABCOCT_SCRATCH_MB")) mb = (size_t)std::max(1L, atol(e));
-  const size_t per = (size_t)c->oph * c->D * sizeof(float);
+  const size_t per = (size_t)c->oph * scratch_pitch(c) * sizeof(float);
   return std::max<size_t>(1, mb * 1024 * 1024 / per);
 }
 
@@ -224,7 +235,6 @@ int enqueue_device(abcoct_ctx* c, GpuState& g, int slot, const uint8_t* d_frames
   const size_t chunkB = std::min(nB, scratch_chunk_bscans(c));
   int rc = ensure_scratch(c, g, slot, chunkB);
   if (rc) return rc;
-  const int groups_total = g.sm_count * c->G;
   for (size_t b0 = 0; b0 < nB; b0 += chunkB) {
     const size_t nb = std::min(chunkB, nB - b0);
     ReconArgs a{};
@@ -234,36 +244,37 @@ int enqueue_device(abcoct_ctx* c, GpuState& g, int slot, const uint8_t* d_frames
     a.W = c->opw;
     a.oph = c->oph;
     a.D = c->D;
+    a.Dp = scratch_pitch(c);
     a.A = c->A;
     a.nB = (int)nb;
     a.npairs = (c->oph + 1) / 2;
-    int Gb = std::max(1, 8 / c->A);
-    while (Gb > 1 && (size_t)a.npairs * ((nb + Gb - 1) / Gb) < (size_t)4 * groups_total) Gb >>= 1;
-    a.Gb = Gb;
-    a.nitems = a.npairs * (int)((nb + Gb - 1) / Gb);
+    if ((size_t)a.npairs * nb > 0x7fff0000u) return fail(c, ABCOCT_ERR_INVALID, "too many A-scan pairs in one chunk");
+    a.nitems = a.npairs * (int)nb;
+    a.nparts = (c->oph + c->plan->d.T - 1) / c->plan->d.T;
     a.gain = g.d_gain;
     a.subg = g.d_subg;
-    a.idxT = reinterpret_cast<const uint16_t*>(g.d_tables);
+    a.idxT = reinterpret_cast<const uint32_t*>(g.d_tables);
     a.scratch = g.d_scratch[slot];
-    a.minmax = g.d_minmax[slot];
+    a.sched = g.d_sched[slot];
+    a.out8 = d_out8 + b0 * c->D * c->oph;
+    a.outdb = d_outdb ? d_outdb + b0 * c->D * c->oph : nullptr;
     a.inv_W = 1.0f / (float)c->opw;
     a.out_scale = 0.5f / (float)c->A;
     a.db_scale = (float)(0.6931471805599453 * (20.0 * (1.0 / 2.303)));
     a.thr = (float)c->p.bscanthreshold;
+    a.clamp_db = (float)c->p.clamp_db;
     a.clamp55 = c->p.clampupper ? 1 : 0;
     const int grid = std::min(g.sm_count, (a.nitems + c->G - 1) / c->G);
-    CU(c, launch_minmax_init(a.minmax, (int)nb, st));
+    CU(c, launch_sched_init(a.sched, (int)nb, st));
     const bool timed = time_it && g.tev_used + 3 <= g.tev.size();
     if (timed) CU(c, cudaEventRecord(g.tev[g.tev_used], st));
     CU(c, c->plan->launch(a, c->has_sub, c->G, grid, st));
-    if (timed) CU(c, cudaEventRecord(g.tev[g.tev_used + 1], st));
-    CU(c, launch_normalise(a.scratch, a.minmax, d_out8 + b0 * c->D * c->oph, d_outdb ? d_outdb + b0 * c->D * c->oph : nullptr, (int)nb,
-                           c->oph, c->D, a.thr, a.clamp55, (float)c->p.clamp_db, st));
     if (timed) {
+      CU(c, cudaEventRecord(g.tev[g.tev_used + 1], st));
       CU(c, cudaEventRecord(g.tev[g.tev_used + 2], st));
       g.tev_used += 3;
     }
-    c->launches += 3;
+    c->launches += 2;
   }
   return ABCOCT_OK;
 }
@@ -494,7 +505,7 @@ void abcoct_destroy(abcoct_ctx* c) {
       cudaFree(g.d_out8[s]);
       cudaFree(g.d_outdb[s]);
       cudaFree(g.d_scratch[s]);
-      cudaFree(g.d_minmax[s]);
+      cudaFree(g.d_sched[s]);
       if (g.h_in[s]) cudaFreeHost(g.h_in[s]);
       if (g.h_out8[s]) cudaFreeHost(g.h_out8[s]);
       if (g.h_outdb[s]) cudaFreeHost(g.h_outdb[s]);

@@ -28,23 +28,23 @@ template <class P>
 static void build_blob_fn(int W, const int* idx, const float* wq, const float* win, std::vector<unsigned char>& blob) {
   const SmemLayout L = make_layout<P>(W, false);
   blob.assign(L.groups, 0);
-  uint16_t* idxT = reinterpret_cast<uint16_t*>(blob.data() + L.idxT);
+  uint32_t* idxT = reinterpret_cast<uint32_t*>(blob.data() + L.idxT);
   float* wqT = reinterpret_cast<float*>(blob.data() + L.wqT);
   float* winS = reinterpret_cast<float*>(blob.data() + L.win);
   float2* tw0 = reinterpret_cast<float2*>(blob.data() + L.tw0);
   float2* tw1 = reinterpret_cast<float2*>(blob.data() + L.tw1);
   for (int b = 0; b < P::N1; ++b) {
-    for (int a = 0; a < P::R0P8; ++a) {
-      const int q = P::N1 * a + b;
-      idxT[((a >> 3) * P::N1 + b) * 8 + (a & 7)] = uint16_t(a < P::R0 ? idx[q] : W);
-    }
     for (int a = 0; a < P::R0P4; ++a) {
       const int q = P::N1 * a + b;
+      const int i = a < P::R0 ? idx[q] : W;  // W = the zero sentinel slot (outside the swizzled range)
+      const unsigned off1 = 8u * unsigned(i >= W ? W : stg_phys(i));
+      const unsigned off0 = 8u * unsigned(i >= W ? W : stg_phys(i - 1));
+      idxT[((a >> 2) * P::N1 + b) * 4 + (a & 3)] = off1 | (off0 << 16);
       wqT[((a >> 2) * P::N1 + b) * 4 + (a & 3)] = a < P::R0 ? wq[q] : 0.f;
     }
     for (int c = 1; c < P::R0; ++c) cossin_exact((long long)b * c, P::N, kFftSign, tw0[(c - 1) * P::N1 + b]);
   }
-  for (int i = 0; i < W; ++i) winS[i] = win[i];
+  cal_swizzle_row(win, winS, W);
   if (P::THREE)
     for (int bp = 0; bp < P::N2; ++bp)
       for (int c1 = 1; c1 < P::R1; ++c1) cossin_exact((long long)bp * c1, P::N1, kFftSign, tw1[(c1 - 1) * P::N2 + bp]);
@@ -127,75 +127,23 @@ int list_plans(int* out, int cap) {
 }
 
 // ------------------------------------------------------------------------------------------------ small kernels
-__global__ void minmax_init_kernel(int* minmax, int nB) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+// Reset the scheduler block of one launch: item ticket, per-B-scan min/max (order-preserving encodings of +inf / -inf)
+// and the completion / hand-out counters.
+__global__ void sched_init_kernel(int* sched, int nB) {
+  const SchedView v = sched_view(sched, nB);
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 32) sched[i] = 0;
   if (i < nB) {
-    minmax[2 * i] = float_to_ordered(__int_as_float(0x7f800000));      // +inf
-    minmax[2 * i + 1] = float_to_ordered(__int_as_float(0xff800000));  // -inf
+    v.minv[i] = float_to_ordered(__int_as_float(0x7f800000));  // +inf
+    v.maxv[i] = float_to_ordered(__int_as_float(0xff800000));  // -inf
+    v.cnt[i] = 0;
+    v.ready[i] = 0;
+    v.claim[i] = 0;
   }
 }
-cudaError_t launch_minmax_init(int* minmax, int nB, cudaStream_t st) {
-  minmax_init_kernel<<<(nB + 127) / 128, 128, 0, st>>>(minmax, nB);
-  return cudaGetLastError();
-}
-
-// threshold, global min-max normalise, transpose to depth-major, quantise (BscanFFT.cpp:1243-1255).
-// tile = 128 A-scans x 32 depth bins; f64 arithmetic mirrors cv::normalize + convertTo(CV_8UC1, 255.0).
-constexpr int NT_ROWS = 128, NT_BINS = 32;
-__global__ void __launch_bounds__(256) normalise_kernel(const float* __restrict__ scratch, const int* __restrict__ minmax,
-                                                        uint8_t* __restrict__ out8, float* __restrict__ outdb, int oph, int D,
-                                                        float thr, int clamp55, float clamp_db) {
-  __shared__ unsigned char t8[NT_BINS][NT_ROWS + 4];
-  __shared__ float tdb[NT_BINS][NT_ROWS + 1];
-  const int b = blockIdx.z, r0 = blockIdx.x * NT_ROWS, d0 = blockIdx.y * NT_BINS;
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  double smin = (double)ordered_to_float(minmax[2 * b]), smax = (double)ordered_to_float(minmax[2 * b + 1]);
-  if (clamp55) {
-    smin = fmin(smin, (double)clamp_db);
-    smax = fmax(smax, (double)clamp_db);
-  }
-  const double scale = (smax - smin > 2.220446049250313e-16) ? 1.0 / (smax - smin) : 0.0;
-  const double shift = 0.0 - smin * scale;
-  const float* src = scratch + (size_t)b * oph * D;
-  const bool want_db = outdb != nullptr;
-  for (int rr = w; rr < NT_ROWS; rr += 8) {
-    const int row = r0 + rr, d = d0 + lane;
-    if (row < oph && d < D) {
-      const float db = src[(size_t)row * D + d];
-      double x = fmax((double)db, (double)thr);
-      if (clamp55 && d == 5 && row == 5) x = (double)clamp_db;
-      const double v = __dadd_rn(__dmul_rn(x, scale), shift);
-      int q = __double2int_rn(v * 255.0);
-      q = q < 0 ? 0 : (q > 255 ? 255 : q);
-      t8[lane][rr] = (unsigned char)q;
-      if (want_db) tdb[lane][rr] = db;
-    }
-  }
-  __syncthreads();
-  for (int dd = w; dd < NT_BINS; dd += 8) {
-    const int d = d0 + dd;
-    if (d >= D) continue;
-    uint8_t* o8 = out8 + ((size_t)b * D + d) * oph + r0;
-    const int rbase = 4 * lane;
-    if (r0 + rbase + 3 < oph && ((((size_t)b * D + d) * oph + r0) & 3) == 0) {
-      *reinterpret_cast<uint32_t*>(o8 + rbase) = *reinterpret_cast<const uint32_t*>(&t8[dd][rbase]);
-    } else {
-      for (int k = 0; k < 4; ++k)
-        if (r0 + rbase + k < oph) o8[rbase + k] = t8[dd][rbase + k];
-    }
-    if (want_db) {
-      float* od = outdb + ((size_t)b * D + d) * oph + r0;
-      for (int k = 0; k < 4; ++k) {
-        const int rr = lane + 32 * k;
-        if (r0 + rr < oph) od[rr] = tdb[dd][rr];
-      }
-    }
-  }
-}
-cudaError_t launch_normalise(const float* scratch, const int* minmax, uint8_t* out8, float* outdb, int nB, int oph, int D,
-                             float thr, int clamp55, float clamp_db, cudaStream_t st) {
-  dim3 grid((oph + NT_ROWS - 1) / NT_ROWS, (D + NT_BINS - 1) / NT_BINS, nB);
-  normalise_kernel<<<grid, 256, 0, st>>>(scratch, minmax, out8, outdb, oph, D, thr, clamp55, clamp_db);
+cudaError_t launch_sched_init(int* sched, int nB, cudaStream_t st) {
+  const int n = nB > 32 ? nB : 32;
+  sched_init_kernel<<<(n + 127) / 128, 128, 0, st>>>(sched, nB);
   return cudaGetLastError();
 }
 

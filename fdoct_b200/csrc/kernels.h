@@ -27,7 +27,5 @@ struct PlanEntry {
 const PlanEntry* find_plan(int N);
 int list_plans(int* out, int cap);
 
-cudaError_t launch_minmax_init(int* minmax, int nB, cudaStream_t st);
-cudaError_t launch_normalise(const float* scratch, const int* minmax, uint8_t* out8, float* outdb, int nB, int oph, int D,
-                             float thr, int clamp55, float clamp_db, cudaStream_t st);
+cudaError_t launch_sched_init(int* sched, int nB, cudaStream_t st);
 }  // namespace abcoct

@@ -12,8 +12,13 @@
 
 namespace abcoct {
 
-constexpr int ceil_div(int a, int b) { return (a + b - 1) / b; }
-constexpr int cmax(int a, int b) { return a > b ? a : b; }
+#ifdef __CUDACC__
+#define ABC_CX __host__ __device__ constexpr
+#else
+#define ABC_CX constexpr
+#endif
+ABC_CX int ceil_div(int a, int b) { return (a + b - 1) / b; }
+ABC_CX int cmax(int a, int b) { return a > b ? a : b; }
 
 template <int N_, int T_, int R0_, int R1_, int RL_>
 struct Plan {

@@ -38,32 +38,56 @@ struct ReconArgs {
   int W;        // samples per A-scan (opw); multiple of 8
   int oph;      // A-scans per frame
   int D;        // numdisplaypoints
+  int Dp;       // scratch pitch in floats: D rounded up to 32 (whole 128-byte lines per A-scan)
   int A;        // averages (frames per B-scan)
   int nB;       // B-scans in this launch
-  int Gb;       // B-scans per work item (calibration rows are reused for Gb*A frames)
   int npairs;   // ceil(oph / 2)
-  int nitems;   // npairs * ceil(nB / Gb)
+  int nitems;   // npairs * nB; item = bscan * npairs + pair
+  int nparts;   // normalisation jobs per B-scan: ceil(oph / T), T = threads per group of the plan
   const float* gain;  // [oph][W]  1 / yb
   const float* subg;  // [oph][W]  (yd + yp) / yb, or nullptr
-  const uint16_t* idxT;
-  const float* wqT;
-  const float* win;
-  const float2* tw0;
-  const float2* tw1;
-  float* scratch;  // [nB][oph][D] dB values, A-scan major
-  int* minmax;     // [nB][2] order-preserving int encodings of min / max
+  const uint32_t* idxT;  // the table blob (shared-memory image), starts with the gather offsets
+  float* scratch;  // [nB][oph][Dp] dB values, A-scan major; lives in L2 between the two halves of the kernel
+  int* sched;      // [0] next item ticket; per B-scan arrays follow (see SchedView)
+  uint8_t* out8;   // [nB][D][oph] display image (BscanFFT.cpp:1254-1255)
+  float* outdb;    // nullable, [nB][D][oph] bscandb (BscanFFT.cpp:1237-1240)
   float inv_W;
   float out_scale;  // 0.5 / A
   float db_scale;   // ln(2) * 20 * (1 / 2.303)
   float thr;        // bscanthreshold
-  int clamp55;      // clampupper: element (5,5) is excluded from the min/max here
+  float clamp_db;   // value forced into element (5,5) when clampupper
+  int clamp55;      // clampupper: element (5,5) is excluded from the min/max of the data
 };
+
+// Scheduler / per-B-scan state in global memory (ints): [0] item ticket, then nB each of
+// minv, maxv (order-preserving int encodings), cnt (pairs finished), ready (all pairs finished), claim (normalise parts taken).
+constexpr int kNormBins = 32;   // depth bins per transposition tile
+struct SchedView {
+  int* ticket;
+  int* minv;
+  int* maxv;
+  int* cnt;
+  int* ready;
+  int* claim;
+};
+__host__ __device__ inline SchedView sched_view(int* base, int nB) {
+  SchedView v;
+  v.ticket = base;
+  v.minv = base + 32;
+  v.maxv = v.minv + nB;
+  v.cnt = v.maxv + nB;
+  v.ready = v.cnt + nB;
+  v.claim = v.ready + nB;
+  return v;
+}
+__host__ __device__ inline size_t sched_ints(int nB) { return 32 + 5 * (size_t)nB; }
+
 
 // ------------------------------------------------------------------------------------------- shared memory map
 struct SmemLayout {
   int idxT, wqT, win, tw0, tw1;  // CTA-wide tables (byte offsets)
   int groups;                    // start of the per-group blocks
-  int g_gain, g_subg, g_stg, g_buf, g_red, g_mbar, group_bytes;
+  int g_gain, g_subg, g_stg, g_buf, g_red, g_mbar, group_bytes;  // g_buf doubles as the normalisation tile
   __host__ __device__ int total(int G) const { return groups + G * group_bytes; }
 };
 __host__ __device__ constexpr int align16(int x) { return (x + 15) & ~15; }
@@ -72,7 +96,7 @@ template <class P>
 __host__ __device__ inline SmemLayout make_layout(int W, bool has_sub) {
   SmemLayout L{};
   int o = 0;
-  L.idxT = o; o = align16(o + P::R0P8 * P::N1 * 2);
+  L.idxT = o; o = align16(o + P::R0P4 * P::N1 * 4);
   L.wqT = o;  o = align16(o + P::R0P4 * P::N1 * 4);
   L.win = o;  o = align16(o + W * 4);
   L.tw0 = o;  o = align16(o + (P::R0 - 1) * P::N1 * 8);
@@ -82,15 +106,15 @@ __host__ __device__ inline SmemLayout make_layout(int W, bool has_sub) {
   L.g_gain = g; g = align16(g + 2 * W * 4);
   L.g_subg = g; g = align16(g + (has_sub ? 2 * W * 4 : 0));
   L.g_stg = g;  g = align16(g + (W + 1) * 8);
-  L.g_buf = g;  g = align16(g + P::BUF * 8);
-  L.g_red = g;  g = align16(g + 2 * P::NWARPS * 4);
+  L.g_buf = g;  g = align16(g + cmax(P::BUF * 8, kNormBins * (P::T + 4)));
+  L.g_red = g;  g = align16(g + 2 * P::NWARPS * 4 + 32);
   L.g_mbar = g; g = align16(g + 16);
   L.group_bytes = g;
   return L;
 }
 
 struct GroupSmem {  // resolved pointers of one group
-  const uint16_t* idxT;
+  const uint32_t* idxT;  // per gathered sample: byte offset of y[i] | byte offset of y[i-1] << 16 (swizzled staging)
   const float* wqT;
   const float* win;
   const float2* tw0;
@@ -100,13 +124,14 @@ struct GroupSmem {  // resolved pointers of one group
   float2* stg;
   float2* buf;
   float* red;
+  int* slot;  // 8 ints: broadcast slots of the group leader (next items, normalise job)
   unsigned long long* mbar;
 };
 template <class P>
 __host__ __device__ inline GroupSmem resolve(unsigned char* base, const SmemLayout& L, int g) {
   unsigned char* gb = base + L.groups + g * L.group_bytes;
   GroupSmem s;
-  s.idxT = reinterpret_cast<const uint16_t*>(base + L.idxT);
+  s.idxT = reinterpret_cast<const uint32_t*>(base + L.idxT);
   s.wqT = reinterpret_cast<const float*>(base + L.wqT);
   s.win = reinterpret_cast<const float*>(base + L.win);
   s.tw0 = reinterpret_cast<const float2*>(base + L.tw0);
@@ -116,8 +141,21 @@ __host__ __device__ inline GroupSmem resolve(unsigned char* base, const SmemLayo
   s.stg = reinterpret_cast<float2*>(gb + L.g_stg);
   s.buf = reinterpret_cast<float2*>(gb + L.g_buf);
   s.red = reinterpret_cast<float*>(gb + L.g_red);
+  s.slot = reinterpret_cast<int*>(gb + L.g_red + 2 * P::NWARPS * 4);
   s.mbar = reinterpret_cast<unsigned long long*>(gb + L.g_mbar);
   return s;
+}
+
+// ------------------------------------------------------------------------------------------- bank-conflict swizzles
+// Staging buffer of the apodised samples (float2 = rows a,b interleaved): every thread stores the four 16-byte units
+// of its 8-sample chunk ch with one STS.128 each; lanes are 64 bytes apart, so unit j of chunk ch lives at unit
+// j ^ ((ch >> 1) & 3) to spread a quarter-warp over all 32 banks.  In sample indices: bits 1..2 ^= bits 4..5.
+ABC_HD int stg_phys(int i) { return i ^ (((i >> 4) & 3) << 1); }
+// Calibration rows and window (f32, 8 floats per chunk read as two LDS.128, lanes 32 bytes apart): the two 16-byte
+// halves of chunk ch are swapped when bit 2 of ch is set.  In float indices: bit 2 ^= bit 5.
+ABC_HD int cal_phys(int i) { return i ^ (((i >> 5) & 1) << 2); }
+inline void cal_swizzle_row(const float* in, float* out, int W) {
+  for (int i = 0; i < W; ++i) out[cal_phys(i)] = in[i];
 }
 
 // ------------------------------------------------------------------------------------------- per-thread state
@@ -144,14 +182,17 @@ ABC_HD float fast_log2(float x) {
   return log2f(x);
 #endif
 }
-ABC_HD uint4 load_raw16(const uint8_t* p) {
+// raw pixels are read exactly once: bypass L1 and mark the lines evict-first in L2 so that they do not push the
+// dB scratch (which must stay L2-resident between reconstruction and normalisation) out to HBM
+ABC_HD uint4 load_raw16(const uint8_t* p, unsigned long long pol) {
 #ifdef __CUDA_ARCH__
   uint4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
                : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-               : "l"(p));
+               : "l"(p), "l"(pol));
   return v;
 #else
+  (void)pol;
   uint4 v;
   memcpy(&v, p, 16);
   return v;
@@ -173,13 +214,13 @@ ABC_HD float ordered_to_float(int i) {
 // ------------------------------------------------------------------------------------------- phases
 // raw pixel prefetch of one frame's row pair into registers
 template <class P>
-ABC_HD void phase_load(int tid, const uint8_t* rowa, const uint8_t* rowb, int W8, ThreadState<P>& r) {
+ABC_HD void phase_load(int tid, const uint8_t* rowa, const uint8_t* rowb, int W8, ThreadState<P>& r, unsigned long long pol = 0) {
 #pragma unroll
   for (int i = 0; i < P::NCH; ++i) {
     int ch = tid + P::T * i;
     if (ch < W8) {
-      r.raw[0][i] = load_raw16(rowa + 16 * ch);
-      r.raw[1][i] = load_raw16(rowb + 16 * ch);
+      r.raw[0][i] = load_raw16(rowa + 16 * ch, pol);
+      r.raw[1][i] = load_raw16(rowb + 16 * ch, pol);
     }
   }
 }
@@ -198,13 +239,14 @@ ABC_HD void phase_pre1(int tid, const GroupSmem& s, int W, ThreadState<P>& r, fl
       for (int row = 0; row < 2; ++row) {
         const uint4 v = r.raw[row][i];
         const unsigned w32[4] = {v.x, v.y, v.z, v.w};
-        const float4 g0 = *reinterpret_cast<const float4*>(s.gain + row * W + 8 * ch);
-        const float4 g1 = *reinterpret_cast<const float4*>(s.gain + row * W + 8 * ch + 4);
+        const int h4 = (ch & 4);  // cal_phys: halves of the chunk swapped when bit 2 of ch is set
+        const float4 g0 = *reinterpret_cast<const float4*>(s.gain + row * W + 8 * ch + h4);
+        const float4 g1 = *reinterpret_cast<const float4*>(s.gain + row * W + 8 * ch + (h4 ^ 4));
         const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
         float q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         if constexpr (HAS_SUB) {
-          const float4 q0 = *reinterpret_cast<const float4*>(s.subg + row * W + 8 * ch);
-          const float4 q1 = *reinterpret_cast<const float4*>(s.subg + row * W + 8 * ch + 4);
+          const float4 q0 = *reinterpret_cast<const float4*>(s.subg + row * W + 8 * ch + h4);
+          const float4 q1 = *reinterpret_cast<const float4*>(s.subg + row * W + 8 * ch + (h4 ^ 4));
           q[0] = q0.x; q[1] = q0.y; q[2] = q0.z; q[3] = q0.w;
           q[4] = q1.x; q[5] = q1.y; q[6] = q1.z; q[7] = q1.w;
         }
@@ -238,10 +280,12 @@ ABC_HD void phase_pre2(int tid, const GroupSmem& s, int W, const ThreadState<P>&
   for (int i = 0; i < P::NCH; ++i) {
     int ch = tid + P::T * i;
     if (ch < W8) {
-      const float4 w0 = *reinterpret_cast<const float4*>(s.win + 8 * ch);
-      const float4 w1 = *reinterpret_cast<const float4*>(s.win + 8 * ch + 4);
+      const int h4 = (ch & 4);
+      const float4 w0 = *reinterpret_cast<const float4*>(s.win + 8 * ch + h4);
+      const float4 w1 = *reinterpret_cast<const float4*>(s.win + 8 * ch + (h4 ^ 4));
       const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
       float4* dst = reinterpret_cast<float4*>(s.stg + 8 * ch);
+      const int sw = (ch >> 1) & 3;  // stg_phys: unit j of the chunk goes to unit j ^ sw
 #pragma unroll
       for (int j = 0; j < 8; j += 2) {
         float4 o;
@@ -249,7 +293,7 @@ ABC_HD void phase_pre2(int tid, const GroupSmem& s, int W, const ThreadState<P>&
         o.y = (r.t[1][i][j] - mb) * w[j];
         o.z = (r.t[0][i][j + 1] - ma) * w[j + 1];
         o.w = (r.t[1][i][j + 1] - mb) * w[j + 1];
-        dst[j >> 1] = o;
+        dst[(j >> 1) ^ sw] = o;
       }
     }
   }
@@ -263,25 +307,20 @@ ABC_HD void phase_pass0(int tid, const GroupSmem& s) {
     const int b = tid + P::T * i;
     if (P::NB0 * P::T == P::N1 || b < P::N1) {
       float2 in[P::R0], out[P::R0];
-      unsigned short idx[P::R0P8];
+      unsigned off[P::R0P4];
       float wq[P::R0P4];
 #pragma unroll
-      for (int c8 = 0; c8 < P::R0P8 / 8; ++c8) {
-        const uint4 v = *reinterpret_cast<const uint4*>(s.idxT + (c8 * P::N1 + b) * 8);
-        const unsigned w32[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          idx[c8 * 8 + j] = static_cast<unsigned short>((j & 1) ? (w32[j >> 1] >> 16) : (w32[j >> 1] & 0xffffu));
-      }
-#pragma unroll
       for (int c4 = 0; c4 < P::R0P4 / 4; ++c4) {
-        const float4 v = *reinterpret_cast<const float4*>(s.wqT + (c4 * P::N1 + b) * 4);
-        wq[c4 * 4 + 0] = v.x; wq[c4 * 4 + 1] = v.y; wq[c4 * 4 + 2] = v.z; wq[c4 * 4 + 3] = v.w;
+        const uint4 v = *reinterpret_cast<const uint4*>(s.idxT + (c4 * P::N1 + b) * 4);
+        off[c4 * 4 + 0] = v.x; off[c4 * 4 + 1] = v.y; off[c4 * 4 + 2] = v.z; off[c4 * 4 + 3] = v.w;
+        const float4 f = *reinterpret_cast<const float4*>(s.wqT + (c4 * P::N1 + b) * 4);
+        wq[c4 * 4 + 0] = f.x; wq[c4 * 4 + 1] = f.y; wq[c4 * 4 + 2] = f.z; wq[c4 * 4 + 3] = f.w;
       }
+      const unsigned char* stgb = reinterpret_cast<const unsigned char*>(s.stg);
 #pragma unroll
       for (int a = 0; a < P::R0; ++a) {
-        const float2 y1 = s.stg[idx[a]];
-        const float2 y0 = s.stg[idx[a] - 1];
+        const float2 y1 = *reinterpret_cast<const float2*>(stgb + (off[a] & 0xffffu));
+        const float2 y0 = *reinterpret_cast<const float2*>(stgb + (off[a] >> 16));
         in[a].x = fmaf(wq[a], y1.x - y0.x, y1.x);
         in[a].y = fmaf(wq[a], y1.y - y0.y, y1.y);
       }
@@ -396,10 +435,9 @@ ABC_HD void phase_finalise(int tid, const ReconArgs& a, float* rowa_out, float* 
               dst[1] = db;
             }
             const bool is55 = a.clamp55 && kk == 5 && (row_a_index + row) == 5;
-            if (!is55) {
-              const float c = fmaxf(db, a.thr);
-              mn = fminf(mn, c);
-              mx = fmaxf(mx, c);
+            if (!is55) {  // min/max of the raw dB; max(., thr) is monotone and is applied to the two scalars afterwards
+              mn = fminf(mn, db);
+              mx = fmaxf(mx, db);
             }
           }
         }
@@ -457,6 +495,153 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ float4 ld_cg4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+// drop a consumed 128-byte scratch line from L2 without writing it back to HBM
+__device__ __forceinline__ void l2_discard128(const void* p) { asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory"); }
+
+// One normalisation job: A-scans [r0, r0 + T) of B-scan b, all D bins.  Threshold, global min-max normalise,
+// transpose to depth-major, quantise (BscanFFT.cpp:1243-1255); optionally the transposed dB image.  The dB scratch
+// is read from L2 (written moments ago by this kernel) and discarded line by line once consumed.
+// Tile = job = T A-scans x 32 bins.  Thread (q = tid / 8, c4 = tid % 8) loads bins [4 c4, 4 c4 + 4) of the rows
+// 4 q' + {0..3} for q' = q + (T / 8) k: four consecutive A-scans per bin become one packed 32-bit word of the
+// transposed byte tile.  The loads of tile t + 1 are in flight while tile t is quantised and stored.
+template <class P>
+__device__ __forceinline__ void normalise_part(const ReconArgs& a, const SchedView& sv, int b, int part, int g, int tid, unsigned char* tile) {
+  constexpr int T = P::T;
+  constexpr int NR = T;          // A-scans per job and per tile: one row quad pair per thread whatever the plan
+  constexpr int TP = NR + 4;     // byte pitch of the u8 tile [kNormBins][TP]
+  constexpr int QPT = NR / 4;    // row quads per tile
+  constexpr int NK = 2;          // row quads per thread (QPT * 8 / T)
+  const int r0 = part * NR;
+  const int nrows = min(NR, a.oph - r0);
+  float mn = ordered_to_float(__ldcg(sv.minv + b)), mx = ordered_to_float(__ldcg(sv.maxv + b));
+  if (a.clamp55) {  // bscandisp.at<double>(5,5) = 50.0 before the min-max (BscanFFT.cpp:1248-1253)
+    mn = fminf(mn, a.clamp_db);
+    mx = fmaxf(mx, a.clamp_db);
+  }
+  const float range = mx - mn;
+  const float sc = range > 2.220446049250313e-16f ? 255.0f / range : 0.f;  // cv::normalize: scale = 0 for a flat image
+  const float thr = a.thr;
+  const float* src = a.scratch + ((size_t)b * a.oph + r0) * a.Dp;
+  const bool has55 = a.clamp55 && r0 <= 5 && 5 < r0 + nrows;
+  const bool vec_ok = (a.oph & 15) == 0 && nrows == NR && (NR % 16) == 0;
+  const int c4 = tid & 7, q0 = tid >> 3;
+  const int ntiles = (a.D + kNormBins - 1) / kNormBins;
+
+  float4 va[NK][4], vb[NK][4];
+  // row pointers and validity once per job; a tile only adds 128 bytes
+  const float* rowp[NK][4];
+  unsigned valid = 0;
+#pragma unroll
+  for (int k = 0; k < NK; ++k) {
+    const int q = q0 + (T / 8) * k;
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      const int row = 4 * q + rr;
+      const bool ok = q < QPT && row < nrows;
+      rowp[k][rr] = src + (size_t)(ok ? row : 0) * a.Dp + 4 * c4;
+      valid |= ok ? (1u << (4 * k + rr)) : 0u;
+    }
+  }
+  auto load_tile = [&](int t, float4 (&v)[NK][4]) {
+#pragma unroll
+    for (int k = 0; k < NK; ++k)
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr)
+        v[k][rr] = ((valid >> (4 * k + rr)) & 1u) ? ld_cg4(rowp[k][rr] + t * kNormBins) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  auto quant = [&](float x) -> unsigned {
+    // round-half-even of (max(x, thr) - mn) * 255 / (mx - mn) in [0, 255]: 1.5 * 2^23 trick, result in the low byte
+    return __float_as_uint(fmaf(fmaxf(x, thr) - mn, sc, 12582912.0f));
+  };
+  auto pack4 = [&](float x0, float x1, float x2, float x3) -> unsigned {
+    const unsigned lo = __byte_perm(quant(x0), quant(x1), 0x0040);  // bytes: x0, x1
+    const unsigned hi = __byte_perm(quant(x2), quant(x3), 0x0040);
+    return __byte_perm(lo, hi, 0x5410);
+  };
+  auto process_tile = [&](int t, float4 (&v)[NK][4]) {
+    const int d0 = t * kNormBins;
+#pragma unroll
+    for (int k = 0; k < NK; ++k) {
+      const int q = q0 + (T / 8) * k;
+      if (q < QPT) {
+        unsigned* tw = reinterpret_cast<unsigned*>(tile + (4 * c4) * TP + 4 * q);
+        tw[0 * (TP / 4)] = pack4(v[k][0].x, v[k][1].x, v[k][2].x, v[k][3].x);
+        tw[1 * (TP / 4)] = pack4(v[k][0].y, v[k][1].y, v[k][2].y, v[k][3].y);
+        tw[2 * (TP / 4)] = pack4(v[k][0].z, v[k][1].z, v[k][2].z, v[k][3].z);
+        tw[3 * (TP / 4)] = pack4(v[k][0].w, v[k][1].w, v[k][2].w, v[k][3].w);
+      }
+    }
+    group_sync<T>(g);
+    if (has55 && d0 == 0) {  // uniform: the forced pixel lives in this tile
+      if (tid == 0) tile[5 * TP + (5 - r0)] = (unsigned char)(quant(a.clamp_db) & 0xffu);
+      group_sync<T>(g);
+    }
+    // ---- store: per bin, T consecutive A-scans = T contiguous bytes, 16 bytes per thread
+    uint8_t* const obase = a.out8 + ((size_t)b * a.D + d0) * a.oph + r0;
+#pragma unroll
+    for (int i = tid; i < kNormBins * (NR / 16); i += T) {
+      const int dd = i / (NR / 16), w16 = i % (NR / 16);
+      const int d = d0 + dd;
+      if (d < a.D) {
+        uint8_t* o = obase + (size_t)dd * a.oph + 16 * w16;
+        const unsigned char* tp = tile + dd * TP + 16 * w16;
+        if (vec_ok) {
+          const unsigned* t32 = reinterpret_cast<const unsigned*>(tp);
+          __stcs(reinterpret_cast<uint4*>(o), make_uint4(t32[0], t32[1], t32[2], t32[3]));
+        } else {
+          for (int k = 0; k < 16 && 16 * w16 + k < nrows; ++k) o[k] = tp[k];
+        }
+      }
+    }
+    if (a.outdb != nullptr) {  // transposed dB image (rarely requested): straight from the registers, 16-byte row quads
+#pragma unroll
+      for (int k = 0; k < NK; ++k) {
+        const int q = q0 + (T / 8) * k;
+        if (q < QPT) {
+          const float col[4][4] = {{v[k][0].x, v[k][1].x, v[k][2].x, v[k][3].x}, {v[k][0].y, v[k][1].y, v[k][2].y, v[k][3].y},
+                                   {v[k][0].z, v[k][1].z, v[k][2].z, v[k][3].z}, {v[k][0].w, v[k][1].w, v[k][2].w, v[k][3].w}};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int d = d0 + 4 * c4 + j;
+            if (d < a.D) {
+              float* o = a.outdb + ((size_t)b * a.D + d) * a.oph + r0 + 4 * q;
+#pragma unroll
+              for (int rr = 0; rr < 4; ++rr)
+                if (4 * q + rr < nrows) o[rr] = col[j][rr];
+            }
+          }
+        }
+      }
+    }
+    group_sync<T>(g);
+    // ---- the lines of this tile are dead: drop them from L2 so that they are never written back
+    for (int row = tid; row < nrows; row += T) l2_discard128(src + (size_t)row * a.Dp + d0);
+  };
+
+  load_tile(0, va);
+  for (int t = 0; t < ntiles; t += 2) {
+    if (t + 1 < ntiles) load_tile(t + 1, vb);
+    process_tile(t, va);
+    if (t + 1 < ntiles) {
+      if (t + 2 < ntiles) load_tile(t + 2, va);
+      process_tile(t + 1, vb);
+    }
+  }
+}
+
 template <class P, int GMAX, bool HAS_SUB, int MINB>
 __global__ void __launch_bounds__(P::T* GMAX, MINB) recon_kernel(const ReconArgs a, const int G) {
   extern __shared__ __align__(16) unsigned char smem[];
@@ -466,6 +651,7 @@ __global__ void __launch_bounds__(P::T* GMAX, MINB) recon_kernel(const ReconArgs
   const int lane = tid & 31, wrp = tid >> 5;
   const GroupSmem s = resolve<P>(smem, L, g);
   const int W = a.W, W8 = W >> 3;
+  const SchedView sv = sched_view(a.sched, a.nB);
 
   // ---- CTA-wide tables: global (L2-resident) -> shared, once per persistent CTA
   {
@@ -478,8 +664,18 @@ __global__ void __launch_bounds__(P::T* GMAX, MINB) recon_kernel(const ReconArgs
     s.stg[W] = make_float2(0.f, 0.f);  // sentinel read by the never-written end points q = 0 and q = N-1
     mbar_init(s.mbar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    // dynamic schedule: every group claims items (one row pair of one B-scan) from a global ticket, two ahead;
+    // the leader decodes ticket -> (pair, bscan) once so that nobody else divides
+    const int t0 = atomicAdd(sv.ticket, 1), t1 = atomicAdd(sv.ticket, 1);
+    s.slot[0] = t0 < a.nitems ? t0 % a.npairs : -1;
+    s.slot[1] = t0 / a.npairs;
+    s.slot[2] = t1 < a.nitems ? t1 % a.npairs : -1;
+    s.slot[3] = t1 / a.npairs;
   }
   __syncthreads();
+
+  unsigned long long pol;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
 
   ThreadState<P> r;
 #pragma unroll
@@ -487,38 +683,53 @@ __global__ void __launch_bounds__(P::T* GMAX, MINB) recon_kernel(const ReconArgs
 #pragma unroll
     for (int j = 0; j < P::RL; ++j) r.acc[i][j][0] = r.acc[i][j][1] = 0.f;
 
+  auto issue_calibration = [&](int pair) {  // TMA bulk copies of the item's two calibration rows (tid 0 only)
+    const int ra = 2 * pair, rb = (ra + 1 < a.oph) ? ra + 1 : ra;
+    const unsigned rowbytes = static_cast<unsigned>(W) * 4u;
+    mbar_expect_tx(s.mbar, rowbytes * (HAS_SUB ? 4u : 2u));
+    bulk_g2s(s.gain, a.gain + static_cast<size_t>(ra) * W, rowbytes, s.mbar);
+    bulk_g2s(s.gain + W, a.gain + static_cast<size_t>(rb) * W, rowbytes, s.mbar);
+    if constexpr (HAS_SUB) {
+      bulk_g2s(s.subg, a.subg + static_cast<size_t>(ra) * W, rowbytes, s.mbar);
+      bulk_g2s(s.subg + W, a.subg + static_cast<size_t>(rb) * W, rowbytes, s.mbar);
+    }
+  };
+  auto prefetch_rows = [&](int pair, int b, int f) {  // raw pixels of frame f of item (pair, b) into registers
+    const int ra = 2 * pair, rb = (ra + 1 < a.oph) ? ra + 1 : ra;
+    const uint8_t* fp = a.frames + (static_cast<size_t>(b) * a.A + f) * a.frame_stride;
+    phase_load<P>(tid, fp + static_cast<size_t>(ra) * a.row_stride, fp + static_cast<size_t>(rb) * a.row_stride, W8, r, pol);
+  };
+
+  int pair = s.slot[0], bscan = s.slot[1], npair = s.slot[2], nbscan = s.slot[3];  // current and next item (pair < 0: none)
+  if (pair >= 0) {
+    if (tid == 0) issue_calibration(pair);
+    prefetch_rows(pair, bscan, 0);
+  }
   unsigned cal_parity = 0;
-  for (int item = blockIdx.x * G + g; item < a.nitems; item += gridDim.x * G) {
-    const int pair = item % a.npairs, bg = item / a.npairs;
+
+  // Normalisation jobs (B-scan b, block of T A-scans) are assigned statically: group `gid` owns jobs
+  // gid, gid + ngroups, ...  A job may start once all npairs row pairs of its B-scan have been counted in sv.cnt.
+  // Every global round trip of the group leader (ticket, completion poll, completion publish) is issued early and
+  // consumed late so that no warp waits for L2 inside an item.
+  const int ngroups = gridDim.x * G;
+  const int njobs = a.nB * a.nparts;
+  int myjob = blockIdx.x * G + g;  // (tid 0) next normalisation job of this group
+  int pending = -1;                // (tid 0) B-scan whose finished pair has not been published yet
+
+  while (pair >= 0) {
     const int ra = 2 * pair;
     const bool rowb_valid = (ra + 1) < a.oph;
-    const int rb = rowb_valid ? ra + 1 : ra;
-    const int b0 = bg * a.Gb;
-    const int nb_here = min(a.Gb, a.nB - b0);
-
-    group_sync<P::T>(g);  // every thread is done with the previous item's calibration rows and buffers
+    int t_next = 0, polled = 0;
     if (tid == 0) {
-      const unsigned rowbytes = static_cast<unsigned>(W) * 4u;
-      mbar_expect_tx(s.mbar, rowbytes * (HAS_SUB ? 4u : 2u));
-      bulk_g2s(s.gain, a.gain + static_cast<size_t>(ra) * W, rowbytes, s.mbar);
-      bulk_g2s(s.gain + W, a.gain + static_cast<size_t>(rb) * W, rowbytes, s.mbar);
-      if constexpr (HAS_SUB) {
-        bulk_g2s(s.subg, a.subg + static_cast<size_t>(ra) * W, rowbytes, s.mbar);
-        bulk_g2s(s.subg + W, a.subg + static_cast<size_t>(rb) * W, rowbytes, s.mbar);
-      }
+      t_next = atomicAdd(sv.ticket, 1);  // the item after next
+      if (myjob < njobs) polled = *reinterpret_cast<volatile const int*>(sv.cnt + myjob / a.nparts);
     }
-    const uint8_t* f0 = a.frames + static_cast<size_t>(b0) * a.A * a.frame_stride;
-    const uint8_t* pa = f0 + static_cast<size_t>(ra) * a.row_stride;
-    const uint8_t* pb = f0 + static_cast<size_t>(rb) * a.row_stride;
-    phase_load<P>(tid, pa, pb, W8, r);
     while (!mbar_try_wait(s.mbar, cal_parity)) {
     }
     cal_parity ^= 1u;
 
-    const int nframes_item = nb_here * a.A;
-    int fa = 0;  // frame index inside the current B-scan
-    int bi = 0;
-    for (int f = 0; f < nframes_item; ++f) {
+    for (int f = 0; f < a.A; ++f) {
+      const bool last = (f + 1 == a.A);
       float sa, sb;
       phase_pre1<P, HAS_SUB>(tid, s, W, r, sa, sb);
       sa = warp_sum(sa);
@@ -528,7 +739,9 @@ __global__ void __launch_bounds__(P::T* GMAX, MINB) recon_kernel(const ReconArgs
           s.red[2 * wrp] = sa;
           s.red[2 * wrp + 1] = sb;
         }
-        group_sync<P::T>(g);
+      }
+      group_sync<P::T>(g);  // row sums visible; nobody reads the calibration rows of this item any more after its last frame
+      if constexpr (P::NWARPS > 1) {
         sa = 0.f;
         sb = 0.f;
 #pragma unroll
@@ -536,40 +749,88 @@ __global__ void __launch_bounds__(P::T* GMAX, MINB) recon_kernel(const ReconArgs
           sa += s.red[2 * w];
           sb += s.red[2 * w + 1];
         }
-      } else {
-        group_sync<P::T>(g);
       }
       phase_pre2<P>(tid, s, W, r, sa * a.inv_W, sb * a.inv_W);
-      if (f + 1 < nframes_item) {  // prefetch the next frame's rows while this one is transformed
-        pa += a.frame_stride;
-        pb += a.frame_stride;
-        phase_load<P>(tid, pa, pb, W8, r);
+      // prefetch while this frame is transformed: next frame of the item, else the first frame (and calibration) of the next item
+      if (!last) {
+        prefetch_rows(pair, bscan, f + 1);
+      } else if (npair >= 0) {
+        if (tid == 0) issue_calibration(npair);
+        prefetch_rows(npair, nbscan, 0);
       }
       group_sync<P::T>(g);
       phase_pass0<P>(tid, s);
+      if (f == 0 && tid == 0 && pending >= 0) {
+        // publish the previous item: its scratch stores were issued a whole pass ago, so the fence finds nothing in flight
+        __threadfence();
+        atomicAdd(sv.cnt + pending, 1);  // result unused -> RED
+        pending = -1;
+      }
+      if (last && tid == 0) {
+        s.slot[4] = t_next < a.nitems ? t_next % a.npairs : -1;
+        s.slot[5] = t_next / a.npairs;
+        int job = -1;
+        if (myjob < njobs && polled >= a.npairs) {
+          __threadfence();  // acquire side of the completion count
+          job = myjob;
+          myjob += ngroups;
+        }
+        s.slot[6] = job;
+      }
       group_sync<P::T>(g);
       if constexpr (P::THREE) {
         phase_pass1<P>(tid, s);
         group_sync<P::T>(g);
       }
       phase_passL<P>(tid, s, r);
+    }
 
-      if (++fa == a.A) {
-        fa = 0;
-        const int bscan = b0 + bi;
-        ++bi;
-        float* oa = a.scratch + (static_cast<size_t>(bscan) * a.oph + ra) * a.D;
-        float* ob = oa + a.D;
-        float mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000);
-        phase_finalise<P>(tid, a, oa, ob, ra, rowb_valid, r, mn, mx);
-        mn = warp_min(mn);
-        mx = warp_max(mx);
-        if (lane == 0 && mn <= mx) {
-          atomicMin(a.minmax + 2 * bscan, float_to_ordered(mn));
-          atomicMax(a.minmax + 2 * bscan + 1, float_to_ordered(mx));
-        }
+    // ---- B-scan `bscan` of this pair is complete: dB to the L2 scratch, min/max
+    {
+      float* oa = a.scratch + (static_cast<size_t>(bscan) * a.oph + ra) * a.Dp;
+      float* ob = oa + a.Dp;
+      float mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000);
+      phase_finalise<P>(tid, a, oa, ob, ra, rowb_valid, r, mn, mx);
+      mn = warp_min(mn);
+      mx = warp_max(mx);
+      if (lane == 0 && mn <= mx) {  // thresholded min/max (BscanFFT.cpp:1247): max(., thr) commutes with min/max
+        atomicMin(sv.minv + bscan, float_to_ordered(fmaxf(mn, a.thr)));
+        atomicMax(sv.maxv + bscan, float_to_ordered(fmaxf(mx, a.thr)));
+      }
+      pending = bscan;
+      const int job = s.slot[6];
+      if (job >= 0) {
+        group_sync<P::T>(g);  // every thread is done with the exchange buffer (it becomes the transposition tile)
+        normalise_part<P>(a, sv, job / a.nparts, job % a.nparts, g, tid, reinterpret_cast<unsigned char*>(s.buf));
       }
     }
+    pair = npair;
+    bscan = nbscan;
+    npair = s.slot[4];
+    nbscan = s.slot[5];
+  }
+
+  // ---- drain: publish the last item, then finish this group's remaining normalisation jobs
+  group_sync<P::T>(g);
+  if (tid == 0 && pending >= 0) {
+    __threadfence();
+    atomicAdd(sv.cnt + pending, 1);
+  }
+  for (;;) {
+    if (tid == 0) {
+      int job = -1;
+      if (myjob < njobs) {
+        while (ld_acquire(sv.cnt + myjob / a.nparts) < a.npairs) __nanosleep(200);
+        job = myjob;
+        myjob += ngroups;
+      }
+      s.slot[6] = job;
+    }
+    group_sync<P::T>(g);
+    const int job = s.slot[6];
+    if (job < 0) break;
+    normalise_part<P>(a, sv, job / a.nparts, job % a.nparts, g, tid, reinterpret_cast<unsigned char*>(s.buf));
+    group_sync<P::T>(g);
   }
 }
 #endif  // __CUDACC__

@@ -44,8 +44,10 @@ static double run_plan(int W, int D, int A, unsigned seed) {
     gain[i] = 1.0f / (20000.f + 10000.f * uf(rng));
     subg[i] = HAS_SUB ? (64.f + 8.f * uf(rng)) * gain[i] : 0.f;
   }
-  memcpy(s.gain, gain.data(), 2 * W * 4);
-  if (HAS_SUB) memcpy(s.subg, subg.data(), 2 * W * 4);
+  for (int row = 0; row < 2; ++row) {  // calibration rows travel in the bank-conflict-free layout (cal_phys)
+    cal_swizzle_row(gain.data() + row * W, s.gain + row * W, W);
+    if (HAS_SUB) cal_swizzle_row(subg.data() + row * W, s.subg + row * W, W);
+  }
 
   std::vector<std::vector<uint16_t>> frames(A, std::vector<uint16_t>(2 * W));
   for (auto& f : frames)
@@ -55,7 +57,7 @@ static double run_plan(int W, int D, int A, unsigned seed) {
     }
 
   ReconArgs a{};
-  a.W = W; a.oph = 2; a.D = D; a.A = A; a.nB = 1; a.Gb = 1; a.npairs = 1; a.nitems = 1;
+  a.W = W; a.oph = 2; a.D = D; a.Dp = (D + 31) / 32 * 32; a.A = A; a.nB = 1; a.npairs = 1; a.nitems = 1;
   a.inv_W = 1.0f / W; a.out_scale = 0.5f / A; a.db_scale = float(0.6931471805599453 * 20.0 * (1.0 / 2.303));
   a.thr = -30.f; a.clamp55 = 0;
   std::vector<ThreadState<P>> st(T);
@@ -76,6 +78,8 @@ static double run_plan(int W, int D, int A, unsigned seed) {
   std::vector<float> oa(D, -999.f), ob(D, -999.f);
   float mn = 1e30f, mx = -1e30f;
   for (int t = 0; t < T; ++t) phase_finalise<P>(t, a, oa.data(), ob.data(), 0, true, st[t], mn, mx);
+  mn = std::fmax(mn, a.thr);
+  mx = std::fmax(mx, a.thr);
 
   // ---- double reference
   std::vector<std::vector<double>> accd(2, std::vector<double>(N / 2, 0.0));
