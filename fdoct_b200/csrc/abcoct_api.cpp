@@ -173,7 +173,7 @@ int upload_calibration(abcoct_ctx* c) {
   for (size_t i = 0; i < n; ++i) {
     const double sub = (dark ? c->yd[i] : 0.0) + (c->have_yp ? c->yp[i] : 0.0);
     gain[i] = (float)(1.0 / c->yb[i]);
-    subg[i] = (float)(sub / c->yb[i]);
+    subg[i] = (float)(sub / c->yb[i] + 1.0);  // + 1: the kernel stages t - 1 (see phase_pre in recon_kernel.cuh)
     has_sub |= (sub != 0.0);
   }
   c->has_sub = has_sub;
@@ -193,15 +193,13 @@ int upload_calibration(abcoct_ctx* c) {
     CU(c, cudaMemcpy(g.d_gain, gain.data(), n * 4, cudaMemcpyHostToDevice));
     CU(c, cudaMemcpy(g.d_subg, subg.data(), n * 4, cudaMemcpyHostToDevice));
   }
-  // occupancy: the most groups per CTA that fit in shared memory
-  int G = c->plan->gmax;
-  while (G > 1 && c->plan->smem_bytes(c->opw, has_sub, G) > 227 * 1024) --G;
+  const int G = c->plan->groups(has_sub);  // compile-time choice of the plan (threads and shared memory at W = N)
   c->G = G;
   c->smem = c->plan->smem_bytes(c->opw, has_sub, G);
   if (c->smem > 227 * 1024) return fail(c, ABCOCT_ERR_UNSUPPORTED, "shared memory budget exceeded (%d bytes)", c->smem);
   for (GpuState& g : c->gpus) {
     CU(c, cudaSetDevice(g.dev));
-    CU(c, c->plan->attrs(has_sub, c->smem, &c->regs));
+    CU(c, c->plan->attrs(has_sub, c->A == 1, c->smem, &c->regs));
   }
   c->cal_dirty = false;
   return ABCOCT_OK;
@@ -268,7 +266,7 @@ int enqueue_device(abcoct_ctx* c, GpuState& g, int slot, const uint8_t* d_frames
     CU(c, launch_sched_init(a.sched, (int)nb, st));
     const bool timed = time_it && g.tev_used + 3 <= g.tev.size();
     if (timed) CU(c, cudaEventRecord(g.tev[g.tev_used], st));
-    CU(c, c->plan->launch(a, c->has_sub, c->G, grid, st));
+    CU(c, c->plan->launch(a, c->has_sub, grid, st));
     if (timed) {
       CU(c, cudaEventRecord(g.tev[g.tev_used + 1], st));
       CU(c, cudaEventRecord(g.tev[g.tev_used + 2], st));

@@ -30,6 +30,7 @@ static void build_blob_fn(int W, const int* idx, const float* wq, const float* w
   blob.assign(L.groups, 0);
   uint32_t* idxT = reinterpret_cast<uint32_t*>(blob.data() + L.idxT);
   float* wqT = reinterpret_cast<float*>(blob.data() + L.wqT);
+  float* vwT = reinterpret_cast<float*>(blob.data() + L.vwT);
   float* winS = reinterpret_cast<float*>(blob.data() + L.win);
   float2* tw0 = reinterpret_cast<float2*>(blob.data() + L.tw0);
   float2* tw1 = reinterpret_cast<float2*>(blob.data() + L.tw1);
@@ -40,7 +41,11 @@ static void build_blob_fn(int W, const int* idx, const float* wq, const float* w
       const unsigned off1 = 8u * unsigned(i >= W ? W : stg_phys(i));
       const unsigned off0 = 8u * unsigned(i >= W ? W : stg_phys(i - 1));
       idxT[((a >> 2) * P::N1 + b) * 4 + (a & 3)] = off1 | (off0 << 16);
+      // {weight, lerp(window)}: the window term carries the row-mean removal through the resampling (see phase_pre)
+      const bool live = a < P::R0 && i < W;
+      const double vw = live ? (double)win[i] + (double)wq[q] * ((double)win[i] - (double)win[i - 1]) : 0.0;
       wqT[((a >> 2) * P::N1 + b) * 4 + (a & 3)] = a < P::R0 ? wq[q] : 0.f;
+      vwT[((a >> 2) * P::N1 + b) * 4 + (a & 3)] = (float)vw;
     }
     for (int c = 1; c < P::R0; ++c) cossin_exact((long long)b * c, P::N, kFftSign, tw0[(c - 1) * P::N1 + b]);
   }
@@ -50,26 +55,41 @@ static void build_blob_fn(int W, const int* idx, const float* wq, const float* w
       for (int c1 = 1; c1 < P::R1; ++c1) cossin_exact((long long)bp * c1, P::N1, kFftSign, tw1[(c1 - 1) * P::N2 + bp]);
 }
 
-template <class P>
+#ifndef ABC_MAX_THREADS
+#define ABC_MAX_THREADS 512  // threads per CTA (one CTA per SM): 128 registers per thread
+#endif
+constexpr int kSmemBudget = 227 * 1024;
+
+// Groups per CTA of a plan: limited by the thread budget and by shared memory at the largest row width (W = N).
+template <class P, bool HAS_SUB>
 struct PlanLimits {
-  static constexpr int GMAX = (384 / P::T) < 1 ? 1 : (384 / P::T);
+  static constexpr SmemLayout L = make_layout<P>(P::N, HAS_SUB);
+  static constexpr int by_threads = (ABC_MAX_THREADS / P::T) < 1 ? 1 : (ABC_MAX_THREADS / P::T);
+  static constexpr int by_smem = (kSmemBudget - L.groups) / L.group_bytes;
+  static constexpr int G = by_smem < 1 ? 1 : (by_smem < by_threads ? by_smem : by_threads);
 };
 
 template <class P>
-static cudaError_t launch_fn(const ReconArgs& a, bool has_sub, int G, int grid, cudaStream_t st) {
-  constexpr int GMAX = PlanLimits<P>::GMAX;
-  if (G < 1 || G > GMAX) return cudaErrorInvalidValue;
-  const int smem = make_layout<P>(a.W, has_sub).total(G);
-  if (has_sub)
-    recon_kernel<P, GMAX, true, 1><<<grid, P::T * G, smem, st>>>(a, G);
-  else
-    recon_kernel<P, GMAX, false, 1><<<grid, P::T * G, smem, st>>>(a, G);
+static int groups_fn(bool has_sub) {
+  return has_sub ? PlanLimits<P, true>::G : PlanLimits<P, false>::G;
+}
+
+template <class P, bool HAS_SUB, bool A1>
+static cudaError_t launch_one(const ReconArgs& a, int grid, cudaStream_t st) {
+  constexpr int G = PlanLimits<P, HAS_SUB>::G;
+  const int smem = make_layout<P>(a.W, HAS_SUB).total(G);
+  recon_kernel<P, G, HAS_SUB, A1><<<grid, P::T * G, smem, st>>>(a);
   return cudaGetLastError();
 }
 template <class P>
-static cudaError_t attrs_fn(bool has_sub, int smem, int* regs) {
-  constexpr int GMAX = PlanLimits<P>::GMAX;
-  const void* f = has_sub ? (const void*)recon_kernel<P, GMAX, true, 1> : (const void*)recon_kernel<P, GMAX, false, 1>;
+static cudaError_t launch_fn(const ReconArgs& a, bool has_sub, int grid, cudaStream_t st) {
+  const bool a1 = a.A == 1;
+  if (has_sub) return a1 ? launch_one<P, true, true>(a, grid, st) : launch_one<P, true, false>(a, grid, st);
+  return a1 ? launch_one<P, false, true>(a, grid, st) : launch_one<P, false, false>(a, grid, st);
+}
+template <class P, bool HAS_SUB, bool A1>
+static cudaError_t attrs_one(int smem, int* regs) {
+  const void* f = (const void*)recon_kernel<P, PlanLimits<P, HAS_SUB>::G, HAS_SUB, A1>;
   cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   cudaFuncAttributes fa;
@@ -77,12 +97,17 @@ static cudaError_t attrs_fn(bool has_sub, int smem, int* regs) {
   if (e == cudaSuccess && regs) *regs = fa.numRegs;
   return e;
 }
+template <class P>
+static cudaError_t attrs_fn(bool has_sub, bool a1, int smem, int* regs) {
+  if (has_sub) return a1 ? attrs_one<P, true, true>(smem, regs) : attrs_one<P, true, false>(smem, regs);
+  return a1 ? attrs_one<P, false, true>(smem, regs) : attrs_one<P, false, false>(smem, regs);
+}
 
 template <class P>
 static PlanEntry make_entry() {
   PlanEntry e;
   e.d = PlanDesc{P::N, P::T, P::R0, P::R1, P::RL};
-  e.gmax = PlanLimits<P>::GMAX;
+  e.groups = &groups_fn<P>;
   e.smem_bytes = &smem_bytes_fn<P>;
   e.table_bytes = &table_bytes_fn<P>;
   e.build_blob = &build_blob_fn<P>;

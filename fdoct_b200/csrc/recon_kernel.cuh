@@ -85,19 +85,22 @@ __host__ __device__ inline size_t sched_ints(int nB) { return 32 + 5 * (size_t)n
 
 // ------------------------------------------------------------------------------------------- shared memory map
 struct SmemLayout {
-  int idxT, wqT, win, tw0, tw1;  // CTA-wide tables (byte offsets)
+  int idxT, wqT, vwT, win, tw0, tw1;  // CTA-wide tables (byte offsets)
   int groups;                    // start of the per-group blocks
-  int g_gain, g_subg, g_stg, g_buf, g_red, g_mbar, group_bytes;  // g_buf doubles as the normalisation tile
-  __host__ __device__ int total(int G) const { return groups + G * group_bytes; }
+  // g_buf is ONE region used in turn as the staging buffer of the apodised samples (phase_pre -> gather), as the FFT
+  // exchange buffer (pass 0 -> last pass) and as the transposition tile of a normalisation job
+  int g_gain, g_subg, g_buf, g_red, g_mbar, group_bytes;
+  __host__ __device__ constexpr int total(int G) const { return groups + G * group_bytes; }
 };
 __host__ __device__ constexpr int align16(int x) { return (x + 15) & ~15; }
 
 template <class P>
-__host__ __device__ inline SmemLayout make_layout(int W, bool has_sub) {
+__host__ __device__ constexpr SmemLayout make_layout(int W, bool has_sub) {
   SmemLayout L{};
   int o = 0;
   L.idxT = o; o = align16(o + P::R0P4 * P::N1 * 4);
   L.wqT = o;  o = align16(o + P::R0P4 * P::N1 * 4);
+  L.vwT = o;  o = align16(o + P::R0P4 * P::N1 * 4);
   L.win = o;  o = align16(o + W * 4);
   L.tw0 = o;  o = align16(o + (P::R0 - 1) * P::N1 * 8);
   L.tw1 = o;  o = align16(o + (P::THREE ? (P::R1 - 1) * P::N2 * 8 : 0));
@@ -105,8 +108,7 @@ __host__ __device__ inline SmemLayout make_layout(int W, bool has_sub) {
   int g = 0;
   L.g_gain = g; g = align16(g + 2 * W * 4);
   L.g_subg = g; g = align16(g + (has_sub ? 2 * W * 4 : 0));
-  L.g_stg = g;  g = align16(g + (W + 1) * 8);
-  L.g_buf = g;  g = align16(g + cmax(P::BUF * 8, kNormBins * (P::T + 4)));
+  L.g_buf = g;  g = align16(g + cmax(cmax((W + 1) * 8, P::BUF * 8), kNormBins * (P::T + 4)));
   L.g_red = g;  g = align16(g + 2 * P::NWARPS * 4 + 32);
   L.g_mbar = g; g = align16(g + 16);
   L.group_bytes = g;
@@ -115,7 +117,8 @@ __host__ __device__ inline SmemLayout make_layout(int W, bool has_sub) {
 
 struct GroupSmem {  // resolved pointers of one group
   const uint32_t* idxT;  // per gathered sample: byte offset of y[i] | byte offset of y[i-1] << 16 (swizzled staging)
-  const float* wqT;
+  const float* wqT;      // per gathered sample: lerp weight
+  const float* vwT;      // per gathered sample: the same lerp applied to the window (carries the row-mean removal)
   const float* win;
   const float2* tw0;
   const float2* tw1;
@@ -133,12 +136,13 @@ __host__ __device__ inline GroupSmem resolve(unsigned char* base, const SmemLayo
   GroupSmem s;
   s.idxT = reinterpret_cast<const uint32_t*>(base + L.idxT);
   s.wqT = reinterpret_cast<const float*>(base + L.wqT);
+  s.vwT = reinterpret_cast<const float*>(base + L.vwT);
   s.win = reinterpret_cast<const float*>(base + L.win);
   s.tw0 = reinterpret_cast<const float2*>(base + L.tw0);
   s.tw1 = reinterpret_cast<const float2*>(base + L.tw1);
   s.gain = reinterpret_cast<float*>(gb + L.g_gain);
   s.subg = reinterpret_cast<float*>(gb + L.g_subg);
-  s.stg = reinterpret_cast<float2*>(gb + L.g_stg);
+  s.stg = reinterpret_cast<float2*>(gb + L.g_buf);  // same region, see SmemLayout
   s.buf = reinterpret_cast<float2*>(gb + L.g_buf);
   s.red = reinterpret_cast<float*>(gb + L.g_red);
   s.slot = reinterpret_cast<int*>(gb + L.g_red + 2 * P::NWARPS * 4);
@@ -162,7 +166,7 @@ inline void cal_swizzle_row(const float* in, float* out, int W) {
 template <class P>
 struct ThreadState {
   uint4 raw[2][P::NCH];          // prefetched pixels (8 x u16) of row a / row b
-  float t[2][P::NCH][8];         // (y - sub) / yb
+  float2 x[P::NB0][P::R0];       // lambda->k resampled inputs of this thread's first-pass butterflies
   float acc[P::NU][P::RL][2];    // 2 * sum over frames of |A[k]|, |B[k]|
 };
 
@@ -225,21 +229,32 @@ ABC_HD void phase_load(int tid, const uint8_t* rowa, const uint8_t* rowb, int W8
   }
 }
 
-// t = (y - yd - yp) / yb as y * gain - subg, and the per-thread partial row sums
+// Fused pre-processing of one frame's row pair (BscanFFT.cpp:987, 1132, 1141; BscanDark.cpp:1269):
+//   t = (y - yd - yp) / yb  as  y * gain - subg,   staged value t * window,   partial row sums of t.
+// The row-mean removal of BscanFFT.cpp:1135-1139 is linear, so it is applied after the resampling instead:
+//   lerp((t - m) w) = lerp((t - 1) w) - (m - 1) lerp(w)      (phase_gather, lerp(w) precomputed per output sample)
+// which keeps t out of the registers.  The constant 1 keeps the staged values small: t is the interferogram normalised
+// by its background, so its DC level is close to 1 and the two terms do not cancel catastrophically in f32 (the
+// identity is exact for any constant).  subg already contains the +1 when HAS_SUB.  Staged pairwise-interleaved (row a -> .x, row b -> .y).
 template <class P, bool HAS_SUB>
-ABC_HD void phase_pre1(int tid, const GroupSmem& s, int W, ThreadState<P>& r, float& sa, float& sb) {
+ABC_HD void phase_pre(int tid, const GroupSmem& s, int W, const ThreadState<P>& r, float& sa, float& sb) {
   const int W8 = W >> 3;
   sa = 0.f;
   sb = 0.f;
+  if (tid == 0) s.stg[W] = make_float2(0.f, 0.f);  // sentinel read by the never-written end points q = 0 and q = N-1
 #pragma unroll
   for (int i = 0; i < P::NCH; ++i) {
-    int ch = tid + P::T * i;
+    const int ch = tid + P::T * i;
     if (ch < W8) {
+      const int h4 = (ch & 4);  // cal_phys: halves of the chunk swapped when bit 2 of ch is set
+      const float4 w0 = *reinterpret_cast<const float4*>(s.win + 8 * ch + h4);
+      const float4 w1 = *reinterpret_cast<const float4*>(s.win + 8 * ch + (h4 ^ 4));
+      const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+      float tw[2][8];
 #pragma unroll
       for (int row = 0; row < 2; ++row) {
         const uint4 v = r.raw[row][i];
         const unsigned w32[4] = {v.x, v.y, v.z, v.w};
-        const int h4 = (ch & 4);  // cal_phys: halves of the chunk swapped when bit 2 of ch is set
         const float4 g0 = *reinterpret_cast<const float4*>(s.gain + row * W + 8 * ch + h4);
         const float4 g1 = *reinterpret_cast<const float4*>(s.gain + row * W + 8 * ch + (h4 ^ 4));
         const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
@@ -259,72 +274,64 @@ ABC_HD void phase_pre1(int tid, const GroupSmem& s, int W, ThreadState<P>& r, fl
           if constexpr (HAS_SUB)
             tv = fmaf(y, g[j], -q[j]);
           else
-            tv = y * g[j];
-          r.t[row][i][j] = tv;
+            tv = fmaf(y, g[j], -1.0f);
           acc += tv;
+          tw[row][j] = tv * w[j];
         }
         if (row == 0)
           sa += acc;
         else
           sb += acc;
       }
-    }
-  }
-}
-
-// DC removal + apodisation, written pairwise-interleaved (row a -> .x, row b -> .y) for the gather
-template <class P>
-ABC_HD void phase_pre2(int tid, const GroupSmem& s, int W, const ThreadState<P>& r, float ma, float mb) {
-  const int W8 = W >> 3;
-#pragma unroll
-  for (int i = 0; i < P::NCH; ++i) {
-    int ch = tid + P::T * i;
-    if (ch < W8) {
-      const int h4 = (ch & 4);
-      const float4 w0 = *reinterpret_cast<const float4*>(s.win + 8 * ch + h4);
-      const float4 w1 = *reinterpret_cast<const float4*>(s.win + 8 * ch + (h4 ^ 4));
-      const float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
       float4* dst = reinterpret_cast<float4*>(s.stg + 8 * ch);
       const int sw = (ch >> 1) & 3;  // stg_phys: unit j of the chunk goes to unit j ^ sw
 #pragma unroll
-      for (int j = 0; j < 8; j += 2) {
-        float4 o;
-        o.x = (r.t[0][i][j] - ma) * w[j];
-        o.y = (r.t[1][i][j] - mb) * w[j];
-        o.z = (r.t[0][i][j + 1] - ma) * w[j + 1];
-        o.w = (r.t[1][i][j + 1] - mb) * w[j + 1];
-        dst[(j >> 1) ^ sw] = o;
-      }
+      for (int j = 0; j < 8; j += 2) dst[(j >> 1) ^ sw] = make_float4(tw[0][j], tw[1][j], tw[0][j + 1], tw[1][j + 1]);
     }
   }
 }
 
-// pass 0: lambda->k gather-lerp (BscanFFT.cpp:1169-1171) fused into the first radix-R0 butterflies
+// lambda->k gather-lerp (BscanFFT.cpp:1169-1171) into registers: the inputs of this thread's radix-R0 butterflies.
+// Runs between two barriers because the exchange buffer written by pass 0 overlays the staging buffer read here.
 template <class P>
-ABC_HD void phase_pass0(int tid, const GroupSmem& s) {
+ABC_HD void phase_gather(int tid, const GroupSmem& s, ThreadState<P>& r, float ma, float mb) {
+  const unsigned char* stgb = reinterpret_cast<const unsigned char*>(s.stg);
 #pragma unroll
   for (int i = 0; i < P::NB0; ++i) {
     const int b = tid + P::T * i;
     if (P::NB0 * P::T == P::N1 || b < P::N1) {
-      float2 in[P::R0], out[P::R0];
-      unsigned off[P::R0P4];
-      float wq[P::R0P4];
 #pragma unroll
       for (int c4 = 0; c4 < P::R0P4 / 4; ++c4) {
         const uint4 v = *reinterpret_cast<const uint4*>(s.idxT + (c4 * P::N1 + b) * 4);
-        off[c4 * 4 + 0] = v.x; off[c4 * 4 + 1] = v.y; off[c4 * 4 + 2] = v.z; off[c4 * 4 + 3] = v.w;
-        const float4 f = *reinterpret_cast<const float4*>(s.wqT + (c4 * P::N1 + b) * 4);
-        wq[c4 * 4 + 0] = f.x; wq[c4 * 4 + 1] = f.y; wq[c4 * 4 + 2] = f.z; wq[c4 * 4 + 3] = f.w;
-      }
-      const unsigned char* stgb = reinterpret_cast<const unsigned char*>(s.stg);
+        const float4 f0 = *reinterpret_cast<const float4*>(s.wqT + (c4 * P::N1 + b) * 4);
+        const float4 f1 = *reinterpret_cast<const float4*>(s.vwT + (c4 * P::N1 + b) * 4);
+        const unsigned off[4] = {v.x, v.y, v.z, v.w};
+        const float wq[4] = {f0.x, f0.y, f0.z, f0.w};
+        const float vw[4] = {f1.x, f1.y, f1.z, f1.w};  // lerp(window) at this output sample
 #pragma unroll
-      for (int a = 0; a < P::R0; ++a) {
-        const float2 y1 = *reinterpret_cast<const float2*>(stgb + (off[a] & 0xffffu));
-        const float2 y0 = *reinterpret_cast<const float2*>(stgb + (off[a] >> 16));
-        in[a].x = fmaf(wq[a], y1.x - y0.x, y1.x);
-        in[a].y = fmaf(wq[a], y1.y - y0.y, y1.y);
+        for (int j = 0; j < 4; ++j) {
+          const int a = 4 * c4 + j;
+          if (a < P::R0) {
+            const float2 y1 = *reinterpret_cast<const float2*>(stgb + (off[j] & 0xffffu));
+            const float2 y0 = *reinterpret_cast<const float2*>(stgb + (off[j] >> 16));
+            r.x[i][a].x = fmaf(-ma, vw[j], fmaf(wq[j], y1.x - y0.x, y1.x));
+            r.x[i][a].y = fmaf(-mb, vw[j], fmaf(wq[j], y1.y - y0.y, y1.y));
+          }
+        }
       }
-      Dft<P::R0, kFftSign, 1, 1>::run(in, out);
+    }
+  }
+}
+
+// pass 0: first radix-R0 butterflies on the gathered inputs
+template <class P>
+ABC_HD void phase_pass0(int tid, const GroupSmem& s, ThreadState<P>& r) {
+#pragma unroll
+  for (int i = 0; i < P::NB0; ++i) {
+    const int b = tid + P::T * i;
+    if (P::NB0 * P::T == P::N1 || b < P::N1) {
+      float2 out[P::R0];
+      Dft<P::R0, kFftSign, 1, 1>::run(r.x[i], out);
       s.buf[b] = out[0];
 #pragma unroll
       for (int c = 1; c < P::R0; ++c) s.buf[P::ROWSTRIDE * c + b] = cmul(out[c], s.tw0[(c - 1) * P::N1 + b]);
@@ -364,7 +371,7 @@ ABC_HD int unit_bin(int u, int j) {
 }
 
 // last pass + two-for-one split + magnitude + accumulation (BscanFFT.cpp:1185-1197)
-template <class P>
+template <class P, bool ACCUM = true>
 ABC_HD void phase_passL(int tid, const GroupSmem& s, ThreadState<P>& r) {
   constexpr int RL = P::RL, S = P::S, JH = (RL + 1) / 2;
 #pragma unroll
@@ -387,8 +394,9 @@ ABC_HD void phase_passL(int tid, const GroupSmem& s, ThreadState<P>& r) {
         for (int j = 0; j < RL; ++j) {
           const float2 Pz = Za[j], Qz = Zb[RL - 1 - j];
           const float sr = Pz.x + Qz.x, di = Pz.y - Qz.y, si = Pz.y + Qz.y, dr = Pz.x - Qz.x;
-          r.acc[i][j][0] += fast_sqrt(fmaf(sr, sr, di * di));
-          r.acc[i][j][1] += fast_sqrt(fmaf(si, si, dr * dr));
+          const float m0 = fast_sqrt(fmaf(sr, sr, di * di)), m1 = fast_sqrt(fmaf(si, si, dr * dr));
+          r.acc[i][j][0] = ACCUM ? r.acc[i][j][0] + m0 : m0;
+          r.acc[i][j][1] = ACCUM ? r.acc[i][j][1] + m1 : m1;
         }
       } else {
 #pragma unroll
@@ -402,8 +410,9 @@ ABC_HD void phase_passL(int tid, const GroupSmem& s, ThreadState<P>& r) {
             Qz = Zb[RL - 1 - (j - JH)];
           }
           const float sr = Pz.x + Qz.x, di = Pz.y - Qz.y, si = Pz.y + Qz.y, dr = Pz.x - Qz.x;
-          r.acc[i][j][0] += fast_sqrt(fmaf(sr, sr, di * di));
-          r.acc[i][j][1] += fast_sqrt(fmaf(si, si, dr * dr));
+          const float m0 = fast_sqrt(fmaf(sr, sr, di * di)), m1 = fast_sqrt(fmaf(si, si, dr * dr));
+          r.acc[i][j][0] = ACCUM ? r.acc[i][j][0] + m0 : m0;
+          r.acc[i][j][1] = ACCUM ? r.acc[i][j][1] + m1 : m1;
         }
       }
     }
@@ -478,6 +487,9 @@ __device__ __forceinline__ void group_sync(int g) {
     __syncwarp();
   else
     asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(T) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -642,8 +654,9 @@ __device__ __forceinline__ void normalise_part(const ReconArgs& a, const SchedVi
   }
 }
 
-template <class P, int GMAX, bool HAS_SUB, int MINB>
-__global__ void __launch_bounds__(P::T* GMAX, MINB) recon_kernel(const ReconArgs a, const int G) {
+// G thread groups per CTA (compile time: the register budget follows from T * G), A1 = averages == 1
+template <class P, int G, bool HAS_SUB, bool A1>
+__global__ void __launch_bounds__(P::T* G, 1) recon_kernel(const ReconArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const SmemLayout L = make_layout<P>(a.W, HAS_SUB);
   const int g = threadIdx.x / P::T;
@@ -661,8 +674,8 @@ __global__ void __launch_bounds__(P::T* GMAX, MINB) recon_kernel(const ReconArgs
     for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = src[i];
   }
   if (tid == 0) {
-    s.stg[W] = make_float2(0.f, 0.f);  // sentinel read by the never-written end points q = 0 and q = N-1
     mbar_init(s.mbar, 1);
+    mbar_init(s.mbar + 1, P::NWARPS);  // "exchange buffer free": one arrival per warp after its last-pass reads
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     // dynamic schedule: every group claims items (one row pair of one B-scan) from a global ticket, two ahead;
     // the leader decodes ticket -> (pair, bscan) once so that nobody else divides
@@ -705,7 +718,8 @@ __global__ void __launch_bounds__(P::T* GMAX, MINB) recon_kernel(const ReconArgs
     if (tid == 0) issue_calibration(pair);
     prefetch_rows(pair, bscan, 0);
   }
-  unsigned cal_parity = 0;
+  unsigned cal_parity = 0, free_parity = 0;
+  bool buf_busy = false;  // a previous frame's last pass may still be reading the exchange / staging buffer
 
   // Normalisation jobs (B-scan b, block of T A-scans) are assigned statically: group `gid` owns jobs
   // gid, gid + ngroups, ...  A job may start once all npairs row pairs of its B-scan have been counted in sv.cnt.
@@ -728,10 +742,21 @@ __global__ void __launch_bounds__(P::T* GMAX, MINB) recon_kernel(const ReconArgs
     }
     cal_parity ^= 1u;
 
-    for (int f = 0; f < a.A; ++f) {
-      const bool last = (f + 1 == a.A);
+    const int nA = A1 ? 1 : a.A;
+    for (int f = 0; f < nA; ++f) {
+      const bool last = A1 || (f + 1 == nA);
+      // Split barrier: the staging buffer written next overlays the exchange buffer that slower warps may still be
+      // reading in the previous frame's last pass.  Every warp signalled "done reading" right after that pass
+      // (mbarrier arrive); the dB conversion, stores and scheduling in between hide the wait.
+      if constexpr (P::NWARPS > 1) {
+        if (buf_busy) {
+          while (!mbar_try_wait(s.mbar + 1, free_parity)) {
+          }
+          free_parity ^= 1u;
+        }
+      }
       float sa, sb;
-      phase_pre1<P, HAS_SUB>(tid, s, W, r, sa, sb);
+      phase_pre<P, HAS_SUB>(tid, s, W, r, sa, sb);
       sa = warp_sum(sa);
       sb = warp_sum(sb);
       if constexpr (P::NWARPS > 1) {
@@ -740,7 +765,14 @@ __global__ void __launch_bounds__(P::T* GMAX, MINB) recon_kernel(const ReconArgs
           s.red[2 * wrp + 1] = sb;
         }
       }
-      group_sync<P::T>(g);  // row sums visible; nobody reads the calibration rows of this item any more after its last frame
+      // prefetch while this frame is transformed: next frame of the item, else the first frame of the next item
+      if (!last) {
+        prefetch_rows(pair, bscan, f + 1);
+      } else if (npair >= 0) {
+        prefetch_rows(npair, nbscan, 0);
+      }
+      group_sync<P::T>(g);  // staged samples and row sums visible; the calibration rows have been consumed
+      if (last && npair >= 0 && tid == 0) issue_calibration(npair);
       if constexpr (P::NWARPS > 1) {
         sa = 0.f;
         sb = 0.f;
@@ -750,16 +782,9 @@ __global__ void __launch_bounds__(P::T* GMAX, MINB) recon_kernel(const ReconArgs
           sb += s.red[2 * w + 1];
         }
       }
-      phase_pre2<P>(tid, s, W, r, sa * a.inv_W, sb * a.inv_W);
-      // prefetch while this frame is transformed: next frame of the item, else the first frame (and calibration) of the next item
-      if (!last) {
-        prefetch_rows(pair, bscan, f + 1);
-      } else if (npair >= 0) {
-        if (tid == 0) issue_calibration(npair);
-        prefetch_rows(npair, nbscan, 0);
-      }
-      group_sync<P::T>(g);
-      phase_pass0<P>(tid, s);
+      phase_gather<P>(tid, s, r, sa * a.inv_W, sb * a.inv_W);
+      group_sync<P::T>(g);  // the staging buffer has been consumed: pass 0 may overwrite it
+      phase_pass0<P>(tid, s, r);
       if (f == 0 && tid == 0 && pending >= 0) {
         // publish the previous item: its scratch stores were issued a whole pass ago, so the fence finds nothing in flight
         __threadfence();
@@ -782,7 +807,12 @@ __global__ void __launch_bounds__(P::T* GMAX, MINB) recon_kernel(const ReconArgs
         phase_pass1<P>(tid, s);
         group_sync<P::T>(g);
       }
-      phase_passL<P>(tid, s, r);
+      phase_passL<P, !A1>(tid, s, r);
+      if constexpr (P::NWARPS > 1) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(s.mbar + 1);
+        buf_busy = true;
+      }
     }
 
     // ---- B-scan `bscan` of this pair is complete: dB to the L2 scratch, min/max
