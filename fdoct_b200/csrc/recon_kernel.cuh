@@ -109,7 +109,7 @@ __host__ __device__ constexpr SmemLayout make_layout(int W, bool has_sub) {
   L.g_gain = g; g = align16(g + 2 * W * 4);
   L.g_subg = g; g = align16(g + (has_sub ? 2 * W * 4 : 0));
   L.g_buf = g;  g = align16(g + cmax(cmax((W + 1) * 8, P::BUF * 8), kNormBins * (P::T + 4)));
-  L.g_red = g;  g = align16(g + 2 * P::NWARPS * 4 + 32);
+  L.g_red = g;  g = align16(g + 2 * P::NWARPS * 4 + 48);
   L.g_mbar = g; g = align16(g + 16);
   L.group_bytes = g;
   return L;
@@ -127,7 +127,7 @@ struct GroupSmem {  // resolved pointers of one group
   float2* stg;
   float2* buf;
   float* red;
-  int* slot;  // 8 ints: broadcast slots of the group leader (next items, normalise job)
+  int* slot;  // 12 ints: broadcast slots of the group leader (next items, normalise job) and its unpublished B-scans
   unsigned long long* mbar;
 };
 template <class P>
@@ -728,7 +728,18 @@ __global__ void __launch_bounds__(P::T* G, 1) recon_kernel(const ReconArgs a) {
   const int ngroups = gridDim.x * G;
   const int njobs = a.nB * a.nparts;
   int myjob = blockIdx.x * G + g;  // (tid 0) next normalisation job of this group
-  int pending = -1;                // (tid 0) B-scan whose finished pair has not been published yet
+  // (tid 0) B-scans whose finished pair has not been published yet.  Publishing needs a gpu-scope fence, which waits
+  // for every memory operation the warp has in flight; it is therefore batched (one fence per kPublishBatch items)
+  // and placed right after the pre-processing phase, when the previous items' scratch stores have long landed and
+  // the next frame's pixel prefetch has not been issued yet.
+  constexpr int kPublishBatch = 4;
+  int* const pend = s.slot + 8;  // kept in shared memory: only the leader touches it
+  int npend = 0;
+  auto publish = [&]() {
+    __threadfence();
+    for (int i = 0; i < npend; ++i) atomicAdd(sv.cnt + pend[i], 1);  // result unused -> RED
+    npend = 0;
+  };
 
   while (pair >= 0) {
     const int ra = 2 * pair;
@@ -765,6 +776,7 @@ __global__ void __launch_bounds__(P::T* G, 1) recon_kernel(const ReconArgs a) {
           s.red[2 * wrp + 1] = sb;
         }
       }
+      if (f == 0 && tid == 0 && npend == kPublishBatch) publish();
       // prefetch while this frame is transformed: next frame of the item, else the first frame of the next item
       if (!last) {
         prefetch_rows(pair, bscan, f + 1);
@@ -785,12 +797,6 @@ __global__ void __launch_bounds__(P::T* G, 1) recon_kernel(const ReconArgs a) {
       phase_gather<P>(tid, s, r, sa * a.inv_W, sb * a.inv_W);
       group_sync<P::T>(g);  // the staging buffer has been consumed: pass 0 may overwrite it
       phase_pass0<P>(tid, s, r);
-      if (f == 0 && tid == 0 && pending >= 0) {
-        // publish the previous item: its scratch stores were issued a whole pass ago, so the fence finds nothing in flight
-        __threadfence();
-        atomicAdd(sv.cnt + pending, 1);  // result unused -> RED
-        pending = -1;
-      }
       if (last && tid == 0) {
         s.slot[4] = t_next < a.nitems ? t_next % a.npairs : -1;
         s.slot[5] = t_next / a.npairs;
@@ -827,7 +833,7 @@ __global__ void __launch_bounds__(P::T* G, 1) recon_kernel(const ReconArgs a) {
         atomicMin(sv.minv + bscan, float_to_ordered(fmaxf(mn, a.thr)));
         atomicMax(sv.maxv + bscan, float_to_ordered(fmaxf(mx, a.thr)));
       }
-      pending = bscan;
+      if (tid == 0) pend[npend++] = bscan;
       const int job = s.slot[6];
       if (job >= 0) {
         group_sync<P::T>(g);  // every thread is done with the exchange buffer (it becomes the transposition tile)
@@ -842,10 +848,7 @@ __global__ void __launch_bounds__(P::T* G, 1) recon_kernel(const ReconArgs a) {
 
   // ---- drain: publish the last item, then finish this group's remaining normalisation jobs
   group_sync<P::T>(g);
-  if (tid == 0 && pending >= 0) {
-    __threadfence();
-    atomicAdd(sv.cnt + pending, 1);
-  }
+  if (tid == 0 && npend > 0) publish();
   for (;;) {
     if (tid == 0) {
       int job = -1;
