@@ -215,7 +215,7 @@ class Context:
 
     def set_calibration_from_frames(self, which: int, frames: np.ndarray):
         frames = np.ascontiguousarray(frames)
-        assert frames.ndim == 3 and frames.dtype == np.uint16
+        assert frames.ndim == 3 and frames.dtype == (np.uint8 if self.params.bpp == 8 else np.uint16)
         self._check(lib().abcoct_set_calibration_from_frames(self._h, which, frames.ctypes.data, frames.shape[0], 0))
 
     def tables(self):
@@ -231,6 +231,8 @@ class Context:
                        outdb: np.ndarray | None = None):
         """Host-buffer call (abcoct_process_bscans). frames: (nframes, h, w) uint16, C-contiguous."""
         assert frames.ndim == 3 and frames.flags.c_contiguous
+        assert frames.dtype == (np.uint8 if self.params.bpp == 8 else np.uint16), frames.dtype
+        assert frames.shape[1:] == (self.params.h, self.params.w), frames.shape
         nframes = frames.shape[0]
         nB = nframes // max(self.A, 1)
         if out8 is None:

@@ -36,6 +36,14 @@ struct GpuState {
   unsigned char* d_tables = nullptr;
   float* d_gain = nullptr;
   float* d_subg = nullptr;
+  // general pre-processing path (prep_kernels.cu): unswizzled f32 calibration, window, FFT twiddles, per-slot work buffers
+  float *d_yb = nullptr, *d_yp = nullptr, *d_yd = nullptr, *d_win = nullptr;
+  float2 *d_twW = nullptr, *d_twM = nullptr;
+  void* d_med[kSlots] = {};
+  void* d_bin[kSlots] = {};
+  float* d_rows[kSlots] = {};
+  float* d_fmm[kSlots] = {};
+  size_t prep_frames[kSlots] = {};
   // per-slot device + pinned staging for the host-buffer API
   uint8_t* d_in[kSlots] = {};
   uint8_t* d_out8[kSlots] = {};
@@ -59,6 +67,9 @@ struct abcoct_ctx {
   std::vector<double> frac, win;
   std::vector<double> yb, yp, yd;
   bool have_yb = false, have_yp = false, have_yd = false, cal_dirty = true, has_sub = false;
+  bool general = false;  // any optional pre-processing stage is on: frames go through prep_kernels.cu first
+  int px_bytes = 2;
+  std::vector<int> radW, radM;
   const PlanEntry* plan = nullptr;
   int G = 1, smem = 0, regs = 0;
   std::vector<GpuState> gpus;
@@ -145,13 +156,23 @@ int validate(const abcoct_params& p, std::string& why, int& code) {
   if (p.numdisplaypoints < 6) return bad("numdisplaypoints < 6 (rows 4 and 5 are addressed, BscanFFT.cpp:1239, 1252)");
   if (p.clampupper && oph < 6) return bad("clampupper needs at least 6 A-scans (element (5,5), BscanFFT.cpp:1252)");
   if (p.variant > 1 || p.weight_mode > 1) return bad("variant / weight_mode out of range");
+  if (p.binx > 1 && p.w % p.binx) return bad("w is not a multiple of the x binning factor (cv::resize would round the size)");
+  if (p.biny > 1 && p.h % p.biny) return bad("h is not a multiple of the y binning factor (cv::resize would round the size)");
+  if (p.mediann < 0 || p.movavgn < 0) return bad("mediann / movavgn must be >= 0");
   code = ABCOCT_ERR_UNSUPPORTED;
-  if (p.bpp != 16) return bad("bpp == 8 frames are not built yet (SURVEY.md section 8f rank 4)");
-  if (p.binx != 1 || p.biny != 1) return bad("input binning > 1 is not built yet (SURVEY.md section 7 step 6)");
-  if (p.mediann > 0) return bad("medianBlur pre-filter is not built yet (SURVEY.md section 8f rank 4)");
-  if (p.movavgn > 0) return bad("smoothmovavg is not built yet (SURVEY.md section 8f rank 4)");
-  if (p.fft_multiplier != 1) return bad("increasefftpointsmultiplier > 1 is not built yet (SURVEY.md section 7 step 5)");
-  if (p.rowwisenormalize || !p.donotnormalize) return bad("rowwisenormalize / !donotnormalize are not built yet (SURVEY.md section 7 step 6)");
+  if (p.mediann != 0 && p.mediann != 3 && p.mediann != 5)
+    return bad("medianBlur kernel sizes other than 3 and 5 are not built (OpenCV itself only takes 3 / 5 for 16-bit frames)");
+  if (p.movavgn > 64) return bad("movavgn > 64 is not built");
+  if (p.fft_multiplier > 1) {
+    unsigned r = opw;
+    for (unsigned f : {2u, 3u, 5u})
+      while (r % f == 0) r /= f;
+    if (r != 1 || (opw & 1)) return bad("increasefftpointsmultiplier > 1 needs w / binx = 2^a 3^b 5^c, even");
+    r = p.fft_multiplier;
+    for (unsigned f : {2u, 3u, 5u})
+      while (r % f == 0) r /= f;
+    if (r != 1) return bad("increasefftpointsmultiplier must be of the form 2^a 3^b 5^c");
+  }
   if (opw % 8) return bad("w / binx must be a multiple of 8");
   if (!find_plan((int)p.numfftpoints)) {
     why = "numfftpoints has no compiled FFT plan; available:";
@@ -162,6 +183,53 @@ int validate(const abcoct_params& p, std::string& why, int& code) {
   }
   code = 0;
   return 0;
+}
+
+std::vector<int> factor_radices(int n) {
+  std::vector<int> r;
+  while (n % 4 == 0) { r.push_back(4); n /= 4; }
+  while (n % 2 == 0) { r.push_back(2); n /= 2; }
+  while (n % 3 == 0) { r.push_back(3); n /= 3; }
+  while (n % 5 == 0) { r.push_back(5); n /= 5; }
+  return r;
+}
+
+// Host restatement of the integer stages in front of the calibration captures (median + INTER_AREA binning,
+// BscanFFT.cpp:953-958): calibration happens once per key press, so it stays on the CPU.
+template <class T>
+void host_median(const T* in, size_t row_stride, T* out, int w, int h, int k) {
+  const int R = k / 2;
+  std::vector<T> v(k * k);
+  for (int y = 0; y < h; ++y)
+    for (int x = 0; x < w; ++x) {
+      int n = 0;
+      for (int dy = -R; dy <= R; ++dy)
+        for (int dx = -R; dx <= R; ++dx) {
+          const int yy = std::min(std::max(y + dy, 0), h - 1), xx = std::min(std::max(x + dx, 0), w - 1);
+          v[n++] = in[(size_t)yy * row_stride + xx];
+        }
+      std::nth_element(v.begin(), v.begin() + n / 2, v.end());
+      out[(size_t)y * w + x] = v[n / 2];
+    }
+}
+template <class T>
+void host_bin(const T* in, size_t row_stride, double* out, int opw, int oph, int bx, int by) {
+  for (int y = 0; y < oph; ++y)
+    for (int x = 0; x < opw; ++x) {
+      unsigned sum = 0;
+      for (int dy = 0; dy < by; ++dy)
+        for (int dx = 0; dx < bx; ++dx) sum += in[(size_t)(y * by + dy) * row_stride + (size_t)x * bx + dx];
+      unsigned r;
+      if (bx == 1 && by == 1) {
+        r = sum;
+      } else if (bx == 2 && by == 2) {
+        r = (sum + 2u) >> 2;
+      } else {
+        const float scale = 1.f / (float)(bx * by);
+        r = (unsigned)std::lrintf((float)sum * scale);  // round half to even (default rounding mode)
+      }
+      out[(size_t)y * opw + x] = (double)r;
+    }
 }
 
 int upload_calibration(abcoct_ctx* c) {
@@ -176,7 +244,24 @@ int upload_calibration(abcoct_ctx* c) {
     subg[i] = (float)(sub / c->yb[i] + 1.0);  // + 1: the kernel stages t - 1 (see phase_pre in recon_kernel.cuh)
     has_sub |= (sub != 0.0);
   }
-  c->has_sub = has_sub;
+  c->has_sub = has_sub && !c->general;
+  if (c->general) {  // unswizzled f32 copies for rowprep_kernel; the fused kernel gets pre-processed rows, no calibration
+    std::vector<float> fb(n), fp(n), fd(n);
+    for (size_t i = 0; i < n; ++i) {
+      fb[i] = (float)c->yb[i];
+      fp[i] = c->have_yp ? (float)c->yp[i] : 0.f;
+      fd[i] = dark ? (float)c->yd[i] : 0.f;
+    }
+    for (GpuState& g : c->gpus) {
+      CU(c, cudaSetDevice(g.dev));
+      if (!g.d_yb) CU(c, cudaMalloc(&g.d_yb, n * 4));
+      if (!g.d_yp) CU(c, cudaMalloc(&g.d_yp, n * 4));
+      if (!g.d_yd) CU(c, cudaMalloc(&g.d_yd, n * 4));
+      CU(c, cudaMemcpy(g.d_yb, fb.data(), n * 4, cudaMemcpyHostToDevice));
+      CU(c, cudaMemcpy(g.d_yp, fp.data(), n * 4, cudaMemcpyHostToDevice));
+      CU(c, cudaMemcpy(g.d_yd, fd.data(), n * 4, cudaMemcpyHostToDevice));
+    }
+  }
   {  // the kernel reads calibration rows in the bank-conflict-free layout (cal_phys in recon_kernel.cuh)
     std::vector<float> tmp(c->opw);
     for (int r = 0; r < c->oph; ++r) {
@@ -193,13 +278,13 @@ int upload_calibration(abcoct_ctx* c) {
     CU(c, cudaMemcpy(g.d_gain, gain.data(), n * 4, cudaMemcpyHostToDevice));
     CU(c, cudaMemcpy(g.d_subg, subg.data(), n * 4, cudaMemcpyHostToDevice));
   }
-  const int G = c->plan->groups(has_sub);  // compile-time choice of the plan (threads and shared memory at W = N)
+  const int G = c->plan->groups(c->has_sub);  // compile-time choice of the plan (threads and shared memory at W = N)
   c->G = G;
-  c->smem = c->plan->smem_bytes(c->opw, has_sub, G);
+  c->smem = c->plan->smem_bytes(c->general ? c->M : c->opw, c->has_sub, G);
   if (c->smem > 227 * 1024) return fail(c, ABCOCT_ERR_UNSUPPORTED, "shared memory budget exceeded (%d bytes)", c->smem);
   for (GpuState& g : c->gpus) {
     CU(c, cudaSetDevice(g.dev));
-    CU(c, c->plan->attrs(has_sub, c->A == 1, c->smem, &c->regs));
+    CU(c, c->plan->attrs(c->has_sub, c->A == 1, c->general, c->smem, &c->regs));
   }
   c->cal_dirty = false;
   return ABCOCT_OK;
@@ -227,12 +312,85 @@ size_t scratch_chunk_bscans(const abcoct_ctx* c) {
   return std::max<size_t>(1, mb * 1024 * 1024 / per);
 }
 
-// Enqueue the two kernels for nB B-scans resident on device g; everything on `st`.
+int ensure_prep(abcoct_ctx* c, GpuState& g, int slot, size_t nframes) {
+  if (g.prep_frames[slot] >= nframes) return ABCOCT_OK;
+  cudaFree(g.d_med[slot]);
+  cudaFree(g.d_bin[slot]);
+  cudaFree(g.d_rows[slot]);
+  cudaFree(g.d_fmm[slot]);
+  g.d_med[slot] = g.d_bin[slot] = nullptr;
+  g.d_rows[slot] = g.d_fmm[slot] = nullptr;
+  g.prep_frames[slot] = 0;
+  if (c->p.mediann > 0) CU(c, cudaMalloc(&g.d_med[slot], nframes * c->p.h * c->p.w * c->px_bytes));
+  CU(c, cudaMalloc(&g.d_bin[slot], nframes * c->oph * c->opw * c->px_bytes));
+  CU(c, cudaMalloc(&g.d_rows[slot], nframes * c->oph * (size_t)c->M * sizeof(float)));
+  CU(c, cudaMalloc(&g.d_fmm[slot], nframes * 2 * sizeof(float)));
+  g.prep_frames[slot] = nframes;
+  return ABCOCT_OK;
+}
+
+// General path: median -> binning -> row preparation (+ Fourier upsample) for `nframes` frames into g.d_rows[slot].
+int run_prep(abcoct_ctx* c, GpuState& g, int slot, const uint8_t* d_frames, size_t nframes, size_t row_stride, size_t frame_stride,
+             cudaStream_t st, int* launches) {
+  const int pb = c->px_bytes;
+  if (row_stride % pb || frame_stride % pb) return fail(c, ABCOCT_ERR_INVALID, "strides must be multiples of the pixel size");
+  const void* src = d_frames;
+  size_t rs = row_stride / pb, fs = frame_stride / pb;
+  int n = 0;
+  if (c->p.mediann > 0) {
+    CU(c, launch_median(src, g.d_med[slot], (int)c->p.bpp, c->p.mediann, (int)c->p.w, (int)c->p.h, rs, fs, (int)nframes, st));
+    src = g.d_med[slot];
+    rs = c->p.w;
+    fs = (size_t)c->p.w * c->p.h;
+    ++n;
+  }
+  // binning (a factor of 1 x 1 just makes the frames dense)
+  CU(c, launch_bin(src, g.d_bin[slot], (int)c->p.bpp, c->opw, c->oph, (int)c->p.binx, (int)c->p.biny, rs, fs, (int)nframes, st));
+  ++n;
+  PrepArgsHost h{};
+  h.binned = g.d_bin[slot];
+  h.bpp = (int)c->p.bpp;
+  h.opw = c->opw;
+  h.oph = c->oph;
+  h.nframes = (int)nframes;
+  h.movavgn = c->p.movavgn;
+  h.yd = (c->p.variant == 1 && c->have_yd) ? g.d_yd : nullptr;
+  h.rowwise = c->p.rowwisenormalize;
+  h.global_norm = c->p.donotnormalize ? 0 : 1;
+  h.frame_minmax = g.d_fmm[slot];
+  h.yb = g.d_yb;
+  h.yp = c->have_yp ? g.d_yp : nullptr;
+  h.win = g.d_win;
+  h.m = (int)c->p.fft_multiplier;
+  h.M = c->M;
+  h.bandpass = c->p.bandpassfilter;
+  h.nradW = (int)c->radW.size();
+  h.nradM = (int)c->radM.size();
+  for (size_t i = 0; i < c->radW.size(); ++i) h.radW[i] = c->radW[i];
+  for (size_t i = 0; i < c->radM.size(); ++i) h.radM[i] = c->radM[i];
+  h.twW = g.d_twW;
+  h.twM = g.d_twM;
+  h.out = g.d_rows[slot];
+  int nl = 0;
+  CU(c, launch_rowprep(h, st, &nl));
+  *launches = n + nl;
+  return ABCOCT_OK;
+}
+
+// Enqueue the kernels for nB B-scans resident on device g; everything on `st`.
 int enqueue_device(abcoct_ctx* c, GpuState& g, int slot, const uint8_t* d_frames, size_t nB, size_t row_stride, size_t frame_stride,
                    uint8_t* d_out8, float* d_outdb, cudaStream_t st, bool time_it) {
-  const size_t chunkB = std::min(nB, scratch_chunk_bscans(c));
+  size_t chunkB = std::min(nB, scratch_chunk_bscans(c));
+  if (c->general) {  // the pre-processed f32 rows of a chunk stay below ~1 GiB
+    const size_t per_bscan = (size_t)c->A * c->oph * c->M * sizeof(float);
+    chunkB = std::min(chunkB, std::max<size_t>(1, ((size_t)1 << 30) / per_bscan));
+  }
   int rc = ensure_scratch(c, g, slot, chunkB);
   if (rc) return rc;
+  if (c->general) {
+    rc = ensure_prep(c, g, slot, chunkB * c->A);
+    if (rc) return rc;
+  }
   for (size_t b0 = 0; b0 < nB; b0 += chunkB) {
     const size_t nb = std::min(chunkB, nB - b0);
     ReconArgs a{};
@@ -240,6 +398,14 @@ int enqueue_device(abcoct_ctx* c, GpuState& g, int slot, const uint8_t* d_frames
     a.frame_stride = frame_stride;
     a.row_stride = row_stride;
     a.W = c->opw;
+    if (c->general) {
+      int nl = 0;
+      rc = run_prep(c, g, slot, a.frames, nb * c->A, row_stride, frame_stride, st, &nl);
+      if (rc) return rc;
+      c->launches += nl;
+      a.frames = reinterpret_cast<const uint8_t*>(g.d_rows[slot]);
+      a.W = c->M;
+    }
     a.oph = c->oph;
     a.D = c->D;
     a.Dp = scratch_pitch(c);
@@ -266,7 +432,7 @@ int enqueue_device(abcoct_ctx* c, GpuState& g, int slot, const uint8_t* d_frames
     CU(c, launch_sched_init(a.sched, (int)nb, st));
     const bool timed = time_it && g.tev_used + 3 <= g.tev.size();
     if (timed) CU(c, cudaEventRecord(g.tev[g.tev_used], st));
-    CU(c, c->plan->launch(a, c->has_sub, grid, st));
+    CU(c, c->plan->launch(a, c->has_sub, c->general, grid, st));
     if (timed) {
       CU(c, cudaEventRecord(g.tev[g.tev_used + 1], st));
       CU(c, cudaEventRecord(g.tev[g.tev_used + 2], st));
@@ -280,7 +446,7 @@ int enqueue_device(abcoct_ctx* c, GpuState& g, int slot, const uint8_t* d_frames
 int ensure_slots(abcoct_ctx* c, GpuState& g, size_t slotB, bool want_db) {
   if (g.slot_bscans >= slotB && (g.slot_db || !want_db)) return ABCOCT_OK;
   CU(c, cudaSetDevice(g.dev));
-  const size_t in_bytes = slotB * c->A * (size_t)c->p.h * c->p.w * 2;
+  const size_t in_bytes = slotB * c->A * (size_t)c->p.h * c->p.w * c->px_bytes;
   const size_t out_px = slotB * (size_t)c->D * c->oph;
   for (int s = 0; s < kSlots; ++s) {
     if (g.d_in[s]) cudaFree(g.d_in[s]);
@@ -432,6 +598,13 @@ int abcoct_create(const abcoct_params* params, const int* gpu_ids, int ngpu, abc
   c->D = params->numdisplaypoints;
   c->A = params->averages;
   c->plan = find_plan(c->N);
+  c->px_bytes = params->bpp == 8 ? 1 : 2;
+  c->general = params->bpp == 8 || params->binx > 1 || params->biny > 1 || params->mediann > 0 || params->movavgn > 0 ||
+               params->fft_multiplier > 1 || params->rowwisenormalize || !params->donotnormalize;
+  if (params->fft_multiplier > 1) {
+    c->radW = factor_radices(c->opw);
+    c->radM = factor_radices(c->M);
+  }
   build_ref_tables(c->opw, params->fft_multiplier, c->N, params->lambdamin, params->lambdamax, c->nk, c->frac);
   build_window(c->opw, c->win);
   // gather tables for the kernel: end points q = 0, N-1 are never written in the reference (BscanFFT.cpp:1164)
@@ -452,7 +625,20 @@ int abcoct_create(const abcoct_params* params, const int* gpu_ids, int ngpu, abc
   }
   for (int i = 0; i < c->opw; ++i) winf[i] = (float)c->win[i];
   std::vector<unsigned char> blob;
-  c->plan->build_blob(c->opw, idx.data(), wq.data(), winf.data(), blob);
+  if (c->general) {  // the fused kernel sees rows of M apodised samples: no window / mean term left to apply there
+    std::vector<float> zero(c->M, 0.f);
+    c->plan->build_blob(c->M, idx.data(), wq.data(), zero.data(), blob);
+  } else {
+    c->plan->build_blob(c->opw, idx.data(), wq.data(), winf.data(), blob);
+  }
+  std::vector<float2> twW, twM;
+  if (params->fft_multiplier > 1) {
+    const double tau = 6.283185307179586476925286766559;
+    twW.resize(c->opw);
+    twM.resize(c->M);
+    for (int k = 0; k < c->opw; ++k) twW[k] = make_float2((float)std::cos(tau * k / c->opw), (float)-std::sin(tau * k / c->opw));
+    for (int k = 0; k < c->M; ++k) twM[k] = make_float2((float)std::cos(tau * k / c->M), (float)std::sin(tau * k / c->M));
+  }
 
   c->gpus.resize(ngpu);
   for (int i = 0; i < ngpu; ++i) {
@@ -481,6 +667,15 @@ int abcoct_create(const abcoct_params* params, const int* gpu_ids, int ngpu, abc
     for (size_t k = 0; k < g.tev.size() && ok; ++k) ok = ok && cudaEventCreate(&g.tev[k]) == cudaSuccess;
     ok = ok && cudaMalloc(&g.d_tables, blob.size()) == cudaSuccess;
     ok = ok && cudaMemcpy(g.d_tables, blob.data(), blob.size(), cudaMemcpyHostToDevice) == cudaSuccess;
+    if (c->general) {
+      ok = ok && cudaMalloc(&g.d_win, winf.size() * 4) == cudaSuccess;
+      ok = ok && cudaMemcpy(g.d_win, winf.data(), winf.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+      if (!twW.empty()) {
+        ok = ok && cudaMalloc(&g.d_twW, twW.size() * 8) == cudaSuccess && cudaMalloc(&g.d_twM, twM.size() * 8) == cudaSuccess;
+        ok = ok && cudaMemcpy(g.d_twW, twW.data(), twW.size() * 8, cudaMemcpyHostToDevice) == cudaSuccess;
+        ok = ok && cudaMemcpy(g.d_twM, twM.data(), twM.size() * 8, cudaMemcpyHostToDevice) == cudaSuccess;
+      }
+    }
     if (!ok) {
       fail(nullptr, ABCOCT_ERR_CUDA, "device %d setup failed: %s", g.dev, cudaGetErrorString(cudaGetLastError()));
       abcoct_destroy(c);
@@ -513,6 +708,18 @@ void abcoct_destroy(abcoct_ctx* c) {
     cudaFree(g.d_tables);
     cudaFree(g.d_gain);
     cudaFree(g.d_subg);
+    cudaFree(g.d_yb);
+    cudaFree(g.d_yp);
+    cudaFree(g.d_yd);
+    cudaFree(g.d_win);
+    cudaFree(g.d_twW);
+    cudaFree(g.d_twM);
+    for (int s2 = 0; s2 < kSlots; ++s2) {
+      cudaFree(g.d_med[s2]);
+      cudaFree(g.d_bin[s2]);
+      cudaFree(g.d_rows[s2]);
+      cudaFree(g.d_fmm[s2]);
+    }
   }
   cudaGetLastError();
   delete c;
@@ -543,16 +750,31 @@ int abcoct_set_dark(abcoct_ctx* c, const double* yd, size_t ld) { return c ? set
 
 int abcoct_set_calibration_from_frames(abcoct_ctx* c, int which, const void* frames, size_t nframes, size_t stride_bytes) {
   if (!c || !frames || nframes == 0 || which < 0 || which > 2) return c ? fail(c, ABCOCT_ERR_INVALID, "bad argument") : ABCOCT_ERR_INVALID;
-  if (stride_bytes == 0) stride_bytes = (size_t)c->p.w * 2;
+  const int pb = c->px_bytes, w = (int)c->p.w, h = (int)c->p.h;
+  if (stride_bytes == 0) stride_bytes = (size_t)w * pb;
+  if (stride_bytes % pb) return fail(c, ABCOCT_ERR_INVALID, "stride_bytes must be a multiple of the pixel size");
   const size_t n = (size_t)c->oph * c->opw;
-  std::vector<double> acc(n, 0.0);  // accumulate(data_y, baccum), BscanFFT.cpp:1043
+  std::vector<double> acc(n, 0.0), one(n);  // accumulate(data_y, baccum), BscanFFT.cpp:1043
+  std::vector<uint8_t> med;
+  if (c->p.mediann > 0) med.resize((size_t)w * h * pb);
   const uint8_t* base = static_cast<const uint8_t*>(frames);
-  for (size_t f = 0; f < nframes; ++f)
-    for (int r = 0; r < c->oph; ++r) {
-      const uint16_t* row = reinterpret_cast<const uint16_t*>(base + (f * c->p.h + r) * stride_bytes);
-      double* a = &acc[(size_t)r * c->opw];
-      for (int x = 0; x < c->opw; ++x) a[x] += (double)row[x];
+  for (size_t f = 0; f < nframes; ++f) {
+    const uint8_t* fr = base + f * h * stride_bytes;
+    size_t rs = stride_bytes / pb;
+    if (c->p.mediann > 0) {  // medianBlur while the numbers are still integers, BscanFFT.cpp:953-954
+      if (pb == 1)
+        host_median(fr, rs, med.data(), w, h, c->p.mediann);
+      else
+        host_median(reinterpret_cast<const uint16_t*>(fr), rs, reinterpret_cast<uint16_t*>(med.data()), w, h, c->p.mediann);
+      fr = med.data();
+      rs = w;
     }
+    if (pb == 1)  // resize(..., INTER_AREA), BscanFFT.cpp:958
+      host_bin(fr, rs, one.data(), c->opw, c->oph, (int)c->p.binx, (int)c->p.biny);
+    else
+      host_bin(reinterpret_cast<const uint16_t*>(fr), rs, one.data(), c->opw, c->oph, (int)c->p.binx, (int)c->p.biny);
+    for (size_t i = 0; i < n; ++i) acc[i] += one[i];
+  }
   const double s = 1.0 / (double)nframes;  // Mat / double multiplies by the reciprocal, BscanFFT.cpp:1057
   for (double& v : acc) v *= s;
   std::vector<double>& dst = which == 0 ? c->yb : which == 1 ? c->yp : c->yd;
@@ -595,8 +817,9 @@ int abcoct_process_bscans_device(abcoct_ctx* c, int gi, const void* d_frames, si
   if (gi < 0 || gi >= (int)c->gpus.size()) return fail(c, ABCOCT_ERR_INVALID, "gpu_index out of range");
   if (!d_frames || !d_u8) return fail(c, ABCOCT_ERR_INVALID, "null buffer");
   if (nframes == 0 || nframes % c->A) return fail(c, ABCOCT_ERR_INVALID, "nframes must be a positive multiple of averages (%d)", c->A);
-  if (stride_bytes == 0) stride_bytes = (size_t)c->p.w * 2;
-  if (stride_bytes % 16 || (reinterpret_cast<uintptr_t>(d_frames) & 15)) return fail(c, ABCOCT_ERR_INVALID, "device frames must be 16-byte aligned with a 16-byte multiple row stride");
+  if (stride_bytes == 0) stride_bytes = (size_t)c->p.w * c->px_bytes;
+  if (!c->general && (stride_bytes % 16 || (reinterpret_cast<uintptr_t>(d_frames) & 15)))
+    return fail(c, ABCOCT_ERR_INVALID, "device frames must be 16-byte aligned with a 16-byte multiple row stride");
   if (c->cal_dirty) {
     int rc = upload_calibration(c);
     if (rc) return rc;
@@ -645,7 +868,7 @@ int abcoct_process_bscans(abcoct_ctx* c, const void* frames, size_t nframes, siz
   if (!c) return ABCOCT_ERR_INVALID;
   if (!frames || !out8) return fail(c, ABCOCT_ERR_INVALID, "null buffer");
   if (nframes == 0 || nframes % c->A) return fail(c, ABCOCT_ERR_INVALID, "nframes must be a positive multiple of averages (%d)", c->A);
-  const size_t dense = (size_t)c->p.w * 2;
+  const size_t dense = (size_t)c->p.w * c->px_bytes;
   if (stride_bytes == 0) stride_bytes = dense;
   if (stride_bytes < dense) return fail(c, ABCOCT_ERR_INVALID, "stride_bytes < w * bytes per pixel");
   if (c->cal_dirty) {

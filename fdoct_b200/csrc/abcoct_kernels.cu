@@ -74,22 +74,23 @@ static int groups_fn(bool has_sub) {
   return has_sub ? PlanLimits<P, true>::G : PlanLimits<P, false>::G;
 }
 
-template <class P, bool HAS_SUB, bool A1>
+template <class P, bool HAS_SUB, bool A1, bool IN_F32>
 static cudaError_t launch_one(const ReconArgs& a, int grid, cudaStream_t st) {
   constexpr int G = PlanLimits<P, HAS_SUB>::G;
   const int smem = make_layout<P>(a.W, HAS_SUB).total(G);
-  recon_kernel<P, G, HAS_SUB, A1><<<grid, P::T * G, smem, st>>>(a);
+  recon_kernel<P, G, HAS_SUB, A1, IN_F32><<<grid, P::T * G, smem, st>>>(a);
   return cudaGetLastError();
 }
 template <class P>
-static cudaError_t launch_fn(const ReconArgs& a, bool has_sub, int grid, cudaStream_t st) {
+static cudaError_t launch_fn(const ReconArgs& a, bool has_sub, bool in_f32, int grid, cudaStream_t st) {
   const bool a1 = a.A == 1;
-  if (has_sub) return a1 ? launch_one<P, true, true>(a, grid, st) : launch_one<P, true, false>(a, grid, st);
-  return a1 ? launch_one<P, false, true>(a, grid, st) : launch_one<P, false, false>(a, grid, st);
+  if (in_f32) return a1 ? launch_one<P, false, true, true>(a, grid, st) : launch_one<P, false, false, true>(a, grid, st);
+  if (has_sub) return a1 ? launch_one<P, true, true, false>(a, grid, st) : launch_one<P, true, false, false>(a, grid, st);
+  return a1 ? launch_one<P, false, true, false>(a, grid, st) : launch_one<P, false, false, false>(a, grid, st);
 }
-template <class P, bool HAS_SUB, bool A1>
+template <class P, bool HAS_SUB, bool A1, bool IN_F32>
 static cudaError_t attrs_one(int smem, int* regs) {
-  const void* f = (const void*)recon_kernel<P, PlanLimits<P, HAS_SUB>::G, HAS_SUB, A1>;
+  const void* f = (const void*)recon_kernel<P, PlanLimits<P, HAS_SUB>::G, HAS_SUB, A1, IN_F32>;
   cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
   cudaFuncAttributes fa;
@@ -98,9 +99,10 @@ static cudaError_t attrs_one(int smem, int* regs) {
   return e;
 }
 template <class P>
-static cudaError_t attrs_fn(bool has_sub, bool a1, int smem, int* regs) {
-  if (has_sub) return a1 ? attrs_one<P, true, true>(smem, regs) : attrs_one<P, true, false>(smem, regs);
-  return a1 ? attrs_one<P, false, true>(smem, regs) : attrs_one<P, false, false>(smem, regs);
+static cudaError_t attrs_fn(bool has_sub, bool a1, bool in_f32, int smem, int* regs) {
+  if (in_f32) return a1 ? attrs_one<P, false, true, true>(smem, regs) : attrs_one<P, false, false, true>(smem, regs);
+  if (has_sub) return a1 ? attrs_one<P, true, true, false>(smem, regs) : attrs_one<P, true, false, false>(smem, regs);
+  return a1 ? attrs_one<P, false, true, false>(smem, regs) : attrs_one<P, false, false, false>(smem, regs);
 }
 
 template <class P>

@@ -20,12 +20,34 @@ struct PlanEntry {
   // pack idx (N entries, already sentinel-remapped, values in [1, M]), weights (N), window (W) and the
   // inter-pass twiddles into the blob the kernel copies to shared memory
   void (*build_blob)(int W, const int* idx, const float* wq, const float* win, std::vector<unsigned char>& blob);
-  cudaError_t (*launch)(const ReconArgs& a, bool has_sub, int grid, cudaStream_t st);  // picks the averages == 1 variant itself
-  cudaError_t (*attrs)(bool has_sub, bool a1, int smem, int* regs);  // opt in to large smem, report registers/thread
+  // in_f32: the frames are pre-processed f32 rows from the general path (no calibration, no prefetch); picks the averages == 1 variant itself
+  cudaError_t (*launch)(const ReconArgs& a, bool has_sub, bool in_f32, int grid, cudaStream_t st);
+  cudaError_t (*attrs)(bool has_sub, bool a1, bool in_f32, int smem, int* regs);  // opt in to large smem, report registers/thread
 };
 
 const PlanEntry* find_plan(int N);
 int list_plans(int* out, int cap);
 
 cudaError_t launch_sched_init(int* sched, int nB, cudaStream_t st);
+
+// ---- general pre-processing path (prep_kernels.cu)
+struct PrepArgsHost {
+  const void* binned;  // [nframes][oph][opw] integer pixels after median + binning
+  int bpp, opw, oph, nframes, movavgn;
+  const float* yd;     // nullable (DARK variant)
+  int rowwise, global_norm;
+  float* frame_minmax;  // [nframes][2], needed when global_norm
+  const float *yb, *yp, *win;
+  int m, M, bandpass;
+  int nradW, nradM;
+  int radW[12], radM[12];
+  const float2 *twW, *twM;  // exp(-2 pi i k / opw), exp(+2 pi i k / M); needed when m > 1
+  float* out;               // [nframes][oph][M]
+};
+cudaError_t launch_median(const void* in, void* out, int bpp, int k, int w, int h, size_t row_stride_elems, size_t frame_stride_elems,
+                          int nframes, cudaStream_t st);
+cudaError_t launch_bin(const void* in, void* out, int bpp, int opw, int oph, int bx, int by, size_t row_stride_elems,
+                       size_t frame_stride_elems, int nframes, cudaStream_t st);
+cudaError_t launch_rowprep(const PrepArgsHost& h, cudaStream_t st, int* launched);
+size_t rowprep_smem_bytes(int opw, int M, int m, int movavgn);
 }  // namespace abcoct

@@ -1,0 +1,375 @@
+// General pre-processing path ("slow path") of the ABC-OCT reconstruction block: every optional stage the reference
+// can switch on in front of the lambda->k resampling, as plain CUDA kernels that turn raw camera frames into the
+// apodised (and optionally Fourier-upsampled) f32 rows the fused reconstruction kernel then resamples and transforms.
+//
+//   median_kernel   medianBlur(mraw, m, mediann)                   BscanFFT.cpp:953-956   (k = 3, 5; replicated border)
+//   bin_kernel      resize(m, opm, ..., INTER_AREA) integer bins   BscanFFT.cpp:958, BscanFFTspinjnt.cpp:1553
+//   rowprep_kernel  convertTo / smoothmovavg / dark subtract / normalizerows / normalize / (y - yp) / yb /
+//                   row-mean removal / Bartlett-Hann window / zeropadrowwise
+//                   BscanFFT.cpp:987-991, 1125-1147, 88-97, 180-245, 247-304; BscanDark.cpp:1269, 218-236
+//
+// The default configuration (16-bit frames, no binning / median / smoothing / normalisation, multiplier 1) never comes
+// here: it is handled entirely inside recon_kernel.  This path trades speed for coverage (it is still two orders of
+// magnitude above any camera's frame rate) and keeps the reference's integer rounding rules bit-exact.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "fft_regs.cuh"
+#include "kernels.h"
+
+namespace abcoct {
+
+// ------------------------------------------------------------------------------------------------ median (k = 3, 5)
+template <class T, int K>
+__global__ void median_kernel(const T* __restrict__ in, T* __restrict__ out, int w, int h, size_t in_row_stride /*elements*/,
+                              size_t in_frame_stride, int nframes) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  const int f = blockIdx.z;
+  if (x >= w || f >= nframes) return;
+  constexpr int R = K / 2, NV = K * K;
+  const T* src = in + (size_t)f * in_frame_stride;
+  T v[NV];
+#pragma unroll
+  for (int dy = -R; dy <= R; ++dy) {
+    const int yy = min(max(y + dy, 0), h - 1);  // cv::medianBlur replicates the border
+#pragma unroll
+    for (int dx = -R; dx <= R; ++dx) {
+      const int xx = min(max(x + dx, 0), w - 1);
+      v[(dy + R) * K + (dx + R)] = src[(size_t)yy * in_row_stride + xx];
+    }
+  }
+  // partial selection sort up to the middle element
+#pragma unroll
+  for (int i = 0; i <= NV / 2; ++i) {
+#pragma unroll
+    for (int j = i + 1; j < NV; ++j) {
+      const T a = v[i], b = v[j];
+      v[i] = a < b ? a : b;
+      v[j] = a < b ? b : a;
+    }
+  }
+  out[((size_t)f * h + y) * w + x] = v[NV / 2];
+}
+
+// ------------------------------------------------------------------------------------------------ INTER_AREA integer binning
+// cv::resize(..., INTER_AREA) with integer scale factors (resizeAreaFast_): 2 x 2 uses (sum + 2) >> 2; every other
+// factor pair multiplies the sum by the f32 reciprocal of the area and rounds half to even (saturate_cast<T>(float)).
+template <class T>
+__global__ void bin_kernel(const T* __restrict__ in, T* __restrict__ out, int opw, int oph, int bx, int by, size_t in_row_stride,
+                           size_t in_frame_stride, int nframes) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
+  const int y = blockIdx.y;
+  const int f = blockIdx.z;
+  if (x >= opw || f >= nframes) return;
+  const T* src = in + (size_t)f * in_frame_stride + (size_t)(y * by) * in_row_stride + (size_t)x * bx;
+  unsigned sum = 0;
+  for (int dy = 0; dy < by; ++dy)
+    for (int dx = 0; dx < bx; ++dx) sum += src[(size_t)dy * in_row_stride + dx];
+  unsigned r;
+  if (bx == 2 && by == 2) {
+    r = (sum + 2u) >> 2;
+  } else {
+    const float scale = 1.f / (float)(bx * by);
+    r = (unsigned)__float2int_rn(__fmul_rn((float)sum, scale));
+    const unsigned mx = sizeof(T) == 1 ? 255u : 65535u;
+    r = r > mx ? mx : r;
+  }
+  out[((size_t)f * oph + y) * opw + x] = (T)r;
+}
+
+// ------------------------------------------------------------------------------------------------ generic block FFT
+// Stockham autosort transform of one row in shared memory by a whole CTA (any n = 2^a 3^b 5^c, radix list from the host):
+//   pass with radix r, current length nc, stride s:  for p < nc / r, q < s
+//     y[q + s (r p + c)] = ( sum_j x[q + s (p + (nc / r) j)] w_r^(jc) ) * w_n^(p c s)
+// (tools/fft_plan_model.py holds the NumPy model of this index algebra).  tw[k] = exp(SGN 2 pi i k / n), k < n.
+struct RadixList {
+  int n;
+  int count;
+  int r[12];
+};
+
+template <int R, int SGN>
+__device__ __forceinline__ void stockham_pass(const float2* __restrict__ x, float2* __restrict__ y, int n, int nc, int s,
+                                              const float2* __restrict__ tw) {
+  const int mq = nc / R;
+  for (int b = threadIdx.x; b < n / R; b += blockDim.x) {
+    const int p = b / s, q = b - p * s;
+    float2 in[R], out[R];
+#pragma unroll
+    for (int j = 0; j < R; ++j) in[j] = x[q + s * (p + mq * j)];
+    Dft<R, SGN, 1, 1>::run(in, out);
+    y[q + s * (R * p)] = out[0];
+#pragma unroll
+    for (int c = 1; c < R; ++c) {
+      const float2 w = tw[(int)(((long long)p * c * s) % n)];
+      y[q + s * (R * p + c)] = cmul(out[c], w);
+    }
+  }
+}
+
+// in-place semantics for the caller: returns the buffer that holds the result (a or b)
+template <int SGN>
+__device__ float2* block_fft(float2* a, float2* b, const RadixList& rl, const float2* __restrict__ tw) {
+  int nc = rl.n, s = 1;
+  float2 *x = a, *y = b;
+  for (int i = 0; i < rl.count; ++i) {
+    const int r = rl.r[i];
+    switch (r) {
+      case 2: stockham_pass<2, SGN>(x, y, rl.n, nc, s, tw); break;
+      case 3: stockham_pass<3, SGN>(x, y, rl.n, nc, s, tw); break;
+      case 4: stockham_pass<4, SGN>(x, y, rl.n, nc, s, tw); break;
+      default: stockham_pass<5, SGN>(x, y, rl.n, nc, s, tw); break;
+    }
+    __syncthreads();
+    nc /= r;
+    s *= r;
+    float2* t = x;
+    x = y;
+    y = t;
+  }
+  return x;
+}
+
+// ------------------------------------------------------------------------------------------------ row preparation
+struct PrepArgs {
+  const void* binned;   // [nframes][oph][opw] integer pixels (after median + binning), u8 or u16
+  int bpp;              // 8 or 16
+  int opw, oph, nframes;
+  int movavgn;          // smoothmovavg half width (0 = off)
+  const float* yd;      // nullable: dark frame (DARK variant)
+  int rowwise;          // normalizerows(data_y, 0, 1)
+  int global_norm;      // normalize(data_y, 0, 1, NORM_MINMAX) over the frame: 0 off, 1 = reduce pass, 2 = apply pass
+  float* frame_minmax;  // [nframes][2] order-preserving ints (global_norm)
+  const float* yb;      // background (f32)
+  const float* yp;      // nullable: pi-shifted frame
+  const float* win;     // [opw]
+  int m, M;             // Fourier upsample factor and output row length m * opw
+  int bandpass;         // BscanDark.cpp:218-236
+  RadixList rlW, rlM;
+  const float2* twW;    // exp(-2 pi i k / opw)
+  const float2* twM;    // exp(+2 pi i k / M)
+  float* out;           // [nframes][oph][M]
+};
+
+__device__ __forceinline__ float block_reduce(float v, float* red, int op /*0 sum, 1 min, 2 max*/) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float u = __shfl_xor_sync(0xffffffffu, v, o);
+    v = op == 0 ? v + u : (op == 1 ? fminf(v, u) : fmaxf(v, u));
+  }
+  __syncthreads();  // red may still be read from a previous reduction
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  float r = red[0];
+  for (int i = 1; i < nw; ++i) r = op == 0 ? r + red[i] : (op == 1 ? fminf(r, red[i]) : fmaxf(r, red[i]));
+  return r;
+}
+
+__device__ __forceinline__ int f2ord(float f) {
+  const int i = __float_as_int(f);
+  return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+__host__ __device__ inline size_t rowbuf_bytes(int opw, int movavgn) {
+  const size_t one = (size_t)((opw + 3) & ~3) * sizeof(float);
+  return (one * (movavgn > 0 ? 2 : 1) + 15) & ~(size_t)15;
+}
+
+// one CTA per (row, frame).  dynamic smem: float x[opw] | float2 a[M] | float2 b[M] (the last two only when m > 1)
+__global__ void __launch_bounds__(256) rowprep_kernel(const PrepArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ float red[8];
+  float* x = reinterpret_cast<float*>(smem_raw);
+  const int row = blockIdx.x, f = blockIdx.y;
+  const int W = a.opw;
+  const size_t pix = ((size_t)f * a.oph + row) * W;
+  // convertTo(data_y, CV_64F)  (BscanFFT.cpp:987); integers up to 65535 are exact in f32
+  if (a.bpp == 8) {
+    const uint8_t* src = static_cast<const uint8_t*>(a.binned) + pix;
+    for (int j = threadIdx.x; j < W; j += blockDim.x) x[j] = (float)src[j];
+  } else {
+    const uint16_t* src = static_cast<const uint16_t*>(a.binned) + pix;
+    for (int j = threadIdx.x; j < W; j += blockDim.x) x[j] = (float)src[j];
+  }
+  __syncthreads();
+  if (a.movavgn > 0) {  // smoothmovavg, BscanFFT.cpp:247-304: 2n+1 taps, centre counted twice, missing taps -> centre
+    const int n = a.movavgn;
+    float* y = x + ((W + 3) & ~3);  // second row buffer (allocated when movavgn > 0, see rowprep_smem_bytes)
+    for (int j = threadIdx.x; j < W; j += blockDim.x) {
+      const float c = x[j];
+      float s = c;
+      for (int k = -n; k <= n; ++k) {
+        const int jj = j + k;
+        s += (jj > -1 && jj < W) ? x[jj] : c;
+      }
+      y[j] = s / 2.f / (float)(n + 1);
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < W; j += blockDim.x) x[j] = y[j];
+    __syncthreads();
+  }
+  if (a.yd) {  // data_y = data_y - data_yd, BscanDark.cpp:1269
+    const float* yd = a.yd + (size_t)row * W;
+    for (int j = threadIdx.x; j < W; j += blockDim.x) x[j] -= yd[j];
+    __syncthreads();
+  }
+  if (a.rowwise) {  // normalizerows(data_y, 0, 1), BscanFFT.cpp:88-97: dst = src * s + (0 - min * s), s = 1 / (max - min)
+    float mn = 3.4e38f, mx = -3.4e38f;
+    for (int j = threadIdx.x; j < W; j += blockDim.x) {
+      mn = fminf(mn, x[j]);
+      mx = fmaxf(mx, x[j]);
+    }
+    mn = block_reduce(mn, red, 1);
+    mx = block_reduce(mx, red, 2);
+    const float s = (mx - mn) > 2.220446049250313e-16f ? 1.f / (mx - mn) : 0.f;
+    const float sh = 0.f - mn * s;
+    for (int j = threadIdx.x; j < W; j += blockDim.x) x[j] = fmaf(x[j], s, sh);
+    __syncthreads();
+  }
+  if (a.global_norm) {  // normalize(data_y, data_y, 0, 1, NORM_MINMAX), BscanFFT.cpp:1128-1129 (whole frame)
+    if (a.global_norm == 1) {
+      float mn = 3.4e38f, mx = -3.4e38f;
+      for (int j = threadIdx.x; j < W; j += blockDim.x) {
+        mn = fminf(mn, x[j]);
+        mx = fmaxf(mx, x[j]);
+      }
+      mn = block_reduce(mn, red, 1);
+      mx = block_reduce(mx, red, 2);
+      if (threadIdx.x == 0) {
+        atomicMin(reinterpret_cast<int*>(a.frame_minmax) + 2 * f, f2ord(mn));
+        atomicMax(reinterpret_cast<int*>(a.frame_minmax) + 2 * f + 1, f2ord(mx));
+      }
+      return;  // reduce pass only
+    }
+    const float mn = ord2f(reinterpret_cast<const int*>(a.frame_minmax)[2 * f]);
+    const float mx = ord2f(reinterpret_cast<const int*>(a.frame_minmax)[2 * f + 1]);
+    const float s = (mx - mn) > 2.220446049250313e-16f ? 1.f / (mx - mn) : 0.f;
+    const float sh = 0.f - mn * s;
+    for (int j = threadIdx.x; j < W; j += blockDim.x) x[j] = fmaf(x[j], s, sh);
+    __syncthreads();
+  }
+  // data_y = (data_y - data_yp) / data_yb, BscanFFT.cpp:1132
+  {
+    const float* yb = a.yb + (size_t)row * W;
+    const float* yp = a.yp ? a.yp + (size_t)row * W : nullptr;
+    float sum = 0.f;
+    for (int j = threadIdx.x; j < W; j += blockDim.x) {
+      const float t = (x[j] - (yp ? yp[j] : 0.f)) / yb[j];
+      x[j] = t;
+      sum += t;
+    }
+    // per-row mean removal and apodisation, BscanFFT.cpp:1135-1143
+    const float mean = block_reduce(sum, red, 0) / (float)W;
+    for (int j = threadIdx.x; j < W; j += blockDim.x) x[j] = (x[j] - mean) * a.win[j];
+    __syncthreads();
+  }
+  float* out = a.out + ((size_t)f * a.oph + row) * a.M;
+  if (a.m <= 1) {
+    for (int j = threadIdx.x; j < W; j += blockDim.x) out[j] = x[j];
+    return;
+  }
+  // zeropadrowwise, BscanFFT.cpp:180-245: forward DFT scaled by 1 / opw, zero-pad the centred spectrum to M, inverse
+  // DFT with DFT_REAL_OUTPUT, which only reads bins 0 .. M/2 - so the -opw/2 (Nyquist) bin is dropped:
+  //   out[n] = Re X[0] + 2 Re sum_{k=1}^{opw/2-1} X[k] exp(2 pi i n k / M),   X[k] = (1 / opw) sum_j x[j] exp(-2 pi i j k / opw)
+  float2* bufa = reinterpret_cast<float2*>(smem_raw + rowbuf_bytes(W, a.movavgn));
+  float2* bufb = bufa + a.M;
+  for (int j = threadIdx.x; j < W; j += blockDim.x) bufa[j] = make_float2(x[j], 0.f);
+  __syncthreads();
+  float2* X = block_fft<-1>(bufa, bufb, a.rlW, a.twW);
+  float2* Y = (X == bufa) ? bufb : bufa;
+  const float sc = 1.f / (float)W;
+  const int half = W / 2;
+  const int lo = a.bandpass ? 3 : 0;  // BscanDark.cpp:218-236 keeps bins [3, floor(opw / 10))
+  const int hi = a.bandpass ? W / 10 : half;
+  for (int k = threadIdx.x; k < a.M; k += blockDim.x) {
+    float2 v = make_float2(0.f, 0.f);
+    if (k < half) {
+      if (k >= lo && k < hi) v = make_float2(X[k].x * sc, k == 0 ? 0.f : X[k].y * sc);
+    } else if (k > a.M - half) {
+      const int kk = a.M - k;
+      if (kk >= lo && kk < hi) v = make_float2(X[kk].x * sc, -X[kk].y * sc);
+    }
+    Y[k] = v;
+  }
+  __syncthreads();
+  float2* R = block_fft<+1>(Y, X, a.rlM, a.twM);
+  for (int j = threadIdx.x; j < a.M; j += blockDim.x) out[j] = R[j].x;
+}
+
+// ------------------------------------------------------------------------------------------------ launchers
+cudaError_t launch_median(const void* in, void* out, int bpp, int k, int w, int h, size_t row_stride_elems, size_t frame_stride_elems,
+                          int nframes, cudaStream_t st) {
+  dim3 grid((w + 127) / 128, h, nframes), block(128);
+  if (bpp == 8 && k == 3)
+    median_kernel<uint8_t, 3><<<grid, block, 0, st>>>((const uint8_t*)in, (uint8_t*)out, w, h, row_stride_elems, frame_stride_elems, nframes);
+  else if (bpp == 8 && k == 5)
+    median_kernel<uint8_t, 5><<<grid, block, 0, st>>>((const uint8_t*)in, (uint8_t*)out, w, h, row_stride_elems, frame_stride_elems, nframes);
+  else if (bpp == 16 && k == 3)
+    median_kernel<uint16_t, 3><<<grid, block, 0, st>>>((const uint16_t*)in, (uint16_t*)out, w, h, row_stride_elems, frame_stride_elems, nframes);
+  else if (bpp == 16 && k == 5)
+    median_kernel<uint16_t, 5><<<grid, block, 0, st>>>((const uint16_t*)in, (uint16_t*)out, w, h, row_stride_elems, frame_stride_elems, nframes);
+  else
+    return cudaErrorInvalidValue;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_bin(const void* in, void* out, int bpp, int opw, int oph, int bx, int by, size_t row_stride_elems,
+                       size_t frame_stride_elems, int nframes, cudaStream_t st) {
+  dim3 grid((opw + 127) / 128, oph, nframes), block(128);
+  if (bpp == 8)
+    bin_kernel<uint8_t><<<grid, block, 0, st>>>((const uint8_t*)in, (uint8_t*)out, opw, oph, bx, by, row_stride_elems, frame_stride_elems, nframes);
+  else
+    bin_kernel<uint16_t><<<grid, block, 0, st>>>((const uint16_t*)in, (uint16_t*)out, opw, oph, bx, by, row_stride_elems, frame_stride_elems, nframes);
+  return cudaGetLastError();
+}
+
+__global__ void minmax_reset_kernel(float* mm, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    reinterpret_cast<int*>(mm)[2 * i] = f2ord(__int_as_float(0x7f800000));
+    reinterpret_cast<int*>(mm)[2 * i + 1] = f2ord(__int_as_float(0xff800000));
+  }
+}
+
+size_t rowprep_smem_bytes(int opw, int M, int m, int movavgn) {
+  size_t b = rowbuf_bytes(opw, movavgn);
+  if (m > 1) b += (size_t)2 * M * sizeof(float2);
+  return b;
+}
+
+// returns the number of kernels launched (through *launched)
+cudaError_t launch_rowprep(const PrepArgsHost& h, cudaStream_t st, int* launched) {
+  PrepArgs a{};
+  a.binned = h.binned; a.bpp = h.bpp; a.opw = h.opw; a.oph = h.oph; a.nframes = h.nframes; a.movavgn = h.movavgn;
+  a.yd = h.yd; a.rowwise = h.rowwise; a.frame_minmax = h.frame_minmax; a.yb = h.yb; a.yp = h.yp; a.win = h.win;
+  a.m = h.m; a.M = h.M; a.bandpass = h.bandpass; a.twW = h.twW; a.twM = h.twM; a.out = h.out;
+  a.rlW.n = h.opw; a.rlW.count = h.nradW;
+  a.rlM.n = h.M; a.rlM.count = h.nradM;
+  for (int i = 0; i < 12; ++i) { a.rlW.r[i] = h.radW[i]; a.rlM.r[i] = h.radM[i]; }
+  const size_t smem = rowprep_smem_bytes(h.opw, h.M, h.m, h.movavgn);
+  static bool attr_done = false;
+  if (!attr_done || smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(rowprep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    attr_done = true;
+  }
+  dim3 grid(h.oph, h.nframes);
+  int n = 0;
+  if (h.global_norm) {
+    minmax_reset_kernel<<<(h.nframes + 127) / 128, 128, 0, st>>>(h.frame_minmax, h.nframes);
+    a.global_norm = 1;
+    rowprep_kernel<<<grid, 256, smem, st>>>(a);
+    a.global_norm = 2;
+    n += 2;
+  }
+  rowprep_kernel<<<grid, 256, smem, st>>>(a);
+  ++n;
+  if (launched) *launched = n;
+  return cudaGetLastError();
+}
+
+}  // namespace abcoct

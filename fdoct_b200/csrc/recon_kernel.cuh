@@ -291,6 +291,28 @@ ABC_HD void phase_pre(int tid, const GroupSmem& s, int W, const ThreadState<P>& 
   }
 }
 
+// General path: the rows are already (t - mean) * window (and Fourier-upsampled) f32 values written by rowprep_kernel;
+// stage them pairwise-interleaved exactly like phase_pre does.  W = samples per row (m * opw), a multiple of 8.
+template <class P>
+ABC_HD void phase_stage_f32(int tid, const GroupSmem& s, int W, const float* rowa, const float* rowb) {
+  const int W8 = W >> 3;
+  if (tid == 0) s.stg[W] = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < P::NCH; ++i) {
+    const int ch = tid + P::T * i;
+    if (ch < W8) {
+      const float4 a0 = *reinterpret_cast<const float4*>(rowa + 8 * ch), a1 = *reinterpret_cast<const float4*>(rowa + 8 * ch + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(rowb + 8 * ch), b1 = *reinterpret_cast<const float4*>(rowb + 8 * ch + 4);
+      float4* dst = reinterpret_cast<float4*>(s.stg + 8 * ch);
+      const int sw = (ch >> 1) & 3;
+      dst[0 ^ sw] = make_float4(a0.x, b0.x, a0.y, b0.y);
+      dst[1 ^ sw] = make_float4(a0.z, b0.z, a0.w, b0.w);
+      dst[2 ^ sw] = make_float4(a1.x, b1.x, a1.y, b1.y);
+      dst[3 ^ sw] = make_float4(a1.z, b1.z, a1.w, b1.w);
+    }
+  }
+}
+
 // lambda->k gather-lerp (BscanFFT.cpp:1169-1171) into registers: the inputs of this thread's radix-R0 butterflies.
 // Runs between two barriers because the exchange buffer written by pass 0 overlays the staging buffer read here.
 template <class P>
@@ -654,8 +676,9 @@ __device__ __forceinline__ void normalise_part(const ReconArgs& a, const SchedVi
   }
 }
 
-// G thread groups per CTA (compile time: the register budget follows from T * G), A1 = averages == 1
-template <class P, int G, bool HAS_SUB, bool A1>
+// G thread groups per CTA (compile time: the register budget follows from T * G), A1 = averages == 1,
+// IN_F32 = the frames are pre-processed f32 rows of the general path (a.W samples each, no calibration)
+template <class P, int G, bool HAS_SUB, bool A1, bool IN_F32>
 __global__ void __launch_bounds__(P::T* G, 1) recon_kernel(const ReconArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   const SmemLayout L = make_layout<P>(a.W, HAS_SUB);
@@ -708,6 +731,7 @@ __global__ void __launch_bounds__(P::T* G, 1) recon_kernel(const ReconArgs a) {
     }
   };
   auto prefetch_rows = [&](int pair, int b, int f) {  // raw pixels of frame f of item (pair, b) into registers
+    if constexpr (IN_F32) return;
     const int ra = 2 * pair, rb = (ra + 1 < a.oph) ? ra + 1 : ra;
     const uint8_t* fp = a.frames + (static_cast<size_t>(b) * a.A + f) * a.frame_stride;
     phase_load<P>(tid, fp + static_cast<size_t>(ra) * a.row_stride, fp + static_cast<size_t>(rb) * a.row_stride, W8, r, pol);
@@ -715,7 +739,7 @@ __global__ void __launch_bounds__(P::T* G, 1) recon_kernel(const ReconArgs a) {
 
   int pair = s.slot[0], bscan = s.slot[1], npair = s.slot[2], nbscan = s.slot[3];  // current and next item (pair < 0: none)
   if (pair >= 0) {
-    if (tid == 0) issue_calibration(pair);
+    if (!IN_F32 && tid == 0) issue_calibration(pair);
     prefetch_rows(pair, bscan, 0);
   }
   unsigned cal_parity = 0, free_parity = 0;
@@ -749,9 +773,11 @@ __global__ void __launch_bounds__(P::T* G, 1) recon_kernel(const ReconArgs a) {
       t_next = atomicAdd(sv.ticket, 1);  // the item after next
       if (myjob < njobs) polled = *reinterpret_cast<volatile const int*>(sv.cnt + myjob / a.nparts);
     }
-    while (!mbar_try_wait(s.mbar, cal_parity)) {
+    if constexpr (!IN_F32) {
+      while (!mbar_try_wait(s.mbar, cal_parity)) {
+      }
+      cal_parity ^= 1u;
     }
-    cal_parity ^= 1u;
 
     const int nA = A1 ? 1 : a.A;
     for (int f = 0; f < nA; ++f) {
@@ -766,14 +792,20 @@ __global__ void __launch_bounds__(P::T* G, 1) recon_kernel(const ReconArgs a) {
           free_parity ^= 1u;
         }
       }
-      float sa, sb;
-      phase_pre<P, HAS_SUB>(tid, s, W, r, sa, sb);
-      sa = warp_sum(sa);
-      sb = warp_sum(sb);
-      if constexpr (P::NWARPS > 1) {
-        if (lane == 0) {
-          s.red[2 * wrp] = sa;
-          s.red[2 * wrp + 1] = sb;
+      float sa = 0.f, sb = 0.f;
+      if constexpr (IN_F32) {
+        const int rb = rowb_valid ? ra + 1 : ra;
+        const float* fp = reinterpret_cast<const float*>(a.frames) + (static_cast<size_t>(bscan) * a.A + f) * a.oph * static_cast<size_t>(W);
+        phase_stage_f32<P>(tid, s, W, fp + static_cast<size_t>(ra) * W, fp + static_cast<size_t>(rb) * W);
+      } else {
+        phase_pre<P, HAS_SUB>(tid, s, W, r, sa, sb);
+        sa = warp_sum(sa);
+        sb = warp_sum(sb);
+        if constexpr (P::NWARPS > 1) {
+          if (lane == 0) {
+            s.red[2 * wrp] = sa;
+            s.red[2 * wrp + 1] = sb;
+          }
         }
       }
       if (f == 0 && tid == 0 && npend == kPublishBatch) publish();
@@ -784,8 +816,8 @@ __global__ void __launch_bounds__(P::T* G, 1) recon_kernel(const ReconArgs a) {
         prefetch_rows(npair, nbscan, 0);
       }
       group_sync<P::T>(g);  // staged samples and row sums visible; the calibration rows have been consumed
-      if (last && npair >= 0 && tid == 0) issue_calibration(npair);
-      if constexpr (P::NWARPS > 1) {
+      if (!IN_F32 && last && npair >= 0 && tid == 0) issue_calibration(npair);
+      if constexpr (P::NWARPS > 1 && !IN_F32) {
         sa = 0.f;
         sb = 0.f;
 #pragma unroll

@@ -117,6 +117,12 @@ def test_create_rejects_reference_undefined_behaviour():
 def test_create_reports_unsupported_not_silently_wrong():
     rc, msg = _create_rc(w=1280, h=8, numfftpoints=1344, numdisplaypoints=512)  # no compiled plan for 1344
     assert rc == api.ERR_UNSUPPORTED and "1280" in msg
+    rc, msg = _create_rc(w=1280, h=8, numfftpoints=1280, numdisplaypoints=512, mediann=7)  # OpenCV: 3 / 5 only for 16-bit
+    assert rc == api.ERR_UNSUPPORTED and "median" in msg
+    rc, msg = _create_rc(w=1288, h=8, numfftpoints=2048, numdisplaypoints=512, binx=2, biny=2, fft_multiplier=2)  # 644 = 4 * 7 * 23
+    assert rc == api.ERR_UNSUPPORTED
+    rc, msg = _create_rc(w=1281, h=8, numfftpoints=1280, numdisplaypoints=512, binx=2, biny=2)  # cv::resize would round the size
+    assert rc == api.ERR_INVALID
 
 
 def test_no_cpu_fallback():

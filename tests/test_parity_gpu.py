@@ -133,6 +133,84 @@ def test_accuracy_vs_exact_f64(w, h, N, D):
     assert e_ours <= 1e-4, e_ours
 
 
+# ------------------------------------------------------------------------------------------- general pre-processing path
+GENERAL = [
+    # name,            w,    h,  N,    D,   A, nB, params
+    ("upsample2", 640, 6, 1280, 512, 1, 2, dict(fft_multiplier=2)),
+    ("shipped_ini", 1280, 12, 2560, 320, 2, 2, dict(binx=2, biny=2, fft_multiplier=4)),  # BscanFFT.ini:25-56 shape
+    ("c3_shape", 1920, 5, 3840, 1024, 1, 1, dict(fft_multiplier=2)),
+    ("spinj_2880", 1440, 8, 2880, 360, 1, 1, dict(binx=2, biny=2, fft_multiplier=4)),
+    ("bin2x2", 2560, 8, 1280, 640, 1, 2, dict(binx=2, biny=2)),
+    ("bin3x3", 1920, 9, 640, 320, 1, 1, dict(binx=3, biny=3)),
+    ("bin2x1_spinjnt", 2048, 5, 1024, 512, 1, 1, dict(binx=2, biny=1)),
+    ("bpp8", 1024, 6, 1024, 512, 2, 1, dict(bpp=8)),
+    ("bpp8_median5_bin2", 1024, 8, 512, 256, 1, 1, dict(bpp=8, mediann=5, binx=2, biny=2)),
+    ("median3_u16", 1024, 7, 1024, 512, 1, 1, dict(mediann=3)),
+    ("median5_u16", 640, 7, 640, 320, 1, 1, dict(mediann=5)),
+    ("movavg2", 1024, 5, 1024, 512, 1, 1, dict(movavgn=2)),
+    ("rowwise", 1024, 5, 1024, 512, 1, 1, dict(rowwisenormalize=True)),
+    ("globalnorm", 1024, 6, 1024, 512, 2, 1, dict(donotnormalize=False)),
+    ("dark_bandpass_up4", 640, 6, 2560, 320, 2, 1, dict(variant=1, fft_multiplier=4, bandpassfilter=True)),
+    ("dark_movavg_rowwise", 1280, 4, 1280, 640, 1, 1, dict(variant=1, movavgn=1, rowwisenormalize=True, pishift=True)),
+]
+
+
+@pytest.mark.parametrize("name,w,h,N,D,A,nB,extra", GENERAL)
+def test_general_path_against_oracle(name, w, h, N, D, A, nB, extra):
+    """Every optional stage in front of the resampling: median, INTER_AREA binning, 8-bit
+    frames, smoothmovavg, row-wise / global normalise, Fourier upsample (+ band-pass), DARK."""
+    from fdoct_b200 import synth
+    from oracle.abcoct_oracle import Oracle, dark_background
+
+    extra = dict(extra)
+    pishift = extra.pop("pishift", False)
+    op = oracle_params(w=w, h=h, numfftpoints=N, numdisplaypoints=D, averages=A, lambdamin=840.5e-9, lambdamax=859.5e-9, **extra)
+    seed = 9000 + w + N + A
+    dark = op.variant == 1
+    u8 = op.bpp == 8
+    kw = dict(full_scale=255, dtype=np.uint8) if u8 else {}
+    frames = synth.make_frames(nB * A, w, h, seed=seed, dark=dark and not u8, **kw)
+    o = Oracle(op)
+    yd = yp = None
+    if dark:
+        yd = o.calib_mean_of_frames(synth.make_dark_frames(2, w, h, seed=seed + 2))
+        yr = o.calib_mean_of_frames(synth.make_background_frames(2, w, h, seed=seed + 1, dark=True))
+        yb = dark_background(yr, yd, yd + 0.02 * (yr - yd))
+        o.set_dark(yd)
+    else:
+        yb = o.calib_mean_of_frames(synth.make_background_frames(2, w, h, seed=seed + 1, **kw))
+    if not op.donotnormalize or op.rowwisenormalize:
+        yb = yb / yb.max()  # the frame is normalised to [0, 1] before the division: a background on the same scale
+        if yd is not None:
+            o.set_dark(yd)
+    if pishift:
+        yp = 0.01 * np.ones_like(yb)
+        o.set_pishift(yp)
+    o.set_background(yb)
+    ref8, refdb = o.process_bscans(frames)
+    out8, outdb = _run_abi(op, frames, yb, yp=yp, yd=yd)
+    _check(out8, outdb, ref8, refdb, name)
+
+
+def test_calibration_from_frames_matches_oracle_capture():
+    """abcoct_set_calibration_from_frames (median + binning + mean on the host, BscanFFT.cpp:1041-1062) == the oracle's."""
+    from fdoct_b200 import api, synth
+    from oracle.abcoct_oracle import Oracle
+
+    w, h, N, D, A = 1280, 8, 640, 320, 4
+    op = oracle_params(w=w, h=h, numfftpoints=N, numdisplaypoints=D, averages=A, binx=2, biny=2, mediann=3, lambdamin=840.5e-9,
+                       lambdamax=859.5e-9)
+    frames = synth.make_frames(A, w, h, seed=77)
+    bframes = synth.make_background_frames(A, w, h, seed=78)
+    o = Oracle(op)
+    o.set_background(o.calib_mean_of_frames(bframes))
+    ref8, refdb = o.process_bscans(frames)
+    with api.Context(abi_params(op)) as ctx:
+        ctx.set_calibration_from_frames(0, bframes)
+        out8, outdb = ctx.process_bscans(frames, want_db=True)
+    _check(out8, outdb, ref8, refdb, "calibration from frames")
+
+
 def test_tables_bit_exact_through_ctx():
     from fdoct_b200 import api
     from oracle.abcoct_oracle import barthann_window, build_tables
