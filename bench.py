@@ -43,7 +43,9 @@ WORKLOADS = {
                desc="C1 1280x960 u16, N=1280, D=640, averages=1, FFT variant"),
     "c2": dict(w=1280, h=960, N=1280, D=640, A=8, variant=1, frames=384, seed=1002,
                desc="C2 1280x960 u16, N=1280, D=640, averages=8, DARK variant"),
-    "c4": dict(w=1920, h=1200, N=1920, D=960, A=1, variant=0, frames=125, seed=1004,
+    "c3": dict(w=1920, h=1200, N=3840, D=1024, A=1, variant=0, frames=48, seed=1003, m=2, twelve_bit=True,
+               desc="C3 1920x1200 u16 (12-bit), increasefftpointsmultiplier=2 -> N=3840, D=1024 (general pre-processing path)"),
+    "c4": dict(w=1920, h=1200, N=1920, D=960, A=1, variant=0, frames=125, seed=1004, twelve_bit=True,
                desc="C4 1920x1200 u16 (12-bit), N=1920, D=960, 125 B-scans per GPU"),
     "c5-1024": dict(w=1024, h=1024, N=1024, D=512, A=1, variant=0, frames=512, seed=1005,
                     desc="C5 1024-sample u16 spectra, 1024 A-scans/frame, D=512"),
@@ -59,12 +61,12 @@ def oracle_params(wl):
     from oracle.abcoct_oracle import Params
 
     return Params(w=wl["w"], h=wl["h"], numfftpoints=wl["N"], numdisplaypoints=wl["D"], averages=wl["A"],
-                  variant=wl["variant"], lambdamin=LMIN, lambdamax=LMAX)
+                  variant=wl["variant"], fft_multiplier=wl.get("m", 1), lambdamin=LMIN, lambdamax=LMAX)
 
 
 def abi_params(api, wl):
     return api.default_params(w=wl["w"], h=wl["h"], bpp=16, binx=1, biny=1, averages=wl["A"], numfftpoints=wl["N"],
-                              numdisplaypoints=wl["D"], lambdamin=LMIN, lambdamax=LMAX, mediann=0, movavgn=0, fft_multiplier=1,
+                              numdisplaypoints=wl["D"], lambdamin=LMIN, lambdamax=LMAX, mediann=0, movavgn=0, fft_multiplier=wl.get("m", 1),
                               rowwisenormalize=0, donotnormalize=1, variant=wl["variant"], weight_mode=0)
 
 
@@ -233,6 +235,8 @@ def run_ours(args, wl, rank, world, local_rank):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
