@@ -181,7 +181,9 @@ ABC_HD float fast_sqrt(float x) {
 }
 ABC_HD float fast_log2(float x) {
 #ifdef __CUDA_ARCH__
-  return __log2f(x);
+  float r;  // the argument is >= 1e-5 (BscanFFT.cpp:1222 adds it), never denormal: one MUFU.LG2, no range fix-up
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
 #else
   return log2f(x);
 #endif
@@ -441,10 +443,13 @@ ABC_HD void phase_passL(int tid, const GroupSmem& s, ThreadState<P>& r) {
   }
 }
 
-// average, +1e-5, ln -> dB, DC-row mask, min/max of the thresholded value (BscanFFT.cpp:1221-1247)
+// average, +1e-5, ln -> dB, DC-row mask, min/max of the dB values (BscanFFT.cpp:1221-1247).
+// Bins 0, 1, 4 and the clampupper element (5,5) can only sit in slot j == 0 of a unit (every other slot holds a bin
+// >= S / 2 >= 8), so only that slot pays for the special cases.
 template <class P>
 ABC_HD void phase_finalise(int tid, const ReconArgs& a, float* rowa_out, float* rowb_out, int row_a_index,
                            bool rowb_valid, ThreadState<P>& r, float& mn, float& mx) {
+  static_assert(P::S / 2 >= 8, "special bins must all fall into slot 0");
 #pragma unroll
   for (int i = 0; i < P::NU; ++i) {
     const int u = tid + P::T * i;
@@ -459,17 +464,23 @@ ABC_HD void phase_finalise(int tid, const ReconArgs& a, float* rowa_out, float* 
           r.acc[i][j][row] = 0.f;
           float* dst = row ? rowb_out : rowa_out;
           const bool valid = (kk < a.D) && (row == 0 || rowb_valid);
-          if (valid && kk >= 2) {
+          if (j == 0) {
+            if (valid && kk >= 2) {
+              dst[kk] = db;
+              if (kk == 4) {  // bscandb.row(4).copyTo(row(1)), row(0): BscanFFT.cpp:1239-1240
+                dst[0] = db;
+                dst[1] = db;
+              }
+              const bool is55 = a.clamp55 && kk == 5 && (row_a_index + row) == 5;
+              if (!is55) {  // min/max of the raw dB; max(., thr) is monotone and is applied to the two scalars afterwards
+                mn = fminf(mn, db);
+                mx = fmaxf(mx, db);
+              }
+            }
+          } else if (valid) {
             dst[kk] = db;
-            if (kk == 4) {  // bscandb.row(4).copyTo(row(1)), row(0): BscanFFT.cpp:1239-1240
-              dst[0] = db;
-              dst[1] = db;
-            }
-            const bool is55 = a.clamp55 && kk == 5 && (row_a_index + row) == 5;
-            if (!is55) {  // min/max of the raw dB; max(., thr) is monotone and is applied to the two scalars afterwards
-              mn = fminf(mn, db);
-              mx = fmaxf(mx, db);
-            }
+            mn = fminf(mn, db);
+            mx = fmaxf(mx, db);
           }
         }
       }
@@ -751,13 +762,18 @@ __global__ void __launch_bounds__(P::T* G, 1) recon_kernel(const ReconArgs a) {
   // consumed late so that no warp waits for L2 inside an item.
   const int ngroups = gridDim.x * G;
   const int njobs = a.nB * a.nparts;
-  int myjob = blockIdx.x * G + g;  // (tid 0) next normalisation job of this group
+  // The group's housekeeping is spread over its warps so that no single warp reaches the barriers late:
+  constexpr int kTicketTid = 32 % P::T;   // claims and decodes the item tickets
+  constexpr int kPublishTid = 64 % P::T;  // publishes finished pairs (fence + RED)
+  constexpr int kJobTid = 96 % P::T;      // polls the completion counters and hands out this group's normalisation jobs
+  int myjob = blockIdx.x * G + g;  // (kJobTid) next normalisation job of this group
+  int myjob_b = myjob / a.nparts;  //           and its B-scan
   // (tid 0) B-scans whose finished pair has not been published yet.  Publishing needs a gpu-scope fence, which waits
   // for every memory operation the warp has in flight; it is therefore batched (one fence per kPublishBatch items)
   // and placed right after the pre-processing phase, when the previous items' scratch stores have long landed and
   // the next frame's pixel prefetch has not been issued yet.
   constexpr int kPublishBatch = 4;
-  int* const pend = s.slot + 8;  // kept in shared memory: only the leader touches it
+  int* const pend = s.slot + 8;  // kept in shared memory: only kPublishTid touches it
   int npend = 0;
   auto publish = [&]() {
     __threadfence();
@@ -769,10 +785,8 @@ __global__ void __launch_bounds__(P::T* G, 1) recon_kernel(const ReconArgs a) {
     const int ra = 2 * pair;
     const bool rowb_valid = (ra + 1) < a.oph;
     int t_next = 0, polled = 0;
-    if (tid == 0) {
-      t_next = atomicAdd(sv.ticket, 1);  // the item after next
-      if (myjob < njobs) polled = *reinterpret_cast<volatile const int*>(sv.cnt + myjob / a.nparts);
-    }
+    if (tid == kTicketTid) t_next = atomicAdd(sv.ticket, 1);  // the item after next
+    if (tid == kJobTid && myjob < njobs) polled = *reinterpret_cast<volatile const int*>(sv.cnt + myjob_b);
     if constexpr (!IN_F32) {
       while (!mbar_try_wait(s.mbar, cal_parity)) {
       }
@@ -808,7 +822,7 @@ __global__ void __launch_bounds__(P::T* G, 1) recon_kernel(const ReconArgs a) {
           }
         }
       }
-      if (f == 0 && tid == 0 && npend == kPublishBatch) publish();
+      if (f == 0 && tid == kPublishTid && npend == kPublishBatch) publish();
       // prefetch while this frame is transformed: next frame of the item, else the first frame of the next item
       if (!last) {
         prefetch_rows(pair, bscan, f + 1);
@@ -829,14 +843,18 @@ __global__ void __launch_bounds__(P::T* G, 1) recon_kernel(const ReconArgs a) {
       phase_gather<P>(tid, s, r, sa * a.inv_W, sb * a.inv_W);
       group_sync<P::T>(g);  // the staging buffer has been consumed: pass 0 may overwrite it
       phase_pass0<P>(tid, s, r);
-      if (last && tid == 0) {
-        s.slot[4] = t_next < a.nitems ? t_next % a.npairs : -1;
-        s.slot[5] = t_next / a.npairs;
+      if (last && tid == kTicketTid) {
+        const int nb = t_next / a.npairs;
+        s.slot[4] = t_next < a.nitems ? t_next - nb * a.npairs : -1;
+        s.slot[5] = nb;
+      }
+      if (last && tid == kJobTid) {
         int job = -1;
         if (myjob < njobs && polled >= a.npairs) {
           __threadfence();  // acquire side of the completion count
           job = myjob;
           myjob += ngroups;
+          myjob_b = myjob / a.nparts;
         }
         s.slot[6] = job;
       }
@@ -865,7 +883,7 @@ __global__ void __launch_bounds__(P::T* G, 1) recon_kernel(const ReconArgs a) {
         atomicMin(sv.minv + bscan, float_to_ordered(fmaxf(mn, a.thr)));
         atomicMax(sv.maxv + bscan, float_to_ordered(fmaxf(mx, a.thr)));
       }
-      if (tid == 0) pend[npend++] = bscan;
+      if (tid == kPublishTid) pend[npend++] = bscan;
       const int job = s.slot[6];
       if (job >= 0) {
         group_sync<P::T>(g);  // every thread is done with the exchange buffer (it becomes the transposition tile)
@@ -880,9 +898,9 @@ __global__ void __launch_bounds__(P::T* G, 1) recon_kernel(const ReconArgs a) {
 
   // ---- drain: publish the last item, then finish this group's remaining normalisation jobs
   group_sync<P::T>(g);
-  if (tid == 0 && npend > 0) publish();
+  if (tid == kPublishTid && npend > 0) publish();
   for (;;) {
-    if (tid == 0) {
+    if (tid == kJobTid) {
       int job = -1;
       if (myjob < njobs) {
         while (ld_acquire(sv.cnt + myjob / a.nparts) < a.npairs) __nanosleep(200);
