@@ -55,16 +55,13 @@ static void build_blob_fn(int W, const int* idx, const float* wq, const float* w
       for (int c1 = 1; c1 < P::R1; ++c1) cossin_exact((long long)bp * c1, P::N1, kFftSign, tw1[(c1 - 1) * P::N2 + bp]);
 }
 
-#ifndef ABC_MAX_THREADS
-#define ABC_MAX_THREADS 512  // threads per CTA (one CTA per SM): 128 registers per thread
-#endif
 constexpr int kSmemBudget = 227 * 1024;
 
 // Groups per CTA of a plan: limited by the thread budget and by shared memory at the largest row width (W = N).
 template <class P, bool HAS_SUB>
 struct PlanLimits {
   static constexpr SmemLayout L = make_layout<P>(P::N, HAS_SUB);
-  static constexpr int by_threads = (ABC_MAX_THREADS / P::T) < 1 ? 1 : (ABC_MAX_THREADS / P::T);
+  static constexpr int by_threads = (P::MAXT / P::T) < 1 ? 1 : (P::MAXT / P::T);
   static constexpr int by_smem = (kSmemBudget - L.groups) / L.group_bytes;
   static constexpr int G = by_smem < 1 ? 1 : (by_smem < by_threads ? by_smem : by_threads);
 };
@@ -123,12 +120,12 @@ static PlanEntry make_entry() {
 using P128 = Plan<128, 32, 16, 1, 8>;  // tiny plan for the 128x96 reference fixtures
 using P256 = Plan<256, 32, 16, 1, 16>;
 using P512 = Plan<512, 32, 8, 8, 8>;
-using P640 = Plan<640, 32, 10, 8, 8>;
+using P640 = Plan<640, 32, 10, 8, 8, 384>;
 using P1024 = Plan<1024, 64, 16, 8, 8>;
-using P1280 = Plan<1280, 64, 20, 8, 8>;
+using P1280 = Plan<1280, 64, 20, 8, 8, 384>;
 using P1920 = Plan<1920, 128, 15, 16, 8>;
 using P2048 = Plan<2048, 128, 16, 16, 8>;
-using P2560 = Plan<2560, 128, 20, 16, 8>;
+using P2560 = Plan<2560, 128, 20, 16, 8, 384>;
 using P2880 = Plan<2880, 96, 30, 12, 8>;
 using P3840 = Plan<3840, 128, 30, 16, 8>;
 using P4096 = Plan<4096, 128, 32, 16, 8>;

@@ -20,9 +20,13 @@ namespace abcoct {
 ABC_CX int ceil_div(int a, int b) { return (a + b - 1) / b; }
 ABC_CX int cmax(int a, int b) { return a > b ? a : b; }
 
-template <int N_, int T_, int R0_, int R1_, int RL_>
+// MAXT_: thread budget of one CTA (sets the register budget: 65536 / MAXT_ per thread)
+#ifndef ABC_DEFAULT_MAXT
+#define ABC_DEFAULT_MAXT 512
+#endif
+template <int N_, int T_, int R0_, int R1_, int RL_, int MAXT_ = ABC_DEFAULT_MAXT>
 struct Plan {
-  static constexpr int N = N_, T = T_, R0 = R0_, R1 = R1_, RL = RL_;
+  static constexpr int N = N_, T = T_, R0 = R0_, R1 = R1_, RL = RL_, MAXT = MAXT_;
   static constexpr bool THREE = (R1_ > 1);
   static constexpr int N1 = N / R0;
   static constexpr int N2 = THREE ? N1 / R1 : N1;
