@@ -278,6 +278,55 @@ def test_host_device_and_batching_bitwise_identical():
         pin.free()
 
 
+@pytest.mark.parametrize("w,h,N,D,A,variant", [(2048, 257, 2048, 1024, 1, 0), (1280, 96, 1280, 640, 3, 1), (1024, 301, 1024, 512, 1, 0),
+                                               (4096, 64, 4096, 2048, 2, 0)])
+def test_repeatable_bit_for_bit(w, h, N, D, A, variant):
+    """The kernel schedules items dynamically and synchronises its groups with barriers, mbarriers and global counters:
+    any race shows up as run-to-run differences.  12 repeats of a multi-wave batch must be bit-identical."""
+    from fdoct_b200 import api, synth
+
+    nB = 24
+    op = oracle_params(w=w, h=h, numfftpoints=N, numdisplaypoints=D, averages=A, variant=variant, lambdamin=840.5e-9, lambdamax=859.5e-9)
+    uniq = synth.make_frames(3 * A, w, h, seed=41, dark=bool(variant))
+    frames = np.ascontiguousarray(uniq[np.arange(nB * A) % (3 * A)])
+    yb = synth.make_background_frames(2, w, h, seed=42, dark=bool(variant)).mean(axis=0)
+    with api.Context(abi_params(op)) as ctx:
+        ctx.set_background(yb)
+        if variant:
+            ctx.set_dark(synth.make_dark_frames(2, w, h, seed=43).mean(axis=0))
+        first8, firstdb = ctx.process_bscans(frames, want_db=True)
+        first8, firstdb = first8.copy(), firstdb.copy()
+        for b in range(3, nB):  # identical input B-scans -> identical outputs, whichever group / SM processed them
+            assert np.array_equal(first8[b], first8[b % 3]) and np.array_equal(firstdb[b], firstdb[b % 3])
+        for _ in range(12):
+            o8, odb = ctx.process_bscans(frames, want_db=True)
+            assert np.array_equal(o8, first8) and np.array_equal(odb, firstdb)
+
+
+def test_strided_rows_and_argument_errors():
+    """Row stride larger than the row (a camera buffer with padding, BscanFFTspin.cpp:1075-1080) through the C entry point."""
+    import ctypes as C
+
+    from fdoct_b200 import api, synth
+
+    w, h, N, D = 1024, 10, 1024, 512
+    op = oracle_params(w=w, h=h, numfftpoints=N, numdisplaypoints=D, lambdamin=840.5e-9, lambdamax=859.5e-9)
+    frames = synth.make_frames(3, w, h, seed=51)
+    yb = synth.make_background_frames(2, w, h, seed=52).mean(axis=0)
+    padded = np.zeros((3, h, w + 24), np.uint16)
+    padded[:, :, :w] = frames
+    with api.Context(abi_params(op)) as ctx:
+        ctx.set_background(yb)
+        ref = ctx.process_bscans(frames)
+        out = np.empty_like(ref)
+        rc = api.lib().abcoct_process_bscans(ctx._h, padded.ctypes.data, 3, (w + 24) * 2, out.ctypes.data, None)
+        assert rc == api.OK and np.array_equal(out, ref)
+        assert api.lib().abcoct_process_bscans(ctx._h, padded.ctypes.data, 0, 0, out.ctypes.data, None) == api.ERR_INVALID  # empty batch
+        assert api.lib().abcoct_process_bscans(ctx._h, padded.ctypes.data, 3, w, out.ctypes.data, None) == api.ERR_INVALID  # stride < row
+        assert api.lib().abcoct_process_bscans(ctx._h, None, 3, 0, out.ctypes.data, None) == api.ERR_INVALID
+        assert b"null" in api.lib().abcoct_last_error(ctx._h)
+
+
 def test_averaging_identical_frames_equals_single():
     """A copies of one frame averaged == that frame alone (mean of equal magnitudes), up to f32 rounding."""
     from fdoct_b200 import synth
