@@ -39,19 +39,19 @@ LMIN, LMAX = 840.5e-9, 859.5e-9
 
 # name -> parameters; `frames` = frames per step and per GPU (weak scaling)
 WORKLOADS = {
-    "c1": dict(w=1280, h=960, N=1280, D=640, A=1, variant=0, frames=384, seed=1001,
+    "c1": dict(w=1280, h=960, N=1280, D=640, A=1, variant=0, frames=1024, seed=1001,
                desc="C1 1280x960 u16, N=1280, D=640, averages=1, FFT variant"),
-    "c2": dict(w=1280, h=960, N=1280, D=640, A=8, variant=1, frames=384, seed=1002,
+    "c2": dict(w=1280, h=960, N=1280, D=640, A=8, variant=1, frames=1024, seed=1002,
                desc="C2 1280x960 u16, N=1280, D=640, averages=8, DARK variant"),
     "c3": dict(w=1920, h=1200, N=3840, D=1024, A=1, variant=0, frames=48, seed=1003, m=2, twelve_bit=True,
                desc="C3 1920x1200 u16 (12-bit), increasefftpointsmultiplier=2 -> N=3840, D=1024 (general pre-processing path)"),
     "c4": dict(w=1920, h=1200, N=1920, D=960, A=1, variant=0, frames=125, seed=1004, twelve_bit=True,
                desc="C4 1920x1200 u16 (12-bit), N=1920, D=960, 125 B-scans per GPU"),
-    "c5-1024": dict(w=1024, h=1024, N=1024, D=512, A=1, variant=0, frames=512, seed=1005,
+    "c5-1024": dict(w=1024, h=1024, N=1024, D=512, A=1, variant=0, frames=2048, seed=1005,
                     desc="C5 1024-sample u16 spectra, 1024 A-scans/frame, D=512"),
-    "c5-2048": dict(w=2048, h=1024, N=2048, D=1024, A=1, variant=0, frames=256, seed=1005,
+    "c5-2048": dict(w=2048, h=1024, N=2048, D=1024, A=1, variant=0, frames=1024, seed=1005,
                     desc="C5 2048-sample u16 spectra, 1024 A-scans/frame, D=1024 (north_star target config)"),
-    "c5-4096": dict(w=4096, h=1024, N=4096, D=2048, A=1, variant=0, frames=128, seed=1005,
+    "c5-4096": dict(w=4096, h=1024, N=4096, D=2048, A=1, variant=0, frames=512, seed=1005,
                     desc="C5 4096-sample u16 spectra, 1024 A-scans/frame, D=2048"),
 }
 DEFAULT_WORKLOAD = "c5-2048"

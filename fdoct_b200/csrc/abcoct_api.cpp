@@ -306,7 +306,7 @@ int ensure_scratch(abcoct_ctx* c, GpuState& g, int slot, size_t nB) {
 }
 
 size_t scratch_chunk_bscans(const abcoct_ctx* c) {
-  size_t mb = 1024;
+  size_t mb = 8192;  // address space only: the scratch lives in L2 between the two halves of the kernel
   if (const char* e = getenv("ABCOCT_SCRATCH_MB")) mb = (size_t)std::max(1L, atol(e));
   const size_t per = (size_t)c->oph * scratch_pitch(c) * sizeof(float);
   return std::max<size_t>(1, mb * 1024 * 1024 / per);
