@@ -68,6 +68,8 @@ struct abcoct_ctx {
   std::vector<double> yb, yp, yd;
   bool have_yb = false, have_yp = false, have_yd = false, cal_dirty = true, has_sub = false;
   bool general = false;  // any optional pre-processing stage is on: frames go through prep_kernels.cu first
+  bool dual = false;     // the plan's dual-pair (packed f32x2) kernel is used (recon2_kernel.cuh)
+  std::vector<unsigned char> blob1, blob2;
   int px_bytes = 2;
   std::vector<int> radW, radM;
   const PlanEntry* plan = nullptr;
@@ -278,13 +280,32 @@ int upload_calibration(abcoct_ctx* c) {
     CU(c, cudaMemcpy(g.d_gain, gain.data(), n * 4, cudaMemcpyHostToDevice));
     CU(c, cudaMemcpy(g.d_subg, subg.data(), n * 4, cudaMemcpyHostToDevice));
   }
-  const int G = c->plan->groups(c->has_sub);  // compile-time choice of the plan (threads and shared memory at W = N)
+  // which kernel: the single-pair kernel is the product path.  The dual-pair (packed f32x2) variant issues 31 % fewer
+  // instructions but halves the warps per SM and measured 2-26 % slower on B200; it stays
+  // available for experiments with ABCOCT_KERNEL=2 where the plan has one (never for the general path).
+  bool dual = false;
+  if (const char* e = getenv("ABCOCT_KERNEL")) dual = atoi(e) == 2 && c->plan->groups2 != nullptr && !c->general;
+  if (dual != c->dual || c->gpus[0].d_tables == nullptr) {
+    c->dual = dual;
+    const std::vector<unsigned char>& blob = dual ? c->blob2 : c->blob1;
+    for (GpuState& g : c->gpus) {
+      CU(c, cudaSetDevice(g.dev));
+      cudaFree(g.d_tables);
+      g.d_tables = nullptr;
+      CU(c, cudaMalloc(&g.d_tables, blob.size()));
+      CU(c, cudaMemcpy(g.d_tables, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    }
+  }
+  const int G = dual ? c->plan->groups2(c->has_sub) : c->plan->groups(c->has_sub);  // compile-time choice of the plan
   c->G = G;
-  c->smem = c->plan->smem_bytes(c->general ? c->M : c->opw, c->has_sub, G);
+  c->smem = dual ? c->plan->smem_bytes2(c->opw, c->has_sub, G) : c->plan->smem_bytes(c->general ? c->M : c->opw, c->has_sub, G);
   if (c->smem > 227 * 1024) return fail(c, ABCOCT_ERR_UNSUPPORTED, "shared memory budget exceeded (%d bytes)", c->smem);
   for (GpuState& g : c->gpus) {
     CU(c, cudaSetDevice(g.dev));
-    CU(c, c->plan->attrs(c->has_sub, c->A == 1, c->general, c->smem, &c->regs));
+    if (dual)
+      CU(c, c->plan->attrs2(c->has_sub, c->A == 1, c->smem, &c->regs));
+    else
+      CU(c, c->plan->attrs(c->has_sub, c->A == 1, c->general, c->smem, &c->regs));
   }
   c->cal_dirty = false;
   return ABCOCT_OK;
@@ -428,11 +449,15 @@ int enqueue_device(abcoct_ctx* c, GpuState& g, int slot, const uint8_t* d_frames
     a.thr = (float)c->p.bscanthreshold;
     a.clamp_db = (float)c->p.clamp_db;
     a.clamp55 = c->p.clampupper ? 1 : 0;
-    const int grid = std::min(g.sm_count, (a.nitems + c->G - 1) / c->G);
+    const int work = c->dual ? (a.nitems + 1) / 2 : a.nitems;  // the dual-pair kernel takes two items per ticket
+    const int grid = std::min(g.sm_count, (work + c->G - 1) / c->G);
     CU(c, launch_sched_init(a.sched, (int)nb, st));
     const bool timed = time_it && g.tev_used + 3 <= g.tev.size();
     if (timed) CU(c, cudaEventRecord(g.tev[g.tev_used], st));
-    CU(c, c->plan->launch(a, c->has_sub, c->general, grid, st));
+    if (c->dual)
+      CU(c, c->plan->launch2(a, c->has_sub, grid, st));
+    else
+      CU(c, c->plan->launch(a, c->has_sub, c->general, grid, st));
     if (timed) {
       CU(c, cudaEventRecord(g.tev[g.tev_used + 1], st));
       CU(c, cudaEventRecord(g.tev[g.tev_used + 2], st));
@@ -624,12 +649,13 @@ int abcoct_create(const abcoct_params* params, const int* gpu_ids, int ngpu, abc
     wq[q] = (float)w;
   }
   for (int i = 0; i < c->opw; ++i) winf[i] = (float)c->win[i];
-  std::vector<unsigned char> blob;
+  std::vector<unsigned char>& blob = c->blob1;
   if (c->general) {  // the fused kernel sees rows of M apodised samples: no window / mean term left to apply there
     std::vector<float> zero(c->M, 0.f);
     c->plan->build_blob(c->M, idx.data(), wq.data(), zero.data(), blob);
   } else {
     c->plan->build_blob(c->opw, idx.data(), wq.data(), winf.data(), blob);
+    if (c->plan->build_blob2) c->plan->build_blob2(c->opw, idx.data(), wq.data(), winf.data(), c->blob2);
   }
   std::vector<float2> twW, twM;
   if (params->fft_multiplier > 1) {
@@ -665,8 +691,6 @@ int abcoct_create(const abcoct_params* params, const int* gpu_ids, int ngpu, abc
     }
     g.tev.assign(3 * kTimedChunks, nullptr);
     for (size_t k = 0; k < g.tev.size() && ok; ++k) ok = ok && cudaEventCreate(&g.tev[k]) == cudaSuccess;
-    ok = ok && cudaMalloc(&g.d_tables, blob.size()) == cudaSuccess;
-    ok = ok && cudaMemcpy(g.d_tables, blob.data(), blob.size(), cudaMemcpyHostToDevice) == cudaSuccess;
     if (c->general) {
       ok = ok && cudaMalloc(&g.d_win, winf.size() * 4) == cudaSuccess;
       ok = ok && cudaMemcpy(g.d_win, winf.data(), winf.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess;

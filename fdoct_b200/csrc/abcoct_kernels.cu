@@ -102,7 +102,108 @@ static cudaError_t attrs_fn(bool has_sub, bool a1, bool in_f32, int smem, int* r
   return a1 ? attrs_one<P, false, true, false>(smem, regs) : attrs_one<P, false, false, false>(smem, regs);
 }
 
+// ------------------------------------------------------------------------------------------------ dual-pair variant
+constexpr int kDualThreads = 256;  // 255 registers per thread: two row pairs live in every thread
+template <class P, bool HAS_SUB>
+struct PlanLimits2 {
+  static constexpr SmemLayout2 L = make_layout2<P>(P::N, HAS_SUB);
+  static constexpr int by_threads = (kDualThreads / P::T) < 1 ? 1 : (kDualThreads / P::T);
+  static constexpr int by_smem = (kSmemBudget - L.groups) / L.group_bytes;
+  static constexpr int G = by_smem < 1 ? 1 : (by_smem < by_threads ? by_smem : by_threads);
+  static constexpr bool fits = by_smem >= 1 && 16 * P::N <= 65535;
+};
 template <class P>
+static int groups2_fn(bool has_sub) {
+  return has_sub ? PlanLimits2<P, true>::G : PlanLimits2<P, false>::G;
+}
+template <class P>
+static int smem_bytes2_fn(int W, bool has_sub, int G) {
+  return make_layout2<P>(W, has_sub).total(G);
+}
+template <class P>
+static void build_blob2_fn(int W, const int* idx, const float* wq, const float* win, std::vector<unsigned char>& blob) {
+  const SmemLayout2 L = make_layout2<P>(W, false);
+  blob.assign(L.groups, 0);
+  uint32_t* offT = reinterpret_cast<uint32_t*>(blob.data() + L.offT);
+  float4* wvT = reinterpret_cast<float4*>(blob.data() + L.wvT);
+  float* winS = reinterpret_cast<float*>(blob.data() + L.win);
+  float4* tw0 = reinterpret_cast<float4*>(blob.data() + L.tw0);
+  float4* tw1 = reinterpret_cast<float4*>(blob.data() + L.tw1);
+  for (int b = 0; b < P::N1; ++b) {
+    for (int a = 0; a < P::R0P4; ++a) {
+      const int q = P::N1 * a + b;
+      const int i = a < P::R0 ? idx[q] : W;  // W = the zero sentinel slot
+      const unsigned off1 = 16u * unsigned(i >= W ? W : stg2_phys(i));
+      const unsigned off0 = 16u * unsigned(i >= W ? W : stg2_phys(i - 1));
+      offT[((a >> 2) * P::N1 + b) * 4 + (a & 3)] = off1 | (off0 << 16);
+      const bool live = a < P::R0 && i < W;
+      const float w = a < P::R0 ? wq[q] : 0.f;
+      const float vw = live ? (float)((double)win[i] + (double)wq[q] * ((double)win[i] - (double)win[i - 1])) : 0.f;
+      wvT[a * P::N1 + b] = make_float4(w, w, vw, vw);
+    }
+    for (int c = 1; c < P::R0; ++c) {
+      float2 t;
+      cossin_exact((long long)b * c, P::N, kFftSign, t);
+      tw0[(c - 1) * P::N1 + b] = make_float4(t.x, t.x, t.y, t.y);
+    }
+  }
+  cal_swizzle_row(win, winS, W);
+  if (P::THREE)
+    for (int bp = 0; bp < P::N2; ++bp)
+      for (int c1 = 1; c1 < P::R1; ++c1) {
+        float2 t;
+        cossin_exact((long long)bp * c1, P::N1, kFftSign, t);
+        tw1[(c1 - 1) * P::N2 + bp] = make_float4(t.x, t.x, t.y, t.y);
+      }
+}
+template <class P, bool HAS_SUB, bool A1>
+static cudaError_t launch2_one(const ReconArgs& a, int grid, cudaStream_t st) {
+  constexpr int G = PlanLimits2<P, HAS_SUB>::G;
+  const int smem = make_layout2<P>(a.W, HAS_SUB).total(G);
+  recon2_kernel<P, G, HAS_SUB, A1><<<grid, P::T * G, smem, st>>>(a);
+  return cudaGetLastError();
+}
+template <class P>
+static cudaError_t launch2_fn(const ReconArgs& a, bool has_sub, int grid, cudaStream_t st) {
+  const bool a1 = a.A == 1;
+  if (has_sub) return a1 ? launch2_one<P, true, true>(a, grid, st) : launch2_one<P, true, false>(a, grid, st);
+  return a1 ? launch2_one<P, false, true>(a, grid, st) : launch2_one<P, false, false>(a, grid, st);
+}
+template <class P, bool HAS_SUB, bool A1>
+static cudaError_t attrs2_one(int smem, int* regs) {
+  const void* f = (const void*)recon2_kernel<P, PlanLimits2<P, HAS_SUB>::G, HAS_SUB, A1>;
+  cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) return e;
+  cudaFuncAttributes fa;
+  e = cudaFuncGetAttributes(&fa, f);
+  if (e == cudaSuccess && regs) *regs = fa.numRegs;
+  return e;
+}
+template <class P>
+static cudaError_t attrs2_fn(bool has_sub, bool a1, int smem, int* regs) {
+  if (has_sub) return a1 ? attrs2_one<P, true, true>(smem, regs) : attrs2_one<P, true, false>(smem, regs);
+  return a1 ? attrs2_one<P, false, true>(smem, regs) : attrs2_one<P, false, false>(smem, regs);
+}
+
+template <class P, bool DUAL>
+static void add_dual(PlanEntry& e) {
+  if constexpr (DUAL) {
+    static_assert(PlanLimits2<P, false>::fits && PlanLimits2<P, true>::fits, "plan does not fit the dual-pair layout");
+    e.groups2 = &groups2_fn<P>;
+    e.smem_bytes2 = &smem_bytes2_fn<P>;
+    e.build_blob2 = &build_blob2_fn<P>;
+    e.launch2 = &launch2_fn<P>;
+    e.attrs2 = &attrs2_fn<P>;
+  } else {
+    e.groups2 = nullptr;
+    e.smem_bytes2 = nullptr;
+    e.build_blob2 = nullptr;
+    e.launch2 = nullptr;
+    e.attrs2 = nullptr;
+  }
+}
+
+template <class P, bool DUAL = false>
 static PlanEntry make_entry() {
   PlanEntry e;
   e.d = PlanDesc{P::N, P::T, P::R0, P::R1, P::RL};
@@ -112,6 +213,7 @@ static PlanEntry make_entry() {
   e.build_blob = &build_blob_fn<P>;
   e.launch = &launch_fn<P>;
   e.attrs = &attrs_fn<P>;
+  add_dual<P, DUAL>(e);
   return e;
 }
 
@@ -132,7 +234,7 @@ using P4096 = Plan<4096, 128, 32, 16, 8>;
 
 static const PlanEntry kPlans[] = {
     make_entry<P128>(),  make_entry<P256>(),  make_entry<P512>(),  make_entry<P640>(),
-    make_entry<P1024>(), make_entry<P1280>(), make_entry<P1920>(), make_entry<P2048>(),
+    make_entry<P1024, true>(), make_entry<P1280, true>(), make_entry<P1920, true>(), make_entry<P2048, true>(),
     make_entry<P2560>(), make_entry<P2880>(), make_entry<P3840>(), make_entry<P4096>(),
 };
 

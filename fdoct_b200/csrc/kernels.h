@@ -7,6 +7,7 @@
 
 #include "plan.h"
 #include "recon_kernel.cuh"
+#include "recon2_kernel.cuh"
 
 namespace abcoct {
 
@@ -23,6 +24,12 @@ struct PlanEntry {
   // in_f32: the frames are pre-processed f32 rows from the general path (no calibration, no prefetch); picks the averages == 1 variant itself
   cudaError_t (*launch)(const ReconArgs& a, bool has_sub, bool in_f32, int grid, cudaStream_t st);
   cudaError_t (*attrs)(bool has_sub, bool a1, bool in_f32, int smem, int* regs);  // opt in to large smem, report registers/thread
+  // dual-pair (packed f32x2) variant, recon2_kernel.cuh; groups2 == nullptr when the plan has none
+  int (*groups2)(bool has_sub);
+  int (*smem_bytes2)(int W, bool has_sub, int G);
+  void (*build_blob2)(int W, const int* idx, const float* wq, const float* win, std::vector<unsigned char>& blob);
+  cudaError_t (*launch2)(const ReconArgs& a, bool has_sub, int grid, cudaStream_t st);
+  cudaError_t (*attrs2)(bool has_sub, bool a1, int smem, int* regs);
 };
 
 const PlanEntry* find_plan(int N);

@@ -211,6 +211,29 @@ def test_calibration_from_frames_matches_oracle_capture():
     _check(out8, outdb, ref8, refdb, "calibration from frames")
 
 
+@pytest.mark.parametrize("w,h,N,D,A,variant", [(2048, 33, 2048, 1024, 1, 0), (1280, 21, 1280, 640, 2, 1), (1024, 7, 1024, 512, 1, 0),
+                                               (1920, 10, 1920, 960, 3, 0)])
+def test_dual_pair_kernel_variant(w, h, N, D, A, variant, monkeypatch):
+    """The opt-in packed-f32x2 kernel (ABCOCT_KERNEL=2, recon2_kernel.cuh): odd numbers of row pairs, units that straddle
+    B-scans, averaging and the DARK variant, against the oracle."""
+    from fdoct_b200 import synth
+    from oracle.abcoct_oracle import Oracle
+
+    monkeypatch.setenv("ABCOCT_KERNEL", "2")
+    nB = 3
+    op = oracle_params(w=w, h=h, numfftpoints=N, numdisplaypoints=D, averages=A, variant=variant, lambdamin=840.5e-9, lambdamax=859.5e-9)
+    frames = synth.make_frames(nB * A, w, h, seed=61, dark=bool(variant))
+    yb = synth.make_background_frames(2, w, h, seed=62, dark=bool(variant)).mean(axis=0)
+    yd = synth.make_dark_frames(2, w, h, seed=63).mean(axis=0) if variant else None
+    o = Oracle(op)
+    o.set_background(yb)
+    if variant:
+        o.set_dark(yd)
+    ref8, refdb = o.process_bscans(frames)
+    out8, outdb = _run_abi(op, frames, yb, yd=yd)
+    _check(out8, outdb, ref8, refdb, f"dual w{w} N{N} A{A}")
+
+
 def test_tables_bit_exact_through_ctx():
     from fdoct_b200 import api
     from oracle.abcoct_oracle import barthann_window, build_tables
