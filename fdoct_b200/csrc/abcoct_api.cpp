@@ -187,12 +187,13 @@ int validate(const abcoct_params& p, std::string& why, int& code) {
   return 0;
 }
 
-std::vector<int> factor_radices(int n) {
+std::vector<int> factor_radices(int n) {  // greedy, largest first; every entry has a register butterfly in prep_kernels.cu
   std::vector<int> r;
-  while (n % 4 == 0) { r.push_back(4); n /= 4; }
-  while (n % 2 == 0) { r.push_back(2); n /= 2; }
-  while (n % 3 == 0) { r.push_back(3); n /= 3; }
-  while (n % 5 == 0) { r.push_back(5); n /= 5; }
+  for (int f : {16, 15, 12, 10, 9, 8, 6, 5, 4, 3, 2})
+    while (n % f == 0) {
+      r.push_back(f);
+      n /= f;
+    }
   return r;
 }
 

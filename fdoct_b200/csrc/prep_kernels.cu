@@ -80,7 +80,8 @@ __global__ void bin_kernel(const T* __restrict__ in, T* __restrict__ out, int op
 }
 
 // ------------------------------------------------------------------------------------------------ generic block FFT
-// Stockham autosort transform of one row in shared memory by a whole CTA (any n = 2^a 3^b 5^c, radix list from the host):
+// Stockham autosort transform of one row in shared memory by a whole CTA (any n = 2^a 3^b 5^c; the host picks the
+// radix list greedily from {16, 15, 12, 10, 9, 8, 6, 5, 4, 3, 2}, e.g. 1920 = 16 15 8, 3840 = 16 16 15):
 //   pass with radix r, current length nc, stride s:  for p < nc / r, q < s
 //     y[q + s (r p + c)] = ( sum_j x[q + s (p + (nc / r) j)] w_r^(jc) ) * w_n^(p c s)
 // (tools/fft_plan_model.py holds the NumPy model of this index algebra).  tw[k] = exp(SGN 2 pi i k / n), k < n.
@@ -102,10 +103,9 @@ __device__ __forceinline__ void stockham_pass(const float2* __restrict__ x, floa
     Dft<R, SGN, 1, 1>::run(in, out);
     y[q + s * (R * p)] = out[0];
 #pragma unroll
-    for (int c = 1; c < R; ++c) {
-      const float2 w = tw[(int)(((long long)p * c * s) % n)];
-      y[q + s * (R * p + c)] = cmul(out[c], w);
-    }
+    const int tb = p * s;  // p < nc / R and s * nc == n: tb * c < n for every c < R, no reduction needed
+#pragma unroll
+    for (int c = 1; c < R; ++c) y[q + s * (R * p + c)] = cmul(out[c], tw[tb * c]);
   }
 }
 
@@ -120,7 +120,14 @@ __device__ float2* block_fft(float2* a, float2* b, const RadixList& rl, const fl
       case 2: stockham_pass<2, SGN>(x, y, rl.n, nc, s, tw); break;
       case 3: stockham_pass<3, SGN>(x, y, rl.n, nc, s, tw); break;
       case 4: stockham_pass<4, SGN>(x, y, rl.n, nc, s, tw); break;
-      default: stockham_pass<5, SGN>(x, y, rl.n, nc, s, tw); break;
+      case 5: stockham_pass<5, SGN>(x, y, rl.n, nc, s, tw); break;
+      case 6: stockham_pass<6, SGN>(x, y, rl.n, nc, s, tw); break;
+      case 8: stockham_pass<8, SGN>(x, y, rl.n, nc, s, tw); break;
+      case 9: stockham_pass<9, SGN>(x, y, rl.n, nc, s, tw); break;
+      case 10: stockham_pass<10, SGN>(x, y, rl.n, nc, s, tw); break;
+      case 12: stockham_pass<12, SGN>(x, y, rl.n, nc, s, tw); break;
+      case 15: stockham_pass<15, SGN>(x, y, rl.n, nc, s, tw); break;
+      default: stockham_pass<16, SGN>(x, y, rl.n, nc, s, tw); break;
     }
     __syncthreads();
     nc /= r;
