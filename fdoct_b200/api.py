@@ -32,7 +32,7 @@ class Params(C.Structure):
         ("lambdamin", C.c_double), ("lambdamax", C.c_double), ("mediann", C.c_int32), ("movavgn", C.c_int32),
         ("fft_multiplier", C.c_uint32), ("rowwisenormalize", C.c_uint8), ("donotnormalize", C.c_uint8),
         ("variant", C.c_uint8), ("weight_mode", C.c_uint8), ("bscanthreshold", C.c_double),
-        ("clampupper", C.c_uint8), ("bandpassfilter", C.c_uint8), ("reserved", C.c_uint8 * 6),
+        ("clampupper", C.c_uint8), ("bandpassfilter", C.c_uint8), ("lowpassfilter", C.c_uint8), ("reserved", C.c_uint8 * 5),
         ("clamp_db", C.c_double),
     ]
 
@@ -53,6 +53,7 @@ class Info(C.Structure):
 EXPORTS = [
     "abcoct_params_default", "abcoct_params_from_ini", "abcoct_create", "abcoct_destroy", "abcoct_last_error",
     "abcoct_set_background", "abcoct_set_pishift", "abcoct_set_dark", "abcoct_set_calibration_from_frames",
+    "abcoct_compose_dark_background", "abcoct_get_calibration",
     "abcoct_build_tables", "abcoct_get_tables", "abcoct_get_window", "abcoct_process_bscans",
     "abcoct_process_bscans_device", "abcoct_timing_reset", "abcoct_timing_read", "abcoct_debug_linearised", "abcoct_host_alloc", "abcoct_host_free", "abcoct_get_info",
 ]
@@ -85,6 +86,8 @@ def lib() -> C.CDLL:
     for n in ("abcoct_set_background", "abcoct_set_pishift", "abcoct_set_dark"):
         getattr(L, n).argtypes = [vp, vp, sz]
     L.abcoct_set_calibration_from_frames.argtypes = [vp, i32, vp, sz, sz]
+    L.abcoct_compose_dark_background.argtypes = [vp]
+    L.abcoct_get_calibration.argtypes = [vp, i32, vp, sz]
     L.abcoct_build_tables.argtypes = [C.POINTER(Params), vp, vp, vp]
     L.abcoct_get_tables.argtypes = [vp, vp, vp]
     L.abcoct_get_window.argtypes = [vp, vp]
@@ -218,6 +221,14 @@ class Context:
         assert frames.ndim == 3 and frames.dtype == (np.uint8 if self.params.bpp == 8 else np.uint16)
         self._check(lib().abcoct_set_calibration_from_frames(self._h, which, frames.ctypes.data, frames.shape[0], 0))
 
+    def get_calibration(self, which: int) -> np.ndarray:
+        out = np.empty((self.oph, self.opw), dtype=np.float64)
+        self._check(lib().abcoct_get_calibration(self._h, which, out.ctypes.data, 0))
+        return out
+
+    def compose_dark_background(self):
+        self._check(lib().abcoct_compose_dark_background(self._h))
+
     def tables(self):
         nk = np.empty(self.params.numfftpoints, dtype=np.int32)
         fr = np.empty(self.params.numfftpoints, dtype=np.float64)
@@ -248,6 +259,14 @@ class Context:
         """Device-pointer call (abcoct_process_bscans_device); pointers are raw integers (e.g. tensor.data_ptr())."""
         self._check(lib().abcoct_process_bscans_device(self._h, gpu_index, d_frames, nframes, stride_bytes, d_out8,
                                                        d_outdb, stream))
+
+    def debug_linearised(self, frame: np.ndarray) -> np.ndarray:
+        """data_ylin of one frame (abcoct_debug_linearised): float32 [oph, numfftpoints]."""
+        frame = np.ascontiguousarray(frame)
+        assert frame.shape == (self.params.h, self.params.w)
+        out = np.empty((self.oph, self.params.numfftpoints), dtype=np.float32)
+        self._check(lib().abcoct_debug_linearised(self._h, frame.ctypes.data, 0, out.ctypes.data))
+        return out
 
     def timing_reset(self):
         self._check(lib().abcoct_timing_reset(self._h))

@@ -65,11 +65,14 @@ struct abcoct_ctx {
   int opw = 0, oph = 0, M = 0, N = 0, D = 0, A = 1;
   std::vector<int32_t> nk;
   std::vector<double> frac, win;
-  std::vector<double> yb, yp, yd;
+  std::vector<double> yb, yp, yd, yr, ys;
+  bool have_yr = false, have_ys = false;
   bool have_yb = false, have_yp = false, have_yd = false, cal_dirty = true, has_sub = false;
   bool general = false;  // any optional pre-processing stage is on: frames go through prep_kernels.cu first
   bool dual = false;     // the plan's dual-pair (packed f32x2) kernel is used (recon2_kernel.cuh)
   std::vector<unsigned char> blob1, blob2;
+  std::vector<int> gidx;      // the kernel's remapped gather indices / weights (debug tap)
+  std::vector<float> gwq;
   int px_bytes = 2;
   std::vector<int> radW, radM;
   const PlanEntry* plan = nullptr;
@@ -235,6 +238,66 @@ void host_bin(const T* in, size_t row_stride, double* out, int opw, int oph, int
     }
 }
 
+// smoothmovavg, BscanFFT.cpp:247-304 (2n+1 taps, centre counted twice, missing taps replaced by the centre sample)
+void host_movavg(std::vector<double>& m, int rows, int cols, int n) {
+  std::vector<double> out(cols);
+  for (int r = 0; r < rows; ++r) {
+    double* x = &m[(size_t)r * cols];
+    for (int j = 0; j < cols; ++j) {
+      double s = 0.0;
+      for (int k = -n; k <= n; ++k) {
+        const int jj = j + k;
+        s = s + ((jj > -1 && jj < cols) ? x[jj] : x[j]);
+      }
+      s = s + x[j];
+      out[j] = s / 2 / (n + 1);
+    }
+    std::copy(out.begin(), out.end(), x);
+  }
+}
+// cv::normalize(src, dst, a, b, NORM_MINMAX) over [first, last): dst = src * scale + (a - min * scale)
+void host_normalize(double* first, double* last, double a, double b) {
+  const auto mm = std::minmax_element(first, last);
+  const double mn = *mm.first, mx = *mm.second;
+  const double scale = (b - a) * ((mx - mn) > 2.220446049250313e-16 ? 1.0 / (mx - mn) : 0.0);
+  const double shift = a - mn * scale;
+  for (double* p = first; p != last; ++p) *p = *p * scale + shift;
+}
+// lpfilter, BscanDark.cpp:119-167: f32 row DFT scaled by 1 / cols, keep the centre 20 % of the shifted spectrum, inverse
+// DFT with DFT_REAL_OUTPUT (which reads bins 0 .. cols/2 only): out[n] = Re X[0] + 2 Re sum_{0<k<cols/10} X[k] e^{2 pi i n k / cols}
+void host_lpfilter(std::vector<double>& m, int rows, int cols) {
+  const int keep = cols / 10;  // bins [0, floor(cols / 10))
+  const double tau = 6.283185307179586476925286766559;
+  std::vector<double> cs(cols), sn(cols), re(keep), im(keep), out(cols);
+  for (int k = 0; k < cols; ++k) {
+    cs[k] = std::cos(tau * k / cols);
+    sn[k] = std::sin(tau * k / cols);
+  }
+  for (int r = 0; r < rows; ++r) {
+    double* x = &m[(size_t)r * cols];
+    for (int k = 0; k < keep; ++k) {
+      double a = 0, b = 0;
+      for (int j = 0; j < cols; ++j) {
+        const double v = (double)(float)x[j];  // convertTo(CV_32F)
+        const int t = (int)(((long long)j * k) % cols);
+        a += v * cs[t];
+        b -= v * sn[t];
+      }
+      re[k] = a / cols;
+      im[k] = b / cols;
+    }
+    for (int n = 0; n < cols; ++n) {
+      double s = keep > 0 ? re[0] : 0.0;
+      for (int k = 1; k < keep; ++k) {
+        const int t = (int)(((long long)n * k) % cols);
+        s += 2.0 * (re[k] * cs[t] - im[k] * sn[t]);
+      }
+      out[n] = (double)(float)s;  // the inverse transform is f32
+    }
+    std::copy(out.begin(), out.end(), x);
+  }
+}
+
 int upload_calibration(abcoct_ctx* c) {
   if (!c->have_yb) return fail(c, ABCOCT_ERR_STATE, "no background set: data_yb is all zeros in the reference until key 'b' (BscanFFT.cpp:562)");
   const size_t n = (size_t)c->oph * c->opw;
@@ -248,7 +311,7 @@ int upload_calibration(abcoct_ctx* c) {
     has_sub |= (sub != 0.0);
   }
   c->has_sub = has_sub && !c->general;
-  if (c->general) {  // unswizzled f32 copies for rowprep_kernel; the fused kernel gets pre-processed rows, no calibration
+  {  // unswizzled f32 copies for rowprep_kernel (general path and debug tap)
     std::vector<float> fb(n), fp(n), fd(n);
     for (size_t i = 0; i < n; ++i) {
       fb[i] = (float)c->yb[i];
@@ -545,7 +608,7 @@ int abcoct_params_from_ini(const char* path, int flavour, abcoct_params* o) {
   if (flavour == ABCOCT_INI_SPINJNT) o->clamp_db = 30.0;  // BscanFFTspinjnt.cpp:1886
   std::ifstream in(path);
   if (!in.is_open()) return ABCOCT_ERR_IO;  // "Unable to open ini file, using defaults." BscanFFT.cpp:484
-  enum F { SKIP, BPP, W, H, BIN, BINX, BINY, AVG, NFFT, MOVAVG, NDISP, LMIN, LMAX, MEDIAN, MULT, ROWNORM, NONORM, BANDPASS };
+  enum F { SKIP, BPP, W, H, BIN, BINX, BINY, AVG, NFFT, MOVAVG, NDISP, LMIN, LMAX, MEDIAN, MULT, ROWNORM, NONORM, BANDPASS, LOWPASS };
   std::vector<F> order = {SKIP /*camgain*/, SKIP /*camtime*/, BPP, W, H};
   const bool offsets = flavour == ABCOCT_INI_BSCANFFT || flavour == ABCOCT_INI_SPINJ || flavour == ABCOCT_INI_SPINJNT;
   if (offsets) {
@@ -561,7 +624,7 @@ int abcoct_params_from_ini(const char* path, int flavour, abcoct_params* o) {
   order.insert(order.end(), {SKIP /*dirdescr*/, AVG, NFFT, SKIP /*saveframes*/, SKIP /*manualaveraging*/, SKIP /*manualaverages*/,
                              SKIP /*saveinterferograms*/, MOVAVG, NDISP, LMIN, LMAX, MEDIAN, MULT});
   if (flavour != ABCOCT_INI_SIM) order.insert(order.end(), {ROWNORM, NONORM});
-  if (flavour == ABCOCT_INI_DARK) order.insert(order.end(), {BANDPASS, SKIP /*lowpassfilter*/});
+  if (flavour == ABCOCT_INI_DARK) order.insert(order.end(), {BANDPASS, LOWPASS});
   std::string tok;
   for (int i = 0; i < 3; ++i)  // "first three lines of ini file are comments" BscanFFT.cpp:420-423
     if (!(in >> tok)) return ABCOCT_OK;
@@ -594,6 +657,7 @@ int abcoct_params_from_ini(const char* path, int flavour, abcoct_params* o) {
       case ROWNORM: o->rowwisenormalize = iv != 0; stop = !numeric; break;
       case NONORM: o->donotnormalize = iv != 0; stop = !numeric; break;
       case BANDPASS: o->bandpassfilter = iv != 0; stop = !numeric; break;
+      case LOWPASS: o->lowpassfilter = iv != 0; stop = !numeric; break;
     }
     if (stop) break;  // an istream in the fail state ignores every later extraction
   }
@@ -650,6 +714,8 @@ int abcoct_create(const abcoct_params* params, const int* gpu_ids, int ngpu, abc
     wq[q] = (float)w;
   }
   for (int i = 0; i < c->opw; ++i) winf[i] = (float)c->win[i];
+  c->gidx = idx;
+  c->gwq = wq;
   std::vector<unsigned char>& blob = c->blob1;
   if (c->general) {  // the fused kernel sees rows of M apodised samples: no window / mean term left to apply there
     std::vector<float> zero(c->M, 0.f);
@@ -692,7 +758,7 @@ int abcoct_create(const abcoct_params* params, const int* gpu_ids, int ngpu, abc
     }
     g.tev.assign(3 * kTimedChunks, nullptr);
     for (size_t k = 0; k < g.tev.size() && ok; ++k) ok = ok && cudaEventCreate(&g.tev[k]) == cudaSuccess;
-    if (c->general) {
+    {
       ok = ok && cudaMalloc(&g.d_win, winf.size() * 4) == cudaSuccess;
       ok = ok && cudaMemcpy(g.d_win, winf.data(), winf.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess;
       if (!twW.empty()) {
@@ -774,7 +840,7 @@ int abcoct_set_pishift(abcoct_ctx* c, const double* yp, size_t ld) { return c ? 
 int abcoct_set_dark(abcoct_ctx* c, const double* yd, size_t ld) { return c ? set_cal(c, c->yd, c->have_yd, yd, ld) : ABCOCT_ERR_INVALID; }
 
 int abcoct_set_calibration_from_frames(abcoct_ctx* c, int which, const void* frames, size_t nframes, size_t stride_bytes) {
-  if (!c || !frames || nframes == 0 || which < 0 || which > 2) return c ? fail(c, ABCOCT_ERR_INVALID, "bad argument") : ABCOCT_ERR_INVALID;
+  if (!c || !frames || nframes == 0 || which < 0 || which > 4) return c ? fail(c, ABCOCT_ERR_INVALID, "bad argument") : ABCOCT_ERR_INVALID;
   const int pb = c->px_bytes, w = (int)c->p.w, h = (int)c->p.h;
   if (stride_bytes == 0) stride_bytes = (size_t)w * pb;
   if (stride_bytes % pb) return fail(c, ABCOCT_ERR_INVALID, "stride_bytes must be a multiple of the pixel size");
@@ -798,14 +864,50 @@ int abcoct_set_calibration_from_frames(abcoct_ctx* c, int which, const void* fra
       host_bin(fr, rs, one.data(), c->opw, c->oph, (int)c->p.binx, (int)c->p.biny);
     else
       host_bin(reinterpret_cast<const uint16_t*>(fr), rs, one.data(), c->opw, c->oph, (int)c->p.binx, (int)c->p.biny);
+    if (c->p.movavgn > 0) host_movavg(one, c->oph, c->opw, c->p.movavgn);  // BscanFFT.cpp:990-991
     for (size_t i = 0; i < n; ++i) acc[i] += one[i];
   }
-  const double s = 1.0 / (double)nframes;  // Mat / double multiplies by the reciprocal, BscanFFT.cpp:1057
-  for (double& v : acc) v *= s;
-  std::vector<double>& dst = which == 0 ? c->yb : which == 1 ? c->yp : c->yd;
-  bool& have = which == 0 ? c->have_yb : which == 1 ? c->have_yp : c->have_yd;
+  if (which != 1) {
+    // BscanFFT.cpp:1050-1057: if (rowwisenormalize) normalizerows(.., 0.0001, 1); if (!donotnormalize) normalize(.., 0.0001, 1); else / n
+    if (c->p.rowwisenormalize)
+      for (int r = 0; r < c->oph; ++r) host_normalize(&acc[(size_t)r * c->opw], &acc[(size_t)r * c->opw] + c->opw, 0.0001, 1.0);
+    if (!c->p.donotnormalize) {
+      host_normalize(acc.data(), acc.data() + n, 0.0001, 1.0);
+    } else {
+      const double s = 1.0 / (double)nframes;  // Mat / double multiplies by the reciprocal
+      for (double& v : acc) v *= s;
+    }
+    if (c->p.lowpassfilter && which >= 2) host_lpfilter(acc, c->oph, c->opw);  // BscanDark.cpp:1070-1074, 1145-1149, 1218-1222
+  } else if (nframes != 1) {
+    return fail(c, ABCOCT_ERR_INVALID, "the pi-shifted frame is a copy of ONE frame (BscanFFT.cpp:1081)");
+  }
+  std::vector<double>& dst = which == 0 ? c->yb : which == 1 ? c->yp : which == 2 ? c->yd : which == 3 ? c->yr : c->ys;
+  bool& have = which == 0 ? c->have_yb : which == 1 ? c->have_yp : which == 2 ? c->have_yd : which == 3 ? c->have_yr : c->have_ys;
   dst.swap(acc);
   have = true;
+  if (which <= 2) c->cal_dirty = true;
+  return ABCOCT_OK;
+}
+
+int abcoct_get_calibration(const abcoct_ctx* c, int which, double* out, size_t ld) {
+  if (!c || !out || which < 0 || which > 4) return ABCOCT_ERR_INVALID;
+  const std::vector<double>& src = which == 0 ? c->yb : which == 1 ? c->yp : which == 2 ? c->yd : which == 3 ? c->yr : c->ys;
+  const bool have = which == 0 ? c->have_yb : which == 1 ? c->have_yp : which == 2 ? c->have_yd : which == 3 ? c->have_yr : c->have_ys;
+  if (!have) return ABCOCT_ERR_STATE;
+  if (ld == 0) ld = c->opw;
+  if (ld < (size_t)c->opw) return ABCOCT_ERR_INVALID;
+  for (int r = 0; r < c->oph; ++r) memcpy(out + (size_t)r * ld, &src[(size_t)r * c->opw], (size_t)c->opw * sizeof(double));
+  return ABCOCT_OK;
+}
+
+int abcoct_compose_dark_background(abcoct_ctx* c) {
+  if (!c) return ABCOCT_ERR_INVALID;
+  if (!c->have_yr || !c->have_ys || !c->have_yd)
+    return fail(c, ABCOCT_ERR_STATE, "need the dark, reference-arm and sample-arm captures first (BscanDark.cpp:996)");
+  const size_t n = (size_t)c->oph * c->opw;
+  c->yb.resize(n);
+  for (size_t i = 0; i < n; ++i) c->yb[i] = (c->yr[i] - c->yd[i]) + (c->ys[i] - c->yd[i]);
+  c->have_yb = true;
   c->cal_dirty = true;
   return ABCOCT_OK;
 }
@@ -975,8 +1077,55 @@ int abcoct_process_bscans(abcoct_ctx* c, const void* frames, size_t nframes, siz
   return ABCOCT_OK;
 }
 
-int abcoct_debug_linearised(abcoct_ctx* c, const void*, size_t, float*) {
-  return c ? fail(c, ABCOCT_ERR_UNSUPPORTED, "debug tap not built yet") : ABCOCT_ERR_INVALID;
+int abcoct_debug_linearised(abcoct_ctx* c, const void* frame, size_t stride_bytes, float* ylin) {
+  if (!c) return ABCOCT_ERR_INVALID;
+  if (!frame || !ylin) return fail(c, ABCOCT_ERR_INVALID, "null buffer");
+  const size_t dense = (size_t)c->p.w * c->px_bytes;
+  if (stride_bytes == 0) stride_bytes = dense;
+  if (stride_bytes < dense) return fail(c, ABCOCT_ERR_INVALID, "stride_bytes < w * bytes per pixel");
+  if (c->cal_dirty) {
+    int rc = upload_calibration(c);
+    if (rc) return rc;
+  }
+  GpuState& g = c->gpus[0];
+  CU(c, cudaSetDevice(g.dev));
+  cudaStream_t st = g.stream[0];
+  // stage the frame densely, then run the general-path kernels for this one frame and the lerp on top
+  std::vector<uint8_t> host((size_t)c->p.h * dense);
+  for (uint32_t r = 0; r < c->p.h; ++r) memcpy(&host[r * dense], static_cast<const uint8_t*>(frame) + r * stride_bytes, dense);
+  uint8_t* d_frame = nullptr;
+  int* d_idx = nullptr;
+  float *d_wq = nullptr, *d_ylin = nullptr;
+  auto cleanup = [&]() {
+    cudaFree(d_frame);
+    cudaFree(d_idx);
+    cudaFree(d_wq);
+    cudaFree(d_ylin);
+  };
+  int rc = ensure_prep(c, g, 0, 1);
+  if (rc) return rc;
+  cudaError_t e = cudaMalloc(&d_frame, host.size());
+  if (e == cudaSuccess) e = cudaMalloc(&d_idx, c->N * sizeof(int));
+  if (e == cudaSuccess) e = cudaMalloc(&d_wq, c->N * sizeof(float));
+  if (e == cudaSuccess) e = cudaMalloc(&d_ylin, (size_t)c->oph * c->N * sizeof(float));
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_frame, host.data(), host.size(), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_idx, c->gidx.data(), c->N * sizeof(int), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_wq, c->gwq.data(), c->N * sizeof(float), cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess) {
+    cleanup();
+    return fail(c, ABCOCT_ERR_CUDA, "debug tap setup: %s", cudaGetErrorString(e));
+  }
+  int nl = 0;
+  rc = run_prep(c, g, 0, d_frame, 1, dense, dense * c->p.h, st, &nl);
+  if (rc == ABCOCT_OK) {
+    e = launch_lerp_rows(g.d_rows[0], d_idx, d_wq, d_ylin, c->M, c->N, c->oph, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(ylin, d_ylin, (size_t)c->oph * c->N * sizeof(float), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = fail(c, ABCOCT_ERR_CUDA, "debug tap: %s", cudaGetErrorString(e));
+    c->launches += nl + 1;
+  }
+  cleanup();
+  return rc;
 }
 
 void* abcoct_host_alloc(size_t bytes) {

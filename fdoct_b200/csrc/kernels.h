@@ -57,4 +57,5 @@ cudaError_t launch_bin(const void* in, void* out, int bpp, int opw, int oph, int
                        size_t frame_stride_elems, int nframes, cudaStream_t st);
 cudaError_t launch_rowprep(const PrepArgsHost& h, cudaStream_t st, int* launched);
 size_t rowprep_smem_bytes(int opw, int M, int m, int movavgn);
+cudaError_t launch_lerp_rows(const float* rows, const int* idx, const float* wq, float* ylin, int M, int N, int oph, cudaStream_t st);
 }  // namespace abcoct

@@ -307,6 +307,22 @@ __global__ void __launch_bounds__(256) rowprep_kernel(const PrepArgs a) {
   for (int j = threadIdx.x; j < a.M; j += blockDim.x) out[j] = R[j].x;
 }
 
+// ------------------------------------------------------------------------------------------------ debug tap
+// data_ylin (BscanFFT.cpp:1151-1177) from prepared rows, for the stage-level parity test only: idx / wq are the kernel's
+// remapped gather tables (idx >= 1, idx == M -> the never-written end points, weight quirk already applied).
+__global__ void lerp_rows_kernel(const float* __restrict__ rows, const int* __restrict__ idx, const float* __restrict__ wq,
+                                 float* __restrict__ ylin, int M, int N, int oph) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+  if (q >= N || r >= oph) return;
+  const float* y = rows + (size_t)r * M;
+  const int i = idx[q];
+  ylin[(size_t)r * N + q] = i >= M ? 0.f : fmaf(wq[q], y[i] - y[i - 1], y[i]);
+}
+cudaError_t launch_lerp_rows(const float* rows, const int* idx, const float* wq, float* ylin, int M, int N, int oph, cudaStream_t st) {
+  lerp_rows_kernel<<<dim3((N + 255) / 256, oph), 256, 0, st>>>(rows, idx, wq, ylin, M, N, oph);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------ launchers
 cudaError_t launch_median(const void* in, void* out, int bpp, int k, int w, int h, size_t row_stride_elems, size_t frame_stride_elems,
                           int nframes, cudaStream_t st) {

@@ -67,7 +67,8 @@ typedef struct abcoct_params {
   double bscanthreshold;     /* BscanFFT.cpp:385, 1247 (default -30.0)                                     */
   uint8_t clampupper;        /* BscanFFT.cpp:374, 1248                                                     */
   uint8_t bandpassfilter;    /* BscanDark.cpp:218-236 (inside the Fourier upsample only)                   */
-  uint8_t reserved[6];
+  uint8_t lowpassfilter;     /* BscanDark.cpp:1070-1074: lpfilter (:119-167) on the captured dark / reference / sample frames */
+  uint8_t reserved[5];
   double clamp_db;           /* 50.0 (BscanFFT.cpp:1252), 30.0 in BscanFFTspinjnt.cpp:1886                 */
 } abcoct_params;
 
@@ -97,10 +98,22 @@ const char* abcoct_last_error(const abcoct_ctx* ctx); /* ctx may be NULL: error 
 int abcoct_set_background(abcoct_ctx* ctx, const double* yb, size_t ld);
 int abcoct_set_pishift(abcoct_ctx* ctx, const double* yp, size_t ld);
 int abcoct_set_dark(abcoct_ctx* ctx, const double* yd, size_t ld);
-/* Mean of nframes raw frames after median + binning, the capture done on keys b / o / r / t
- * (BscanFFT.cpp:1041-1062; BscanDark.cpp:1045-1225).  which: 0 background, 1 pishift (nframes==1), 2 dark. */
+/* The capture done on keys b / p / o / r / t (BscanFFT.cpp:1041-1062, 1081; BscanDark.cpp:1045-1225): data_y of
+ * `nframes` raw frames (after median, binning, convertTo, smoothmovavg) is accumulated, then - except for the pi-shifted
+ * frame, which is a plain copy of one frame - normalised to [0.0001, 1] row-wise (rowwisenormalize) and / or globally
+ * (!donotnormalize), else divided by nframes, with the reference's `if (rowwise) ...; if (!donotnormalize) ...; else /n`
+ * structure; the DARK captures are low-pass filtered when `lowpassfilter` is set.  Runs on the host (once per key press).
+ *   which: 0 background data_yb, 1 pishift data_yp, 2 dark data_yd, 3 reference arm data_yr, 4 sample arm data_ys. */
 int abcoct_set_calibration_from_frames(abcoct_ctx* ctx, int which, const void* frames, size_t nframes,
                                        size_t stride_bytes);
+
+/* Read a calibration frame back (oph x opw doubles, row stride `ld`, 0 = dense), e.g. to save data_yb as spectrum.ocv
+ * like BscanFFTspinj.cpp:1788-1789.  which as in abcoct_set_calibration_from_frames; ABCOCT_ERR_STATE if it was never set. */
+int abcoct_get_calibration(const abcoct_ctx* ctx, int which, double* out, size_t ld);
+
+/* BscanDark's key 'b': data_yb = (data_yr - data_yd) + (data_ys - data_yd) (BscanDark.cpp:996) from the captures
+ * which = 3, 4 and the current dark frame. */
+int abcoct_compose_dark_background(abcoct_ctx* ctx);
 
 /* Host-only (no GPU needed): the one-time precompute of BscanFFT.cpp:615-698 and :936-944 for `params`.
  * nearestkindex / fractionalk have numfftpoints entries, barthannwin has w / binx; any may be NULL. */
@@ -135,8 +148,9 @@ int abcoct_process_bscans_device(abcoct_ctx* ctx, int gpu_index, const void* d_f
 int abcoct_timing_reset(abcoct_ctx* ctx);
 int abcoct_timing_read(abcoct_ctx* ctx, int gpu_index, uint32_t* nchunks, double* recon_ms, double* norm_ms);
 
-/* Linear (pre-log) averaged magnitude `bscan` (BscanFFT.cpp:1220-1222) of the LAST device/host call's
- * first B-scan and per-stage debug taps are exposed for the parity tests only. */
+/* Stage-level debug tap for the parity tests: data_ylin (BscanFFT.cpp:1151-1177), i.e. one frame after every
+ * pre-processing stage and the lambda->k gather-lerp, oph x numfftpoints floats.  It runs the general pre-processing
+ * kernels (prep_kernels.cu) whatever the configuration; the fused kernel never materialises this intermediate. */
 int abcoct_debug_linearised(abcoct_ctx* ctx, const void* frame, size_t stride_bytes, float* ylin /* oph x N */);
 
 /* Pinned host memory for zero-staging ingest (the caller's ring buffer). */

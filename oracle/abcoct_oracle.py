@@ -79,6 +79,7 @@ class Params:
     clampupper: bool = False
     clamp_db: float = 50.0  # BscanFFT.cpp:1252 (30.0 in BscanFFTspinjnt.cpp:1886)
     bandpassfilter: bool = False  # BscanDark.cpp:218-236, only inside zeropadrowwise
+    lowpassfilter: bool = False  # BscanDark.cpp:1070-1074: lpfilter on the captured calibration frames
 
     @property
     def opw(self) -> int:
@@ -201,6 +202,21 @@ def zeropadrowwise(sm: np.ndarray, sn: int, bandpassfilter: bool = False) -> np.
     return inv.astype(np.float64)  # :242
 
 
+def lpfilter(sm: np.ndarray) -> np.ndarray:
+    """BscanDark.cpp:119-167: row-wise FFT-domain low-pass (keeps the centre 20 % of the shifted spectrum). Returns f64."""
+    orig = sm.astype(np.float32)
+    ft = cv2.dft(orig, flags=cv2.DFT_SCALE | cv2.DFT_COMPLEX_OUTPUT | cv2.DFT_ROWS)
+    ft = _swap_halves(ft)
+    cols = ft.shape[1]
+    dcl = cols // 2 - int(math.floor(cols / 10))
+    dcr = cols // 2 + int(math.floor(cols / 10))
+    ft[:, 0:dcl] = 0
+    ft[:, dcr : dcr + dcl] = 0
+    ft = _swap_halves(ft)
+    inv = cv2.dft(ft, flags=cv2.DFT_INVERSE | cv2.DFT_REAL_OUTPUT | cv2.DFT_ROWS)
+    return inv.astype(np.float64)
+
+
 def bin_frame(mraw: np.ndarray, p: Params) -> np.ndarray:
     """medianBlur + INTER_AREA binning on the integer frame, BscanFFT.cpp:953-958 (x/y: BscanFFTspinjnt.cpp:1553)."""
     m = cv2.medianBlur(mraw, p.mediann) if p.mediann > 0 else mraw
@@ -248,6 +264,29 @@ class Oracle:
         for f in frames:
             acc += bin_frame(f, self.p).astype(np.float64)
         return acc * (1.0 / len(frames))  # Mat / double == Mat * (1/double) in OpenCV
+
+    def calib_capture(self, frames, lowpass: bool = False) -> np.ndarray:
+        """The full capture on keys b / o / r / t: accumulate data_y (after median, binning, convertTo, smoothmovavg) over the
+        frames, then normalizerows / normalize to [0.0001, 1] or divide by the count - with the reference's if / if-else
+        structure (BscanFFT.cpp:1041-1057; BscanDark.cpp:1045-1067, 1107-1114, 1180-1187) - and optionally lpfilter
+        (BscanDark.cpp:1070-1074, 1145-1149, 1218-1222)."""
+        p = self.p
+        acc = np.zeros((p.oph, p.opw), dtype=np.float64)
+        for f in frames:
+            y = bin_frame(f, p).astype(np.float64)
+            if p.movavgn > 0:
+                y = smoothmovavg(y, p.movavgn)
+            acc += y
+        out = acc
+        if p.rowwisenormalize:
+            out = normalizerows(out, 0.0001, 1)
+        if not p.donotnormalize:
+            out = cv2.normalize(out, None, 0.0001, 1, cv2.NORM_MINMAX)
+        else:
+            out = out * (1.0 / len(frames))
+        if lowpass:
+            out = lpfilter(out)
+        return out
 
     # per-frame stages ------------------------------------------------------------
     def linearised(self, mraw: np.ndarray, dump: dict | None = None) -> np.ndarray:

@@ -78,7 +78,7 @@ def test_ini_positional_parser(name, flavour):
         assert (p.rowwisenormalize, p.donotnormalize) == (0, 1)
     assert p.variant == (1 if flavour == api.INI_DARK else 0)
     if flavour == api.INI_DARK:
-        assert p.bandpassfilter == 1
+        assert p.bandpassfilter == 1 and p.lowpassfilter == 0
 
 
 def test_ini_wrong_flavour_misparses_like_the_reference():

@@ -203,7 +203,7 @@ def test_calibration_from_frames_matches_oracle_capture():
     frames = synth.make_frames(A, w, h, seed=77)
     bframes = synth.make_background_frames(A, w, h, seed=78)
     o = Oracle(op)
-    o.set_background(o.calib_mean_of_frames(bframes))
+    o.set_background(o.calib_capture(bframes))
     ref8, refdb = o.process_bscans(frames)
     with api.Context(abi_params(op)) as ctx:
         ctx.set_calibration_from_frames(0, bframes)
@@ -232,6 +232,94 @@ def test_dual_pair_kernel_variant(w, h, N, D, A, variant, monkeypatch):
     ref8, refdb = o.process_bscans(frames)
     out8, outdb = _run_abi(op, frames, yb, yd=yd)
     _check(out8, outdb, ref8, refdb, f"dual w{w} N{N} A{A}")
+
+
+@pytest.mark.parametrize("w,h,N,extra", [(1280, 9, 1280, {}), (1024, 6, 2048, {}), (640, 5, 2560, dict(fft_multiplier=4)),
+                                         (1280, 8, 640, dict(binx=2, biny=2, movavgn=1)), (1280, 6, 1280, dict(variant=1))])
+def test_stage_parity_linearised(w, h, N, extra):
+    """Stage-level parity: data_ylin after pre-processing + lambda->k gather-lerp, <= 1e-6 of the row scale
+    (2e-6 with the f32 Fourier upsample in the way)."""
+    from fdoct_b200 import api, synth
+    from oracle.abcoct_oracle import Oracle
+
+    op = oracle_params(w=w, h=h, numfftpoints=N, numdisplaypoints=min(N // 2, 256), lambdamin=840.5e-9, lambdamax=859.5e-9, **extra)
+    dark = op.variant == 1
+    frame = synth.make_frames(1, w, h, seed=71, dark=dark)[0]
+    o = Oracle(op)
+    yb = o.calib_mean_of_frames(synth.make_background_frames(2, w, h, seed=72, dark=dark))
+    o.set_background(yb)
+    yd = None
+    if dark:
+        yd = o.calib_mean_of_frames(synth.make_dark_frames(2, w, h, seed=73))
+        o.set_dark(yd)
+    ref = o.linearised(frame)
+    with api.Context(abi_params(op)) as ctx:
+        ctx.set_background(yb)
+        if dark:
+            ctx.set_dark(yd)
+        got = ctx.debug_linearised(frame)
+    scale = np.abs(ref).max(axis=1, keepdims=True)
+    err = float((np.abs(got - ref) / scale).max())
+    assert err <= (2e-6 if op.fft_multiplier > 1 else 1e-6), err
+    assert (got[:, 0] == 0).all() and (got[:, -1] == 0).all()  # never written in the reference (BscanFFT.cpp:1164)
+
+
+def test_calibration_captures_match_oracle():
+    """Every capture kind and normalise branch, read back with abcoct_get_calibration, against the oracle's capture."""
+    from fdoct_b200 import api, synth
+    from oracle.abcoct_oracle import Oracle, bin_frame, smoothmovavg
+
+    w, h = 640, 10
+    bf = synth.make_background_frames(3, w, h, seed=91, dark=True)
+    for extra in (dict(), dict(rowwisenormalize=True), dict(donotnormalize=False), dict(rowwisenormalize=True, donotnormalize=False),
+                  dict(movavgn=2, mediann=3, binx=2, biny=2), dict(lowpassfilter=True), dict(lowpassfilter=True, donotnormalize=False)):
+        op = oracle_params(w=w, h=h, numfftpoints=1280, numdisplaypoints=64, variant=1, lambdamin=840.5e-9, lambdamax=859.5e-9, **extra)
+        o = Oracle(op)
+        with api.Context(abi_params(op)) as ctx:
+            with pytest.raises(api.AbcoctError):
+                ctx.get_calibration(3)
+            for which in (0, 2, 3, 4):
+                ctx.set_calibration_from_frames(which, bf)
+                got = ctx.get_calibration(which)
+                ref = o.calib_capture(bf, lowpass=op.lowpassfilter and which >= 2)
+                tol = 2e-6 if (op.lowpassfilter and which >= 2) else 1e-12  # lpfilter is an f32 FFT in the reference
+                assert np.abs(got - ref).max() <= tol * np.abs(ref).max(), (extra, which, np.abs(got - ref).max())
+            ctx.set_calibration_from_frames(1, bf[:1])  # key 'p': data_y.copyTo(data_yp), no normalisation (BscanFFT.cpp:1081)
+            yp = bin_frame(bf[0], op).astype(np.float64)
+            if op.movavgn > 0:
+                yp = smoothmovavg(yp, op.movavgn)
+            assert np.abs(ctx.get_calibration(1) - yp).max() <= 1e-12 * yp.max()
+
+
+@pytest.mark.parametrize("extra", [dict(), dict(lowpassfilter=True), dict(movavgn=1, rowwisenormalize=True)])
+def test_dark_calibration_flow(extra):
+    """BscanDark's calibration sequence on keys o / r / t / b (BscanDark.cpp:996-1225) through the capture entry points:
+    dark, reference-arm and sample-arm captures (with the normalise branches and lpfilter), composed background."""
+    from fdoct_b200 import api, synth
+    from oracle.abcoct_oracle import Oracle, dark_background
+
+    w, h, N, D, A = 1280, 12, 1280, 640, 2
+    op = oracle_params(w=w, h=h, numfftpoints=N, numdisplaypoints=D, averages=A, variant=1, lambdamin=840.5e-9, lambdamax=859.5e-9, **extra)
+    dk = synth.make_dark_frames(A, w, h, seed=81)
+    rf = synth.make_background_frames(A, w, h, seed=82, dark=True)
+    sm = (0.3 * synth.make_background_frames(A, w, h, seed=83, dark=True)).astype(np.uint16) + 40
+    frames = synth.make_frames(2 * A, w, h, seed=84, dark=True)
+    o = Oracle(op)
+    lp = op.lowpassfilter
+    yd, yr, ys = o.calib_capture(dk, lp), o.calib_capture(rf, lp), o.calib_capture(sm, lp)
+    o.set_dark(yd)
+    o.set_background(dark_background(yr, yd, ys))
+    ref8, refdb = o.process_bscans(frames)
+    with api.Context(abi_params(op)) as ctx:
+        with pytest.raises(api.AbcoctError) as e:
+            ctx.compose_dark_background()
+        assert e.value.code == api.ERR_STATE
+        ctx.set_calibration_from_frames(2, dk)
+        ctx.set_calibration_from_frames(3, rf)
+        ctx.set_calibration_from_frames(4, sm)
+        ctx.compose_dark_background()
+        out8, outdb = ctx.process_bscans(frames, want_db=True)
+    _check(out8, outdb, ref8, refdb, f"dark calibration {extra}")
 
 
 def test_tables_bit_exact_through_ctx():
