@@ -53,7 +53,7 @@ class Info(C.Structure):
 EXPORTS = [
     "abcoct_params_default", "abcoct_params_from_ini", "abcoct_create", "abcoct_destroy", "abcoct_last_error",
     "abcoct_set_background", "abcoct_set_pishift", "abcoct_set_dark", "abcoct_set_calibration_from_frames",
-    "abcoct_compose_dark_background", "abcoct_get_calibration",
+    "abcoct_compose_dark_background", "abcoct_get_calibration", "abcoct_set_threshold", "abcoct_set_clampupper", "abcoct_set_averages",
     "abcoct_build_tables", "abcoct_get_tables", "abcoct_get_window", "abcoct_process_bscans",
     "abcoct_process_bscans_device", "abcoct_timing_reset", "abcoct_timing_read", "abcoct_debug_linearised", "abcoct_host_alloc", "abcoct_host_free", "abcoct_get_info",
 ]
@@ -86,6 +86,9 @@ def lib() -> C.CDLL:
     for n in ("abcoct_set_background", "abcoct_set_pishift", "abcoct_set_dark"):
         getattr(L, n).argtypes = [vp, vp, sz]
     L.abcoct_set_calibration_from_frames.argtypes = [vp, i32, vp, sz, sz]
+    L.abcoct_set_threshold.argtypes = [vp, C.c_double]
+    L.abcoct_set_clampupper.argtypes = [vp, i32]
+    L.abcoct_set_averages.argtypes = [vp, C.c_uint32]
     L.abcoct_compose_dark_background.argtypes = [vp]
     L.abcoct_get_calibration.argtypes = [vp, i32, vp, sz]
     L.abcoct_build_tables.argtypes = [C.POINTER(Params), vp, vp, vp]
@@ -220,6 +223,16 @@ class Context:
         frames = np.ascontiguousarray(frames)
         assert frames.ndim == 3 and frames.dtype == (np.uint8 if self.params.bpp == 8 else np.uint16)
         self._check(lib().abcoct_set_calibration_from_frames(self._h, which, frames.ctypes.data, frames.shape[0], 0))
+
+    def set_threshold(self, thr: float):
+        self._check(lib().abcoct_set_threshold(self._h, thr))
+
+    def set_clampupper(self, on: bool):
+        self._check(lib().abcoct_set_clampupper(self._h, int(on)))
+
+    def set_averages(self, averages: int):
+        self._check(lib().abcoct_set_averages(self._h, averages))
+        self.A = averages
 
     def get_calibration(self, which: int) -> np.ndarray:
         out = np.empty((self.oph, self.opw), dtype=np.float64)

@@ -54,7 +54,7 @@ struct GpuState {
   float* d_scratch[kSlots] = {};
   int* d_sched[kSlots] = {};
   size_t scratch_bscans[kSlots] = {};
-  size_t slot_bscans = 0;  // capacity of the per-slot staging buffers, in B-scans
+  size_t slot_in_bytes = 0, slot_out_px = 0;  // capacity of the per-slot staging buffers
   bool slot_db = false;
 };
 
@@ -533,10 +533,12 @@ int enqueue_device(abcoct_ctx* c, GpuState& g, int slot, const uint8_t* d_frames
 }
 
 int ensure_slots(abcoct_ctx* c, GpuState& g, size_t slotB, bool want_db) {
-  if (g.slot_bscans >= slotB && (g.slot_db || !want_db)) return ABCOCT_OK;
-  CU(c, cudaSetDevice(g.dev));
   const size_t in_bytes = slotB * c->A * (size_t)c->p.h * c->p.w * c->px_bytes;
   const size_t out_px = slotB * (size_t)c->D * c->oph;
+  if (g.slot_in_bytes >= in_bytes && g.slot_out_px >= out_px && (g.slot_db || !want_db)) return ABCOCT_OK;
+  CU(c, cudaSetDevice(g.dev));
+  g.slot_in_bytes = g.slot_out_px = 0;  // nothing is valid until every buffer below exists
+  g.slot_db = false;
   for (int s = 0; s < kSlots; ++s) {
     if (g.d_in[s]) cudaFree(g.d_in[s]);
     if (g.d_out8[s]) cudaFree(g.d_out8[s]);
@@ -557,7 +559,8 @@ int ensure_slots(abcoct_ctx* c, GpuState& g, size_t slotB, bool want_db) {
       CU(c, cudaMallocHost(&g.h_outdb[s], out_px * 4));
     }
   }
-  g.slot_bscans = slotB;
+  g.slot_in_bytes = in_bytes;
+  g.slot_out_px = out_px;
   g.slot_db = want_db;
   return ABCOCT_OK;
 }
@@ -814,6 +817,26 @@ void abcoct_destroy(abcoct_ctx* c) {
   }
   cudaGetLastError();
   delete c;
+}
+
+int abcoct_set_threshold(abcoct_ctx* c, double thr) {
+  if (!c) return ABCOCT_ERR_INVALID;
+  c->p.bscanthreshold = thr;
+  return ABCOCT_OK;
+}
+int abcoct_set_clampupper(abcoct_ctx* c, int on) {
+  if (!c) return ABCOCT_ERR_INVALID;
+  if (on && c->oph < 6) return fail(c, ABCOCT_ERR_INVALID, "clampupper needs at least 6 A-scans (element (5,5), BscanFFT.cpp:1252)");
+  c->p.clampupper = on ? 1 : 0;
+  return ABCOCT_OK;
+}
+int abcoct_set_averages(abcoct_ctx* c, uint32_t averages) {
+  if (!c) return ABCOCT_ERR_INVALID;
+  if (averages == 0) return fail(c, ABCOCT_ERR_INVALID, "averages must be >= 1");
+  c->p.averages = averages;
+  c->A = (int)averages;
+  c->cal_dirty = true;  // the averages == 1 kernel variant has its own attributes
+  return ABCOCT_OK;
 }
 
 static int set_cal(abcoct_ctx* c, std::vector<double>& dst, bool& have, const double* src, size_t ld) {

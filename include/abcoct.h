@@ -91,6 +91,14 @@ int abcoct_create(const abcoct_params* params, const int* gpu_ids, int ngpu, abc
 void abcoct_destroy(abcoct_ctx* ctx);
 const char* abcoct_last_error(const abcoct_ctx* ctx); /* ctx may be NULL: error of the last failed create */
 
+/* Run-time state the reference's key handler mutates between frames (no re-creation needed):
+ *   bscanthreshold   keys '[' / ']' (BscanFFT.cpp:1759-1775)
+ *   clampupper       BscanFFT.cpp:374, 1248
+ *   averages         key 'a' toggles averagestoggle between 1 and `averages` (BscanFFT.cpp:1874-1877); >= 1 */
+int abcoct_set_threshold(abcoct_ctx* ctx, double bscanthreshold);
+int abcoct_set_clampupper(abcoct_ctx* ctx, int on);
+int abcoct_set_averages(abcoct_ctx* ctx, uint32_t averages);
+
 /* Calibration state, oph x opw doubles with a row stride of `ld` elements.
  *   background = data_yb (BscanFFT.cpp:1050-1057; BscanDark.cpp:996), required before processing;
  *   pishift    = data_yp (BscanFFT.cpp:1081), NULL -> zeros (BscanFFT.cpp:563);

@@ -322,6 +322,30 @@ def test_dark_calibration_flow(extra):
     _check(out8, outdb, ref8, refdb, f"dark calibration {extra}")
 
 
+def test_runtime_keys_threshold_clamp_averages():
+    """The state the reference's key handler changes between frames ('[' ']' 'a', clampupper) without re-creating the context."""
+    from fdoct_b200 import api, synth
+    from oracle.abcoct_oracle import Oracle
+
+    w, h, N, D = 1024, 12, 1024, 512
+    frames = synth.make_frames(4, w, h, seed=95)
+    yb = synth.make_background_frames(2, w, h, seed=96).mean(axis=0)
+    base = oracle_params(w=w, h=h, numfftpoints=N, numdisplaypoints=D, averages=1, lambdamin=840.5e-9, lambdamax=859.5e-9)
+    with api.Context(abi_params(base)) as ctx:
+        ctx.set_background(yb)
+        for thr, clamp, A in [(-30.0, False, 1), (-12.0, False, 1), (5.0, True, 2), (-31.0, False, 4), (-30.0, True, 1)]:
+            op = oracle_params(w=w, h=h, numfftpoints=N, numdisplaypoints=D, averages=A, bscanthreshold=thr, clampupper=clamp,
+                               lambdamin=840.5e-9, lambdamax=859.5e-9)
+            o = Oracle(op)
+            o.set_background(yb)
+            ref8, refdb = o.process_bscans(frames)
+            ctx.set_threshold(thr)
+            ctx.set_clampupper(clamp)
+            ctx.set_averages(A)
+            out8, outdb = ctx.process_bscans(frames, want_db=True)
+            _check(out8, outdb, ref8, refdb, f"thr {thr} clamp {clamp} A {A}")
+
+
 def test_tables_bit_exact_through_ctx():
     from fdoct_b200 import api
     from oracle.abcoct_oracle import barthann_window, build_tables
