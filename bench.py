@@ -186,6 +186,17 @@ class ClockSampler:
                 "power_w_max": max(r[2] for r in rows) if rows else None, "samples": in_region, "reasons": reasons}
 
 
+def measured_traffic(workload, nframes):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the fused kernel from the committed ncu capture
+    (profiles/r01_traffic.json), or None when this workload / batch was not captured."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            t = json.load(f)[workload][str(nframes)]
+        return int(t["dram_read"]) + int(t["dram_write"])
+    except Exception:
+        return None
+
+
 def measured_hbm_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -324,7 +335,8 @@ def run_ours(args, wl, rank, world, local_rank):
             "e2e": {"value": e2e_value, "unit": "A-scans/s", "h2d_bytes_per_step": int(frames.nbytes) * world,
                     "d2h_bytes_per_step": int(nB * D * h) * world, "steps": e2e_steps, "matches_device_leg": ok},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None,
+                         "frac": (achieved / peak) if achieved else None, "traffic": measured_traffic(args.workload, nframes),
+                         "algorithmic_bytes_per_launch": bytes_per_ascan * ascans_per_launch,
                          "kernel": "recon_kernel (fused reconstruction)", "bytes_per_ascan": bytes_per_ascan,
                          "ascans_per_launch": ascans_per_launch, "launch_ms": recon_launch_ms, "peak_source": peak_src,
                          "whole_step_frac": bytes_per_ascan * value / world / 1e9 / peak},

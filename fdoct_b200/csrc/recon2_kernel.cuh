@@ -284,7 +284,7 @@ ABC_HD void phase2_passL(int tid, const GroupSmem2& s, Thread2State<P>& r) {
 // dB conversion and stores of both pairs; out[q][row], rows[q] = first camera row of pair q, valid[q][row]
 template <class P>
 ABC_HD void phase2_finalise(int tid, const ReconArgs& a, float* const (&out)[2][2], const int (&rowa)[2], const bool (&valid)[2][2],
-                            Thread2State<P>& r, float (&mn)[2], float (&mx)[2]) {
+                            Thread2State<P>& r, float (&mn)[2], float (&mx)[2], unsigned long long keep_pol = 0) {
   static_assert(P::S / 2 >= 8, "special bins must all fall into slot 0");
   const V2 scale = v2_make(a.out_scale, a.out_scale), eps = v2_make(1e-5f, 1e-5f);
 #pragma unroll
@@ -306,10 +306,10 @@ ABC_HD void phase2_finalise(int tid, const ReconArgs& a, float* const (&out)[2][
             const bool ok = (kk < a.D) && valid[q][row];
             if (j == 0) {
               if (ok && kk >= 2) {
-                dst[kk] = db;
+                store_scratch(dst + kk, db, keep_pol);
                 if (kk == 4) {  // bscandb.row(4).copyTo(row(1)), row(0): BscanFFT.cpp:1239-1240
-                  dst[0] = db;
-                  dst[1] = db;
+                  store_scratch(dst, db, keep_pol);
+                  store_scratch(dst + 1, db, keep_pol);
                 }
                 const bool is55 = a.clamp55 && kk == 5 && (rowa[q] + row) == 5;
                 if (!is55) {
@@ -318,7 +318,7 @@ ABC_HD void phase2_finalise(int tid, const ReconArgs& a, float* const (&out)[2][
                 }
               }
             } else if (ok) {
-              dst[kk] = db;
+              store_scratch(dst + kk, db, keep_pol);
               mn[q] = fminf(mn[q], db);
               mx[q] = fmaxf(mx[q], db);
             }
@@ -368,8 +368,9 @@ __global__ void __launch_bounds__(P::T* G, 1) recon2_kernel(const ReconArgs a) {
   }
   __syncthreads();
 
-  unsigned long long pol;
+  unsigned long long pol, keep_pol;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep_pol));
 
   Thread2State<P> r;
 #pragma unroll
@@ -515,7 +516,7 @@ __global__ void __launch_bounds__(P::T* G, 1) recon2_kernel(const ReconArgs a) {
       float* const out[2][2] = {{o00, o00 + a.Dp}, {o10, o10 + a.Dp}};
       float mn[2] = {__int_as_float(0x7f800000), __int_as_float(0x7f800000)};
       float mx[2] = {__int_as_float(0xff800000), __int_as_float(0xff800000)};
-      phase2_finalise<P>(tid, a, out, rowa, valid, r, mn, mx);
+      phase2_finalise<P>(tid, a, out, rowa, valid, r, mn, mx, keep_pol);
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         mn[q] = warp_min(mn[q]);

@@ -27,6 +27,9 @@
 #include "plan.h"
 
 #define ABC_HD __host__ __device__ __forceinline__
+#ifndef ABC_PUBLISH_BATCH
+#define ABC_PUBLISH_BATCH 4
+#endif
 
 namespace abcoct {
 
@@ -202,6 +205,16 @@ ABC_HD uint4 load_raw16(const uint8_t* p, unsigned long long pol) {
   uint4 v;
   memcpy(&v, p, 16);
   return v;
+#endif
+}
+// dB scratch store: the line must survive in L2 until the normalisation half of the kernel has consumed (and discarded)
+// it, so it is written with an evict-last policy (`pol`, 0 on the host = plain store)
+ABC_HD void store_scratch(float* p, float v, unsigned long long pol) {
+#ifdef __CUDA_ARCH__
+  asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+#else
+  (void)pol;
+  *p = v;
 #endif
 }
 // order-preserving float <-> int (for atomicMin / atomicMax on floats)
@@ -448,7 +461,7 @@ ABC_HD void phase_passL(int tid, const GroupSmem& s, ThreadState<P>& r) {
 // >= S / 2 >= 8), so only that slot pays for the special cases.
 template <class P>
 ABC_HD void phase_finalise(int tid, const ReconArgs& a, float* rowa_out, float* rowb_out, int row_a_index,
-                           bool rowb_valid, ThreadState<P>& r, float& mn, float& mx) {
+                           bool rowb_valid, ThreadState<P>& r, float& mn, float& mx, unsigned long long keep_pol = 0) {
   static_assert(P::S / 2 >= 8, "special bins must all fall into slot 0");
 #pragma unroll
   for (int i = 0; i < P::NU; ++i) {
@@ -466,10 +479,10 @@ ABC_HD void phase_finalise(int tid, const ReconArgs& a, float* rowa_out, float* 
           const bool valid = (kk < a.D) && (row == 0 || rowb_valid);
           if (j == 0) {
             if (valid && kk >= 2) {
-              dst[kk] = db;
+              store_scratch(dst + kk, db, keep_pol);
               if (kk == 4) {  // bscandb.row(4).copyTo(row(1)), row(0): BscanFFT.cpp:1239-1240
-                dst[0] = db;
-                dst[1] = db;
+                store_scratch(dst, db, keep_pol);
+                store_scratch(dst + 1, db, keep_pol);
               }
               const bool is55 = a.clamp55 && kk == 5 && (row_a_index + row) == 5;
               if (!is55) {  // min/max of the raw dB; max(., thr) is monotone and is applied to the two scalars afterwards
@@ -478,7 +491,7 @@ ABC_HD void phase_finalise(int tid, const ReconArgs& a, float* rowa_out, float* 
               }
             }
           } else if (valid) {
-            dst[kk] = db;
+            store_scratch(dst + kk, db, keep_pol);
             mn = fminf(mn, db);
             mx = fmaxf(mx, db);
           }
@@ -721,8 +734,9 @@ __global__ void __launch_bounds__(P::T* G, 1) recon_kernel(const ReconArgs a) {
   }
   __syncthreads();
 
-  unsigned long long pol;
+  unsigned long long pol, keep_pol;
   asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(keep_pol));
 
   ThreadState<P> r;
 #pragma unroll
@@ -772,7 +786,7 @@ __global__ void __launch_bounds__(P::T* G, 1) recon_kernel(const ReconArgs a) {
   // for every memory operation the warp has in flight; it is therefore batched (one fence per kPublishBatch items)
   // and placed right after the pre-processing phase, when the previous items' scratch stores have long landed and
   // the next frame's pixel prefetch has not been issued yet.
-  constexpr int kPublishBatch = 4;
+  constexpr int kPublishBatch = ABC_PUBLISH_BATCH;
   int* const pend = s.slot + 8;  // kept in shared memory: only kPublishTid touches it
   int npend = 0;
   auto publish = [&]() {
@@ -876,7 +890,7 @@ __global__ void __launch_bounds__(P::T* G, 1) recon_kernel(const ReconArgs a) {
       float* oa = a.scratch + (static_cast<size_t>(bscan) * a.oph + ra) * a.Dp;
       float* ob = oa + a.Dp;
       float mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000);
-      phase_finalise<P>(tid, a, oa, ob, ra, rowb_valid, r, mn, mx);
+      phase_finalise<P>(tid, a, oa, ob, ra, rowb_valid, r, mn, mx, keep_pol);
       mn = warp_min(mn);
       mx = warp_max(mx);
       if (lane == 0 && mn <= mx) {  // thresholded min/max (BscanFFT.cpp:1247): max(., thr) commutes with min/max
