@@ -63,15 +63,13 @@ struct ReconArgs {
 };
 
 // Scheduler / per-B-scan state in global memory (ints): [0] item ticket, then nB each of
-// minv, maxv (order-preserving int encodings), cnt (pairs finished), ready (all pairs finished), claim (normalise parts taken).
+// minv, maxv (order-preserving int encodings) and cnt (row pairs finished and published).
 constexpr int kNormBins = 32;   // depth bins per transposition tile
 struct SchedView {
   int* ticket;
   int* minv;
   int* maxv;
   int* cnt;
-  int* ready;
-  int* claim;
 };
 __host__ __device__ inline SchedView sched_view(int* base, int nB) {
   SchedView v;
@@ -79,11 +77,9 @@ __host__ __device__ inline SchedView sched_view(int* base, int nB) {
   v.minv = base + 32;
   v.maxv = v.minv + nB;
   v.cnt = v.maxv + nB;
-  v.ready = v.cnt + nB;
-  v.claim = v.ready + nB;
   return v;
 }
-__host__ __device__ inline size_t sched_ints(int nB) { return 32 + 5 * (size_t)nB; }
+__host__ __device__ inline size_t sched_ints(int nB) { return 32 + 3 * (size_t)nB; }
 
 
 // ------------------------------------------------------------------------------------------- shared memory map
