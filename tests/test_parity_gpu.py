@@ -346,6 +346,30 @@ def test_runtime_keys_threshold_clamp_averages():
             _check(out8, outdb, ref8, refdb, f"thr {thr} clamp {clamp} A {A}")
 
 
+@pytest.mark.parametrize("w,h,N", [(1024, 16, 1024), (1280, 12, 1280), (1920, 8, 1920), (2048, 16, 2048), (2880, 6, 2880), (4096, 8, 4096)])
+def test_fft_stage_cross_check_with_cufft(w, h, N):
+    """Offline cross-check of the row DFT + magnitude stage (BscanFFT.cpp:1181-1190) against cuFFT (torch.fft): the library's own
+    data_ylin tap goes through cuFFT's unscaled inverse transform and must give the magnitudes the fused kernel produced.
+    cuFFT is used here only; the product path has its own register / shared-memory FFT."""
+    import torch
+
+    from fdoct_b200 import api, synth
+
+    D = N // 2
+    op = oracle_params(w=w, h=h, numfftpoints=N, numdisplaypoints=D, lambdamin=840.5e-9, lambdamax=859.5e-9)
+    frame = synth.make_frames(1, w, h, seed=101)
+    yb = synth.make_background_frames(2, w, h, seed=102).mean(axis=0)
+    with api.Context(abi_params(op)) as ctx:
+        ctx.set_background(yb)
+        ylin = ctx.debug_linearised(frame[0])
+        _, outdb = ctx.process_bscans(frame, want_db=True)
+    z = torch.fft.ifft(torch.from_numpy(ylin).cuda().to(torch.complex64), dim=1, norm="forward")  # unscaled, e^{+i...}
+    mag = z.abs()[:, :D].T.cpu().numpy().astype(np.float64)[None]
+    mag[:, 0] = mag[:, 4]
+    mag[:, 1] = mag[:, 4]
+    assert mag_err(db_to_mag(outdb), mag) <= MAG_RTOL
+
+
 def test_tables_bit_exact_through_ctx():
     from fdoct_b200 import api
     from oracle.abcoct_oracle import barthann_window, build_tables
