@@ -1,8 +1,8 @@
-"""GPU-side probe: deviation of the CUDA path and of the reference's OpenCV f32 path from an exact f64 evaluation of
+"""GPU-side probe (test infrastructure: it uses the oracle, so it lives under tests/): deviation of the CUDA path and of the reference's OpenCV f32 path from an exact f64 evaluation of
 the same block, under the parity metric |a-b| / max(|b|, floor * A-scan max).  Run under gpurun."""
 import sys, os
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # repo root
 from fdoct_b200 import api, synth
 from oracle.abcoct_oracle import Oracle, Params
 
