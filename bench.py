@@ -197,6 +197,15 @@ def measured_traffic(workload, nframes):
         return None
 
 
+def ncu_summary(workload):
+    """Secondary-roof evidence of the committed ncu capture (issue slots, FMA pipe, shared-memory wavefronts), if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            return json.load(f)[workload]["ncu"]
+    except Exception:
+        return None
+
+
 def measured_hbm_peak():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
@@ -337,6 +346,7 @@ def run_ours(args, wl, rank, world, local_rank):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": (achieved / peak) if achieved else None, "traffic": measured_traffic(args.workload, nframes),
                          "algorithmic_bytes_per_launch": bytes_per_ascan * ascans_per_launch,
+                         "secondary_roofs_ncu": ncu_summary(args.workload),
                          "kernel": "recon_kernel (fused reconstruction)", "bytes_per_ascan": bytes_per_ascan,
                          "ascans_per_launch": ascans_per_launch, "launch_ms": recon_launch_ms, "peak_source": peak_src,
                          "whole_step_frac": bytes_per_ascan * value / world / 1e9 / peak},
