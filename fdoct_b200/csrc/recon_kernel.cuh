@@ -28,7 +28,7 @@
 
 #define ABC_HD __host__ __device__ __forceinline__
 #ifndef ABC_PUBLISH_BATCH
-#define ABC_PUBLISH_BATCH 4
+#define ABC_PUBLISH_BATCH 2
 #endif
 
 namespace abcoct {
