@@ -181,17 +181,10 @@ __device__ __forceinline__ int f2ord(float f) {
 }
 __device__ __forceinline__ float ord2f(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
 
-__host__ __device__ inline size_t rowbuf_bytes(int opw, int movavgn) {
-  const size_t one = (size_t)((opw + 3) & ~3) * sizeof(float);
-  return (one * (movavgn > 0 ? 2 : 1) + 15) & ~(size_t)15;
-}
 
-// one CTA per (row, frame).  dynamic smem: float x[opw] | float2 a[M] | float2 b[M] (the last two only when m > 1)
-__global__ void __launch_bounds__(256) rowprep_kernel(const PrepArgs a) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  __shared__ float red[8];
-  float* x = reinterpret_cast<float*>(smem_raw);
-  const int row = blockIdx.x, f = blockIdx.y;
+// Stages of one row up to the apodised samples in shared memory (x, and a second buffer behind it when movavgn > 0).
+// Returns true when this was the reduce-only pass of the global normalisation.
+__device__ bool rowprep_one(const PrepArgs& a, int row, int f, float* x, float* red) {
   const int W = a.opw;
   const size_t pix = ((size_t)f * a.oph + row) * W;
   // convertTo(data_y, CV_64F)  (BscanFFT.cpp:987); integers up to 65535 are exact in f32
@@ -250,7 +243,7 @@ __global__ void __launch_bounds__(256) rowprep_kernel(const PrepArgs a) {
         atomicMin(reinterpret_cast<int*>(a.frame_minmax) + 2 * f, f2ord(mn));
         atomicMax(reinterpret_cast<int*>(a.frame_minmax) + 2 * f + 1, f2ord(mx));
       }
-      return;  // reduce pass only
+      return true;  // reduce pass only
     }
     const float mn = ord2f(reinterpret_cast<const int*>(a.frame_minmax)[2 * f]);
     const float mx = ord2f(reinterpret_cast<const int*>(a.frame_minmax)[2 * f + 1]);
@@ -260,51 +253,81 @@ __global__ void __launch_bounds__(256) rowprep_kernel(const PrepArgs a) {
     __syncthreads();
   }
   // data_y = (data_y - data_yp) / data_yb, BscanFFT.cpp:1132
-  {
-    const float* yb = a.yb + (size_t)row * W;
-    const float* yp = a.yp ? a.yp + (size_t)row * W : nullptr;
-    float sum = 0.f;
-    for (int j = threadIdx.x; j < W; j += blockDim.x) {
-      const float t = (x[j] - (yp ? yp[j] : 0.f)) / yb[j];
-      x[j] = t;
-      sum += t;
-    }
-    // per-row mean removal and apodisation, BscanFFT.cpp:1135-1143
-    const float mean = block_reduce(sum, red, 0) / (float)W;
-    for (int j = threadIdx.x; j < W; j += blockDim.x) x[j] = (x[j] - mean) * a.win[j];
-    __syncthreads();
+  const float* yb = a.yb + (size_t)row * W;
+  const float* yp = a.yp ? a.yp + (size_t)row * W : nullptr;
+  float sum = 0.f;
+  for (int j = threadIdx.x; j < W; j += blockDim.x) {
+    const float t = (x[j] - (yp ? yp[j] : 0.f)) / yb[j];
+    x[j] = t;
+    sum += t;
   }
-  float* out = a.out + ((size_t)f * a.oph + row) * a.M;
+  // per-row mean removal and apodisation, BscanFFT.cpp:1135-1143
+  const float mean = block_reduce(sum, red, 0) / (float)W;
+  for (int j = threadIdx.x; j < W; j += blockDim.x) x[j] = (x[j] - mean) * a.win[j];
+  __syncthreads();
+  return false;
+}
+
+__host__ __device__ inline size_t rowbuf_bytes(int opw, int movavgn) {
+  const size_t one = (size_t)((opw + 3) & ~3) * sizeof(float);
+  return (one * (movavgn > 0 ? 2 : 1) + 15) & ~(size_t)15;
+}
+
+// One CTA per (row pair, frame): the two rows share the Fourier upsample as the real and imaginary part of ONE complex
+// transform each way.  Dynamic smem: 2 x row buffers | float2 a[M] | float2 b[M] (the last two only when m > 1).
+__global__ void __launch_bounds__(256) rowprep_kernel(const PrepArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ float red[8];
+  const int W = a.opw, f = blockIdx.y;
+  const int r0 = 2 * blockIdx.x;
+  const bool has1 = r0 + 1 < a.oph;
+  const int r1 = has1 ? r0 + 1 : r0;
+  const size_t rb = rowbuf_bytes(W, a.movavgn);
+  float* x0 = reinterpret_cast<float*>(smem_raw);
+  float* x1 = reinterpret_cast<float*>(smem_raw + rb);
+  const bool reduce_only = rowprep_one(a, r0, f, x0, red);
+  if (has1) rowprep_one(a, r1, f, x1, red);
+  if (reduce_only) return;
+  float* out0 = a.out + ((size_t)f * a.oph + r0) * a.M;
+  float* out1 = a.out + ((size_t)f * a.oph + r1) * a.M;
   if (a.m <= 1) {
-    for (int j = threadIdx.x; j < W; j += blockDim.x) out[j] = x[j];
+    for (int j = threadIdx.x; j < W; j += blockDim.x) {
+      out0[j] = x0[j];
+      if (has1) out1[j] = x1[j];
+    }
     return;
   }
-  // zeropadrowwise, BscanFFT.cpp:180-245: forward DFT scaled by 1 / opw, zero-pad the centred spectrum to M, inverse
-  // DFT with DFT_REAL_OUTPUT, which only reads bins 0 .. M/2 - so the -opw/2 (Nyquist) bin is dropped:
-  //   out[n] = Re X[0] + 2 Re sum_{k=1}^{opw/2-1} X[k] exp(2 pi i n k / M),   X[k] = (1 / opw) sum_j x[j] exp(-2 pi i j k / opw)
-  float2* bufa = reinterpret_cast<float2*>(smem_raw + rowbuf_bytes(W, a.movavgn));
+  // zeropadrowwise, BscanFFT.cpp:180-245: forward DFT scaled by 1 / opw, zero-pad the centred spectrum to M, inverse DFT
+  // with DFT_REAL_OUTPUT, which only reads bins 0 .. M/2 - so the -opw/2 (Nyquist) bin is dropped.  For two real rows
+  // z = row0 + i row1 this is: Z = DFT(z) / opw, keep Z[k] (0 <= k < opw/2) at k and Z[opw - k] (1 <= k < opw/2) at M - k,
+  // z' = inverse DFT of length M; row0' = Re z', row1' = Im z'.
+  float2* bufa = reinterpret_cast<float2*>(smem_raw + 2 * rb);
   float2* bufb = bufa + a.M;
-  for (int j = threadIdx.x; j < W; j += blockDim.x) bufa[j] = make_float2(x[j], 0.f);
+  for (int j = threadIdx.x; j < W; j += blockDim.x) bufa[j] = make_float2(x0[j], has1 ? x1[j] : 0.f);
   __syncthreads();
   float2* X = block_fft<-1>(bufa, bufb, a.rlW, a.twW);
   float2* Y = (X == bufa) ? bufb : bufa;
   const float sc = 1.f / (float)W;
   const int half = W / 2;
-  const int lo = a.bandpass ? 3 : 0;  // BscanDark.cpp:218-236 keeps bins [3, floor(opw / 10))
+  const int lo = a.bandpass ? 3 : 0;  // BscanDark.cpp:218-236 keeps bins [3, floor(opw / 10)) of either sign
   const int hi = a.bandpass ? W / 10 : half;
   for (int k = threadIdx.x; k < a.M; k += blockDim.x) {
     float2 v = make_float2(0.f, 0.f);
     if (k < half) {
-      if (k >= lo && k < hi) v = make_float2(X[k].x * sc, k == 0 ? 0.f : X[k].y * sc);
+      if (k >= lo && k < hi) v = make_float2(X[k].x * sc, X[k].y * sc);
     } else if (k > a.M - half) {
       const int kk = a.M - k;
-      if (kk >= lo && kk < hi) v = make_float2(X[kk].x * sc, -X[kk].y * sc);
+      if (kk >= lo && kk < hi) v = make_float2(X[W - kk].x * sc, X[W - kk].y * sc);
     }
     Y[k] = v;
   }
   __syncthreads();
   float2* R = block_fft<+1>(Y, X, a.rlM, a.twM);
-  for (int j = threadIdx.x; j < a.M; j += blockDim.x) out[j] = R[j].x;
+  for (int j = threadIdx.x; j < a.M; j += blockDim.x) {
+    const float2 v = R[j];
+    out0[j] = v.x;
+    if (has1) out1[j] = v.y;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------ debug tap
@@ -359,7 +382,7 @@ __global__ void minmax_reset_kernel(float* mm, int n) {
 }
 
 size_t rowprep_smem_bytes(int opw, int M, int m, int movavgn) {
-  size_t b = rowbuf_bytes(opw, movavgn);
+  size_t b = 2 * rowbuf_bytes(opw, movavgn);  // two rows per CTA
   if (m > 1) b += (size_t)2 * M * sizeof(float2);
   return b;
 }
@@ -380,7 +403,7 @@ cudaError_t launch_rowprep(const PrepArgsHost& h, cudaStream_t st, int* launched
     if (e != cudaSuccess) return e;
     attr_done = true;
   }
-  dim3 grid(h.oph, h.nframes);
+  dim3 grid((h.oph + 1) / 2, h.nframes);  // one CTA per row pair
   int n = 0;
   if (h.global_norm) {
     minmax_reset_kernel<<<(h.nframes + 127) / 128, 128, 0, st>>>(h.frame_minmax, h.nframes);
