@@ -14,7 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libabcoct.so")
 SOURCES = ["abcoct_kernels.cu", "prep_kernels.cu", "abcoct_api.cpp"]
-HEADERS = ["fft_regs.cuh", "plan.h", "recon_kernel.cuh", "kernels.h", os.path.join("..", "..", "include", "abcoct.h")]
+HEADERS = ["fft_regs.cuh", "fft_v.cuh", "plan.h", "recon_kernel.cuh", "recon2_kernel.cuh", "kernels.h",
+           os.path.join("..", "..", "include", "abcoct.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
@@ -32,22 +33,58 @@ def _stale(target: str, deps: list[str]) -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
+FLAGS = ["-std=c++17", "-O3", *ARCH, "-lineinfo", "-Xcompiler", "-fPIC,-ffp-contract=off"]
+STAMP = LIB + ".stamp"
+
+
+def _source_digest() -> str:
+    """sha256 over every file the library is built from (all of csrc/, the public header, this script's flags): the
+    library is rebuilt when the CONTENT changes, never because a copy of the tree got new time stamps."""
+    import hashlib
+
+    h = hashlib.sha256(" ".join(FLAGS).encode())
+    files = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h", ".cpp")))
+    files.append(os.path.join(HERE, "..", "include", "abcoct.h"))
+    for f in files:
+        h.update(os.path.basename(f).encode())
+        with open(f, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS] + [os.path.abspath(__file__)]
-    if not force and not _stale(LIB, deps):
+    """Build fdoct_b200/libabcoct.so if its sources changed.  Safe to call from several processes at once (torchrun
+    ranks, pytest-xdist): one builds under a file lock, the others wait and reuse the result."""
+    import fcntl
+
+    digest = _source_digest()
+
+    def up_to_date() -> bool:
+        try:
+            return os.path.exists(LIB) and open(STAMP).read().strip() == digest
+        except OSError:
+            return False
+
+    if not force and up_to_date():
         return LIB
-    objs = []
-    for s in SOURCES:
-        o = os.path.join(CSRC, s + ".o")
-        cmd = [_nvcc(), "-std=c++17", "-O3", *ARCH, "-lineinfo", "-Xcompiler", "-fPIC,-ffp-contract=off",
-               "-x", "cu", "-c", os.path.join(CSRC, s), "-o", o]
-        if verbose:
-            cmd.insert(1, "-Xptxas=-v")
-            print(" ".join(cmd), flush=True)
-        subprocess.run(cmd, check=True)
-        objs.append(o)
-    cmd = [_nvcc(), "-shared", *ARCH, "-o", LIB, *objs, "-lcudart_static", "-lpthread", "-ldl", "-lrt"]
-    subprocess.run(cmd, check=True)
+    with open(os.path.join(HERE, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and up_to_date():  # somebody else built it while we waited
+            return LIB
+        objs = []
+        for s in SOURCES:
+            o = os.path.join(CSRC, s + ".o")
+            cmd = [_nvcc(), *FLAGS, "-x", "cu", "-c", os.path.join(CSRC, s), "-o", o]
+            if verbose:
+                cmd.insert(1, "-Xptxas=-v")
+                print(" ".join(cmd), flush=True)
+            subprocess.run(cmd, check=True)
+            objs.append(o)
+        tmp = LIB + ".tmp.%d" % os.getpid()
+        subprocess.run([_nvcc(), "-shared", *ARCH, "-o", tmp, *objs, "-lcudart_static", "-lpthread", "-ldl", "-lrt"], check=True)
+        os.replace(tmp, LIB)
+        with open(STAMP, "w") as f:
+            f.write(digest + "\n")
     return LIB
 
 

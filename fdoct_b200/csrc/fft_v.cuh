@@ -28,10 +28,7 @@ __host__ __device__ __forceinline__ V2 v2_make(float lo, float hi) {
 }
 __host__ __device__ __forceinline__ float v2_lo(V2 a) {
 #ifdef __CUDA_ARCH__
-  float lo, hi;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v));
-  (void)hi;
-  return lo;
+  return __uint_as_float(static_cast<unsigned>(a.v));
 #else
   float t[2];
   memcpy(t, &a.v, 8);
@@ -40,10 +37,7 @@ __host__ __device__ __forceinline__ float v2_lo(V2 a) {
 }
 __host__ __device__ __forceinline__ float v2_hi(V2 a) {
 #ifdef __CUDA_ARCH__
-  float lo, hi;
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v));
-  (void)lo;
-  return hi;
+  return __uint_as_float(static_cast<unsigned>(a.v >> 32));
 #else
   float t[2];
   memcpy(t, &a.v, 8);

@@ -102,7 +102,6 @@ __device__ __forceinline__ void stockham_pass(const float2* __restrict__ x, floa
     for (int j = 0; j < R; ++j) in[j] = x[q + s * (p + mq * j)];
     Dft<R, SGN, 1, 1>::run(in, out);
     y[q + s * (R * p)] = out[0];
-#pragma unroll
     const int tb = p * s;  // p < nc / R and s * nc == n: tb * c < n for every c < R, no reduction needed
 #pragma unroll
     for (int c = 1; c < R; ++c) y[q + s * (R * p + c)] = cmul(out[c], tw[tb * c]);
