@@ -99,6 +99,27 @@ def test_window_and_helpers():
     assert up.shape == (1, 64) and np.allclose(up[0, ::2], x[0], atol=1e-5)
 
 
+def test_upsample_closed_form_used_by_the_cuda_path():
+    """zeropadrowwise == zero-padding the scaled spectrum with the Nyquist bin dropped (what DFT_REAL_OUTPUT does), and two real
+    rows can share one complex transform each way: the closed form rowprep_kernel implements (prep_kernels.cu)."""
+    rng = np.random.default_rng(0)
+    for W, m, bp in [(32, 2, False), (640, 4, False), (1920, 2, False), (720, 4, True), (96, 3, False)]:
+        M = m * W
+        x = rng.normal(size=(2, W)) * 100 + 1000
+        ref = zeropadrowwise(x, m, bp)
+        z = x[0].astype(np.float32).astype(np.float64) + 1j * x[1].astype(np.float32).astype(np.float64)
+        Z = np.fft.fft(z) / W
+        lo, hi = (3, W // 10) if bp else (0, W // 2)
+        Y = np.zeros(M, dtype=complex)
+        for k in range(lo, hi):
+            Y[k] = Z[k]
+            if k >= 1:
+                Y[M - k] = Z[W - k]
+        out = np.fft.ifft(Y) * M
+        scale = max(np.abs(ref).max(), 1e-30)
+        assert np.abs(out.real - ref[0]).max() <= 2e-6 * scale and np.abs(out.imag - ref[1]).max() <= 2e-6 * scale, (W, m, bp)
+
+
 def test_oracle_rejects_undefined_reference_behaviour():
     with pytest.raises(ValueError):
         Oracle(oracle_params(w=256, h=4, numfftpoints=128))  # N < M reads past fractionalk (BscanFFT.cpp:1170)

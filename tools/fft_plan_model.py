@@ -79,7 +79,45 @@ def split_pairs(Z, R0, R1, RL):
     return magA, magB
 
 
+def stockham(x, radices, sign):
+    """Index algebra of block_fft / stockham_pass in fdoct_b200/csrc/prep_kernels.cu (autosort, natural order out):
+    pass with radix r, current length nc, stride s: y[q + s (r p + c)] = (sum_j x[q + s (p + (nc/r) j)] w_r^(jc)) w_n^(p c s),
+    with p c s < n so that the twiddle table needs no index reduction."""
+    n = x.size
+    a = x.astype(np.complex128).copy()
+    s, ncur = 1, n
+    tab = np.exp(sign * 2j * np.pi * np.arange(n) / n)
+    for r in radices:
+        mq = ncur // r
+        y = np.zeros(n, dtype=np.complex128)
+        F = dft_mat(r, sign)
+        for p in range(mq):
+            for q in range(s):
+                assert p * s * (r - 1) < n
+                y[q + s * (r * p + np.arange(r))] = (F @ a[q + s * (p + mq * np.arange(r))]) * tab[p * np.arange(r) * s]
+        a, ncur, s = y, mq, s * r
+    return a
+
+
+def greedy_radices(n):
+    out = []
+    for f in (16, 15, 12, 10, 9, 8, 6, 5, 4, 3, 2):
+        while n % f == 0:
+            out.append(f)
+            n //= f
+    assert n == 1
+    return out
+
+
 if __name__ == "__main__":
+    rng0 = np.random.default_rng(1)
+    for n in (640, 720, 1920, 2560, 2880, 3840, 96):
+        z = rng0.normal(size=n) + 1j * rng0.normal(size=n)
+        for sgn in (+1, -1):
+            ref = np.fft.ifft(z) * n if sgn > 0 else np.fft.fft(z)
+            err = np.abs(stockham(z, greedy_radices(n), sgn) - ref).max() / np.abs(ref).max()
+            assert err < 1e-12, (n, sgn, err)
+        print("ok stockham", n, greedy_radices(n))
     rng = np.random.default_rng(0)
     plans = [(1024, 16, 8, 8), (2048, 16, 16, 8), (4096, 32, 16, 8), (1280, 20, 8, 8), (1920, 15, 16, 8),
              (3840, 30, 16, 8), (2560, 20, 16, 8), (2880, 30, 12, 8), (1280, 16, 16, 5), (1024, 32, 1, 32),
