@@ -552,7 +552,11 @@ __global__ void __launch_bounds__(P::T* G, 1) recon2_kernel(const ReconArgs a) {
     if (tid == kJobTid) {
       int job = -1;
       if (myjob < njobs) {
-        while (ld_acquire(sv.cnt + myjob / a.nparts) < a.npairs) __nanosleep(200);
+        const unsigned long long t0 = global_ns();
+        while (ld_acquire(sv.cnt + myjob / a.nparts) < a.npairs) {
+          __nanosleep(200);
+          if (global_ns() - t0 > kWatchdogNs) __trap();
+        }
         job = myjob;
         myjob += ngroups;
       }

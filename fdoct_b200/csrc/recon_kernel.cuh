@@ -549,6 +549,14 @@ __device__ __forceinline__ float warp_max(float v) {
   return v;
 }
 
+// The only wait on another group's progress (the drain loop) is bounded: a scheduling bug must surface as a launch failure,
+// not as a hung GPU.
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+constexpr unsigned long long kWatchdogNs = 20ull * 1000 * 1000 * 1000;
 __device__ __forceinline__ int ld_acquire(const int* p) {
   int v;
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -913,7 +921,11 @@ __global__ void __launch_bounds__(P::T* G, 1) recon_kernel(const ReconArgs a) {
     if (tid == kJobTid) {
       int job = -1;
       if (myjob < njobs) {
-        while (ld_acquire(sv.cnt + myjob / a.nparts) < a.npairs) __nanosleep(200);
+        const unsigned long long t0 = global_ns();
+        while (ld_acquire(sv.cnt + myjob / a.nparts) < a.npairs) {
+          __nanosleep(200);
+          if (global_ns() - t0 > kWatchdogNs) __trap();
+        }
         job = myjob;
         myjob += ngroups;
       }

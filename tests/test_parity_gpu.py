@@ -370,6 +370,37 @@ def test_fft_stage_cross_check_with_cufft(w, h, N):
     assert mag_err(db_to_mag(outdb), mag) <= MAG_RTOL
 
 
+def test_degenerate_inputs_flat_and_saturated():
+    """Edge cases of the block: a frame that is an exact multiple of the background (nothing left after the mean removal: every
+    dB value is thresholded, the min-max normalise of a flat image gives all zeros), a saturated frame, and a frame of zeros."""
+    from oracle.abcoct_oracle import Oracle
+
+    w, h, N, D = 1024, 10, 1024, 512
+    op = oracle_params(w=w, h=h, numfftpoints=N, numdisplaypoints=D, lambdamin=840.5e-9, lambdamax=859.5e-9)
+    rng = np.random.default_rng(3)
+    yb = rng.integers(2000, 30000, size=(h, w)).astype(np.float64)
+    flat = (2 * yb).astype(np.uint16)                       # t == 2 everywhere -> zero after DC removal
+    sat = np.full((h, w), 65535, np.uint16)
+    zero = np.zeros((h, w), np.uint16)
+    mixed = flat.copy()
+    mixed[3] = rng.integers(0, 65535, size=w)               # one live A-scan among flat ones
+    frames = np.stack([flat, sat, zero, mixed])
+    o = Oracle(op)
+    o.set_background(yb)
+    ref8, refdb = o.process_bscans(frames)
+    out8, outdb = _run_abi(op, frames, yb)
+    assert (ref8[0] == 0).all() and (out8[0] == 0).all()     # flat image: cv::normalize scale 0
+    assert np.isfinite(outdb).all()
+    # flat B-scans: every value is far below the threshold in both; compare after thresholding
+    thr = op.bscanthreshold
+    assert np.array_equal(np.maximum(outdb[0], thr), np.maximum(refdb[0], thr).astype(np.float32))
+    assert np.array_equal(out8[2], ref8[2])
+    for b in (1, 3):
+        assert np.abs(out8[b].astype(int) - ref8[b].astype(int)).max() <= 1
+        live = refdb[b] > thr + 1.0
+        assert np.abs(outdb[b][live] - refdb[b][live]).max() < 2e-2
+
+
 def test_tables_bit_exact_through_ctx():
     from fdoct_b200 import api
     from oracle.abcoct_oracle import barthann_window, build_tables
