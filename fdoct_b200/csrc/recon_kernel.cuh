@@ -1,24 +1,25 @@
-// Fused per-frame B-scan reconstruction kernel (sm_100a).
+// Fused per-frame B-scan reconstruction kernel (sm_100a): the whole block BscanFFT.cpp:987-1255 in one launch.
 //
-// Replaces the reference's inline OpenCV block BscanFFT.cpp:987-1209 + the dB part of 1220-1240 (and the
-// BscanDark.cpp:1269 dark subtraction): for every pair of camera rows (two A-scans packed as the real and
-// imaginary part of one complex transform) a group of T threads
-//   1. reads the raw uint16 pixels once from HBM (128-bit coalesced loads, prefetched one frame ahead),
-//   2. applies (y - yd - yp) / yb as one FFMA against calibration rows staged in shared memory by TMA
-//      bulk copies (cp.async.bulk + mbarrier), removes the row mean (warp-shuffle + smem reduction) and
-//      multiplies by the Bartlett-Hann window (BscanFFT.cpp:1132-1143),
-//   3. resamples lambda -> k with the precomputed index/weight tables while loading the first FFT pass
-//      from shared memory (BscanFFT.cpp:1151-1177),
-//   4. runs the N-point transform as 2 or 3 in-register mixed-radix passes with in-place shared-memory
-//      exchanges (replaces cv::dft, BscanFFT.cpp:1185), splits the two A-scans, takes magnitudes and
-//      accumulates them over `averages` frames in registers (BscanFFT.cpp:1189-1209),
-//   5. converts to dB, applies the DC-row mask (BscanFFT.cpp:1221-1240) and writes an A-scan-major f32
-//      scratch image plus a per-B-scan min/max (needed by the global normalize at BscanFFT.cpp:1254).
-// A second, tiny kernel (normalise_kernel in abcoct_kernels.cu) thresholds, normalises, transposes and
-// quantises to the 8-bit display image (BscanFFT.cpp:1247-1255).
+// Persistent grid, one CTA per SM, G independent thread groups per CTA.  A group of T threads takes "items" - one pair of
+// camera rows (two A-scans packed as the real and imaginary part of one complex transform) of one B-scan - from a global
+// ticket and, per frame of the item,
+//   1. (phase_pre) takes the raw uint16 pixels read once from HBM (128-bit loads, prefetched one frame ahead, L2
+//      evict-first), applies (y - yd - yp) / yb - 1 as one FFMA against calibration rows staged in shared memory by TMA bulk
+//      copies (cp.async.bulk + mbarrier), multiplies by the Bartlett-Hann window and stages the result; the row-mean removal
+//      (BscanFFT.cpp:1132-1143) is linear and is carried through the resampling as a second term,
+//   2. (phase_gather) resamples lambda -> k with the precomputed offset / weight tables straight into the registers of the
+//      first FFT pass (BscanFFT.cpp:1151-1177),
+//   3. (phase_pass0 / 1 / L) runs the N-point transform as 2 or 3 in-register mixed-radix passes with in-place shared-memory
+//      exchanges (replaces cv::dft, BscanFFT.cpp:1185), splits the two A-scans, takes magnitudes and accumulates them over
+//      `averages` frames in registers (BscanFFT.cpp:1189-1209),
+//   4. (phase_finalise, last frame) converts to dB, applies the DC-row mask (BscanFFT.cpp:1221-1240), writes an A-scan-major
+//      f32 scratch row that is meant to live in L2, and folds its min / max into the B-scan's (BscanFFT.cpp:1247, 1254).
+// The second half runs in the same kernel: once every pair of a B-scan has been published (a counter in global memory) the
+// groups pick up its normalisation jobs (normalise_part): threshold, min-max normalise, transpose to depth-major, quantise
+// to the 8-bit display image (BscanFFT.cpp:1243-1255), and drop the consumed scratch lines from L2.
 //
-// The per-thread phases are plain __host__ __device__ functions so that tests/native/test_group_host.cu can
-// run the very same index logic thread-by-thread on the CPU.
+// The per-thread phases are plain __host__ __device__ functions so that tests/native/test_group_host.cu can run the very
+// same index logic thread-by-thread on the CPU.
 #pragma once
 #include <cstdint>
 #include <cstring>
