@@ -1,4 +1,5 @@
-// CUDA translation unit: plan instantiations, the display-normalisation kernel and the launchers.
+// CUDA translation unit: plan instantiations of the fused kernel (and of its opt-in dual-pair variant), table builders,
+// the scheduler-reset kernel and the launchers.
 #include <cmath>
 #include <cstdio>
 #include <cstring>

@@ -151,8 +151,9 @@ int abcoct_process_bscans_device(abcoct_ctx* ctx, int gpu_index, const void* d_f
 
 /* Kernel timing of the device entry point (bench.py's roofline): every chunk enqueued by
  * abcoct_process_bscans_device after abcoct_timing_reset is bracketed by CUDA events ON THE LAUNCHING STREAM
- * (up to 512 chunks); abcoct_timing_read waits for them and returns the summed durations of the fused
- * reconstruction kernel and of the display-normalisation kernel, and how many chunks were timed. */
+ * (up to 512 chunks); abcoct_timing_read waits for them and returns the summed duration of the fused kernel
+ * (reconstruction and display normalisation run in ONE launch, so norm_ms is the ~0 gap after it) and how many
+ * chunks were timed. */
 int abcoct_timing_reset(abcoct_ctx* ctx);
 int abcoct_timing_read(abcoct_ctx* ctx, int gpu_index, uint32_t* nchunks, double* recon_ms, double* norm_ms);
 
