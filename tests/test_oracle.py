@@ -120,6 +120,48 @@ def test_upsample_closed_form_used_by_the_cuda_path():
         assert np.abs(out.real - ref[0]).max() <= 2e-6 * scale and np.abs(out.imag - ref[1]).max() <= 2e-6 * scale, (W, m, bp)
 
 
+def test_opencv_rules_the_cuda_path_reimplements():
+    """The integer / rounding rules of the OpenCV calls on the path, pinned against cv2 itself: these are what
+    bin_kernel, median_kernel, normalise_part and the host capture code re-implement (prep_kernels.cu, recon_kernel.cuh)."""
+    import cv2
+
+    rng = np.random.default_rng(9)
+    for dt, hi in ((np.uint16, 65535), (np.uint8, 255)):
+        img = rng.integers(0, hi + 1, size=(24, 36)).astype(dt)
+        # INTER_AREA with integer factors: 2 x 2 -> (sum + 2) >> 2; anything else -> f32 sum * (1 / area), round half to even
+        for bx, by in ((2, 2), (3, 3), (2, 1), (1, 2), (4, 4), (3, 2)):
+            ref = cv2.resize(img, None, fx=1.0 / bx, fy=1.0 / by, interpolation=cv2.INTER_AREA)
+            blocks = img.reshape(24 // by, by, 36 // bx, bx).astype(np.uint32).sum(axis=(1, 3))
+            if (bx, by) == (2, 2):
+                mine = (blocks + 2) >> 2
+            else:
+                mine = np.rint(blocks.astype(np.float32) * np.float32(1.0 / (bx * by)))
+            assert np.array_equal(ref, np.clip(mine, 0, hi).astype(dt)), (dt, bx, by)
+        # medianBlur replicates the border
+        for k in (3, 5):
+            ref = cv2.medianBlur(img, k)
+            pad = np.pad(img, k // 2, mode="edge")
+            win = np.lib.stride_tricks.sliding_window_view(pad, (k, k)).reshape(24, 36, k * k)
+            assert np.array_equal(ref, np.sort(win, axis=2)[:, :, k * k // 2]), (dt, k)
+    # normalize(NORM_MINMAX): dst = src * scale + (a - min * scale), scale = (b - a) / (max - min); flat image -> all a
+    x = rng.normal(size=(5, 7)) * 40.0
+    for a, b in ((0.0, 1.0), (0.0001, 1.0)):
+        mn, mx = x.min(), x.max()
+        sc = (b - a) / (mx - mn)
+        assert np.allclose(cv2.normalize(x, None, a, b, cv2.NORM_MINMAX), x * sc + (a - mn * sc), rtol=0, atol=1e-15)
+    assert (cv2.normalize(np.full((3, 3), 2.5), None, 0, 1, cv2.NORM_MINMAX) == 0).all()
+    # convertTo(CV_8UC1, 255.0): round half to even, saturate (convertScaleAbs shares the saturate_cast<uchar>(double) path)
+    v = np.array([[0.5 / 255, 1.5 / 255, 2.5 / 255, 254.5 / 255, 1.2, 0.0]])
+    assert np.array_equal(cv2.convertScaleAbs(v, alpha=255.0), np.array([[0, 2, 2, 254, 255, 0]], np.uint8))
+    # dft: DFT_ROWS | DFT_INVERSE is the unscaled e^{+i...} transform; DFT_SCALE forward divides by the row length
+    z = (rng.normal(size=(3, 40)) + 1j * rng.normal(size=(3, 40))).astype(np.complex64)
+    c = np.stack([z.real, z.imag], axis=-1).astype(np.float32)
+    inv = cv2.dft(c, flags=cv2.DFT_ROWS | cv2.DFT_INVERSE)
+    assert np.allclose(inv[..., 0] + 1j * inv[..., 1], np.fft.ifft(z, axis=1) * 40, rtol=0, atol=2e-4)
+    fwd = cv2.dft(c[..., 0].copy(), flags=cv2.DFT_ROWS | cv2.DFT_SCALE | cv2.DFT_COMPLEX_OUTPUT)
+    assert np.allclose(fwd[..., 0] + 1j * fwd[..., 1], np.fft.fft(z.real, axis=1) / 40, rtol=0, atol=1e-5)
+
+
 def test_oracle_rejects_undefined_reference_behaviour():
     with pytest.raises(ValueError):
         Oracle(oracle_params(w=256, h=4, numfftpoints=128))  # N < M reads past fractionalk (BscanFFT.cpp:1170)
