@@ -50,12 +50,23 @@ class Info(C.Structure):
     ]
 
 
+class Outputs(C.Structure):
+    """abcoct_outputs (include/abcoct.h): nullable image pointers of the *_ex entry points."""
+    _fields_ = [("bscan_u8", C.c_void_p), ("bscan_db", C.c_void_p), ("bscan_lin", C.c_void_p), ("bscan_bgr", C.c_void_p),
+                ("jsub_u8", C.c_void_p), ("jsub_bgr", C.c_void_p), ("reserved", C.c_void_p * 2)]
+
+
+# name -> (dtype, trailing shape) of every image an *_ex call can produce
+OUTPUT_KINDS = {"bscan_u8": (np.uint8, ()), "bscan_db": (np.float32, ()), "bscan_lin": (np.float32, ()),
+                "bscan_bgr": (np.uint8, (3,)), "jsub_u8": (np.uint8, ()), "jsub_bgr": (np.uint8, (3,))}
+
 EXPORTS = [
     "abcoct_params_default", "abcoct_params_from_ini", "abcoct_create", "abcoct_destroy", "abcoct_last_error",
     "abcoct_set_background", "abcoct_set_pishift", "abcoct_set_dark", "abcoct_set_calibration_from_frames",
     "abcoct_compose_dark_background", "abcoct_get_calibration", "abcoct_set_threshold", "abcoct_set_clampupper", "abcoct_set_averages",
     "abcoct_build_tables", "abcoct_get_tables", "abcoct_get_window", "abcoct_process_bscans",
     "abcoct_process_bscans_device", "abcoct_timing_reset", "abcoct_timing_read", "abcoct_debug_linearised", "abcoct_host_alloc", "abcoct_host_free", "abcoct_get_info",
+    "abcoct_set_jscan", "abcoct_process_bscans_ex", "abcoct_process_bscans_device_ex",
 ]
 
 _lib = None
@@ -96,6 +107,9 @@ def lib() -> C.CDLL:
     L.abcoct_get_window.argtypes = [vp, vp]
     L.abcoct_process_bscans.argtypes = [vp, vp, sz, sz, vp, vp]
     L.abcoct_process_bscans_device.argtypes = [vp, i32, vp, sz, sz, vp, vp, vp]
+    L.abcoct_set_jscan.argtypes = [vp, vp, sz]
+    L.abcoct_process_bscans_ex.argtypes = [vp, vp, sz, sz, C.POINTER(Outputs)]
+    L.abcoct_process_bscans_device_ex.argtypes = [vp, i32, vp, sz, sz, C.POINTER(Outputs), vp]
     L.abcoct_timing_reset.argtypes = [vp]
     L.abcoct_timing_read.argtypes = [vp, i32, C.POINTER(C.c_uint32), C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.abcoct_debug_linearised.argtypes = [vp, vp, sz, vp]
@@ -272,6 +286,39 @@ class Context:
         """Device-pointer call (abcoct_process_bscans_device); pointers are raw integers (e.g. tensor.data_ptr())."""
         self._check(lib().abcoct_process_bscans_device(self._h, gpu_index, d_frames, nframes, stride_bytes, d_out8,
                                                        d_outdb, stream))
+
+    def set_jscan(self, jscan: np.ndarray | None):
+        """Key 'j' / 'c' (BscanFFT.cpp:1292-1303): keep a linear B-scan (D x oph float32) as the lock-in reference, None = off."""
+        if jscan is None:
+            self._check(lib().abcoct_set_jscan(self._h, None, 0))
+            return
+        j = np.ascontiguousarray(jscan, dtype=np.float32)
+        assert j.shape == (self.D, self.oph), j.shape
+        self._check(lib().abcoct_set_jscan(self._h, j.ctypes.data, 0))
+
+    def process_bscans_ex(self, frames: np.ndarray, want=("bscan_u8",)) -> dict:
+        """abcoct_process_bscans_ex: returns {name: array} for the requested images (see OUTPUT_KINDS); bscan_u8 always."""
+        assert frames.ndim == 3 and frames.flags.c_contiguous
+        assert frames.dtype == (np.uint8 if self.params.bpp == 8 else np.uint16), frames.dtype
+        assert frames.shape[1:] == (self.params.h, self.params.w), frames.shape
+        nframes = frames.shape[0]
+        nB = nframes // max(self.A, 1)
+        res, o = {}, Outputs()
+        for name in set(want) | {"bscan_u8"}:
+            dt, tail = OUTPUT_KINDS[name]
+            res[name] = np.empty((nB, self.D, self.oph) + tail, dtype=dt)
+            setattr(o, name, res[name].ctypes.data)
+        self._check(lib().abcoct_process_bscans_ex(self._h, frames.ctypes.data, nframes, 0, C.byref(o)))
+        return res
+
+    def process_bscans_device_ex(self, d_frames: int, nframes: int, d_out: dict, stream: int | None = None, gpu_index: int = 0,
+                                 stride_bytes: int = 0):
+        """abcoct_process_bscans_device_ex; d_out maps output names to raw device pointers."""
+        o = Outputs()
+        for name, ptr in d_out.items():
+            assert name in OUTPUT_KINDS, name
+            setattr(o, name, ptr)
+        self._check(lib().abcoct_process_bscans_device_ex(self._h, gpu_index, d_frames, nframes, stride_bytes, C.byref(o), stream))
 
     def debug_linearised(self, frame: np.ndarray) -> np.ndarray:
         """data_ylin of one frame (abcoct_debug_linearised): float32 [oph, numfftpoints]."""

@@ -13,7 +13,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libabcoct.so")
-SOURCES = ["abcoct_kernels.cu", "prep_kernels.cu", "abcoct_api.cpp"]
+SOURCES = ["abcoct_kernels.cu", "prep_kernels.cu", "post_kernels.cu", "abcoct_api.cpp"]
 HEADERS = ["fft_regs.cuh", "fft_v.cuh", "plan.h", "recon_kernel.cuh", "recon2_kernel.cuh", "kernels.h",
            os.path.join("..", "..", "include", "abcoct.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]

@@ -26,6 +26,18 @@ thread_local std::string g_create_error;
 constexpr int kTimedChunks = 512;  // timing-event pool size (chunks timed between two abcoct_timing_reset calls)
 constexpr int kSlots = 3;  // pinned-ring depth per GPU (>= 3 streams per GPU)
 
+// the images one call can produce (abcoct_outputs), bytes per pixel of each
+enum { O_U8 = 0, O_DB, O_LIN, O_BGR, O_JSUB, O_JBGR, O_COUNT };
+constexpr size_t kOutBpp[O_COUNT] = {1, 4, 4, 3, 1, 3};
+struct OutPtrs {
+  void* p[O_COUNT] = {};
+  unsigned mask() const {
+    unsigned m = 0;
+    for (int k = 0; k < O_COUNT; ++k) m |= p[k] ? 1u << k : 0u;
+    return m;
+  }
+};
+
 struct GpuState {
   int dev = 0;
   int sm_count = 0;
@@ -46,16 +58,20 @@ struct GpuState {
   size_t prep_frames[kSlots] = {};
   // per-slot device + pinned staging for the host-buffer API
   uint8_t* d_in[kSlots] = {};
-  uint8_t* d_out8[kSlots] = {};
-  float* d_outdb[kSlots] = {};
   uint8_t* h_in[kSlots] = {};
-  uint8_t* h_out8[kSlots] = {};
-  float* h_outdb[kSlots] = {};
+  void* d_o[O_COUNT][kSlots] = {};  // device / pinned staging of every requested output image
+  void* h_o[O_COUNT][kSlots] = {};
+  // J0 lock-in: the reference B-scan, per-B-scan min/max words, and temporaries of the device entry point
+  float* d_jscan = nullptr;
+  int* d_jmm[kSlots] = {};
+  float* d_dc01[kSlots] = {};   // dB of bins 0, 1 before the DC-row mask, [chunk B-scans][oph][2]
+  void* d_tmp[3][kSlots] = {};  // [0] linear, [1] subtracted u8, [2] dB image when needed but not asked for by the caller
+  size_t tmp_bytes[3][kSlots] = {};
   float* d_scratch[kSlots] = {};
   int* d_sched[kSlots] = {};
   size_t scratch_bscans[kSlots] = {};
   size_t slot_in_bytes = 0, slot_out_px = 0;  // capacity of the per-slot staging buffers
-  bool slot_db = false;
+  unsigned slot_mask = 0;                      // which output images the slots hold
 };
 
 }  // namespace
@@ -66,6 +82,8 @@ struct abcoct_ctx {
   std::vector<int32_t> nk;
   std::vector<double> frac, win;
   std::vector<double> yb, yp, yd, yr, ys;
+  std::vector<float> jscan;  // jscansave (BscanFFT.cpp:572, 1294): D x oph linear B-scan, empty = lock-in off
+  bool jscan_dirty = false;
   bool have_yr = false, have_ys = false;
   bool have_yb = false, have_yp = false, have_yd = false, cal_dirty = true, has_sub = false;
   bool general = false;  // any optional pre-processing stage is on: frames go through prep_kernels.cu first
@@ -381,11 +399,17 @@ int ensure_scratch(abcoct_ctx* c, GpuState& g, int slot, size_t nB) {
   if (g.scratch_bscans[slot] >= nB) return ABCOCT_OK;
   if (g.d_scratch[slot]) cudaFree(g.d_scratch[slot]);
   if (g.d_sched[slot]) cudaFree(g.d_sched[slot]);
+  if (g.d_jmm[slot]) cudaFree(g.d_jmm[slot]);
+  if (g.d_dc01[slot]) cudaFree(g.d_dc01[slot]);
+  g.d_dc01[slot] = nullptr;
   g.d_scratch[slot] = nullptr;
   g.d_sched[slot] = nullptr;
+  g.d_jmm[slot] = nullptr;
   g.scratch_bscans[slot] = 0;
   CU(c, cudaMalloc(&g.d_scratch[slot], nB * c->oph * (size_t)scratch_pitch(c) * sizeof(float)));
   CU(c, cudaMalloc(&g.d_sched[slot], sched_ints((int)nB) * sizeof(int)));
+  CU(c, cudaMalloc(&g.d_jmm[slot], 2 * nB * sizeof(int)));
+  CU(c, cudaMalloc(&g.d_dc01[slot], 2 * nB * c->oph * sizeof(float)));
   g.scratch_bscans[slot] = nB;
   return ABCOCT_OK;
 }
@@ -462,9 +486,59 @@ int run_prep(abcoct_ctx* c, GpuState& g, int slot, const uint8_t* d_frames, size
   return ABCOCT_OK;
 }
 
-// Enqueue the kernels for nB B-scans resident on device g; everything on `st`.
+int ensure_tmp(abcoct_ctx* c, GpuState& g, int which, int slot, size_t bytes) {
+  if (g.tmp_bytes[which][slot] >= bytes) return ABCOCT_OK;
+  if (g.d_tmp[which][slot]) cudaFree(g.d_tmp[which][slot]);
+  g.d_tmp[which][slot] = nullptr;
+  g.tmp_bytes[which][slot] = 0;
+  CU(c, cudaMalloc(&g.d_tmp[which][slot], bytes));
+  g.tmp_bytes[which][slot] = bytes;
+  return ABCOCT_OK;
+}
+
+int upload_jscan(abcoct_ctx* c) {
+  for (GpuState& g : c->gpus) {
+    CU(c, cudaSetDevice(g.dev));
+    CU(c, cudaDeviceSynchronize());  // no launch may still be reading the old reference
+    if (!g.d_jscan) CU(c, cudaMalloc(&g.d_jscan, (size_t)c->D * c->oph * sizeof(float)));
+    CU(c, cudaMemcpy(g.d_jscan, c->jscan.data(), c->jscan.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  c->jscan_dirty = false;
+  return ABCOCT_OK;
+}
+
+// Enqueue the kernels for nB B-scans resident on device g; everything on `st`.  `o` holds DEVICE pointers.
 int enqueue_device(abcoct_ctx* c, GpuState& g, int slot, const uint8_t* d_frames, size_t nB, size_t row_stride, size_t frame_stride,
-                   uint8_t* d_out8, float* d_outdb, cudaStream_t st, bool time_it) {
+                   const OutPtrs& o_in, cudaStream_t st, bool time_it) {
+  OutPtrs o = o_in;
+  const size_t px = (size_t)c->D * c->oph;
+  const bool want_j = o.p[O_JSUB] || o.p[O_JBGR];
+  if (want_j) {
+    if (c->jscan.empty()) return fail(c, ABCOCT_ERR_STATE, "jsub output requested but no jscan is set (abcoct_set_jscan)");
+    if (c->jscan_dirty) {
+      int rc = upload_jscan(c);
+      if (rc) return rc;
+      CU(c, cudaSetDevice(g.dev));
+    }
+    if (!o.p[O_LIN]) {  // the lock-in works on the linear image: keep it in a temporary
+      int rc = ensure_tmp(c, g, 0, slot, nB * px * sizeof(float));
+      if (rc) return rc;
+      o.p[O_LIN] = g.d_tmp[0][slot];
+    }
+    if (!o.p[O_JSUB]) {
+      int rc = ensure_tmp(c, g, 1, slot, nB * px);
+      if (rc) return rc;
+      o.p[O_JSUB] = g.d_tmp[1][slot];
+    }
+  }
+  if (o.p[O_LIN] && !o.p[O_DB]) {  // the linear image is derived from the dB image
+    int rc = ensure_tmp(c, g, 2, slot, nB * px * sizeof(float));
+    if (rc) return rc;
+    o.p[O_DB] = g.d_tmp[2][slot];
+  }
+  uint8_t* d_out8 = static_cast<uint8_t*>(o.p[O_U8]);
+  float* d_outdb = static_cast<float*>(o.p[O_DB]);
+  float* d_outlin = static_cast<float*>(o.p[O_LIN]);
   size_t chunkB = std::min(nB, scratch_chunk_bscans(c));
   if (c->general) {  // the pre-processed f32 rows of a chunk stay below ~1 GiB
     const size_t per_bscan = (size_t)c->A * c->oph * c->M * sizeof(float);
@@ -507,6 +581,7 @@ int enqueue_device(abcoct_ctx* c, GpuState& g, int slot, const uint8_t* d_frames
     a.sched = g.d_sched[slot];
     a.out8 = d_out8 + b0 * c->D * c->oph;
     a.outdb = d_outdb ? d_outdb + b0 * c->D * c->oph : nullptr;
+    a.dc01 = d_outlin ? g.d_dc01[slot] : nullptr;
     a.inv_W = 1.0f / (float)c->opw;
     a.out_scale = 0.5f / (float)c->A;
     a.db_scale = (float)(0.6931471805599453 * (20.0 * (1.0 / 2.303)));
@@ -528,40 +603,60 @@ int enqueue_device(abcoct_ctx* c, GpuState& g, int slot, const uint8_t* d_frames
       g.tev_used += 3;
     }
     c->launches += 2;
+    // consumers of the finished B-scans (post_kernels.cu), same stream
+    float* lin = d_outlin ? d_outlin + b0 * px : nullptr;
+    if (lin) {
+      int nl = 0;
+      const float inv = (float)(1.0 / (0.6931471805599453 * (20.0 * (1.0 / 2.303))));
+      CU(c, launch_lin_from_db(a.outdb, a.dc01, lin, c->oph, px, (int)nb, inv, g.sm_count, st, &nl));
+      c->launches += nl;
+    }
+    if (o.p[O_BGR]) {
+      CU(c, launch_jet(a.out8, static_cast<uint8_t*>(o.p[O_BGR]) + 3 * b0 * px, nb * px, g.sm_count, st));
+      c->launches += 1;
+    }
+    if (want_j) {
+      int nl = 0;
+      uint8_t* jsub = static_cast<uint8_t*>(o.p[O_JSUB]) + b0 * px;
+      CU(c, launch_jsub(lin, g.d_jscan, g.d_jmm[slot], jsub, px, (int)nb, a.db_scale, a.thr, g.sm_count, st, &nl));
+      c->launches += nl;
+      if (o.p[O_JBGR]) {
+        CU(c, launch_jet(jsub, static_cast<uint8_t*>(o.p[O_JBGR]) + 3 * b0 * px, nb * px, g.sm_count, st));
+        c->launches += 1;
+      }
+    }
   }
   return ABCOCT_OK;
 }
 
-int ensure_slots(abcoct_ctx* c, GpuState& g, size_t slotB, bool want_db) {
+int ensure_slots(abcoct_ctx* c, GpuState& g, size_t slotB, unsigned want) {
   const size_t in_bytes = slotB * c->A * (size_t)c->p.h * c->p.w * c->px_bytes;
   const size_t out_px = slotB * (size_t)c->D * c->oph;
-  if (g.slot_in_bytes >= in_bytes && g.slot_out_px >= out_px && (g.slot_db || !want_db)) return ABCOCT_OK;
+  if (g.slot_in_bytes >= in_bytes && g.slot_out_px >= out_px && (g.slot_mask & want) == want) return ABCOCT_OK;
   CU(c, cudaSetDevice(g.dev));
+  want |= g.slot_mask;
   g.slot_in_bytes = g.slot_out_px = 0;  // nothing is valid until every buffer below exists
-  g.slot_db = false;
+  g.slot_mask = 0;
   for (int s = 0; s < kSlots; ++s) {
     if (g.d_in[s]) cudaFree(g.d_in[s]);
-    if (g.d_out8[s]) cudaFree(g.d_out8[s]);
-    if (g.d_outdb[s]) cudaFree(g.d_outdb[s]);
     if (g.h_in[s]) cudaFreeHost(g.h_in[s]);
-    if (g.h_out8[s]) cudaFreeHost(g.h_out8[s]);
-    if (g.h_outdb[s]) cudaFreeHost(g.h_outdb[s]);
-    g.d_in[s] = g.d_out8[s] = nullptr;
-    g.d_outdb[s] = nullptr;
-    g.h_in[s] = g.h_out8[s] = nullptr;
-    g.h_outdb[s] = nullptr;
-    CU(c, cudaMalloc(&g.d_in[s], in_bytes));
-    CU(c, cudaMalloc(&g.d_out8[s], out_px));
-    CU(c, cudaMallocHost(&g.h_in[s], in_bytes));
-    CU(c, cudaMallocHost(&g.h_out8[s], out_px));
-    if (want_db) {
-      CU(c, cudaMalloc(&g.d_outdb[s], out_px * 4));
-      CU(c, cudaMallocHost(&g.h_outdb[s], out_px * 4));
+    g.d_in[s] = g.h_in[s] = nullptr;
+    for (int k = 0; k < O_COUNT; ++k) {
+      if (g.d_o[k][s]) cudaFree(g.d_o[k][s]);
+      if (g.h_o[k][s]) cudaFreeHost(g.h_o[k][s]);
+      g.d_o[k][s] = g.h_o[k][s] = nullptr;
     }
+    CU(c, cudaMalloc(&g.d_in[s], in_bytes));
+    CU(c, cudaMallocHost(&g.h_in[s], in_bytes));
+    for (int k = 0; k < O_COUNT; ++k)
+      if (want & (1u << k)) {
+        CU(c, cudaMalloc(&g.d_o[k][s], out_px * kOutBpp[k]));
+        CU(c, cudaMallocHost(&g.h_o[k][s], out_px * kOutBpp[k]));
+      }
   }
   g.slot_in_bytes = in_bytes;
   g.slot_out_px = out_px;
-  g.slot_db = want_db;
+  g.slot_mask = want;
   return ABCOCT_OK;
 }
 
@@ -761,6 +856,7 @@ int abcoct_create(const abcoct_params* params, const int* gpu_ids, int ngpu, abc
     }
     g.tev.assign(3 * kTimedChunks, nullptr);
     for (size_t k = 0; k < g.tev.size() && ok; ++k) ok = ok && cudaEventCreate(&g.tev[k]) == cudaSuccess;
+    ok = ok && post_init_device() == cudaSuccess;
     {
       ok = ok && cudaMalloc(&g.d_win, winf.size() * 4) == cudaSuccess;
       ok = ok && cudaMemcpy(g.d_win, winf.data(), winf.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess;
@@ -789,13 +885,19 @@ void abcoct_destroy(abcoct_ctx* c) {
       if (g.stream[s]) cudaStreamDestroy(g.stream[s]);
       if (g.slot_done[s]) cudaEventDestroy(g.slot_done[s]);
       cudaFree(g.d_in[s]);
-      cudaFree(g.d_out8[s]);
-      cudaFree(g.d_outdb[s]);
+      for (int k = 0; k < O_COUNT; ++k) {
+        cudaFree(g.d_o[k][s]);
+        if (g.h_o[k][s]) cudaFreeHost(g.h_o[k][s]);
+      }
+      cudaFree(g.d_jmm[s]);
+      if (s == 0) cudaFree(g.d_jscan);
+      cudaFree(g.d_tmp[0][s]);
+      cudaFree(g.d_tmp[1][s]);
+      cudaFree(g.d_tmp[2][s]);
+      cudaFree(g.d_dc01[s]);
       cudaFree(g.d_scratch[s]);
       cudaFree(g.d_sched[s]);
       if (g.h_in[s]) cudaFreeHost(g.h_in[s]);
-      if (g.h_out8[s]) cudaFreeHost(g.h_out8[s]);
-      if (g.h_outdb[s]) cudaFreeHost(g.h_outdb[s]);
     }
     for (cudaEvent_t e : g.tev)
       if (e) cudaEventDestroy(e);
@@ -961,11 +1063,12 @@ int abcoct_get_window(const abcoct_ctx* c, double* w) {
   return ABCOCT_OK;
 }
 
-int abcoct_process_bscans_device(abcoct_ctx* c, int gi, const void* d_frames, size_t nframes, size_t stride_bytes, uint8_t* d_u8,
-                                 float* d_db, void* cuda_stream) {
+int abcoct_process_bscans_device_ex(abcoct_ctx* c, int gi, const void* d_frames, size_t nframes, size_t stride_bytes,
+                                    const abcoct_outputs* d_out, void* cuda_stream) {
   if (!c) return ABCOCT_ERR_INVALID;
   if (gi < 0 || gi >= (int)c->gpus.size()) return fail(c, ABCOCT_ERR_INVALID, "gpu_index out of range");
-  if (!d_frames || !d_u8) return fail(c, ABCOCT_ERR_INVALID, "null buffer");
+  if (!d_frames || !d_out || !d_out->bscan_u8) return fail(c, ABCOCT_ERR_INVALID, "null buffer");
+  if (d_out->reserved[0] || d_out->reserved[1]) return fail(c, ABCOCT_ERR_INVALID, "abcoct_outputs.reserved must be NULL");
   if (nframes == 0 || nframes % c->A) return fail(c, ABCOCT_ERR_INVALID, "nframes must be a positive multiple of averages (%d)", c->A);
   if (stride_bytes == 0) stride_bytes = (size_t)c->p.w * c->px_bytes;
   if (!c->general && (stride_bytes % 16 || (reinterpret_cast<uintptr_t>(d_frames) & 15)))
@@ -977,10 +1080,39 @@ int abcoct_process_bscans_device(abcoct_ctx* c, int gi, const void* d_frames, si
   GpuState& g = c->gpus[gi];
   CU(c, cudaSetDevice(g.dev));
   cudaStream_t st = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : g.stream[0];
-  int rc = enqueue_device(c, g, 0, static_cast<const uint8_t*>(d_frames), nframes / c->A, stride_bytes, stride_bytes * c->p.h, d_u8, d_db, st,
-                          true);
+  OutPtrs o;
+  o.p[O_U8] = d_out->bscan_u8;
+  o.p[O_DB] = d_out->bscan_db;
+  o.p[O_LIN] = d_out->bscan_lin;
+  o.p[O_BGR] = d_out->bscan_bgr;
+  o.p[O_JSUB] = d_out->jsub_u8;
+  o.p[O_JBGR] = d_out->jsub_bgr;
+  int rc = enqueue_device(c, g, 0, static_cast<const uint8_t*>(d_frames), nframes / c->A, stride_bytes, stride_bytes * c->p.h, o, st, true);
   if (rc) return rc;
   if (!cuda_stream) CU(c, cudaStreamSynchronize(st));
+  return ABCOCT_OK;
+}
+
+int abcoct_process_bscans_device(abcoct_ctx* c, int gi, const void* d_frames, size_t nframes, size_t stride_bytes, uint8_t* d_u8,
+                                 float* d_db, void* cuda_stream) {
+  abcoct_outputs o{};
+  o.bscan_u8 = d_u8;
+  o.bscan_db = d_db;
+  return abcoct_process_bscans_device_ex(c, gi, d_frames, nframes, stride_bytes, &o, cuda_stream);
+}
+
+int abcoct_set_jscan(abcoct_ctx* c, const float* jscan, size_t ld) {
+  if (!c) return ABCOCT_ERR_INVALID;
+  if (!jscan) {  // key 'c': lock-in off
+    c->jscan.clear();
+    c->jscan_dirty = false;
+    return ABCOCT_OK;
+  }
+  if (ld == 0) ld = (size_t)c->oph;
+  if (ld < (size_t)c->oph) return fail(c, ABCOCT_ERR_INVALID, "ld < oph");
+  c->jscan.resize((size_t)c->D * c->oph);
+  for (int d = 0; d < c->D; ++d) memcpy(&c->jscan[(size_t)d * c->oph], jscan + (size_t)d * ld, (size_t)c->oph * sizeof(float));
+  c->jscan_dirty = true;
   return ABCOCT_OK;
 }
 
@@ -1015,14 +1147,36 @@ int abcoct_timing_read(abcoct_ctx* c, int gi, uint32_t* nchunks, double* recon_m
 }
 
 int abcoct_process_bscans(abcoct_ctx* c, const void* frames, size_t nframes, size_t stride_bytes, uint8_t* out8, float* outdb) {
+  abcoct_outputs o{};
+  o.bscan_u8 = out8;
+  o.bscan_db = outdb;
+  return abcoct_process_bscans_ex(c, frames, nframes, stride_bytes, &o);
+}
+
+int abcoct_process_bscans_ex(abcoct_ctx* c, const void* frames, size_t nframes, size_t stride_bytes, const abcoct_outputs* out) {
   if (!c) return ABCOCT_ERR_INVALID;
-  if (!frames || !out8) return fail(c, ABCOCT_ERR_INVALID, "null buffer");
+  if (!frames || !out || !out->bscan_u8) return fail(c, ABCOCT_ERR_INVALID, "null buffer");
+  if (out->reserved[0] || out->reserved[1]) return fail(c, ABCOCT_ERR_INVALID, "abcoct_outputs.reserved must be NULL");
   if (nframes == 0 || nframes % c->A) return fail(c, ABCOCT_ERR_INVALID, "nframes must be a positive multiple of averages (%d)", c->A);
+  OutPtrs host;
+  host.p[O_U8] = out->bscan_u8;
+  host.p[O_DB] = out->bscan_db;
+  host.p[O_LIN] = out->bscan_lin;
+  host.p[O_BGR] = out->bscan_bgr;
+  host.p[O_JSUB] = out->jsub_u8;
+  host.p[O_JBGR] = out->jsub_bgr;
+  const unsigned want = host.mask();
+  if ((want & ((1u << O_JSUB) | (1u << O_JBGR))) && c->jscan.empty())
+    return fail(c, ABCOCT_ERR_STATE, "jsub output requested but no jscan is set (abcoct_set_jscan)");
   const size_t dense = (size_t)c->p.w * c->px_bytes;
   if (stride_bytes == 0) stride_bytes = dense;
   if (stride_bytes < dense) return fail(c, ABCOCT_ERR_INVALID, "stride_bytes < w * bytes per pixel");
   if (c->cal_dirty) {
     int rc = upload_calibration(c);
+    if (rc) return rc;
+  }
+  if (c->jscan_dirty) {
+    int rc = upload_jscan(c);
     if (rc) return rc;
   }
   const size_t nB = nframes / c->A;
@@ -1035,11 +1189,12 @@ int abcoct_process_bscans(abcoct_ctx* c, const void* frames, size_t nframes, siz
   size_t slotB = std::max<size_t>(1, (64u << 20) / bscan_in_dev);
   slotB = std::min(slotB, std::max<size_t>(1, (nB + ngpu * kSlots - 1) / (ngpu * kSlots)));
   for (GpuState& g : c->gpus) {
-    int rc = ensure_slots(c, g, slotB, outdb != nullptr);
+    int rc = ensure_slots(c, g, slotB, want);
     if (rc) return rc;
   }
   const bool in_pinned = is_pinned(frames) && stride_bytes == dense;
-  const bool out_pinned = is_pinned(out8) && (!outdb || is_pinned(outdb));
+  bool out_pinned = true;
+  for (int k = 0; k < O_COUNT; ++k) out_pinned = out_pinned && (!host.p[k] || is_pinned(host.p[k]));
   struct Pending {
     size_t b0 = 0, nb = 0;
     bool busy = false;
@@ -1051,10 +1206,9 @@ int abcoct_process_bscans(abcoct_ctx* c, const void* frames, size_t nframes, siz
     GpuState& g = c->gpus[gi];
     CU(c, cudaSetDevice(g.dev));
     CU(c, cudaEventSynchronize(g.slot_done[s]));
-    if (!out_pinned) {
-      memcpy(out8 + pd.b0 * out_px, g.h_out8[s], pd.nb * out_px);
-      if (outdb) memcpy(outdb + pd.b0 * out_px, g.h_outdb[s], pd.nb * out_px * 4);
-    }
+    if (!out_pinned)
+      for (int k = 0; k < O_COUNT; ++k)
+        if (host.p[k]) memcpy(static_cast<uint8_t*>(host.p[k]) + pd.b0 * out_px * kOutBpp[k], g.h_o[k][s], pd.nb * out_px * kOutBpp[k]);
     pd.busy = false;
     return ABCOCT_OK;
   };
@@ -1081,14 +1235,15 @@ int abcoct_process_bscans(abcoct_ctx* c, const void* frames, size_t nframes, siz
       }
       CU(c, cudaMemcpyAsync(g.d_in[s], g.h_in[s], nfr * frame_dev, cudaMemcpyHostToDevice, st));
     }
-    rc = enqueue_device(c, g, s, g.d_in[s], nb, dense, frame_dev, g.d_out8[s], outdb ? g.d_outdb[s] : nullptr, st, false);
+    OutPtrs dev;
+    for (int k = 0; k < O_COUNT; ++k) dev.p[k] = host.p[k] ? g.d_o[k][s] : nullptr;
+    rc = enqueue_device(c, g, s, g.d_in[s], nb, dense, frame_dev, dev, st, false);
     if (rc) return rc;
-    uint8_t* dst8 = out_pinned ? out8 + b0 * out_px : g.h_out8[s];
-    CU(c, cudaMemcpyAsync(dst8, g.d_out8[s], nb * out_px, cudaMemcpyDeviceToHost, st));
-    if (outdb) {
-      float* dstdb = out_pinned ? outdb + b0 * out_px : g.h_outdb[s];
-      CU(c, cudaMemcpyAsync(dstdb, g.d_outdb[s], nb * out_px * 4, cudaMemcpyDeviceToHost, st));
-    }
+    for (int k = 0; k < O_COUNT; ++k)
+      if (host.p[k]) {
+        void* dst = out_pinned ? static_cast<void*>(static_cast<uint8_t*>(host.p[k]) + b0 * out_px * kOutBpp[k]) : g.h_o[k][s];
+        CU(c, cudaMemcpyAsync(dst, g.d_o[k][s], nb * out_px * kOutBpp[k], cudaMemcpyDeviceToHost, st));
+      }
     CU(c, cudaEventRecord(g.slot_done[s], st));
     pend[gi * kSlots + s] = Pending{b0, nb, true};
   }

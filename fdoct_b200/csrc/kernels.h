@@ -58,4 +58,14 @@ cudaError_t launch_bin(const void* in, void* out, int bpp, int opw, int oph, int
 cudaError_t launch_rowprep(const PrepArgsHost& h, cudaStream_t st, int* launched);
 size_t rowprep_smem_bytes(int opw, int M, int m, int movavgn);
 cudaError_t launch_lerp_rows(const float* rows, const int* idx, const float* wq, float* ylin, int M, int N, int oph, cudaStream_t st);
+
+// ---- consumers of a finished B-scan (post_kernels.cu)
+cudaError_t post_init_device();  // once per device: the JET table
+// linear bscan (BscanFFT.cpp:1220-1222) from the dB image [nB][px] and the unmasked DC rows dc01 [nB][oph][2]
+cudaError_t launch_lin_from_db(const float* db, const float* dc01, float* lin, int oph, size_t px, int nB, float inv_db_scale,
+                               int sm_count, cudaStream_t st, int* launched);
+// 'Bscan subtracted' display of the J0 lock-in (BscanFFT.cpp:1225-1231, 1257-1267): lin [nB][px] linear B-scans, jscan [px], mm [2 nB] ints
+cudaError_t launch_jsub(const float* lin, const float* jscan, int* mm, uint8_t* out, size_t px, int nB, float db_scale, float thr,
+                        int sm_count, cudaStream_t st, int* launched);
+cudaError_t launch_jet(const uint8_t* in, uint8_t* out, size_t n, int sm_count, cudaStream_t st);  // applyColorMap(., COLORMAP_JET)
 }  // namespace abcoct

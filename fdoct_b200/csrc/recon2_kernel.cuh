@@ -316,6 +316,8 @@ ABC_HD void phase2_finalise(int tid, const ReconArgs& a, float* const (&out)[2][
                   mn[q] = fminf(mn[q], db);
                   mx[q] = fmaxf(mx[q], db);
                 }
+              } else if (ok && a.dc01 != nullptr) {
+                a.dc01[2 * (size_t)((dst - a.scratch) / a.Dp) + kk] = db;
               }
             } else if (ok) {
               store_scratch(dst + kk, db, keep_pol);

@@ -55,6 +55,7 @@ struct ReconArgs {
   int* sched;      // [0] next item ticket; per B-scan arrays follow (see SchedView)
   uint8_t* out8;   // [nB][D][oph] display image (BscanFFT.cpp:1254-1255)
   float* outdb;    // nullable, [nB][D][oph] bscandb (BscanFFT.cpp:1237-1240)
+  float* dc01;     // nullable, [nB][oph][2]: the dB value of bins 0 and 1 before the DC-row mask (for the linear `bscan` output)
   float inv_W;
   float out_scale;  // 0.5 / A
   float db_scale;   // ln(2) * 20 * (1 / 2.303)
@@ -458,7 +459,8 @@ ABC_HD void phase_passL(int tid, const GroupSmem& s, ThreadState<P>& r) {
 // >= S / 2 >= 8), so only that slot pays for the special cases.
 template <class P>
 ABC_HD void phase_finalise(int tid, const ReconArgs& a, float* rowa_out, float* rowb_out, int row_a_index,
-                           bool rowb_valid, ThreadState<P>& r, float& mn, float& mx, unsigned long long keep_pol = 0) {
+                           bool rowb_valid, ThreadState<P>& r, float& mn, float& mx, unsigned long long keep_pol = 0,
+                           float* dc = nullptr /* [2 rows][2]: dB of bins 0, 1 before the mask, on request */) {
   static_assert(P::S / 2 >= 8, "special bins must all fall into slot 0");
 #pragma unroll
   for (int i = 0; i < P::NU; ++i) {
@@ -486,6 +488,8 @@ ABC_HD void phase_finalise(int tid, const ReconArgs& a, float* rowa_out, float* 
                 mn = fminf(mn, db);
                 mx = fmaxf(mx, db);
               }
+            } else if (valid && dc != nullptr) {  // bins 0, 1: masked in every display image, kept only on request
+              dc[2 * row + kk] = db;
             }
           } else if (valid) {
             store_scratch(dst + kk, db, keep_pol);
@@ -895,7 +899,8 @@ __global__ void __launch_bounds__(P::T* G, 1) recon_kernel(const ReconArgs a) {
       float* oa = a.scratch + (static_cast<size_t>(bscan) * a.oph + ra) * a.Dp;
       float* ob = oa + a.Dp;
       float mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000);
-      phase_finalise<P>(tid, a, oa, ob, ra, rowb_valid, r, mn, mx, keep_pol);
+      float* dc = a.dc01 != nullptr ? a.dc01 + 2 * (static_cast<size_t>(bscan) * a.oph + ra) : nullptr;
+      phase_finalise<P>(tid, a, oa, ob, ra, rowb_valid, r, mn, mx, keep_pol, dc);
       mn = warp_min(mn);
       mx = warp_max(mx);
       if (lane == 0 && mn <= mx) {  // thresholded min/max (BscanFFT.cpp:1247): max(., thr) commutes with min/max

@@ -149,6 +149,36 @@ int abcoct_process_bscans_device(abcoct_ctx* ctx, int gpu_index, const void* d_f
                                  size_t stride_bytes, uint8_t* d_bscan_u8, float* d_bscan_db,
                                  void* cuda_stream);
 
+/* ---- consumers of a finished B-scan (the statements that follow the block in the reference's loop) ----------------
+ * Every image is nB x D x oph, depth-major like bscan_u8; all but bscan_u8 may be NULL.
+ *   bscan_lin   float, the linear `bscan` Mat: mean magnitude + 1e-5 before the log and before the DC-row mask
+ *               (BscanFFT.cpp:1220-1222) - what key 'j' copies into jscansave (:1292-1296).
+ *   bscan_bgr   3 bytes per pixel, applyColorMap(bscandisp, COLORMAP_JET) (BscanFFT.cpp:1284), OpenCV's own table.
+ *   jsub_u8     the 'Bscan subtracted' display of the J0 lock-in (BscanFFT.cpp:1225-1231, 1257-1267):
+ *               max(bscan - jscansave, 0) + 0.001 -> ln * 20 / 2.303 -> max(., bscanthreshold) -> min-max normalise -> u8
+ *               (no DC-row mask, no clampupper, as in the reference).  Needs abcoct_set_jscan, else ABCOCT_ERR_STATE.
+ *   jsub_bgr    applyColorMap(jsub_u8, COLORMAP_JET) (BscanFFT.cpp:1268). */
+typedef struct abcoct_outputs {
+  uint8_t* bscan_u8;
+  float* bscan_db;
+  float* bscan_lin;
+  uint8_t* bscan_bgr;
+  uint8_t* jsub_u8;
+  uint8_t* jsub_bgr;
+  void* reserved[2]; /* must be NULL */
+} abcoct_outputs;
+
+/* Key 'j' (BscanFFT.cpp:1292-1296): keep one linear B-scan (D x oph floats, row stride `ld` elements, 0 = dense; a
+ * bscan_lin output of an earlier call) as the lock-in reference.  NULL switches the lock-in off (key 'c', :1298-1303). */
+int abcoct_set_jscan(abcoct_ctx* ctx, const float* jscan, size_t ld);
+
+/* abcoct_process_bscans with the extra outputs above (host buffers; same ring, same multi-GPU split). */
+int abcoct_process_bscans_ex(abcoct_ctx* ctx, const void* frames, size_t nframes, size_t stride_bytes,
+                             const abcoct_outputs* out);
+/* abcoct_process_bscans_device with the extra outputs above (device pointers on GPU `gpu_index`). */
+int abcoct_process_bscans_device_ex(abcoct_ctx* ctx, int gpu_index, const void* d_frames, size_t nframes,
+                                    size_t stride_bytes, const abcoct_outputs* d_out, void* cuda_stream);
+
 /* Kernel timing of the device entry point (bench.py's roofline): every chunk enqueued by
  * abcoct_process_bscans_device after abcoct_timing_reset is bracketed by CUDA events ON THE LAUNCHING STREAM
  * (up to 512 chunks); abcoct_timing_read waits for them and returns the summed duration of the fused kernel

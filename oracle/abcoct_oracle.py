@@ -371,20 +371,44 @@ class Oracle:
             return db, disp
         return None
 
-    def process_bscans(self, frames: np.ndarray):
-        """frames: (nframes, h, w) integer array; nframes % averages == 0.  Returns (u8 [nB,D,oph], dB f64 [nB,D,oph])."""
+    def process_bscans(self, frames: np.ndarray, want_linear: bool = False):
+        """frames: (nframes, h, w) integer array; nframes % averages == 0.  Returns (u8 [nB,D,oph], dB f64 [nB,D,oph]) and,
+        with want_linear, the linear `bscan` f64 [nB,D,oph] (BscanFFT.cpp:1220-1222) as a third element."""
         p = self.p
         assert frames.shape[0] % p.averages == 0
         nB = frames.shape[0] // p.averages
         out8 = np.empty((nB, p.numdisplaypoints, p.oph), dtype=np.uint8)
         outdb = np.empty((nB, p.numdisplaypoints, p.oph), dtype=np.float64)
+        outlin = np.empty((nB, p.numdisplaypoints, p.oph), dtype=np.float64) if want_linear else None
         b = 0
         for f in frames:
-            r = self.push_frame(f)
+            dump = {} if want_linear else None
+            r = self.push_frame(f, dump)
             if r is not None:
                 outdb[b], out8[b] = r
+                if want_linear:
+                    outlin[b] = dump["bscan"]
                 b += 1
-        return out8, outdb
+        return (out8, outdb, outlin) if want_linear else (out8, outdb)
+
+
+def jlockin_display(bscan: np.ndarray, jscansave: np.ndarray, bscanthreshold: float) -> np.ndarray:
+    """The 'Bscan subtracted' image of the J0 lock-in, BscanFFT.cpp:1225-1231 and 1257-1267.  bscan / jscansave: linear f64
+    D x oph (finalise()[0]).  No DC-row mask and no clampupper on this image in the reference.  Returns u8 D x oph."""
+    jdiff = np.asarray(bscan, dtype=np.float64) - np.asarray(jscansave, dtype=np.float64)  # :1227
+    positivediff = cv2.max(jdiff, 0.0)  # makeonlypositive, :173-178, 1229
+    positivediff = positivediff + 0.001  # :1230
+    bscansublog = cv2.log(positivediff)  # :1260
+    manual = bscansublog * (20.0 * (1.0 / 2.303))  # :1261
+    manual = np.maximum(manual, bscanthreshold)  # :1264
+    manual = cv2.normalize(manual, None, 0, 1, cv2.NORM_MINMAX)  # :1266
+    return np.clip(np.rint(manual * 255.0), 0, 255).astype(np.uint8)  # :1267
+
+
+def colormap_jet(img8: np.ndarray) -> np.ndarray:
+    """applyColorMap(., COLORMAP_JET), BscanFFT.cpp:1268, 1284: u8 (...) -> BGR u8 (..., 3)."""
+    a = np.ascontiguousarray(img8, dtype=np.uint8)
+    return cv2.applyColorMap(a.reshape(-1, 1), cv2.COLORMAP_JET).reshape(a.shape + (3,))
 
 
 def dark_background(yr, yd, ys):

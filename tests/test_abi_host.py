@@ -34,14 +34,16 @@ def test_struct_layout_matches_header(tmp_path):
     import subprocess
 
     src = tmp_path / "layout.c"
-    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "abcoct.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu\\n",'
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "abcoct.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                    'sizeof(abcoct_params),offsetof(abcoct_params,lambdamin),offsetof(abcoct_params,bscanthreshold),'
-                   'offsetof(abcoct_params,clamp_db),sizeof(abcoct_info),offsetof(abcoct_info,kernel_launches));return 0;}\n')
+                   'offsetof(abcoct_params,clamp_db),sizeof(abcoct_info),offsetof(abcoct_info,kernel_launches),'
+                   'sizeof(abcoct_outputs),offsetof(abcoct_outputs,jsub_u8),offsetof(abcoct_outputs,reserved));return 0;}\n')
     exe = tmp_path / "layout"
     subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     assert got == [C.sizeof(api.Params), api.Params.lambdamin.offset, api.Params.bscanthreshold.offset, api.Params.clamp_db.offset,
-                   C.sizeof(api.Info), api.Info.kernel_launches.offset]
+                   C.sizeof(api.Info), api.Info.kernel_launches.offset,
+                   C.sizeof(api.Outputs), api.Outputs.jsub_u8.offset, api.Outputs.reserved.offset]
     p = api.default_params()
     assert (p.w, p.h, p.bpp, p.numfftpoints, p.numdisplaypoints, p.mediann) == (640, 480, 8, 1024, 512, 5)
     assert p.bscanthreshold == -30.0 and p.clamp_db == 50.0 and p.donotnormalize == 1

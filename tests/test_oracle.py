@@ -5,7 +5,7 @@ import os
 import numpy as np
 import pytest
 
-from util import GOLDEN, oracle_params
+from util import GOLDEN, ROOT, oracle_params
 
 from oracle.abcoct_oracle import (Oracle, barthann_window, build_tables, build_tables_linear_scan, smoothmovavg,
                                   zeropadrowwise)
@@ -165,3 +165,35 @@ def test_opencv_rules_the_cuda_path_reimplements():
 def test_oracle_rejects_undefined_reference_behaviour():
     with pytest.raises(ValueError):
         Oracle(oracle_params(w=256, h=4, numfftpoints=128))  # N < M reads past fractionalk (BscanFFT.cpp:1170)
+
+
+def test_jlockin_display_known_answer():
+    """BscanFFT.cpp:1225-1231, 1257-1267 on a hand-made pair of linear images, against plain f64 arithmetic."""
+    from oracle.abcoct_oracle import jlockin_display
+
+    bscan = np.array([[5.0, 1.0, 0.5], [2.0, 2.0, 100.0]])
+    jscan = np.array([[1.0, 3.0, 0.5], [1.0, 2.5, 0.0]])
+    pos = np.maximum(bscan - jscan, 0.0) + 0.001  # [[4.001, .001, .001], [1.001, .001, 100.001]]
+    db = np.maximum(20.0 * np.log(pos) / 2.303, -30.0)  # 0.001 -> -60 dB -> clamped to the threshold
+    want = np.rint((db - db.min()) / (db.max() - db.min()) * 255.0).astype(np.uint8)
+    got = jlockin_display(bscan, jscan, -30.0)
+    assert np.array_equal(got, want)
+    assert got[0, 1] == 0 and got[1, 2] == 255 and 0 < got[1, 0] < got[0, 0] < 255
+    # the lock-in reference against itself: positivediff == 0.001 everywhere, a flat image, which cv::normalize maps to zeros
+    assert (jlockin_display(bscan, bscan, -30.0) == 0).all()
+
+
+def test_jet_table_in_the_cuda_sources_is_opencvs():
+    """fdoct_b200/csrc/jet_lut.h (generated by tools/gen_jet_lut.py) must be cv2's COLORMAP_JET table, entry for entry."""
+    import re
+
+    import cv2
+    from oracle.abcoct_oracle import colormap_jet
+
+    txt = open(os.path.join(ROOT, "fdoct_b200", "csrc", "jet_lut.h")).read()
+    body = txt[txt.index("= {") + 3:txt.rindex("}")]
+    tab = np.array([int(x) for x in re.findall(r"\d+", body)], dtype=np.uint8).reshape(256, 3)
+    assert np.array_equal(tab, colormap_jet(np.arange(256, dtype=np.uint8)))
+    assert tuple(tab[0]) == (128, 0, 0) and tuple(tab[255]) == (0, 0, 128)  # BGR: dark blue ... dark red
+    img = np.array([[0, 128], [255, 7]], dtype=np.uint8)
+    assert np.array_equal(colormap_jet(img), cv2.applyColorMap(img, cv2.COLORMAP_JET))
