@@ -65,8 +65,8 @@ struct GpuState {
   float* d_jscan = nullptr;
   int* d_jmm[kSlots] = {};
   float* d_dc01[kSlots] = {};   // dB of bins 0, 1 before the DC-row mask, [chunk B-scans][oph][2]
-  void* d_tmp[3][kSlots] = {};  // [0] linear, [1] subtracted u8, [2] dB image when needed but not asked for by the caller
-  size_t tmp_bytes[3][kSlots] = {};
+  void* d_tmp[2][kSlots] = {};  // [0] subtracted u8, [1] dB image when needed but not asked for by the caller
+  size_t tmp_bytes[2][kSlots] = {};
   float* d_scratch[kSlots] = {};
   int* d_sched[kSlots] = {};
   size_t scratch_bscans[kSlots] = {};
@@ -520,21 +520,19 @@ int enqueue_device(abcoct_ctx* c, GpuState& g, int slot, const uint8_t* d_frames
       if (rc) return rc;
       CU(c, cudaSetDevice(g.dev));
     }
-    if (!o.p[O_LIN]) {  // the lock-in works on the linear image: keep it in a temporary
-      int rc = ensure_tmp(c, g, 0, slot, nB * px * sizeof(float));
-      if (rc) return rc;
-      o.p[O_LIN] = g.d_tmp[0][slot];
-    }
     if (!o.p[O_JSUB]) {
-      int rc = ensure_tmp(c, g, 1, slot, nB * px);
+      int rc = ensure_tmp(c, g, 0, slot, nB * px);
       if (rc) return rc;
-      o.p[O_JSUB] = g.d_tmp[1][slot];
+      o.p[O_JSUB] = g.d_tmp[0][slot];
     }
   }
-  if (o.p[O_LIN] && !o.p[O_DB]) {  // the linear image is derived from the dB image
-    int rc = ensure_tmp(c, g, 2, slot, nB * px * sizeof(float));
+  // the linear image - stored on request, or evaluated on the fly by the lock-in kernels - is derived from the dB image and
+  // the unmasked DC rows
+  const bool need_db = o.p[O_LIN] || want_j;
+  if (need_db && !o.p[O_DB]) {
+    int rc = ensure_tmp(c, g, 1, slot, nB * px * sizeof(float));
     if (rc) return rc;
-    o.p[O_DB] = g.d_tmp[2][slot];
+    o.p[O_DB] = g.d_tmp[1][slot];
   }
   uint8_t* d_out8 = static_cast<uint8_t*>(o.p[O_U8]);
   float* d_outdb = static_cast<float*>(o.p[O_DB]);
@@ -581,7 +579,7 @@ int enqueue_device(abcoct_ctx* c, GpuState& g, int slot, const uint8_t* d_frames
     a.sched = g.d_sched[slot];
     a.out8 = d_out8 + b0 * c->D * c->oph;
     a.outdb = d_outdb ? d_outdb + b0 * c->D * c->oph : nullptr;
-    a.dc01 = d_outlin ? g.d_dc01[slot] : nullptr;
+    a.dc01 = need_db ? g.d_dc01[slot] : nullptr;
     a.inv_W = 1.0f / (float)c->opw;
     a.out_scale = 0.5f / (float)c->A;
     a.db_scale = (float)(0.6931471805599453 * (20.0 * (1.0 / 2.303)));
@@ -605,9 +603,9 @@ int enqueue_device(abcoct_ctx* c, GpuState& g, int slot, const uint8_t* d_frames
     c->launches += 2;
     // consumers of the finished B-scans (post_kernels.cu), same stream
     float* lin = d_outlin ? d_outlin + b0 * px : nullptr;
+    const float inv = (float)(1.0 / (0.6931471805599453 * (20.0 * (1.0 / 2.303))));
     if (lin) {
       int nl = 0;
-      const float inv = (float)(1.0 / (0.6931471805599453 * (20.0 * (1.0 / 2.303))));
       CU(c, launch_lin_from_db(a.outdb, a.dc01, lin, c->oph, px, (int)nb, inv, g.sm_count, st, &nl));
       c->launches += nl;
     }
@@ -618,7 +616,8 @@ int enqueue_device(abcoct_ctx* c, GpuState& g, int slot, const uint8_t* d_frames
     if (want_j) {
       int nl = 0;
       uint8_t* jsub = static_cast<uint8_t*>(o.p[O_JSUB]) + b0 * px;
-      CU(c, launch_jsub(lin, g.d_jscan, g.d_jmm[slot], jsub, px, (int)nb, a.db_scale, a.thr, g.sm_count, st, &nl));
+      CU(c, launch_jsub(lin, a.outdb, a.dc01, g.d_jscan, g.d_jmm[slot], jsub, c->oph, px, (int)nb, a.db_scale, inv, a.thr, g.sm_count,
+                        st, &nl));
       c->launches += nl;
       if (o.p[O_JBGR]) {
         CU(c, launch_jet(jsub, static_cast<uint8_t*>(o.p[O_JBGR]) + 3 * b0 * px, nb * px, g.sm_count, st));
@@ -893,7 +892,6 @@ void abcoct_destroy(abcoct_ctx* c) {
       if (s == 0) cudaFree(g.d_jscan);
       cudaFree(g.d_tmp[0][s]);
       cudaFree(g.d_tmp[1][s]);
-      cudaFree(g.d_tmp[2][s]);
       cudaFree(g.d_dc01[s]);
       cudaFree(g.d_scratch[s]);
       cudaFree(g.d_sched[s]);

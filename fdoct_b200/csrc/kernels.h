@@ -64,8 +64,9 @@ cudaError_t post_init_device();  // once per device: the JET table
 // linear bscan (BscanFFT.cpp:1220-1222) from the dB image [nB][px] and the unmasked DC rows dc01 [nB][oph][2]
 cudaError_t launch_lin_from_db(const float* db, const float* dc01, float* lin, int oph, size_t px, int nB, float inv_db_scale,
                                int sm_count, cudaStream_t st, int* launched);
-// 'Bscan subtracted' display of the J0 lock-in (BscanFFT.cpp:1225-1231, 1257-1267): lin [nB][px] linear B-scans, jscan [px], mm [2 nB] ints
-cudaError_t launch_jsub(const float* lin, const float* jscan, int* mm, uint8_t* out, size_t px, int nB, float db_scale, float thr,
-                        int sm_count, cudaStream_t st, int* launched);
+// 'Bscan subtracted' display of the J0 lock-in (BscanFFT.cpp:1225-1231, 1257-1267).  Source: lin [nB][px] when the linear image
+// exists, else (lin == nullptr) the dB image + dc01 and the linear value is derived on the fly; jscan [px], mm [2 nB] ints
+cudaError_t launch_jsub(const float* lin, const float* db, const float* dc01, const float* jscan, int* mm, uint8_t* out, int oph,
+                        size_t px, int nB, float db_scale, float inv_db_scale, float thr, int sm_count, cudaStream_t st, int* launched);
 cudaError_t launch_jet(const uint8_t* in, uint8_t* out, size_t n, int sm_count, cudaStream_t st);  // applyColorMap(., COLORMAP_JET)
 }  // namespace abcoct
