@@ -569,6 +569,18 @@ def test_multi_gpu_context_matches_single():
     a8, adb = _run_abi(op, frames, yb)
     b8, bdb = _run_abi(op, frames, yb, ngpu=2)
     assert np.array_equal(a8, b8) and np.array_equal(adb, bdb)
+    # every consumer image too: the lock-in reference lives on both GPUs
+    from fdoct_b200 import api
+
+    res = []
+    for ngpu in (1, 2):
+        with api.Context(abi_params(op), ngpu=ngpu) as ctx:
+            ctx.set_background(yb)
+            ctx.set_jscan(ctx.process_bscans_ex(frames[:1], want=("bscan_lin",))["bscan_lin"][0])
+            res.append(ctx.process_bscans_ex(frames, want=tuple(api.OUTPUT_KINDS)))
+    for k in api.OUTPUT_KINDS:
+        assert np.array_equal(res[0][k], res[1][k]), k
+    assert np.array_equal(res[0]["bscan_u8"], a8)
 
 
 # ------------------------------------------------------------------------------------------- consumers of a finished B-scan
