@@ -431,7 +431,7 @@ int ensure_prep(abcoct_ctx* c, GpuState& g, int slot, size_t nframes) {
   g.d_rows[slot] = g.d_fmm[slot] = nullptr;
   g.prep_frames[slot] = 0;
   if (c->p.mediann > 0) CU(c, cudaMalloc(&g.d_med[slot], nframes * c->p.h * c->p.w * c->px_bytes));
-  CU(c, cudaMalloc(&g.d_bin[slot], nframes * c->oph * c->opw * c->px_bytes));
+  if (c->p.binx > 1 || c->p.biny > 1) CU(c, cudaMalloc(&g.d_bin[slot], nframes * c->oph * c->opw * c->px_bytes));
   CU(c, cudaMalloc(&g.d_rows[slot], nframes * c->oph * (size_t)c->M * sizeof(float)));
   CU(c, cudaMalloc(&g.d_fmm[slot], nframes * 2 * sizeof(float)));
   g.prep_frames[slot] = nframes;
@@ -453,11 +453,17 @@ int run_prep(abcoct_ctx* c, GpuState& g, int slot, const uint8_t* d_frames, size
     fs = (size_t)c->p.w * c->p.h;
     ++n;
   }
-  // binning (a factor of 1 x 1 just makes the frames dense)
-  CU(c, launch_bin(src, g.d_bin[slot], (int)c->p.bpp, c->opw, c->oph, (int)c->p.binx, (int)c->p.biny, rs, fs, (int)nframes, st));
-  ++n;
+  if (c->p.binx > 1 || c->p.biny > 1) {
+    CU(c, launch_bin(src, g.d_bin[slot], (int)c->p.bpp, c->opw, c->oph, (int)c->p.binx, (int)c->p.biny, rs, fs, (int)nframes, st));
+    src = g.d_bin[slot];
+    rs = c->opw;
+    fs = (size_t)c->opw * c->oph;
+    ++n;
+  }
   PrepArgsHost h{};
-  h.binned = g.d_bin[slot];
+  h.binned = src;  // without binning the row kernel reads the caller's (or the median's) frames through their strides
+  h.row_stride = rs;
+  h.frame_stride = fs;
   h.bpp = (int)c->p.bpp;
   h.opw = c->opw;
   h.oph = c->oph;

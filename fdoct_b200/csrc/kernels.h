@@ -39,7 +39,8 @@ cudaError_t launch_sched_init(int* sched, int nB, cudaStream_t st);
 
 // ---- general pre-processing path (prep_kernels.cu)
 struct PrepArgsHost {
-  const void* binned;  // [nframes][oph][opw] integer pixels after median + binning
+  const void* binned;  // integer pixels after median + binning: frames of oph rows of opw pixels
+  size_t row_stride, frame_stride;  // of `binned`, in pixels
   int bpp, opw, oph, nframes, movavgn;
   const float* yd;     // nullable (DARK variant)
   int rowwise, global_norm;

@@ -722,3 +722,38 @@ def test_consumers_device_entry_and_chunking(monkeypatch):
         torch.cuda.synchronize()
         ctx.process_bscans_device_ex(d_in.data_ptr(), nB, {"bscan_u8": d_8.data_ptr(), "jsub_bgr": d_j.data_ptr()})
         assert np.array_equal(d_j.cpu().numpy(), host["jsub_bgr"])
+
+
+# ------------------------------------------------------------------------------------------- BASELINE configs at full size
+FULL = [
+    # name, w, h, N, D, A, variant, extra, B-scans
+    ("C1", 1280, 960, 1280, 640, 1, 0, {}, 12),
+    ("C2", 1280, 960, 1280, 640, 8, 1, {}, 3),
+    ("C3", 1920, 1200, 3840, 1024, 1, 0, dict(fft_multiplier=2), 4),
+    ("C4", 1920, 1200, 1920, 960, 1, 0, {}, 10),
+]
+
+
+@pytest.mark.parametrize("name,w,h,N,D,A,variant,extra,nB", FULL)
+def test_full_size_baseline_configs(name, w, h, N, D, A, variant, extra, nB):
+    """BASELINE configs C1-C4 at their real frame sizes: one B-scan against the oracle, and the size-independent properties
+    on the whole batch - repeated inputs give identical B-scans wherever they sit in the batch, every display image spans
+    0..255, the DC rows mirror row 4, a one-B-scan call equals the same B-scan of the batched call bit for bit."""
+    from fdoct_b200 import api
+
+    op, frames, o, yb, yd = _consumer_setup(w, h, N, D, A, 2, variant, extra, seed=9000 + w + A)
+    batch = np.ascontiguousarray(frames[np.arange(nB * A) % (2 * A)])  # B-scans 0, 1, 0, 1, ...
+    with api.Context(abi_params(op)) as ctx:
+        ctx.set_background(yb)
+        if yd is not None:
+            ctx.set_dark(yd)
+        out8, outdb = ctx.process_bscans(batch, want_db=True)
+        one8, onedb = ctx.process_bscans(np.ascontiguousarray(frames[A:2 * A]), want_db=True)
+    for b in range(2, nB):
+        assert np.array_equal(out8[b], out8[b % 2]) and np.array_equal(outdb[b], outdb[b % 2]), (name, b)
+    assert np.array_equal(one8[0], out8[1]) and np.array_equal(onedb[0], outdb[1])
+    assert (out8.reshape(nB, -1).min(axis=1) == 0).all() and (out8.reshape(nB, -1).max(axis=1) == 255).all()
+    assert np.array_equal(outdb[:, 0], outdb[:, 4]) and np.array_equal(outdb[:, 1], outdb[:, 4])
+    assert np.isfinite(outdb).all()
+    ref8, refdb = o.process_bscans(frames[:A])
+    _check(out8[:1], outdb[:1], ref8, refdb, name + " full size")
