@@ -244,6 +244,28 @@ def run_reference(args, wl, rank):
     print(json.dumps(line), flush=True)
 
 
+def bind_near_gpu(gpu_index):
+    """Multi-rank runs: keep this rank's threads - and with them its pinned staging buffers (first touch) - on the CPUs next to
+    its GPU (NVML's ideal affinity), so that 8 ranks do not pull their H2D traffic across the socket interconnect.  Returns a
+    short description for the JSON line; never fatal."""
+    try:
+        import pynvml as nv
+
+        nv.nvmlInit()
+        h = nv.nvmlDeviceGetHandleByIndex(gpu_index)
+        ncpu = os.cpu_count() or 1
+        words = nv.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        near = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (int(wd) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        use = near & allowed
+        if not use or use == allowed:
+            return "none (NVML affinity covers every allowed CPU)" if use else "none (no allowed CPU near the GPU)"
+        os.sched_setaffinity(0, use)
+        return f"{len(use)} of {len(allowed)} CPUs"
+    except Exception as e:  # noqa: BLE001
+        return "none (" + type(e).__name__ + ")"
+
+
 def run_ours(args, wl, rank, world, local_rank):
     import torch
     import torch.distributed as dist
@@ -252,6 +274,7 @@ def run_ours(args, wl, rank, world, local_rank):
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device - the product path has no CPU fallback")
+    affinity = bind_near_gpu(local_rank) if world > 1 and os.environ.get("ABCOCT_BENCH_NO_AFFINITY") != "1" else "not set"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -354,7 +377,8 @@ def run_ours(args, wl, rank, world, local_rank):
                      "smem_bytes": info.smem_bytes, "regs_per_thread": info.regs_per_thread, "sm_count": info.sm_count},
             "clocks": clocks,
         }
-        if not args.no_cpu and world >= 1:
+        line["config"]["cpu_affinity"] = affinity
+        if not args.no_cpu and world == 1:  # the CPU baseline is a single-GPU-run figure (rank 0 at N = 1 only)
             cores = os.cpu_count() or 1
             per_core = calibrate_cpu_sample(wl, uniq, yb, yd, target_s=args.cpu_seconds)
             v, dt, sample = time_cpu_reference(wl, uniq, yb, yd, cores, per_core)
