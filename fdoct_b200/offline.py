@@ -5,9 +5,10 @@ Input, as written by the triggered capture (BscanFFTspinj.cpp:258-448, 1683-1719
     <dirname>/Trig{NNN}-{iii}.png   Mono16 raw frames, NNN = capture (B-scan) counter, iii = 0 .. manualaverages-1
     <dirname>/spectrum.ocv          data_yb, CV_64F oph x opw (the background captured on key 'b')
     <dirname>/KTrig{NNN}-{iii}.png  optional J0 frames (ignored here)
-Output, the files the live program saves on key 's' (BscanFFTspinj.cpp:2040-2044):
+Output, the files the live program saves on key 's' (BscanFFTspinj.cpp:2040-2045):
     <dirname>/bscan{NNN}.ocv        bscandb, CV_64F D x oph
     <dirname>/bscan{NNN}.png        bscandisp, 8-bit D x oph
+    <dirname>/bscanc{NNN}.png       cmagI = applyColorMap(bscandisp, COLORMAP_JET), 8-bit BGR D x oph
 
     python -m fdoct_b200.offline DIRNAME MANUALAVERAGES [--ini BscanFFTspinj.ini] [--flavour spinj] [--gpus N]
 
@@ -80,11 +81,12 @@ def run(dirname: str, averages: int, params: api.Params, ngpu: int = 1, write_pn
         for i in range(0, len(numbers), batch_bscans):
             chunk = numbers[i:i + batch_bscans]
             frames = load_frames([p for n in chunk for p in caps[n]], params.w, params.h)
-            out8, outdb = ctx.process_bscans(frames, want_db=True)
+            r = ctx.process_bscans_ex(frames, want=("bscan_u8", "bscan_db") + (("bscan_bgr",) if write_png else ()))
             for j, n in enumerate(chunk):
-                write_ocv(os.path.join(dirname, f"bscan{n:03d}.ocv"), outdb[j].astype(np.float64))
+                write_ocv(os.path.join(dirname, f"bscan{n:03d}.ocv"), r["bscan_db"][j].astype(np.float64))
                 if write_png:
-                    cv2.imwrite(os.path.join(dirname, f"bscan{n:03d}.png"), out8[j])
+                    cv2.imwrite(os.path.join(dirname, f"bscan{n:03d}.png"), r["bscan_u8"][j])
+                    cv2.imwrite(os.path.join(dirname, f"bscanc{n:03d}.png"), r["bscan_bgr"][j])
     return numbers
 
 

@@ -69,3 +69,6 @@ def test_offline_tool_end_to_end(tmp_path):
     assert got_db.dtype == np.float64 and got_db.shape == refdb.shape
     assert mag_rel_err(got_db, refdb) <= 1e-4
     assert_display_parity(got8, ref8, "offline tool")
+    for n, g8 in zip(done, got8):  # the colour image the live program saves next to it (BscanFFTspinj.cpp:2044-2045)
+        col = cv2.imread(os.path.join(d, f"bscanc{n:03d}.png"), cv2.IMREAD_UNCHANGED)
+        assert col.shape == g8.shape + (3,) and np.array_equal(col, cv2.applyColorMap(g8, cv2.COLORMAP_JET))
