@@ -757,3 +757,73 @@ def test_full_size_baseline_configs(name, w, h, N, D, A, variant, extra, nB):
     assert np.isfinite(outdb).all()
     ref8, refdb = o.process_bscans(frames[:A])
     _check(out8[:1], outdb[:1], ref8, refdb, name + " full size")
+
+
+# ------------------------------------------------------------------------------------------- randomised configuration sweep
+def _random_config(seed):
+    """A valid parameter combination drawn from everything abcoct_create accepts (small frames, every switch of the path)."""
+    rng = np.random.default_rng(seed)
+    N = int(rng.choice([128, 256, 512, 640, 1024, 1280, 1920, 2048, 2560, 2880, 3840, 4096]))
+    binx = int(rng.choice([1, 1, 1, 2, 3]))
+    biny = int(rng.choice([1, 1, 2]))
+    m = int(rng.choice([1, 1, 1, 2, 3]))
+    # opw: a multiple of 8 (even and 2^a 3^b 5^c when upsampled) with m * opw <= N
+    cands = [o for o in (16, 24, 32, 40, 48, 64, 80, 96, 120, 128, 160, 192, 240, 256, 320, 384, 480, 512, 640, 960, 1024, 1280, 1920, 2048) if m * o <= N]
+    opw = int(rng.choice(cands[-4:]))  # prefer rows that fill most of the transform
+    oph = int(rng.integers(6, 40))
+    A = int(rng.choice([1, 1, 2, 3, 5]))
+    D = int(rng.integers(6, N // 2 + 1))
+    variant = int(rng.integers(0, 2))
+    extra = dict(binx=binx, biny=biny, fft_multiplier=m, mediann=int(rng.choice([0, 0, 3, 5])), movavgn=int(rng.choice([0, 0, 1, 3])),
+                 clampupper=bool(rng.integers(0, 2)), bscanthreshold=float(rng.choice([-30.0, -10.0, 5.0])),
+                 weight_mode=int(rng.integers(0, 2)))
+    norm = int(rng.integers(0, 4))
+    if norm == 1:
+        extra.update(rowwisenormalize=True, donotnormalize=True)
+    elif norm == 2:
+        extra.update(donotnormalize=False)
+    if variant == 1 and m > 1 and opw >= 64:  # below 40 samples the band [3, opw / 10) is empty and the image degenerates to a constant
+        extra["bandpassfilter"] = bool(rng.integers(0, 2))
+    return dict(w=opw * binx, h=oph * biny, N=N, D=D, A=A, variant=variant, extra=extra, nB=int(rng.integers(1, 4)))
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_configurations_against_oracle(seed):
+    from fdoct_b200 import synth
+    from oracle.abcoct_oracle import Oracle, dark_background
+
+    c = _random_config(4200 + seed)
+    w, h, A, variant = c["w"], c["h"], c["A"], c["variant"]
+    op = oracle_params(w=w, h=h, numfftpoints=c["N"], numdisplaypoints=c["D"], averages=A, variant=variant, lambdamin=840.5e-9,
+                       lambdamax=859.5e-9, **c["extra"])
+    frames = synth.make_frames(c["nB"] * A, w, h, seed=seed, dark=variant == 1)
+    o = Oracle(op)
+    yd = None
+    if variant == 1:
+        yd = o.calib_capture(synth.make_dark_frames(2, w, h, seed=seed + 2))  # keys o / r: the same normalise branches as the frames
+        yr = o.calib_capture(synth.make_background_frames(2, w, h, seed=seed + 1, dark=True))
+        yb = dark_background(yr, yd, yd + 0.02 * (yr - yd))
+        o.set_dark(yd)
+    else:
+        yb = o.calib_capture(synth.make_background_frames(2, w, h, seed=seed + 1))  # key b
+    o.set_background(yb)
+    ref8, refdb = o.process_bscans(frames)
+    out8, outdb = _run_abi(op, frames, yb, yd=yd)
+    what = f"random config {c}"
+    assert np.isfinite(outdb).all(), what
+    assert_display_parity(out8, ref8, what)
+    err = mag_rel_err(outdb, refdb)
+    if err > MAG_RTOL:
+        # Two correct f32 transforms can disagree by slightly more than 1e-4 in the tail of a sweep (each is ~5e-5 from the exact
+        # result, profiles/r01_precision_probe.txt).  Then the CUDA path must at least be no further from an exact f64 evaluation
+        # of the last transform than the reference's own OpenCV f32 DFT is.
+        assert err <= 2e-4, f"{what}: magnitude error {err:.3g}"
+        N, D = c["N"], c["D"]
+        exact = np.zeros_like(refdb)
+        for b in range(c["nB"]):
+            acc = sum(np.abs(np.fft.ifft(o.linearised(f), axis=1) * N)[:, :D] for f in frames[b * A:(b + 1) * A])
+            exact[b] = (acc / A).T
+        exact[:, 0] = exact[:, 4]
+        exact[:, 1] = exact[:, 4]
+        e_ours, e_ref = mag_err(db_to_mag(outdb), exact), mag_err(db_to_mag(refdb), exact)
+        assert e_ours <= 1.25 * e_ref, f"{what}: {e_ours:.3g} from exact, the reference {e_ref:.3g}"
