@@ -13,6 +13,7 @@
 #include <cstring>
 #include <fstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "kernels.h"
@@ -665,6 +666,30 @@ int ensure_slots(abcoct_ctx* c, GpuState& g, size_t slotB, unsigned want) {
   return ABCOCT_OK;
 }
 
+// Staging copies between pageable caller memory and the pinned ring.  One core moves ~10 GB/s, a PCIe 5 x16 link takes 50+:
+// large copies are split over a few threads (the slot is 64 MiB; thread start-up is ~50 us each).
+void staging_copy(void* dst, const void* src, size_t bytes) {
+  constexpr size_t kMinPerThread = 4u << 20;
+  unsigned hw = std::thread::hardware_concurrency();
+  size_t nt = std::min<size_t>({bytes / kMinPerThread, hw ? hw / 2 : 1, 8});
+  if (const char* e = getenv("ABCOCT_COPY_THREADS")) nt = std::min<size_t>((size_t)std::max(1L, atol(e)), 64);
+  if (nt <= 1) {
+    memcpy(dst, src, bytes);
+    return;
+  }
+  const size_t per = ((bytes + nt - 1) / nt + 63) & ~(size_t)63;
+  std::vector<std::thread> th;
+  th.reserve(nt - 1);
+  for (size_t t = 1; t < nt; ++t) {
+    const size_t o = t * per;
+    if (o >= bytes) break;
+    const size_t n = std::min(per, bytes - o);
+    th.emplace_back([=] { memcpy(static_cast<char*>(dst) + o, static_cast<const char*>(src) + o, n); });
+  }
+  memcpy(dst, src, std::min(per, bytes));
+  for (std::thread& t : th) t.join();
+}
+
 bool is_pinned(const void* p) {
   cudaPointerAttributes at;
   if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
@@ -1212,7 +1237,7 @@ int abcoct_process_bscans_ex(abcoct_ctx* c, const void* frames, size_t nframes, 
     CU(c, cudaEventSynchronize(g.slot_done[s]));
     if (!out_pinned)
       for (int k = 0; k < O_COUNT; ++k)
-        if (host.p[k]) memcpy(static_cast<uint8_t*>(host.p[k]) + pd.b0 * out_px * kOutBpp[k], g.h_o[k][s], pd.nb * out_px * kOutBpp[k]);
+        if (host.p[k]) staging_copy(static_cast<uint8_t*>(host.p[k]) + pd.b0 * out_px * kOutBpp[k], g.h_o[k][s], pd.nb * out_px * kOutBpp[k]);
     pd.busy = false;
     return ABCOCT_OK;
   };
@@ -1233,7 +1258,7 @@ int abcoct_process_bscans_ex(abcoct_ctx* c, const void* frames, size_t nframes, 
     } else {
       // pageable (or pitched) caller memory: stage through the pinned ring
       if (stride_bytes == dense) {
-        memcpy(g.h_in[s], src, nfr * frame_dev);
+        staging_copy(g.h_in[s], src, nfr * frame_dev);
       } else {
         for (size_t r = 0; r < nfr * c->p.h; ++r) memcpy(g.h_in[s] + r * dense, src + r * stride_bytes, dense);
       }
