@@ -85,6 +85,11 @@ __global__ void bin_kernel(const T* __restrict__ in, T* __restrict__ out, int op
 //   pass with radix r, current length nc, stride s:  for p < nc / r, q < s
 //     y[q + s (r p + c)] = ( sum_j x[q + s (p + (nc / r) j)] w_r^(jc) ) * w_n^(p c s)
 // (tools/fft_plan_model.py holds the NumPy model of this index algebra).  tw[k] = exp(SGN 2 pi i k / n), k < n.
+// The transform buffers carry one float2 of padding per 16: the first pass (s == 1) writes y[R p + c] from consecutive threads
+// p, a stride of R float2 that lands 16 lanes on one bank pair (ncu: 58 % of the shared-memory wavefronts of the unpadded kernel
+// were conflicts); with the padding the stride becomes R + R / 16.  Reads are consecutive in the thread index either way.
+__host__ __device__ __forceinline__ int fpad(int i) { return i + (i >> 4); }
+
 struct RadixList {
   int n;
   int count;
@@ -99,12 +104,12 @@ __device__ __forceinline__ void stockham_pass(const float2* __restrict__ x, floa
     const int p = b / s, q = b - p * s;
     float2 in[R], out[R];
 #pragma unroll
-    for (int j = 0; j < R; ++j) in[j] = x[q + s * (p + mq * j)];
+    for (int j = 0; j < R; ++j) in[j] = x[fpad(q + s * (p + mq * j))];
     Dft<R, SGN, 1, 1>::run(in, out);
-    y[q + s * (R * p)] = out[0];
+    y[fpad(q + s * (R * p))] = out[0];
     const int tb = p * s;  // p < nc / R and s * nc == n: tb * c < n for every c < R, no reduction needed
 #pragma unroll
-    for (int c = 1; c < R; ++c) y[q + s * (R * p + c)] = cmul(out[c], tw[tb * c]);
+    for (int c = 1; c < R; ++c) y[fpad(q + s * (R * p + c))] = cmul(out[c], tw[tb * c]);
   }
 }
 
@@ -268,6 +273,8 @@ __device__ bool rowprep_one(const PrepArgs& a, int row, int f, float* x, float* 
   return false;
 }
 
+__host__ __device__ inline int fft_buf_slots(int M) { return (fpad(M) + 2) & ~1; }  // float2 slots of one padded transform buffer, 16-B multiple
+
 __host__ __device__ inline size_t rowbuf_bytes(int opw, int movavgn) {
   const size_t one = (size_t)((opw + 3) & ~3) * sizeof(float);
   return (one * (movavgn > 0 ? 2 : 1) + 15) & ~(size_t)15;
@@ -285,7 +292,7 @@ __global__ void __launch_bounds__(256) rowprep_kernel(const PrepArgs a) {
   const int r1 = has1 ? r0 + 1 : r0;
   const size_t rb = rowbuf_bytes(W, a.movavgn);
   float2* bufa = reinterpret_cast<float2*>(smem_raw);
-  float2* bufb = bufa + a.M;
+  float2* bufb = bufa + fft_buf_slots(a.M);
   unsigned char* rows_at = a.m > 1 ? reinterpret_cast<unsigned char*>(bufb) : smem_raw;
   float* x0 = reinterpret_cast<float*>(rows_at);
   float* x1 = reinterpret_cast<float*>(rows_at + rb);
@@ -305,7 +312,7 @@ __global__ void __launch_bounds__(256) rowprep_kernel(const PrepArgs a) {
   // with DFT_REAL_OUTPUT, which only reads bins 0 .. M/2 - so the -opw/2 (Nyquist) bin is dropped.  For two real rows
   // z = row0 + i row1 this is: Z = DFT(z) / opw, keep Z[k] (0 <= k < opw/2) at k and Z[opw - k] (1 <= k < opw/2) at M - k,
   // z' = inverse DFT of length M; row0' = Re z', row1' = Im z'.
-  for (int j = threadIdx.x; j < W; j += blockDim.x) bufa[j] = make_float2(x0[j], has1 ? x1[j] : 0.f);
+  for (int j = threadIdx.x; j < W; j += blockDim.x) bufa[fpad(j)] = make_float2(x0[j], has1 ? x1[j] : 0.f);
   __syncthreads();
   float2* X = block_fft<-1>(bufa, bufb, a.rlW, a.twW);
   float2* Y = (X == bufa) ? bufb : bufa;
@@ -316,17 +323,17 @@ __global__ void __launch_bounds__(256) rowprep_kernel(const PrepArgs a) {
   for (int k = threadIdx.x; k < a.M; k += blockDim.x) {
     float2 v = make_float2(0.f, 0.f);
     if (k < half) {
-      if (k >= lo && k < hi) v = make_float2(X[k].x * sc, X[k].y * sc);
+      if (k >= lo && k < hi) v = make_float2(X[fpad(k)].x * sc, X[fpad(k)].y * sc);
     } else if (k > a.M - half) {
       const int kk = a.M - k;
-      if (kk >= lo && kk < hi) v = make_float2(X[W - kk].x * sc, X[W - kk].y * sc);
+      if (kk >= lo && kk < hi) v = make_float2(X[fpad(W - kk)].x * sc, X[fpad(W - kk)].y * sc);
     }
-    Y[k] = v;
+    Y[fpad(k)] = v;
   }
   __syncthreads();
   float2* R = block_fft<+1>(Y, X, a.rlM, a.twM);
   for (int j = threadIdx.x; j < a.M; j += blockDim.x) {
-    const float2 v = R[j];
+    const float2 v = R[fpad(j)];
     out0[j] = v.x;
     if (has1) out1[j] = v.y;
   }
@@ -386,7 +393,7 @@ __global__ void minmax_reset_kernel(float* mm, int n) {
 size_t rowprep_smem_bytes(int opw, int M, int m, int movavgn) {
   const size_t rows = 2 * rowbuf_bytes(opw, movavgn);  // two rows per CTA
   if (m <= 1) return rows;
-  const size_t one = (size_t)M * sizeof(float2);
+  const size_t one = (size_t)fft_buf_slots(M) * sizeof(float2);
   return one + (rows > one ? rows : one);  // the rows alias the second transform buffer
 }
 
