@@ -94,14 +94,17 @@ struct RadixList {
   int n;
   int count;
   int r[12];
+  int nc[12], s[12];  // per pass: remaining length n / (r[0] .. r[i-1]) and stride r[0] .. r[i-1]
 };
 
 template <int R, int SGN>
 __device__ __forceinline__ void stockham_pass(const float2* __restrict__ x, float2* __restrict__ y, int n, int nc, int s,
                                               const float2* __restrict__ tw) {
   const int mq = nc / R;
+  const float inv_s = 1.0f / (float)s;
   for (int b = threadIdx.x; b < n / R; b += blockDim.x) {
-    const int p = b / s, q = b - p * s;
+    // b / s without an integer division: (b + 0.5) / s sits at least 0.5 / s away from an integer, far more than the f32 error
+    const int p = __float2int_rz(((float)b + 0.5f) * inv_s), q = b - p * s;
     float2 in[R], out[R];
 #pragma unroll
     for (int j = 0; j < R; ++j) in[j] = x[fpad(q + s * (p + mq * j))];
@@ -116,10 +119,9 @@ __device__ __forceinline__ void stockham_pass(const float2* __restrict__ x, floa
 // in-place semantics for the caller: returns the buffer that holds the result (a or b)
 template <int SGN>
 __device__ float2* block_fft(float2* a, float2* b, const RadixList& rl, const float2* __restrict__ tw) {
-  int nc = rl.n, s = 1;
   float2 *x = a, *y = b;
   for (int i = 0; i < rl.count; ++i) {
-    const int r = rl.r[i];
+    const int r = rl.r[i], nc = rl.nc[i], s = rl.s[i];  // current length and stride of pass i, filled in by the host
     switch (r) {
       case 2: stockham_pass<2, SGN>(x, y, rl.n, nc, s, tw); break;
       case 3: stockham_pass<3, SGN>(x, y, rl.n, nc, s, tw); break;
@@ -134,8 +136,6 @@ __device__ float2* block_fft(float2* a, float2* b, const RadixList& rl, const fl
       default: stockham_pass<16, SGN>(x, y, rl.n, nc, s, tw); break;
     }
     __syncthreads();
-    nc /= r;
-    s *= r;
     float2* t = x;
     x = y;
     y = t;
@@ -273,6 +273,61 @@ __device__ bool rowprep_one(const PrepArgs& a, int row, int f, float* x, float* 
   return false;
 }
 
+// The common case of the general path (no smoothing, no normalisation - e.g. C3, which is here only for the Fourier upsample):
+// both rows in ONE vectorised pass - 8 pixels per 16-byte load, the calibration rows as float4 - straight to the divided
+// samples and the two row sums.  Same arithmetic, in the same order per sample, as rowprep_one.
+template <class PX>
+__device__ __forceinline__ void rowpair_fast(const PrepArgs& a, const PX* src0, const PX* src1, int row0, int row1, float* x0, float* x1,
+                                             float& sum0, float& sum1) {
+  const int W = a.opw;
+  const float* rows[2] = {a.yb + (size_t)row0 * W, a.yb + (size_t)row1 * W};
+  const float* yps[2] = {a.yp ? a.yp + (size_t)row0 * W : nullptr, a.yp ? a.yp + (size_t)row1 * W : nullptr};
+  const float* yds[2] = {a.yd ? a.yd + (size_t)row0 * W : nullptr, a.yd ? a.yd + (size_t)row1 * W : nullptr};
+  const PX* srcs[2] = {src0, src1};
+  float* xs[2] = {x0, x1};
+  float sums[2] = {0.f, 0.f};
+  for (int ch = threadIdx.x; ch < W / 8; ch += blockDim.x) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+      float v[8];
+      if (sizeof(PX) == 2) {
+        const uint4 p = __ldg(reinterpret_cast<const uint4*>(srcs[r]) + ch);
+        const unsigned w32[4] = {p.x, p.y, p.z, p.w};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = (float)((k & 1) ? (w32[k >> 1] >> 16) : (w32[k >> 1] & 0xffffu));
+      } else {
+        const uint2 p = __ldg(reinterpret_cast<const uint2*>(srcs[r]) + ch);
+        const unsigned w32[2] = {p.x, p.y};
+#pragma unroll
+        for (int k = 0; k < 8; ++k) v[k] = (float)((w32[k >> 2] >> (8 * (k & 3))) & 0xffu);
+      }
+      float b[8], s[8], d[8];
+      *reinterpret_cast<float4*>(b) = __ldg(reinterpret_cast<const float4*>(rows[r]) + 2 * ch);
+      *reinterpret_cast<float4*>(b + 4) = __ldg(reinterpret_cast<const float4*>(rows[r]) + 2 * ch + 1);
+      if (yps[r]) {
+        *reinterpret_cast<float4*>(s) = __ldg(reinterpret_cast<const float4*>(yps[r]) + 2 * ch);
+        *reinterpret_cast<float4*>(s + 4) = __ldg(reinterpret_cast<const float4*>(yps[r]) + 2 * ch + 1);
+      }
+      if (yds[r]) {
+        *reinterpret_cast<float4*>(d) = __ldg(reinterpret_cast<const float4*>(yds[r]) + 2 * ch);
+        *reinterpret_cast<float4*>(d + 4) = __ldg(reinterpret_cast<const float4*>(yds[r]) + 2 * ch + 1);
+      }
+      float t[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float x = v[k];
+        if (yds[r]) x -= d[k];                      // BscanDark.cpp:1269
+        t[k] = (x - (yps[r] ? s[k] : 0.f)) / b[k];  // BscanFFT.cpp:1132
+        sums[r] += t[k];
+      }
+      *reinterpret_cast<float4*>(xs[r] + 8 * ch) = make_float4(t[0], t[1], t[2], t[3]);
+      *reinterpret_cast<float4*>(xs[r] + 8 * ch + 4) = make_float4(t[4], t[5], t[6], t[7]);
+    }
+  }
+  sum0 = sums[0];
+  sum1 = sums[1];
+}
+
 __host__ __device__ inline int fft_buf_slots(int M) { return (fpad(M) + 2) & ~1; }  // float2 slots of one padded transform buffer, 16-B multiple
 
 __host__ __device__ inline size_t rowbuf_bytes(int opw, int movavgn) {
@@ -296,9 +351,30 @@ __global__ void __launch_bounds__(256) rowprep_kernel(const PrepArgs a) {
   unsigned char* rows_at = a.m > 1 ? reinterpret_cast<unsigned char*>(bufb) : smem_raw;
   float* x0 = reinterpret_cast<float*>(rows_at);
   float* x1 = reinterpret_cast<float*>(rows_at + rb);
-  const bool reduce_only = rowprep_one(a, r0, f, x0, red);
-  if (has1) rowprep_one(a, r1, f, x1, red);
-  if (reduce_only) return;
+  const size_t px = (size_t)(a.bpp == 8 ? 1 : 2);
+  const unsigned char* s0 = static_cast<const unsigned char*>(a.binned) + ((size_t)f * a.frame_stride + (size_t)r0 * a.row_stride) * px;
+  const unsigned char* s1 = static_cast<const unsigned char*>(a.binned) + ((size_t)f * a.frame_stride + (size_t)r1 * a.row_stride) * px;
+  const bool fast = a.movavgn == 0 && !a.rowwise && !a.global_norm && (W & 7) == 0 &&
+                    ((reinterpret_cast<uintptr_t>(s0) | reinterpret_cast<uintptr_t>(s1)) & (8 * px - 1)) == 0;
+  if (fast) {  // uniform over the CTA
+    float sum0, sum1;
+    if (a.bpp == 8)
+      rowpair_fast<uint8_t>(a, s0, s1, r0, r1, x0, x1, sum0, sum1);
+    else
+      rowpair_fast<uint16_t>(a, reinterpret_cast<const uint16_t*>(s0), reinterpret_cast<const uint16_t*>(s1), r0, r1, x0, x1, sum0, sum1);
+    const float mean0 = block_reduce(sum0, red, 0) / (float)W;  // BscanFFT.cpp:1135-1143; the barrier inside also publishes x0 / x1
+    const float mean1 = block_reduce(sum1, red, 0) / (float)W;
+    for (int j = threadIdx.x; j < W; j += blockDim.x) {
+      const float wj = a.win[j];
+      x0[j] = (x0[j] - mean0) * wj;
+      x1[j] = (x1[j] - mean1) * wj;
+    }
+    __syncthreads();
+  } else {
+    const bool reduce_only = rowprep_one(a, r0, f, x0, red);
+    if (has1) rowprep_one(a, r1, f, x1, red);
+    if (reduce_only) return;
+  }
   float* out0 = a.out + ((size_t)f * a.oph + r0) * a.M;
   float* out1 = a.out + ((size_t)f * a.oph + r1) * a.M;
   if (a.m <= 1) {
@@ -406,6 +482,15 @@ cudaError_t launch_rowprep(const PrepArgsHost& h, cudaStream_t st, int* launched
   a.rlW.n = h.opw; a.rlW.count = h.nradW;
   a.rlM.n = h.M; a.rlM.count = h.nradM;
   for (int i = 0; i < 12; ++i) { a.rlW.r[i] = h.radW[i]; a.rlM.r[i] = h.radM[i]; }
+  for (RadixList* rl : {&a.rlW, &a.rlM}) {
+    int nc = rl->n, st = 1;
+    for (int i = 0; i < rl->count && i < 12; ++i) {
+      rl->nc[i] = nc;
+      rl->s[i] = st;
+      nc /= rl->r[i];
+      st *= rl->r[i];
+    }
+  }
   const size_t smem = rowprep_smem_bytes(h.opw, h.M, h.m, h.movavgn);
   static bool attr_done = false;
   if (!attr_done || smem > 48 * 1024) {
