@@ -32,7 +32,8 @@ class Params(C.Structure):
         ("lambdamin", C.c_double), ("lambdamax", C.c_double), ("mediann", C.c_int32), ("movavgn", C.c_int32),
         ("fft_multiplier", C.c_uint32), ("rowwisenormalize", C.c_uint8), ("donotnormalize", C.c_uint8),
         ("variant", C.c_uint8), ("weight_mode", C.c_uint8), ("bscanthreshold", C.c_double),
-        ("clampupper", C.c_uint8), ("bandpassfilter", C.c_uint8), ("lowpassfilter", C.c_uint8), ("reserved", C.c_uint8 * 5),
+        ("clampupper", C.c_uint8), ("bandpassfilter", C.c_uint8), ("lowpassfilter", C.c_uint8), ("output_rebin", C.c_uint8),
+        ("bscanbinx", C.c_uint8), ("bscanbiny", C.c_uint8), ("reserved", C.c_uint8 * 2),
         ("clamp_db", C.c_double),
     ]
 

@@ -187,6 +187,9 @@ int validate(const abcoct_params& p, std::string& why, int& code) {
   if (p.mediann != 0 && p.mediann != 3 && p.mediann != 5)
     return bad("medianBlur kernel sizes other than 3 and 5 are not built (OpenCV itself only takes 3 / 5 for 16-bit frames)");
   if (p.movavgn > 64) return bad("movavgn > 64 is not built");
+  if (p.output_rebin && (p.bscanbinx > 1 || p.bscanbiny > 1 || p.binx > 1 || p.biny > 1))
+    return bad("BscanFFTspinjnt's output re-binning of the linear B-scan (INTER_AREA down, x multiplyfactor, INTER_CUBIC up; "
+               "BscanFFTspinjnt.cpp:1856-1862, active whenever any binning factor exceeds 1) is not built");
   if (p.fft_multiplier > 1) {
     unsigned r = opw;
     for (unsigned f : {2u, 3u, 5u})
@@ -726,6 +729,7 @@ void abcoct_params_default(abcoct_params* o) {
   o->bscanthreshold = -30.0;  // :385
   o->clampupper = 0;          // :374
   o->clamp_db = 50.0;         // :1252
+  o->bscanbinx = o->bscanbiny = 1;  // BscanFFTspinjnt.cpp:707
 }
 
 int abcoct_params_from_ini(const char* path, int flavour, abcoct_params* o) {
@@ -733,10 +737,13 @@ int abcoct_params_from_ini(const char* path, int flavour, abcoct_params* o) {
   if (flavour < ABCOCT_INI_BSCANFFT || flavour > ABCOCT_INI_SIM) return ABCOCT_ERR_INVALID;
   abcoct_params_default(o);
   if (flavour == ABCOCT_INI_DARK) o->variant = 1;
-  if (flavour == ABCOCT_INI_SPINJNT) o->clamp_db = 30.0;  // BscanFFTspinjnt.cpp:1886
+  if (flavour == ABCOCT_INI_SPINJNT) {
+    o->clamp_db = 30.0;   // BscanFFTspinjnt.cpp:1886
+    o->output_rebin = 1;  // BscanFFTspinjnt.cpp:1856-1862
+  }
   std::ifstream in(path);
   if (!in.is_open()) return ABCOCT_ERR_IO;  // "Unable to open ini file, using defaults." BscanFFT.cpp:484
-  enum F { SKIP, BPP, W, H, BIN, BINX, BINY, AVG, NFFT, MOVAVG, NDISP, LMIN, LMAX, MEDIAN, MULT, ROWNORM, NONORM, BANDPASS, LOWPASS };
+  enum F { SKIP, BPP, W, H, BIN, BINX, BINY, OBINX, OBINY, AVG, NFFT, MOVAVG, NDISP, LMIN, LMAX, MEDIAN, MULT, ROWNORM, NONORM, BANDPASS, LOWPASS };
   std::vector<F> order = {SKIP /*camgain*/, SKIP /*camtime*/, BPP, W, H};
   const bool offsets = flavour == ABCOCT_INI_BSCANFFT || flavour == ABCOCT_INI_SPINJ || flavour == ABCOCT_INI_SPINJNT;
   if (offsets) {
@@ -745,7 +752,7 @@ int abcoct_params_from_ini(const char* path, int flavour, abcoct_params* o) {
   }
   for (int i = 0; i < 4; ++i) order.push_back(SKIP);  // camspeed cambinx cambiny usbtraffic
   if (flavour == ABCOCT_INI_SPINJNT) {
-    order.insert(order.end(), {BINX, BINY, SKIP /*bscanbinx*/, SKIP /*bscanbiny*/});
+    order.insert(order.end(), {BINX, BINY, OBINX, OBINY});
   } else {
     order.push_back(BIN);
   }
@@ -774,6 +781,8 @@ int abcoct_params_from_ini(const char* path, int flavour, abcoct_params* o) {
       case BIN: o->binx = o->biny = (uint32_t)iv; stop = !numeric; break;
       case BINX: o->binx = (uint32_t)iv; stop = !numeric; break;
       case BINY: o->biny = (uint32_t)iv; stop = !numeric; break;
+      case OBINX: o->bscanbinx = (uint8_t)std::min(255L, std::max(0L, iv)); stop = !numeric; break;
+      case OBINY: o->bscanbiny = (uint8_t)std::min(255L, std::max(0L, iv)); stop = !numeric; break;
       case AVG: o->averages = (uint32_t)iv; stop = !numeric; break;
       case NFFT: o->numfftpoints = (uint32_t)iv; stop = !numeric; break;
       case MOVAVG: o->movavgn = (int32_t)iv; stop = !numeric; break;

@@ -68,7 +68,13 @@ typedef struct abcoct_params {
   uint8_t clampupper;        /* BscanFFT.cpp:374, 1248                                                     */
   uint8_t bandpassfilter;    /* BscanDark.cpp:218-236 (inside the Fourier upsample only)                   */
   uint8_t lowpassfilter;     /* BscanDark.cpp:1070-1074: lpfilter (:119-167) on the captured dark / reference / sample frames */
-  uint8_t reserved[5];
+  uint8_t output_rebin;      /* 1 = the caller is BscanFFTspinjnt, whose block re-bins the LINEAR B-scan before the log whenever
+                                any of binx / biny / bscanbinx / bscanbiny exceeds 1 (resize INTER_AREA down by bscanbinx/y, times
+                                multiplyfactor, resize INTER_CUBIC up by bscanbinx * binvaluey and bscanbiny,
+                                BscanFFTspinjnt.cpp:835, 1856-1862).  Set by the ABCOCT_INI_SPINJNT parser.  That stage is NOT built:
+                                abcoct_create answers ABCOCT_ERR_UNSUPPORTED instead of returning the un-rebinned image.       */
+  uint8_t bscanbinx, bscanbiny; /* BscanFFTspinjnt.cpp:795-797; only looked at when output_rebin is set                       */
+  uint8_t reserved[2];
   double clamp_db;           /* 50.0 (BscanFFT.cpp:1252), 30.0 in BscanFFTspinjnt.cpp:1886                 */
 } abcoct_params;
 
