@@ -7,6 +7,8 @@
                 lambdamin/lambdamax (BscanFFT.cpp:381-382, which are that generator's +-2 sigma range).
                 Inputs are stored as arrays (the PNG files themselves are not copied), outputs are the oracle's.
 * synth_*.npz   small seeded synthetic cases (fdoct_b200.synth) with the oracle's outputs, one per variant.
+* consumers_*.npz  the consumers of a finished B-scan (BscanFFT.cpp:1220-1231, 1257-1268, 1284): the linear bscan, the J0 lock-in
+                display against a second scene and the JET colour images, all from the oracle.
 * *.ini         parameter files in the reference's positional layout (written by this script, not copied).
 """
 import os
@@ -19,7 +21,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 from fdoct_b200 import synth  # noqa: E402
-from oracle.abcoct_oracle import Oracle, Params, dark_background  # noqa: E402
+from oracle.abcoct_oracle import Oracle, Params, colormap_jet, dark_background, jlockin_display  # noqa: E402
 
 REF = "/root/reference/Matlab files"
 
@@ -57,6 +59,21 @@ def synth_case(name, *, w, h, N, D, A, variant, seed, nB=2, thr=-30.0, clampuppe
     out8, outdb = o.process_bscans(frames)
     np.savez_compressed(os.path.join(HERE, name + ".npz"), frames=frames, yb=yb, out8=out8, outdb=outdb.astype(np.float32),
                         params=np.array([w, h, N, D, A, variant, seed, int(clampupper), weight_mode]), thr=thr, **extra)
+
+
+def consumers_case(name, *, w, h, N, D, A, seed, thr=-30.0):
+    p = Params(w=w, h=h, numfftpoints=N, numdisplaypoints=D, averages=A, lambdamin=840.5e-9, lambdamax=859.5e-9, bscanthreshold=thr)
+    frames = synth.make_frames(2 * A, w, h, seed=seed)
+    jframes = synth.make_frames(A, w, h, seed=seed + 7)  # the scene key 'j' was pressed on
+    o = Oracle(p, strict=True)
+    yb = o.calib_mean_of_frames(synth.make_background_frames(2, w, h, seed=seed + 1))
+    o.set_background(yb)
+    _, _, jscan = o.process_bscans(jframes, want_linear=True)
+    out8, outdb, lin = o.process_bscans(frames, want_linear=True)
+    jsub = np.stack([jlockin_display(b, jscan[0], thr) for b in lin])
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), frames=frames, jframes=jframes, yb=yb, out8=out8, lin=lin.astype(np.float32),
+                        jscan=jscan[0].astype(np.float32), jsub=jsub, bgr=colormap_jet(out8), jbgr=colormap_jet(jsub),
+                        params=np.array([w, h, N, D, A, seed]), thr=thr)
 
 
 INI_ORDER = {
@@ -97,5 +114,6 @@ if __name__ == "__main__":
     synth_case("synth_fft_1280x32", w=1280, h=32, N=1280, D=640, A=1, variant=0, seed=1001)
     synth_case("synth_dark_1280x16_a4", w=1280, h=16, N=1280, D=640, A=4, variant=1, seed=1002)
     synth_case("synth_fft_1024x17_n2048_clamp", w=1024, h=17, N=2048, D=700, A=2, variant=0, seed=1005, thr=5.0, clampupper=True)
+    consumers_case("consumers_1024x24_a2", w=1024, h=24, N=1024, D=400, A=2, seed=1011)
     write_inis()
     print("golden fixtures written to", HERE)

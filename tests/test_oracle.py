@@ -197,3 +197,24 @@ def test_jet_table_in_the_cuda_sources_is_opencvs():
     assert tuple(tab[0]) == (128, 0, 0) and tuple(tab[255]) == (0, 0, 128)  # BGR: dark blue ... dark red
     img = np.array([[0, 128], [255, 7]], dtype=np.uint8)
     assert np.array_equal(colormap_jet(img), cv2.applyColorMap(img, cv2.COLORMAP_JET))
+
+
+def test_golden_consumers_regression():
+    """The committed consumer fixture (linear bscan, J0 lock-in display, JET images) against a fresh run of the vectorised oracle."""
+    from oracle.abcoct_oracle import colormap_jet, jlockin_display
+
+    z = np.load(os.path.join(GOLDEN, "consumers_1024x24_a2.npz"))
+    w, h, N, D, A, seed = [int(x) for x in z["params"]]
+    thr = float(z["thr"])
+    p = oracle_params(w=w, h=h, numfftpoints=N, numdisplaypoints=D, averages=A, lambdamin=840.5e-9, lambdamax=859.5e-9, bscanthreshold=thr)
+    o = Oracle(p, strict=False)
+    o.set_background(z["yb"])
+    _, _, jscan = o.process_bscans(z["jframes"], want_linear=True)
+    out8, _, lin = o.process_bscans(z["frames"], want_linear=True)
+    assert np.allclose(lin, z["lin"], rtol=2e-6, atol=0) and np.allclose(jscan[0], z["jscan"], rtol=2e-6, atol=0)
+    assert np.abs(out8.astype(int) - z["out8"].astype(int)).max() <= 1
+    # the J0 display and the colour mapping are functions of the stored images alone: exact
+    jsub = np.stack([jlockin_display(b.astype(np.float64), z["jscan"].astype(np.float64), thr) for b in z["lin"]])
+    assert np.abs(jsub.astype(int) - z["jsub"].astype(int)).max() <= 1 and (jsub != z["jsub"]).mean() < 1e-3
+    assert np.array_equal(colormap_jet(z["out8"]), z["bgr"]) and np.array_equal(colormap_jet(z["jsub"]), z["jbgr"])
+    assert z["jsub"].min() == 0 and z["jsub"].max() == 255

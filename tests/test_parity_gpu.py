@@ -53,6 +53,29 @@ def test_golden_synth(name):
     _check(out8, outdb, z["out8"], z["outdb"], name)
 
 
+def test_golden_consumers():
+    """Committed consumer fixture: linear bscan within 1e-4, JET images exact, the J0 display +-1 LSB on the fixture's own linear
+    images (stage parity) and statistically end to end."""
+    from fdoct_b200 import api
+    from oracle.abcoct_oracle import colormap_jet
+
+    z = np.load(os.path.join(GOLDEN, "consumers_1024x24_a2.npz"))
+    w, h, N, D, A, seed = [int(x) for x in z["params"]]
+    op = oracle_params(w=w, h=h, numfftpoints=N, numdisplaypoints=D, averages=A, lambdamin=840.5e-9, lambdamax=859.5e-9,
+                       bscanthreshold=float(z["thr"]))
+    with api.Context(abi_params(op)) as ctx:
+        ctx.set_background(z["yb"])
+        ctx.set_jscan(z["jscan"])  # the fixture's reference B-scan: the lock-in stage sees bit-identical inputs on its jscansave side
+        r = ctx.process_bscans_ex(z["frames"], want=tuple(api.OUTPUT_KINDS))
+    assert_display_parity(r["bscan_u8"], z["out8"], "consumers fixture")
+    assert mag_err(r["bscan_lin"][:, 2:].astype(np.float64) - 1e-5, z["lin"][:, 2:].astype(np.float64) - 1e-5) <= MAG_RTOL
+    assert np.array_equal(r["bscan_bgr"], colormap_jet(r["bscan_u8"])) and np.array_equal(r["jsub_bgr"], colormap_jet(r["jsub_u8"]))
+    same_px = r["bscan_u8"] == z["out8"]
+    assert np.array_equal(r["bscan_bgr"][same_px], z["bgr"][same_px])
+    d = np.abs(r["jsub_u8"].astype(np.int16) - z["jsub"].astype(np.int16))
+    assert (d > 1).mean() <= 0.01, f"{(d > 1).mean():.4f} of the lock-in pixels differ by more than 1 LSB from the fixture"
+
+
 # ------------------------------------------------------------------------------------------- live oracle
 CASES = [
     # w,    h,  N,    D,    A, nB, variant, extras
