@@ -683,13 +683,19 @@ void staging_copy(void* dst, const void* src, size_t bytes) {
   const size_t per = ((bytes + nt - 1) / nt + 63) & ~(size_t)63;
   std::vector<std::thread> th;
   th.reserve(nt - 1);
+  size_t done_to = std::min(per, bytes);  // [0, done_to) is copied by this thread, the rest by the helpers that could be started
   for (size_t t = 1; t < nt; ++t) {
     const size_t o = t * per;
     if (o >= bytes) break;
     const size_t n = std::min(per, bytes - o);
-    th.emplace_back([=] { memcpy(static_cast<char*>(dst) + o, static_cast<const char*>(src) + o, n); });
+    try {
+      th.emplace_back([=] { memcpy(static_cast<char*>(dst) + o, static_cast<const char*>(src) + o, n); });
+    } catch (...) {  // no thread to be had (resource limit): this thread takes the remainder, nothing crosses the C ABI
+      memcpy(static_cast<char*>(dst) + o, static_cast<const char*>(src) + o, bytes - o);
+      break;
+    }
   }
-  memcpy(dst, src, std::min(per, bytes));
+  memcpy(dst, src, done_to);
   for (std::thread& t : th) t.join();
 }
 
