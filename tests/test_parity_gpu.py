@@ -822,20 +822,34 @@ def test_random_configurations_against_oracle(seed):
     w, h, A, variant = c["w"], c["h"], c["A"], c["variant"]
     op = oracle_params(w=w, h=h, numfftpoints=c["N"], numdisplaypoints=c["D"], averages=A, variant=variant, lambdamin=840.5e-9,
                        lambdamax=859.5e-9, **c["extra"])
+    from fdoct_b200 import api
+
     frames = synth.make_frames(c["nB"] * A, w, h, seed=seed, dark=variant == 1)
+    dark_frames = synth.make_dark_frames(2, w, h, seed=seed + 2)
+    bg_frames = synth.make_background_frames(2, w, h, seed=seed + 1, dark=variant == 1)
     o = Oracle(op)
-    yd = None
-    if variant == 1:
-        yd = o.calib_capture(synth.make_dark_frames(2, w, h, seed=seed + 2))  # keys o / r: the same normalise branches as the frames
-        yr = o.calib_capture(synth.make_background_frames(2, w, h, seed=seed + 1, dark=True))
-        yb = dark_background(yr, yd, yd + 0.02 * (yr - yd))
-        o.set_dark(yd)
-    else:
-        yb = o.calib_capture(synth.make_background_frames(2, w, h, seed=seed + 1))  # key b
+    what = f"random config {c}"
+
+    def same(a, b):  # the library's host-side captures follow the reference's f64 arithmetic exactly
+        return np.abs(a - b).max() <= 1e-12 * np.abs(b).max()
+
+    with api.Context(abi_params(op)) as ctx:  # calibration through the capture entry points, like the reference's key presses
+        if variant == 1:
+            yd = o.calib_capture(dark_frames)  # keys o / r: the same normalise branches as the frames
+            yr = o.calib_capture(bg_frames)
+            yb = dark_background(yr, yd, yd + 0.02 * (yr - yd))
+            o.set_dark(yd)
+            ctx.set_calibration_from_frames(2, dark_frames)
+            ctx.set_calibration_from_frames(3, bg_frames)
+            assert same(ctx.get_calibration(2), yd) and same(ctx.get_calibration(3), yr), what
+            ctx.set_background(yb)
+        else:
+            yb = o.calib_capture(bg_frames)  # key b
+            ctx.set_calibration_from_frames(0, bg_frames)
+            assert same(ctx.get_calibration(0), yb), what
+        out8, outdb = ctx.process_bscans(np.ascontiguousarray(frames), want_db=True)
     o.set_background(yb)
     ref8, refdb = o.process_bscans(frames)
-    out8, outdb = _run_abi(op, frames, yb, yd=yd)
-    what = f"random config {c}"
     assert np.isfinite(outdb).all(), what
     assert_display_parity(out8, ref8, what)
     # The floor of the tolerance comes from the larger A-scan of each packed pair (util.mag_err_pairwise).
