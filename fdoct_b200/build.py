@@ -13,8 +13,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libabcoct.so")
-SOURCES = ["abcoct_kernels.cu", "prep_kernels.cu", "post_kernels.cu", "abcoct_api.cpp"]
-HEADERS = ["fft_regs.cuh", "fft_v.cuh", "plan.h", "recon_kernel.cuh", "recon2_kernel.cuh", "kernels.h",
+SOURCES = ["wrow_kernels.cu", "plans_large.cu", "plans_small.cu", "abcoct_kernels.cu", "prep_kernels.cu", "post_kernels.cu", "abcoct_api.cpp"]
+HEADERS = ["fft_regs.cuh", "plan.h", "recon_kernel.cuh", "wrow_kernel.cuh", "wrow_prims.cuh", "kernels.h", "plan_registry.cuh",
            os.path.join("..", "..", "include", "abcoct.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
@@ -71,15 +71,23 @@ def build(force: bool = False, verbose: bool = False) -> str:
         fcntl.flock(lock, fcntl.LOCK_EX)
         if not force and up_to_date():  # somebody else built it while we waited
             return LIB
-        objs = []
-        for s in SOURCES:
+        from concurrent.futures import ThreadPoolExecutor
+
+        def compile_one(s: str) -> str:  # the translation units are independent: one nvcc per core
             o = os.path.join(CSRC, s + ".o")
             cmd = [_nvcc(), *FLAGS, "-x", "cu", "-c", os.path.join(CSRC, s), "-o", o]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")
                 print(" ".join(cmd), flush=True)
-            subprocess.run(cmd, check=True)
-            objs.append(o)
+            r = subprocess.run(cmd, capture_output=True, text=True)
+            if verbose or r.returncode:
+                sys.stderr.write(r.stdout + r.stderr)
+            if r.returncode:
+                raise subprocess.CalledProcessError(r.returncode, cmd)
+            return o
+
+        with ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as pool:
+            objs = list(pool.map(compile_one, SOURCES))
         tmp = LIB + ".tmp.%d" % os.getpid()
         subprocess.run([_nvcc(), "-shared", *ARCH, "-o", tmp, *objs, "-lcudart_static", "-lpthread", "-ldl", "-lrt"], check=True)
         os.replace(tmp, LIB)
@@ -97,7 +105,7 @@ def build_native_test(name: str, out_dir: str | None = None) -> str:
     exe = os.path.join(out_dir, name)
     deps = [src] + [os.path.join(CSRC, h) for h in HEADERS + SOURCES]
     if _stale(exe, deps):
-        subprocess.run([_nvcc(), "-std=c++17", "-O2", *ARCH, "-o", exe, src], check=True)
+        subprocess.run([_nvcc(), "-std=c++17", "-O2", *ARCH, "-o", exe, src, "-lpthread"], check=True)
     return exe
 
 

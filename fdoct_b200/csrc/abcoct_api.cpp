@@ -26,6 +26,7 @@ thread_local std::string g_create_error;
 
 constexpr int kTimedChunks = 512;  // timing-event pool size (chunks timed between two abcoct_timing_reset calls)
 constexpr int kSlots = 3;  // pinned-ring depth per GPU (>= 3 streams per GPU)
+constexpr int kWrowDefaultWarps = 16;  // warps per CTA of the warp-per-A-scan kernel unless ABCOCT_WROW_NW says otherwise
 
 // the images one call can produce (abcoct_outputs), bytes per pixel of each
 enum { O_U8 = 0, O_DB, O_LIN, O_BGR, O_JSUB, O_JBGR, O_COUNT };
@@ -49,6 +50,7 @@ struct GpuState {
   unsigned char* d_tables = nullptr;
   float* d_gain = nullptr;
   float* d_subg = nullptr;
+  size_t cal_floats = 0;  // capacity of d_gain / d_subg
   // general pre-processing path (prep_kernels.cu): unswizzled f32 calibration, window, FFT twiddles, per-slot work buffers
   float *d_yb = nullptr, *d_yp = nullptr, *d_yd = nullptr, *d_win = nullptr;
   float2 *d_twW = nullptr, *d_twM = nullptr;
@@ -88,8 +90,11 @@ struct abcoct_ctx {
   bool have_yr = false, have_ys = false;
   bool have_yb = false, have_yp = false, have_yd = false, cal_dirty = true, has_sub = false;
   bool general = false;  // any optional pre-processing stage is on: frames go through prep_kernels.cu first
-  bool dual = false;     // the plan's dual-pair (packed f32x2) kernel is used (recon2_kernel.cuh)
-  std::vector<unsigned char> blob1, blob2;
+  // warp-per-A-scan kernel (wrow_kernel.cuh): eligible configurations and the plan in use (nullptr: recon_kernel.cuh)
+  bool wrow_eligible = false;
+  const WPlanEntry* wplan = nullptr;
+  std::vector<unsigned char> blob1, wblob;
+  const std::vector<unsigned char>* blob_loaded = nullptr;  // which blob d_tables holds
   std::vector<int> gidx;      // the kernel's remapped gather indices / weights (debug tap)
   std::vector<float> gwq;
   int px_bytes = 2;
@@ -350,30 +355,50 @@ int upload_calibration(abcoct_ctx* c) {
       CU(c, cudaMemcpy(g.d_yd, fd.data(), n * 4, cudaMemcpyHostToDevice));
     }
   }
-  {  // the kernel reads calibration rows in the bank-conflict-free layout (cal_phys in recon_kernel.cuh)
-    std::vector<float> tmp(c->opw);
-    for (int r = 0; r < c->oph; ++r) {
-      cal_swizzle_row(&gain[(size_t)r * c->opw], tmp.data(), c->opw);
-      std::copy(tmp.begin(), tmp.end(), gain.begin() + (size_t)r * c->opw);
-      cal_swizzle_row(&subg[(size_t)r * c->opw], tmp.data(), c->opw);
-      std::copy(tmp.begin(), tmp.end(), subg.begin() + (size_t)r * c->opw);
+  // which kernel: the warp-per-A-scan kernel wherever it applies (wrow_kernel.cuh); ABCOCT_KERNEL=1 forces the group-per-row-pair
+  // kernel (recon_kernel.cuh, the fallback for every other transform length and for the general path) for A/B measurements,
+  // ABCOCT_WROW_NW = 12 | 16 picks the occupancy point of the plan.
+  const WPlanEntry* wp = nullptr;
+  if (c->wrow_eligible) {
+    int force = 0, nw = 0;
+    if (const char* e = getenv("ABCOCT_KERNEL")) force = atoi(e);
+    if (const char* e = getenv("ABCOCT_WROW_NW")) nw = atoi(e);
+    if (force != 1) {
+      wp = nw ? find_wplan(c->N, nw) : nullptr;
+      if (!wp) wp = find_wplan(c->N, kWrowDefaultWarps);
     }
   }
-  for (GpuState& g : c->gpus) {
-    CU(c, cudaSetDevice(g.dev));
-    if (!g.d_gain) CU(c, cudaMalloc(&g.d_gain, n * 4));
-    if (!g.d_subg) CU(c, cudaMalloc(&g.d_subg, n * 4));
-    CU(c, cudaMemcpy(g.d_gain, gain.data(), n * 4, cudaMemcpyHostToDevice));
-    CU(c, cudaMemcpy(g.d_subg, subg.data(), n * 4, cudaMemcpyHostToDevice));
+  c->wplan = wp;
+  const size_t pitch = wp ? (size_t)wp->wmax : (size_t)c->opw;
+  {  // calibration rows in the layout the chosen kernel reads (wrow_permute_cal_row / cal_swizzle_row)
+    std::vector<float> pg((size_t)c->oph * pitch, 0.f), ps((size_t)c->oph * pitch, 0.f);
+    for (int r = 0; r < c->oph; ++r) {
+      if (wp) {
+        wp->permute_cal_row(&gain[(size_t)r * c->opw], c->opw, &pg[(size_t)r * pitch]);
+        wp->permute_cal_row(&subg[(size_t)r * c->opw], c->opw, &ps[(size_t)r * pitch]);
+      } else {
+        cal_swizzle_row(&gain[(size_t)r * c->opw], &pg[(size_t)r * pitch], c->opw);
+        cal_swizzle_row(&subg[(size_t)r * c->opw], &ps[(size_t)r * pitch], c->opw);
+      }
+    }
+    for (GpuState& g : c->gpus) {
+      CU(c, cudaSetDevice(g.dev));
+      CU(c, cudaDeviceSynchronize());  // no launch may still be reading the old calibration (async device entry point)
+      if (g.cal_floats < pg.size()) {
+        cudaFree(g.d_gain);
+        cudaFree(g.d_subg);
+        g.d_gain = g.d_subg = nullptr;
+        g.cal_floats = 0;
+        CU(c, cudaMalloc(&g.d_gain, pg.size() * 4));
+        CU(c, cudaMalloc(&g.d_subg, pg.size() * 4));
+        g.cal_floats = pg.size();
+      }
+      CU(c, cudaMemcpy(g.d_gain, pg.data(), pg.size() * 4, cudaMemcpyHostToDevice));
+      CU(c, cudaMemcpy(g.d_subg, ps.data(), ps.size() * 4, cudaMemcpyHostToDevice));
+    }
   }
-  // which kernel: the single-pair kernel is the product path.  The dual-pair (packed f32x2) variant issues 31 % fewer
-  // instructions but halves the warps per SM and measured 2-26 % slower on B200; it stays
-  // available for experiments with ABCOCT_KERNEL=2 where the plan has one (never for the general path).
-  bool dual = false;
-  if (const char* e = getenv("ABCOCT_KERNEL")) dual = atoi(e) == 2 && c->plan->groups2 != nullptr && !c->general;
-  if (dual != c->dual || c->gpus[0].d_tables == nullptr) {
-    c->dual = dual;
-    const std::vector<unsigned char>& blob = dual ? c->blob2 : c->blob1;
+  const std::vector<unsigned char>& blob = wp ? c->wblob : c->blob1;
+  if (c->blob_loaded != &blob || c->gpus[0].d_tables == nullptr) {
     for (GpuState& g : c->gpus) {
       CU(c, cudaSetDevice(g.dev));
       cudaFree(g.d_tables);
@@ -381,17 +406,24 @@ int upload_calibration(abcoct_ctx* c) {
       CU(c, cudaMalloc(&g.d_tables, blob.size()));
       CU(c, cudaMemcpy(g.d_tables, blob.data(), blob.size(), cudaMemcpyHostToDevice));
     }
+    c->blob_loaded = &blob;
   }
-  const int G = dual ? c->plan->groups2(c->has_sub) : c->plan->groups(c->has_sub);  // compile-time choice of the plan
-  c->G = G;
-  c->smem = dual ? c->plan->smem_bytes2(c->opw, c->has_sub, G) : c->plan->smem_bytes(c->general ? c->M : c->opw, c->has_sub, G);
-  if (c->smem > 227 * 1024) return fail(c, ABCOCT_ERR_UNSUPPORTED, "shared memory budget exceeded (%d bytes)", c->smem);
-  for (GpuState& g : c->gpus) {
-    CU(c, cudaSetDevice(g.dev));
-    if (dual)
-      CU(c, c->plan->attrs2(c->has_sub, c->A == 1, c->smem, &c->regs));
-    else
+  if (wp) {
+    c->G = wp->nw;
+    c->smem = wp->smem_bytes;
+    for (GpuState& g : c->gpus) {
+      CU(c, cudaSetDevice(g.dev));
+      CU(c, wp->attrs(c->has_sub, c->A == 1, c->D == c->N / 2, &c->regs));
+    }
+  } else {
+    const int G = c->plan->groups(c->has_sub);  // compile-time choice of the plan
+    c->G = G;
+    c->smem = c->plan->smem_bytes(c->general ? c->M : c->opw, c->has_sub, G);
+    if (c->smem > 227 * 1024) return fail(c, ABCOCT_ERR_UNSUPPORTED, "shared memory budget exceeded (%d bytes)", c->smem);
+    for (GpuState& g : c->gpus) {
+      CU(c, cudaSetDevice(g.dev));
       CU(c, c->plan->attrs(c->has_sub, c->A == 1, c->general, c->smem, &c->regs));
+    }
   }
   c->cal_dirty = false;
   return ABCOCT_OK;
@@ -582,6 +614,17 @@ int enqueue_device(abcoct_ctx* c, GpuState& g, int slot, const uint8_t* d_frames
     if ((size_t)a.npairs * nb > 0x7fff0000u) return fail(c, ABCOCT_ERR_INVALID, "too many A-scan pairs in one chunk");
     a.nitems = a.npairs * (int)nb;
     a.nparts = (c->oph + c->plan->d.T - 1) / c->plan->d.T;
+    int grid = 0;
+    if (c->wplan) {  // one item per row, normalisation parts of 32 A-scans split into depth-tile ranges for short launches
+      if ((size_t)c->oph * nb > 0x7fff0000u) return fail(c, ABCOCT_ERR_INVALID, "too many A-scans in one chunk");
+      a.nitems = c->oph * (int)nb;
+      a.nparts = (c->oph + 31) / 32;
+      a.calpitch = c->wplan->wmax;
+      grid = std::min(g.sm_count, (a.nitems + c->wplan->nw - 1) / c->wplan->nw);
+      const int ntiles = (c->D + 31) / 32;
+      const long long warps = (long long)grid * c->wplan->nw, parts = (long long)a.nparts * (long long)nb;
+      a.nsplit = (int)std::max<long long>(1, std::min<long long>(ntiles, warps / parts));
+    }
     a.gain = g.d_gain;
     a.subg = g.d_subg;
     a.idxT = reinterpret_cast<const uint32_t*>(g.d_tables);
@@ -596,13 +639,12 @@ int enqueue_device(abcoct_ctx* c, GpuState& g, int slot, const uint8_t* d_frames
     a.thr = (float)c->p.bscanthreshold;
     a.clamp_db = (float)c->p.clamp_db;
     a.clamp55 = c->p.clampupper ? 1 : 0;
-    const int work = c->dual ? (a.nitems + 1) / 2 : a.nitems;  // the dual-pair kernel takes two items per ticket
-    const int grid = std::min(g.sm_count, (work + c->G - 1) / c->G);
+    if (!c->wplan) grid = std::min(g.sm_count, (a.nitems + c->G - 1) / c->G);
     CU(c, launch_sched_init(a.sched, (int)nb, st));
     const bool timed = time_it && g.tev_used + 3 <= g.tev.size();
     if (timed) CU(c, cudaEventRecord(g.tev[g.tev_used], st));
-    if (c->dual)
-      CU(c, c->plan->launch2(a, c->has_sub, grid, st));
+    if (c->wplan)
+      CU(c, c->wplan->launch(a, c->has_sub, grid, st));
     else
       CU(c, c->plan->launch(a, c->has_sub, c->general, grid, st));
     if (timed) {
@@ -865,7 +907,17 @@ int abcoct_create(const abcoct_params* params, const int* gpu_ids, int ngpu, abc
     c->plan->build_blob(c->M, idx.data(), wq.data(), zero.data(), blob);
   } else {
     c->plan->build_blob(c->opw, idx.data(), wq.data(), winf.data(), blob);
-    if (c->plan->build_blob2) c->plan->build_blob2(c->opw, idx.data(), wq.data(), winf.data(), c->blob2);
+  }
+  // warp-per-A-scan kernel: 16-bit frames straight into the transform (no optional pre-processing stage), the reference's
+  // source-indexed resampling weight (BscanFFT.cpp:1170), a transform length it has a plan for, and no gather from sample 0
+  // (whose slope the reference copies from sample 1, :1161 - the fallback kernel handles that corner)
+  c->wrow_eligible = !c->general && params->weight_mode == 0 && params->bpp == 16 && find_wplan(c->N, kWrowDefaultWarps) != nullptr;
+  for (int q = 1; q + 1 < c->N && c->wrow_eligible; ++q) c->wrow_eligible = c->nk[q] >= 1 && c->nk[q] < c->opw;
+  if (c->wrow_eligible) {
+    std::vector<int> widx(c->N);
+    for (int q = 0; q < c->N; ++q) widx[q] = (q == 0 || q == c->N - 1) ? -1 : c->nk[q];
+    WrowTablesHost wt{c->opw, widx.data(), c->frac.data(), c->win.data()};
+    find_wplan(c->N, kWrowDefaultWarps)->build_blob(wt, c->wblob);  // the blob does not depend on the warps per CTA
   }
   std::vector<float2> twW, twM;
   if (params->fft_multiplier > 1) {
@@ -1371,10 +1423,10 @@ int abcoct_get_info(const abcoct_ctx* c, abcoct_info* o) {
   o->N = c->N;
   o->D = c->D;
   o->averages = c->A;
-  o->fft_threads = c->plan->d.T;
-  o->fft_radix[0] = c->plan->d.R0;
-  o->fft_radix[1] = c->plan->d.R1;
-  o->fft_radix[2] = c->plan->d.RL;
+  o->fft_threads = c->wplan ? 32 : c->plan->d.T;
+  o->fft_radix[0] = c->wplan ? c->wplan->R : c->plan->d.R0;
+  o->fft_radix[1] = c->wplan ? 1 : c->plan->d.R1;
+  o->fft_radix[2] = c->wplan ? 32 : c->plan->d.RL;
   o->groups_per_cta = c->G;
   o->ctas_per_sm = 1;
   o->smem_bytes = c->smem;

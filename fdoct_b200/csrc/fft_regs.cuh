@@ -68,8 +68,51 @@ __host__ __device__ constexpr CtCS ct_cossin(long long num, long long den) {
 }
 
 // ---------------------------------------------------------------- complex helpers
-__host__ __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-__host__ __device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// The re / im pair of ONE complex value is an aligned 64-bit register pair, so complex add / sub / scale are single packed
+// sm_100 instructions (add / sub / mul / fma .f32x2 -> SASS FADD2 / FMUL2 / FFMA2, which also take a broadcast immediate):
+// they halve the issue slots of the butterflies without needing any extra registers.
+typedef unsigned long long abc_u64;
+__host__ __device__ __forceinline__ float2 pk_add(float2 a, float2 b) {
+#ifdef __CUDA_ARCH__
+  float2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<abc_u64*>(&r)) : "l"(*reinterpret_cast<abc_u64*>(&a)), "l"(*reinterpret_cast<abc_u64*>(&b)));
+  return r;
+#else
+  return make_float2(a.x + b.x, a.y + b.y);
+#endif
+}
+__host__ __device__ __forceinline__ float2 pk_sub(float2 a, float2 b) {
+#ifdef __CUDA_ARCH__
+  float2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<abc_u64*>(&r)) : "l"(*reinterpret_cast<abc_u64*>(&a)), "l"(*reinterpret_cast<abc_u64*>(&b)));
+  return r;
+#else
+  return make_float2(a.x - b.x, a.y - b.y);
+#endif
+}
+__host__ __device__ __forceinline__ float2 pk_mul(float2 a, float2 b) {
+#ifdef __CUDA_ARCH__
+  float2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(*reinterpret_cast<abc_u64*>(&r)) : "l"(*reinterpret_cast<abc_u64*>(&a)), "l"(*reinterpret_cast<abc_u64*>(&b)));
+  return r;
+#else
+  return make_float2(a.x * b.x, a.y * b.y);
+#endif
+}
+__host__ __device__ __forceinline__ float2 pk_fma(float2 a, float2 b, float2 c) {
+#ifdef __CUDA_ARCH__
+  float2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(*reinterpret_cast<abc_u64*>(&r))
+      : "l"(*reinterpret_cast<abc_u64*>(&a)), "l"(*reinterpret_cast<abc_u64*>(&b)), "l"(*reinterpret_cast<abc_u64*>(&c)));
+  return r;
+#else
+  return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
+}
+__host__ __device__ __forceinline__ float2 pk_scale(float2 a, float s) { return pk_mul(a, make_float2(s, s)); }
+__host__ __device__ __forceinline__ float2 cadd(float2 a, float2 b) { return pk_add(a, b); }
+__host__ __device__ __forceinline__ float2 csub(float2 a, float2 b) { return pk_sub(a, b); }
 __host__ __device__ __forceinline__ float2 cmul(float2 a, float2 w) {
   return make_float2(fmaf(-a.y, w.y, a.x * w.x), fmaf(a.y, w.x, a.x * w.y));
 }
@@ -104,9 +147,10 @@ __host__ __device__ __forceinline__ float2 mul_w(float2 z) {
       constexpr bool cp = cs.c > 0, sp = (SGN > 0 ? cs.s : -cs.s) > 0;
       float re = (cp ? z.x : -z.x) - (sp ? z.y : -z.y);
       float im = (sp ? z.x : -z.x) + (cp ? z.y : -z.y);
-      return make_float2(h * re, h * im);
+      return pk_scale(make_float2(re, im), h);
     } else {
-      return make_float2(fmaf(-s, z.y, c * z.x), fmaf(s, z.x, c * z.y));
+      const float2 t = pk_scale(z, c);
+      return make_float2(fmaf(-s, z.y, t.x), fmaf(s, z.x, t.y));
     }
   }
 }
@@ -184,8 +228,8 @@ struct Dft<3, SGN, IS, OS> {
     constexpr float kS = 0.86602540378443864676f;  // sin(2 pi / 3)
     float2 a0 = in[0], a1 = in[IS], a2 = in[2 * IS];
     float2 s = cadd(a1, a2), d = csub(a1, a2);
-    float2 m = make_float2(fmaf(-0.5f, s.x, a0.x), fmaf(-0.5f, s.y, a0.y));
-    float2 r = mul_i<SGN>(make_float2(kS * d.x, kS * d.y));
+    float2 m = pk_fma(s, make_float2(-0.5f, -0.5f), a0);
+    float2 r = mul_i<SGN>(pk_scale(d, kS));
     out[0] = cadd(a0, s);
     out[OS] = cadd(m, r);
     out[2 * OS] = csub(m, r);
@@ -201,11 +245,11 @@ struct Dft<5, SGN, IS, OS> {
     constexpr float s2 = 0.58778525229247312917f;   // sin(4 pi / 5)
     float2 a0 = in[0], a1 = in[IS], a2 = in[2 * IS], a3 = in[3 * IS], a4 = in[4 * IS];
     float2 p1 = cadd(a1, a4), p2 = cadd(a2, a3), d1 = csub(a1, a4), d2 = csub(a2, a3);
-    float2 m1 = make_float2(fmaf(c2, p2.x, fmaf(c1, p1.x, a0.x)), fmaf(c2, p2.y, fmaf(c1, p1.y, a0.y)));
-    float2 m2 = make_float2(fmaf(c1, p2.x, fmaf(c2, p1.x, a0.x)), fmaf(c1, p2.y, fmaf(c2, p1.y, a0.y)));
-    float2 r1 = mul_i<SGN>(make_float2(fmaf(s2, d2.x, s1 * d1.x), fmaf(s2, d2.y, s1 * d1.y)));
-    float2 r2 = mul_i<SGN>(make_float2(fmaf(-s1, d2.x, s2 * d1.x), fmaf(-s1, d2.y, s2 * d1.y)));
-    out[0] = make_float2(a0.x + p1.x + p2.x, a0.y + p1.y + p2.y);
+    float2 m1 = pk_fma(p2, make_float2(c2, c2), pk_fma(p1, make_float2(c1, c1), a0));
+    float2 m2 = pk_fma(p2, make_float2(c1, c1), pk_fma(p1, make_float2(c2, c2), a0));
+    float2 r1 = mul_i<SGN>(pk_fma(d2, make_float2(s2, s2), pk_scale(d1, s1)));
+    float2 r2 = mul_i<SGN>(pk_fma(d2, make_float2(-s1, -s1), pk_scale(d1, s2)));
+    out[0] = cadd(cadd(a0, p1), p2);
     out[OS] = cadd(m1, r1);
     out[4 * OS] = csub(m1, r1);
     out[2 * OS] = cadd(m2, r2);

@@ -7,7 +7,7 @@
 
 #include "plan.h"
 #include "recon_kernel.cuh"
-#include "recon2_kernel.cuh"
+#include "wrow_kernel.cuh"
 
 namespace abcoct {
 
@@ -24,13 +24,17 @@ struct PlanEntry {
   // in_f32: the frames are pre-processed f32 rows from the general path (no calibration, no prefetch); picks the averages == 1 variant itself
   cudaError_t (*launch)(const ReconArgs& a, bool has_sub, bool in_f32, int grid, cudaStream_t st);
   cudaError_t (*attrs)(bool has_sub, bool a1, bool in_f32, int smem, int* regs);  // opt in to large smem, report registers/thread
-  // dual-pair (packed f32x2) variant, recon2_kernel.cuh; groups2 == nullptr when the plan has none
-  int (*groups2)(bool has_sub);
-  int (*smem_bytes2)(int W, bool has_sub, int G);
-  void (*build_blob2)(int W, const int* idx, const float* wq, const float* win, std::vector<unsigned char>& blob);
-  cudaError_t (*launch2)(const ReconArgs& a, bool has_sub, int grid, cudaStream_t st);
-  cudaError_t (*attrs2)(bool has_sub, bool a1, int smem, int* regs);
 };
+
+// One compiled plan of the warp-per-A-scan kernel (wrow_kernel.cuh).
+struct WPlanEntry {
+  int N, R, nw, wmax, smem_bytes;
+  void (*build_blob)(const WrowTablesHost& t, std::vector<unsigned char>& blob);
+  void (*permute_cal_row)(const float* in, int W, float* out);  // one calibration row into the kernel's layout (wmax floats)
+  cudaError_t (*launch)(const ReconArgs& a, bool has_sub, int grid, cudaStream_t st);  // picks A1 / FULLD from the arguments
+  cudaError_t (*attrs)(bool has_sub, bool a1, bool fulld, int* regs);
+};
+const WPlanEntry* find_wplan(int N, int nw);
 
 const PlanEntry* find_plan(int N);
 int list_plans(int* out, int cap);

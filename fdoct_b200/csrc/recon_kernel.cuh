@@ -62,6 +62,9 @@ struct ReconArgs {
   float thr;        // bscanthreshold
   float clamp_db;   // value forced into element (5,5) when clampupper
   int clamp55;      // clampupper: element (5,5) is excluded from the min/max of the data
+  // warp-per-A-scan kernel (wrow_kernel.cuh) only
+  int calpitch;     // floats per calibration row in its permuted layout
+  int nsplit;       // depth-tile ranges a normalisation part is split into (small launches: more, shorter jobs)
 };
 
 // Scheduler / per-B-scan state in global memory (ints): [0] item ticket, then nB each of

@@ -1,0 +1,608 @@
+// Warp-per-A-scan fused reconstruction kernel (sm_100a): the whole block BscanFFT.cpp:987-1255 in one launch, one WARP per
+// camera row, no block-level barrier anywhere on the path.
+//
+// Why this shape (round-2 analysis): the round-1 kernel (recon_kernel.cuh: 128 threads per packed row
+// pair, three FFT passes, two shared-memory exchanges, group barriers) was bound by the SM's L1 / shared-memory data pipe
+// (70 % busy at 58 % issue utilisation, 1130 wavefronts per A-scan) and by barrier / short-scoreboard stalls.  Here
+//   * a real row of N samples is ONE N/2-point complex transform (z[j] = x[2j] + i x[2j+1]) plus a split step, so a warp holds
+//     the whole transform in registers (N/64 complex values per lane) and needs TWO in-register radix passes with ONE exchange
+//     through shared memory (__syncwarp only); every row has its own f32 noise floor (no two-for-one packing of different rows);
+//   * the reference's resampling weight is indexed by the SOURCE sample (BscanFFT.cpp:1170: fractionalk.at(nearestkindex)), so
+//     y[i] + w[i] (y[i] - y[i-1]) depends on i only: it is evaluated once per source sample before staging and the
+//     lambda -> k resampling itself becomes a pure 4-byte gather with one offset table (no weights, no second tap);
+//   * the row mean (BscanFFT.cpp:1135-1139) is a warp-shuffle reduction over samples that never leave the registers;
+//   * calibration rows are read straight from L2 into registers (no shared-memory staging), raw pixel rows are pulled into L2
+//     ahead of time by the TMA unit (cp.async.bulk.prefetch.L2), re / im pairs are processed with the packed f32x2
+//     instructions (fft_regs.cuh).
+// Per A-scan this is ~2.0 k warp instructions and ~0.75 k data-pipe wavefronts against 3.7 k / 1.13 k before.
+//
+// Data flow of one row (W samples, N-point transform, R = N / 64 values per lane in pass A):
+//   pre   : 8-sample runs (run = lane + 32 j): u16 -> f32, t = y * gain - subg (one FFMA; BscanFFT.cpp:987, 1132,
+//           BscanDark.cpp:1269), warp sum -> mean, s = t - mean, v[i] = P[i] s[i] - Q[i] s[i-1] with P = (1 + F) win[i],
+//           Q = F win[i-1] (window BscanFFT.cpp:1141 and resampling weight :1169-1171 folded), staged as two planes (even /
+//           odd samples) so that the stride-2 gather below is bank-conflict free;
+//   pass A: lane b gathers x[q] = v[nearestkindex[q]], q = 2 (b + 32 a) + {0, 1}, a < R, radix-R DFT over a, twiddle w^(b c);
+//   xchg  : [c / 2][b][c % 2] float2, 16-byte stores, 8-byte loads, row pitch 33 * 16 bytes;
+//   pass B: lane c < R: radix-32 DFT over b -> Z[c + R d], d < 32;
+//   split : X[k] = (A + B) / 2, X[N/2 - k] = conj(A - B) / 2 with A = Z[k] + conj Z[N/2 - k], B = -i w_N^k (Z[k] - conj Z[N/2 - k]);
+//           the partner values come from lane R - c by warp shuffle; magnitudes (BscanFFT.cpp:1189-1190), accumulation over
+//           `averages` frames in registers (:1193-1209);
+//   final : /A, + 1e-5, ln -> dB (2.303), DC-row mask (:1221-1240) -> f32 row in the L2 scratch, min / max by CREDUX;
+//   norm  : when a B-scan is complete its jobs (32 A-scans x a range of 32-bin tiles) are picked up by the warps: threshold,
+//           global min-max normalise, round-half-even to u8 (:1243-1255), transposed 32-byte-sector stores, scratch lines dropped.
+#pragma once
+#include <cstdint>
+#include <cstring>
+
+#include "fft_regs.cuh"
+#include "plan.h"
+#include "recon_kernel.cuh"
+#include "wrow_prims.cuh"
+
+namespace abcoct {
+
+template <int N_, int NW_>
+struct WPlan {
+  static constexpr int N = N_, N2 = N_ / 2, R = N_ / 64, NW = NW_;
+  static_assert(N_ % 128 == 0 && R <= 32 && R >= 8, "N must be 128 * even, 512 <= N <= 2048");
+  static constexpr int NCH = (N / 8 + 31) / 32;  // 8-sample runs per lane
+  static constexpr int WMAX = NCH * 256;         // padded row length (calibration pitch, staging planes)
+  static constexpr int PO = WMAX / 2 + 4;        // word offset of the odd-sample plane; words [WMAX/2, WMAX/2 + 4) stay zero
+  static constexpr int STAGE_BYTES = (PO + WMAX / 2) * 4;
+  static constexpr int XPITCH = 33 * 16;  // exchange rows: 32 lanes x 16 bytes + 16 bytes of padding (conflict-free 8-byte reads)
+  static constexpr int XCH_BYTES = (R / 2) * XPITCH;
+  static constexpr int WBUF = ((cmax(STAGE_BYTES, XCH_BYTES) + 15) / 16) * 16;
+  // table blob = shared-memory image (bytes)
+  static constexpr int T_OFFS = 0;                          // uint4 [R/2][32]: byte offsets of the 4 samples of a = 2 a2, 2 a2 + 1
+  static constexpr int T_PQ = T_OFFS + (R / 2) * 32 * 16;   // float4 [NCH][4][32]: P[0..3], P[4..7], Q[0..3], Q[4..7] of a run
+  static constexpr int T_TWA = T_PQ + NCH * 4 * 32 * 16;    // float4 [R/2][32]: w^(b 2p), w^(b (2p+1))
+  static constexpr int T_TWP = T_TWA + (R / 2) * 32 * 16;   // float4 [8][32]: T[c + R 2 d2], T[c + R (2 d2 + 1)]
+  static constexpr int TABLE_BYTES = T_TWP + 8 * 32 * 16;
+  static constexpr int SMEM_BYTES = TABLE_BYTES + NW * WBUF;
+  static constexpr int ZERO_OFF = (WMAX / 2) * 4;  // byte offset of the zero sentinel inside a warp buffer
+};
+
+// byte offset of staged sample i inside a warp buffer (two planes: even samples, then odd samples)
+template <class WP>
+__host__ __device__ constexpr int wrow_stage_off(int i) {
+  return 4 * ((i & 1) ? WP::PO + (i >> 1) : (i >> 1));
+}
+
+struct WrowTablesHost {  // inputs of the blob builder (host)
+  int W;
+  const int* idx;     // N gather indices: source sample of output q, or -1 for "never written" (q = 0, N - 1: zero)
+  const double* frac;  // fractionalk (BscanFFT.cpp:692-698), indexed by SOURCE sample (the reference's quirk), >= W entries
+  const double* win;   // W window values
+};
+
+template <class WP>
+inline void wrow_build_blob(const WrowTablesHost& t, unsigned char* blob /* WP::TABLE_BYTES, zeroed by the caller */) {
+  constexpr int R = WP::R;
+  uint32_t* offs = reinterpret_cast<uint32_t*>(blob + WP::T_OFFS);
+  float* pq = reinterpret_cast<float*>(blob + WP::T_PQ);
+  float* twa = reinterpret_cast<float*>(blob + WP::T_TWA);
+  float* twp = reinterpret_cast<float*>(blob + WP::T_TWP);
+  auto off_of = [&](int q) -> uint32_t {
+    const int i = t.idx[q];
+    return i < 0 ? (uint32_t)WP::ZERO_OFF : (uint32_t)wrow_stage_off<WP>(i);
+  };
+  for (int a2 = 0; a2 < R / 2; ++a2)
+    for (int b = 0; b < 32; ++b) {
+      uint32_t* o = offs + (a2 * 32 + b) * 4;
+      const int q0 = 2 * (b + 32 * (2 * a2)), q1 = 2 * (b + 32 * (2 * a2 + 1));
+      o[0] = off_of(q0);
+      o[1] = off_of(q0 + 1);
+      o[2] = off_of(q1);
+      o[3] = off_of(q1 + 1);
+    }
+  for (int j = 0; j < WP::NCH; ++j)
+    for (int lane = 0; lane < 32; ++lane)
+      for (int e = 0; e < 8; ++e) {
+        const int i = 8 * (lane + 32 * j) + e;
+        double P = 0.0, Q = 0.0;
+        if (i >= 1 && i < t.W) {  // v[i] = y[i] + F[i] (y[i] - y[i-1]) on the apodised samples y = s * win
+          P = (1.0 + t.frac[i]) * t.win[i];
+          Q = t.frac[i] * t.win[i - 1];
+        }
+        pq[((j * 4 + (e >> 2)) * 32 + lane) * 4 + (e & 3)] = (float)P;
+        pq[((j * 4 + 2 + (e >> 2)) * 32 + lane) * 4 + (e & 3)] = (float)Q;
+      }
+  const double tau = 6.283185307179586476925286766559;
+  for (int p = 0; p < R / 2; ++p)
+    for (int b = 0; b < 32; ++b)
+      for (int h = 0; h < 2; ++h) {
+        const long long num = ((long long)b * (2 * p + h)) % WP::N2;
+        const double ang = tau * (double)num / (double)WP::N2;
+        twa[(p * 32 + b) * 4 + 2 * h] = (float)std::cos(ang);
+        twa[(p * 32 + b) * 4 + 2 * h + 1] = (float)(kFftSign * std::sin(ang));
+      }
+  for (int d2 = 0; d2 < 8; ++d2)
+    for (int c = 0; c < R; ++c)
+      for (int h = 0; h < 2; ++h) {
+        const int k = c + R * (2 * d2 + h);
+        const double ang = tau * (double)k / (double)WP::N;
+        // T_k = -i w_N^k (kFftSign = +1): sin - i cos;  for the forward sign it would be +i w^-k
+        twp[(d2 * 32 + c) * 4 + 2 * h] = (float)std::sin(ang);
+        twp[(d2 * 32 + c) * 4 + 2 * h + 1] = (float)(-kFftSign * std::cos(ang));
+      }
+}
+
+// calibration rows as the kernel reads them: [row][j][h][lane][4] floats, pitch WP::WMAX (zeros beyond W)
+template <class WP>
+inline void wrow_permute_cal_row(const float* in, int W, float* out /* WP::WMAX */) {
+  for (int j = 0; j < WP::NCH; ++j)
+    for (int h = 0; h < 2; ++h)
+      for (int lane = 0; lane < 32; ++lane)
+        for (int e = 0; e < 4; ++e) {
+          const int i = 8 * (lane + 32 * j) + 4 * h + e;
+          out[((2 * j + h) * 32 + lane) * 4 + e] = i < W ? in[i] : 0.f;
+        }
+}
+
+// ------------------------------------------------------------------------------------------------- normalisation job
+// One job: A-scans [32 part, 32 part + 32) of B-scan b, tiles [t0, t1) of 32 depth bins.  Lane (q = lane / 4, cg = lane % 4)
+// loads the rows 4 q .. 4 q + 3 at the bin quads cg and cg + 4 of the tile (16-byte L2 loads, 64 contiguous bytes per row and
+// instruction) and packs the four rows of a bin into one 32-bit word, so that the eight lanes of a bin quad write one full
+// 32-byte sector of the depth-major display image per bin - no shared-memory transposition.
+template <class WP>
+WROW_HD void wrow_normalise(const ReconArgs& a, const SchedView& sv, int job) {
+  const int lane = w_lane();
+  const int per_b = a.nparts * a.nsplit;
+  const int b = job / per_b;
+  const int rem = job - b * per_b;
+  const int part = rem / a.nsplit, split = rem - part * a.nsplit;
+  const int r0 = part * 32;
+  const int nrows = (a.oph - r0) < 32 ? (a.oph - r0) : 32;
+  const int ntiles = (a.D + 31) >> 5;
+  const int tps = (ntiles + a.nsplit - 1) / a.nsplit;
+  const int t0 = split * tps;
+  const int t1 = (t0 + tps) < ntiles ? (t0 + tps) : ntiles;
+  if (t0 >= t1) return;
+
+  float mn = ordered_to_float(w_ld_cg_i(sv.minv + b)), mx = ordered_to_float(w_ld_cg_i(sv.maxv + b));
+  if (a.clamp55) {  // bscandisp.at<double>(5,5) = 50.0 before the min-max (BscanFFT.cpp:1248-1253)
+    mn = fminf(mn, a.clamp_db);
+    mx = fmaxf(mx, a.clamp_db);
+  }
+  const float range = mx - mn;
+  const float sc = range > 2.220446049250313e-16f ? 255.0f / range : 0.f;  // cv::normalize: scale = 0 for a flat image
+  const float thr = a.thr;
+  const int q = lane >> 2, cg = lane & 3;
+  const float* src = a.scratch + ((size_t)b * a.oph + r0) * a.Dp;
+  unsigned valid = 0;
+  const float* rowp[4];
+#pragma unroll
+  for (int rr = 0; rr < 4; ++rr) {
+    const int row = 4 * q + rr;
+    const bool ok = row < nrows;
+    rowp[rr] = src + (size_t)(ok ? row : 0) * a.Dp + 4 * cg;
+    valid |= ok ? (1u << rr) : 0u;
+  }
+  const bool has55 = a.clamp55 && part == 0 && nrows > 5;
+  const bool word_ok = (a.oph & 3) == 0 && valid == 0xfu && (reinterpret_cast<uintptr_t>(a.out8) & 3) == 0;
+  const bool db_vec_ok = a.outdb != nullptr && (a.oph & 3) == 0 && valid == 0xfu && (reinterpret_cast<uintptr_t>(a.outdb) & 15) == 0;
+
+  auto load_tile = [&](int t, float4 (&v)[2][4]) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k)
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr)
+        v[k][rr] = ((valid >> rr) & 1u) ? w_ld_cg16(rowp[rr] + 32 * t + 16 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  auto quant = [&](float x) -> unsigned {
+    // round-half-even of (max(x, thr) - mn) * 255 / (mx - mn) in [0, 255]: 1.5 * 2^23 trick, result in the low byte
+    float r = fmaf(fmaxf(x, thr) - mn, sc, 12582912.0f);
+    unsigned u;
+    memcpy(&u, &r, 4);
+    return u;
+  };
+  auto pack4 = [&](float x0, float x1, float x2, float x3) -> unsigned {
+    const unsigned lo = w_byte_perm(quant(x0), quant(x1), 0x0040);  // bytes: x0, x1
+    const unsigned hi = w_byte_perm(quant(x2), quant(x3), 0x0040);
+    return w_byte_perm(lo, hi, 0x5410);
+  };
+  auto process_tile = [&](int t, float4 (&v)[2][4]) {
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      const int bin0 = 32 * t + 16 * k + 4 * cg;
+      const float col[4][4] = {{v[k][0].x, v[k][1].x, v[k][2].x, v[k][3].x}, {v[k][0].y, v[k][1].y, v[k][2].y, v[k][3].y},
+                               {v[k][0].z, v[k][1].z, v[k][2].z, v[k][3].z}, {v[k][0].w, v[k][1].w, v[k][2].w, v[k][3].w}};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int bin = bin0 + j;
+        if (bin < a.D) {
+          unsigned word = pack4(col[j][0], col[j][1], col[j][2], col[j][3]);
+          if (has55 && bin == 5 && q == 1)  // element (5,5): row 5 = byte 1 of the quad 4..7
+            word = (word & 0xffff00ffu) | ((quant(a.clamp_db) & 0xffu) << 8);
+          uint8_t* o = a.out8 + ((size_t)b * a.D + bin) * a.oph + r0 + 4 * q;
+          if (word_ok) {
+            w_st_stream_u32(o, word);
+          } else {
+#pragma unroll
+            for (int rr = 0; rr < 4; ++rr)
+              if ((valid >> rr) & 1u) o[rr] = (uint8_t)((word >> (8 * rr)) & 0xffu);
+          }
+          if (a.outdb != nullptr) {  // transposed dB image (rarely requested)
+            float* od = a.outdb + ((size_t)b * a.D + bin) * a.oph + r0 + 4 * q;
+            if (db_vec_ok) {
+              w_st_stream_f4(od, make_float4(col[j][0], col[j][1], col[j][2], col[j][3]));
+            } else {
+#pragma unroll
+              for (int rr = 0; rr < 4; ++rr)
+                if ((valid >> rr) & 1u) od[rr] = col[j][rr];
+            }
+          }
+        }
+      }
+    }
+    w_syncwarp();  // every lane has consumed its loads of this tile: the lines are dead, drop them from L2 without a write-back
+    if (lane < nrows) w_discard128(src + (size_t)lane * a.Dp + 32 * t);
+  };
+
+  float4 va[2][4], vb[2][4];
+  load_tile(t0, va);
+  for (int t = t0; t < t1; t += 2) {
+    if (t + 1 < t1) load_tile(t + 1, vb);
+    process_tile(t, va);
+    if (t + 1 < t1) {
+      if (t + 2 < t1) load_tile(t + 2, va);
+      process_tile(t + 1, vb);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------- the kernel body
+constexpr unsigned long long kWrowWatchdogNs = 20ull * 1000 * 1000 * 1000;
+
+template <class WP, bool HAS_SUB, bool A1, bool FULLD>
+WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
+  constexpr int R = WP::R, NCH = WP::NCH, N2 = WP::N2;
+  const int lane = w_lane(), warp = w_warp_in_cta();
+  {  // tables: global (L2-resident) -> shared, once per persistent CTA
+    const uint4* src = reinterpret_cast<const uint4*>(a.idxT);
+    uint4* dst = reinterpret_cast<uint4*>(smem);
+    for (int i = warp * 32 + lane; i < WP::TABLE_BYTES / 16; i += WP::NW * 32) dst[i] = src[i];
+  }
+  w_syncthreads();
+  const uint4* t_offs = reinterpret_cast<const uint4*>(smem + WP::T_OFFS);
+  const float4* t_pq = reinterpret_cast<const float4*>(smem + WP::T_PQ);
+  const float4* t_twa = reinterpret_cast<const float4*>(smem + WP::T_TWA);
+  const float4* t_twp = reinterpret_cast<const float4*>(smem + WP::T_TWP);
+  unsigned char* const wbuf = smem + WP::TABLE_BYTES + warp * WP::WBUF;
+  const WPolicies pol = w_make_policies();
+  const SchedView sv = sched_view(a.sched, a.nB);
+  const int W8 = a.W >> 3;
+  const unsigned rowbytes = (unsigned)a.W * 2u;
+
+  const int nwarps = w_ncta() * WP::NW;
+  const int njobs = a.nB * a.nparts * a.nsplit;
+  const int per_b = a.nparts * a.nsplit;
+  int myjob = w_cta() * WP::NW + warp;  // normalisation jobs are assigned statically: myjob, myjob + nwarps, ...
+
+  auto row_ptr = [&](int b, int row, int f) -> const uint8_t* {
+    return a.frames + ((size_t)b * a.A + f) * a.frame_stride + (size_t)row * a.row_stride;
+  };
+  auto claim = [&]() -> int {  // dynamic schedule: one ticket = one row of one B-scan
+    int t = 0;
+    if (lane == 0) t = w_atomic_add(sv.ticket, 1);
+    return t;
+  };
+
+  // partner lane of the split step and the validity of this lane's outputs
+  const int pl = (lane == 0 || lane >= R) ? lane : R - lane;
+  const bool lane_ok = (R == 32) || lane < R;
+  const int cc = (R == 32) ? lane : (lane < R ? lane : R - 1);
+
+  // pending completion counts (lane 0): published in batches of two so that the gpu-scope fence is paid every other row
+  int pend0 = -1;
+  int cache_b = -1;
+  float cache_mn = 0.f, cache_mx = 0.f;
+
+  int tk = w_shfl_i(claim(), 0);
+  if (tk < a.nitems && lane == 0) {
+    const int b = tk / a.oph;
+    w_prefetch_l2(row_ptr(b, tk - b * a.oph, 0), rowbytes);
+  }
+
+  float acc1[16], acc2[16];
+  if constexpr (!A1) {
+#pragma unroll
+    for (int d = 0; d < 16; ++d) acc1[d] = acc2[d] = 0.f;
+  }
+
+  while (tk < a.nitems) {
+    const int bscan = tk / a.oph;
+    const int row = tk - bscan * a.oph;
+    const int tn_raw = claim();  // the next item; consumed (broadcast) in the middle of the first frame
+    int tn = 0;
+    int polled = 0;
+    if (lane == 0 && myjob < njobs) polled = w_ld_relaxed(sv.cnt + myjob / per_b);
+    const float* gp = a.gain + (size_t)row * a.calpitch + 4 * lane;
+    const float* sp = HAS_SUB ? a.subg + (size_t)row * a.calpitch + 4 * lane : nullptr;
+
+    const int nA = A1 ? 1 : a.A;
+    for (int f = 0; f < nA; ++f) {
+      const bool last = A1 || (f + 1 == nA);
+      // ---------------------------------------------------------------- pre: pixels -> s = t - mean (registers)
+      const uint8_t* rp = row_ptr(bscan, row, f) + 16 * lane;
+      uint4 raw[NCH];
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) {
+        raw[j] = make_uint4(0u, 0u, 0u, 0u);
+        if (NCH * 32 * 8 == WP::N && a.W == WP::N ? true : (lane + 32 * j) < W8) raw[j] = w_ldg_stream16(rp + 512 * j, pol.stream);
+      }
+      float2 s[NCH][4];  // 8 samples of run j as 4 packed pairs
+      float2 sum2 = make_float2(0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) {
+        const bool run_ok = (lane + 32 * j) < W8;
+        float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0, q0 = g0, q1 = g0;
+        if (run_ok) {
+          g0 = w_ldg_cal16(gp + (2 * j) * 128, pol.keep);
+          g1 = w_ldg_cal16(gp + (2 * j + 1) * 128, pol.keep);
+          if constexpr (HAS_SUB) {
+            q0 = w_ldg_cal16(sp + (2 * j) * 128, pol.keep);
+            q1 = w_ldg_cal16(sp + (2 * j + 1) * 128, pol.keep);
+          }
+        }
+        const unsigned w32[4] = {raw[j].x, raw[j].y, raw[j].z, raw[j].w};
+        const float2 gg[4] = {make_float2(g0.x, g0.y), make_float2(g0.z, g0.w), make_float2(g1.x, g1.y), make_float2(g1.z, g1.w)};
+        const float2 qq[4] = {make_float2(q0.x, q0.y), make_float2(q0.z, q0.w), make_float2(q1.x, q1.y), make_float2(q1.z, q1.w)};
+#pragma unroll
+        for (int e2 = 0; e2 < 4; ++e2) {
+          // u16 -> f32 without a conversion instruction: 0x4B00hhll is the float 2^23 + pixel, the subtraction is exact
+          unsigned lo = w_byte_perm(w32[e2], 0x4B000000u, 0x7610), hi = w_byte_perm(w32[e2], 0x4B000000u, 0x7632);
+          float2 y;
+          memcpy(&y.x, &lo, 4);
+          memcpy(&y.y, &hi, 4);
+          y = pk_sub(y, make_float2(8388608.f, 8388608.f));
+          // t - 1 = y * gain - (subg + 1): the constant keeps the staged values small (t ~ 1 for a normalised interferogram)
+          float2 tv;
+          if constexpr (HAS_SUB)
+            tv = pk_fma(y, gg[e2], make_float2(-qq[e2].x, -qq[e2].y));
+          else
+            tv = pk_fma(y, gg[e2], make_float2(-1.f, -1.f));
+          if (!run_ok) tv = make_float2(0.f, 0.f);
+          s[j][e2] = tv;
+          sum2 = pk_add(sum2, tv);
+        }
+      }
+      if (f == 0) tn = w_shfl_i(tn_raw, 0);
+      // prefetch (TMA unit -> L2): the next frame of this row, else the first frame of the next row
+      if (lane == 0) {
+        if (!last) {
+          w_prefetch_l2(row_ptr(bscan, row, f + 1), rowbytes);
+        } else if (tn < a.nitems) {
+          const int nb = tn / a.oph;
+          w_prefetch_l2(row_ptr(nb, tn - nb * a.oph, 0), rowbytes);
+        }
+      }
+      const float mean = w_sum(sum2.x + sum2.y) * a.inv_W;
+      const float2 mean2 = make_float2(mean, mean);
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) {
+        const bool run_ok = (lane + 32 * j) < W8;
+#pragma unroll
+        for (int e2 = 0; e2 < 4; ++e2) s[j][e2] = run_ok ? pk_sub(s[j][e2], mean2) : make_float2(0.f, 0.f);
+      }
+      // ---------------------------------------------------------------- stage v[i] = P[i] s[i] - Q[i] s[i-1]
+      if (lane == 0) *reinterpret_cast<float4*>(wbuf + WP::ZERO_OFF) = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) {
+        // s[i-1] of the run's first sample lives in the previous lane (lane 0: in lane 31's previous run)
+        const float sendv = (lane == 31) ? (j > 0 ? s[j > 0 ? j - 1 : 0][3].y : 0.f) : s[j][3].y;
+        const float prev = w_shfl(sendv, (lane + 31) & 31);
+        if ((lane + 32 * j) < W8) {
+          const float4 P0 = t_pq[(j * 4 + 0) * 32 + lane], P1 = t_pq[(j * 4 + 1) * 32 + lane];
+          const float4 Q0 = t_pq[(j * 4 + 2) * 32 + lane], Q1 = t_pq[(j * 4 + 3) * 32 + lane];
+          const float sv8[8] = {s[j][0].x, s[j][0].y, s[j][1].x, s[j][1].y, s[j][2].x, s[j][2].y, s[j][3].x, s[j][3].y};
+          const float P[8] = {P0.x, P0.y, P0.z, P0.w, P1.x, P1.y, P1.z, P1.w};
+          const float Q[8] = {Q0.x, Q0.y, Q0.z, Q0.w, Q1.x, Q1.y, Q1.z, Q1.w};
+          float v[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) v[e] = fmaf(-Q[e], e == 0 ? prev : sv8[e - 1], P[e] * sv8[e]);
+          const int run = lane + 32 * j;
+          *reinterpret_cast<float4*>(wbuf + 16 * run) = make_float4(v[0], v[2], v[4], v[6]);
+          *reinterpret_cast<float4*>(wbuf + 4 * WP::PO + 16 * run) = make_float4(v[1], v[3], v[5], v[7]);
+        }
+      }
+      w_syncwarp();
+      // ---------------------------------------------------------------- pass A: gather, radix-R, twiddle, exchange
+      float2 x[R], y[R];
+#pragma unroll
+      for (int a2 = 0; a2 < R / 2; ++a2) {
+        const uint4 o = t_offs[a2 * 32 + lane];
+        x[2 * a2].x = *reinterpret_cast<const float*>(wbuf + o.x);
+        x[2 * a2].y = *reinterpret_cast<const float*>(wbuf + o.y);
+        x[2 * a2 + 1].x = *reinterpret_cast<const float*>(wbuf + o.z);
+        x[2 * a2 + 1].y = *reinterpret_cast<const float*>(wbuf + o.w);
+      }
+      Dft<R, kFftSign, 1, 1>::run(x, y);
+      w_syncwarp();  // every lane has gathered: the exchange rows may overwrite the staging planes
+#pragma unroll
+      for (int p = 0; p < R / 2; ++p) {
+        const float4 tw = t_twa[p * 32 + lane];
+        const float2 y0 = p == 0 ? y[0] : cmul(y[2 * p], make_float2(tw.x, tw.y));
+        const float2 y1 = cmul(y[2 * p + 1], make_float2(tw.z, tw.w));
+        *reinterpret_cast<float4*>(wbuf + p * WP::XPITCH + 16 * lane) = make_float4(y0.x, y0.y, y1.x, y1.y);
+      }
+      w_syncwarp();
+      // ---------------------------------------------------------------- pass B: radix-32 over the lanes of pass A
+      float2 u[32], Z[32];
+      {
+        const unsigned char* xb = wbuf + (cc >> 1) * WP::XPITCH + (cc & 1) * 8;
+#pragma unroll
+        for (int b = 0; b < 32; ++b) u[b] = *reinterpret_cast<const float2*>(xb + 16 * b);
+      }
+      w_syncwarp();  // the buffer is free for the next row's staging
+      Dft<32, kFftSign, 1, 1>::run(u, Z);
+      // ---------------------------------------------------------------- split + magnitude
+      float m1[16], m2[16];
+#pragma unroll
+      for (int d = 0; d < 16; ++d) {
+        const int e = 31 - d;
+        // partner value Z[N/2 - k]: slot 31 - d of lane R - c; lane 0 pairs slot d with slot 32 - d of ITSELF (d = 0: slot 16)
+        float2 sv2 = Z[e];
+        if (lane == 0) sv2 = e < 31 ? Z[e < 31 ? e + 1 : e] : Z[16];
+        float2 Rv;
+        Rv.x = w_shfl(sv2.x, pl);
+        Rv.y = w_shfl(sv2.y, pl);
+        const float4 tq = t_twp[(d >> 1) * 32 + lane];
+        const float Tr = (d & 1) ? tq.z : tq.x, Ti = (d & 1) ? tq.w : tq.y;
+        const float2 z = Z[d];
+        const float Ar = z.x + Rv.x, Ai = z.y - Rv.y, Dr = z.x - Rv.x, Di = z.y + Rv.y;
+        const float Br = fmaf(-Ti, Di, Tr * Dr), Bi = fmaf(Ti, Dr, Tr * Di);
+        const float pr = Ar + Br, pi = Ai + Bi, qr = Ar - Br, qi = Ai - Bi;
+        float a1 = fast_sqrt(fmaf(pr, pr, pi * pi)), a2 = fast_sqrt(fmaf(qr, qr, qi * qi));
+        if (d == 0 && lane == 0) {  // the two self-conjugate bins: X[0] = Re Z0 + Im Z0, |X[N/4]| = |Z[N/4]| (same 1/2 scale as the rest)
+          a1 = 2.f * fabsf(z.x + z.y);
+          a2 = 2.f * fast_sqrt(fmaf(Rv.x, Rv.x, Rv.y * Rv.y));
+        }
+        m1[d] = a1;
+        m2[d] = a2;
+      }
+      if constexpr (!A1) {
+#pragma unroll
+        for (int d = 0; d < 16; ++d) {
+          acc1[d] += m1[d];
+          acc2[d] += m2[d];
+          if (last) {
+            m1[d] = acc1[d];
+            m2[d] = acc2[d];
+            acc1[d] = acc2[d] = 0.f;
+          }
+        }
+      }
+      if (!last) continue;
+      // ---------------------------------------------------------------- finalise: dB row to the L2 scratch, min / max
+      float* srow = a.scratch + ((size_t)bscan * a.oph + row) * a.Dp;
+      float* s1 = srow + lane;          // bin k1 = lane + R d
+      float* s2 = srow + (N2 - lane);   // bin k2 = N/2 - lane - R d
+      float mn = w_inf(false), mx = w_inf(true);
+#pragma unroll
+      for (int d = 0; d < 16; ++d) {
+        const float db1 = fast_log2(fmaf(m1[d], a.out_scale, 1e-5f)) * a.db_scale;
+        const float db2 = fast_log2(fmaf(m2[d], a.out_scale, 1e-5f)) * a.db_scale;
+        const int k1 = lane + R * d;
+        int k2 = N2 - lane - R * d;
+        bool ok1 = lane_ok && (FULLD || k1 < a.D);
+        bool ok2 = lane_ok && (FULLD || k2 < a.D);
+        if (d == 0) {
+          // special bins live in slot 0 only: 0, 1 (masked), 4 (the mask source), 5 (clampupper), and lane 0's second
+          // output is bin N/4 instead of the non-existent bin N/2
+          if (lane == 0) k2 = N2 / 2;
+          ok2 = lane_ok && (lane == 0 ? (FULLD || N2 / 2 < a.D) : ok2);
+          if (lane < 2) {
+            if (a.dc01 != nullptr && ok1) a.dc01[2 * ((size_t)bscan * a.oph + row) + lane] = db1;  // kept on request only
+            ok1 = false;  // bscandb.row(4).copyTo(row(1)), row(0): BscanFFT.cpp:1239-1240
+          }
+          if (lane == 4 && ok1) {
+            w_st_keep(srow, db1, pol.keep);
+            w_st_keep(srow + 1, db1, pol.keep);
+          }
+          if (ok1) w_st_keep(s1, db1, pol.keep);
+          if (ok2) w_st_keep(lane == 0 ? srow + N2 / 2 : s2, db2, pol.keep);
+          const bool is55 = a.clamp55 && lane == 5 && row == 5;  // forced element: excluded from the min / max of the data
+          if (ok1 && !is55) {
+            mn = fminf(mn, db1);
+            mx = fmaxf(mx, db1);
+          }
+          if (ok2) {
+            mn = fminf(mn, db2);
+            mx = fmaxf(mx, db2);
+          }
+        } else if (FULLD && R == 32) {
+          w_st_keep(s1 + R * d, db1, pol.keep);
+          w_st_keep(s2 - R * d, db2, pol.keep);
+          mn = w_min3(mn, db1, db2);
+          mx = w_max3(mx, db1, db2);
+        } else {
+          if (ok1) {
+            w_st_keep(s1 + R * d, db1, pol.keep);
+            mn = fminf(mn, db1);
+            mx = fmaxf(mx, db1);
+          }
+          if (ok2) {
+            w_st_keep(s2 - R * d, db2, pol.keep);
+            mn = fminf(mn, db2);
+            mx = fmaxf(mx, db2);
+          }
+        }
+      }
+      // thresholded min / max of the B-scan (BscanFFT.cpp:1247, 1254): max(., thr) commutes with min / max
+      const int imn = w_redux_min(float_to_ordered(fmaxf(mn, a.thr)));
+      const int imx = w_redux_max(float_to_ordered(fmaxf(mx, a.thr)));
+      w_syncwarp();  // orders every lane's scratch stores before lane 0's publication below
+      if (lane == 0) {
+        const float fmn = ordered_to_float(imn), fmx = ordered_to_float(imx);
+        if (fmn <= fmx) {
+          // most rows do not move the B-scan's extrema: skip the atomics when this warp already pushed tighter bounds
+          if (cache_b != bscan) {
+            cache_b = bscan;
+            cache_mn = w_inf(false);
+            cache_mx = w_inf(true);
+          }
+          if (fmn < cache_mn) {
+            w_atomic_min(sv.minv + bscan, imn);
+            cache_mn = fmn;
+          }
+          if (fmx > cache_mx) {
+            w_atomic_max(sv.maxv + bscan, imx);
+            cache_mx = fmx;
+          }
+        }
+        if (pend0 < 0) {
+          pend0 = bscan;
+        } else {
+          if (pend0 == bscan) {
+            w_release_add(sv.cnt + bscan, 2);
+          } else {
+            w_release_add(sv.cnt + pend0, 1);
+            w_atomic_add(sv.cnt + bscan, 1);
+          }
+          pend0 = -1;
+        }
+      }
+    }
+
+    // ---- a normalisation job of this warp whose B-scan is complete?
+    {
+      int ready = 0;
+      if (lane == 0 && myjob < njobs && polled >= a.oph) {
+        w_acquire_fence();
+        ready = 1;
+      }
+      ready = w_shfl_i(ready, 0);
+      if (ready) {
+        wrow_normalise<WP>(a, sv, myjob);
+        myjob += nwarps;
+      }
+    }
+    tk = tn;
+  }
+
+  // ---- drain: publish what is pending, then finish this warp's remaining normalisation jobs
+  if (lane == 0 && pend0 >= 0) w_release_add(sv.cnt + pend0, 1);
+  while (myjob < njobs) {
+    if (lane == 0) {
+      const unsigned long long t0 = w_now_ns();
+      while (w_ld_acquire(sv.cnt + myjob / per_b) < a.oph) {
+        w_backoff();
+        if (w_now_ns() - t0 > kWrowWatchdogNs) w_trap();  // a scheduling bug must surface as a launch failure, not as a hung GPU
+      }
+    }
+    w_syncwarp();
+    wrow_normalise<WP>(a, sv, myjob);
+    myjob += nwarps;
+  }
+}
+
+#ifdef __CUDACC__
+template <class WP, bool HAS_SUB, bool A1, bool FULLD>
+__global__ void __launch_bounds__(WP::NW * 32, 1) wrow_kernel(const ReconArgs a) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  wrow_body<WP, HAS_SUB, A1, FULLD>(a, smem);
+}
+#endif
+
+}  // namespace abcoct

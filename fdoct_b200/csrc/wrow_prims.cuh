@@ -1,0 +1,345 @@
+// Warp-level primitives of the warp-per-A-scan kernel (wrow_kernel.cuh): lane identity, shuffles, warp reductions, cache-hinted
+// global accesses, TMA L2 prefetch and the few global atomics of the scheduler.
+//
+// Every primitive has two bodies.  On the device it is the sm_100a instruction.  When the translation unit is compiled with
+// ABC_WROW_HOST_EMU (tests/native/test_wrow_host.cu only - never the product library) the very same kernel body is a
+// __host__ __device__ function and the primitives call into a small lock-step emulator (32 host threads per warp, a barrier per
+// shuffle), so that the index algebra, table layouts, pairing logic and the scheduling protocol of the kernel can be checked on
+// a machine without a GPU.  The emulator is test infrastructure; the product path has no CPU fallback.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstring>
+
+#ifdef ABC_WROW_HOST_EMU
+#define WROW_HD __host__ __device__ __forceinline__
+namespace wemu {  // implemented by the test harness
+int lane();
+int warp_in_cta();
+int cta();
+int ncta();
+int nwarps();
+unsigned shfl_u32(unsigned v, int src);
+void syncwarp();
+void syncthreads();
+int redux_min(int v);
+int redux_max(int v);
+int atomic_add(int* p, int v);
+void atomic_min(int* p, int v);
+void atomic_max(int* p, int v);
+int load_acquire(const int* p);
+void check_smem(const void* p, int bytes, int align);
+void backoff();
+}  // namespace wemu
+#else
+#define WROW_HD __device__ __forceinline__
+#endif
+
+namespace abcoct {
+
+#if defined(__CUDA_ARCH__) || !defined(ABC_WROW_HOST_EMU)
+#define WROW_DEVICE_BODY 1
+#else
+#define WROW_DEVICE_BODY 0
+#endif
+
+WROW_HD int w_lane() {
+#if WROW_DEVICE_BODY
+  return threadIdx.x & 31;
+#else
+  return wemu::lane();
+#endif
+}
+WROW_HD int w_warp_in_cta() {
+#if WROW_DEVICE_BODY
+  return threadIdx.x >> 5;
+#else
+  return wemu::warp_in_cta();
+#endif
+}
+WROW_HD int w_cta() {
+#if WROW_DEVICE_BODY
+  return blockIdx.x;
+#else
+  return wemu::cta();
+#endif
+}
+WROW_HD int w_ncta() {
+#if WROW_DEVICE_BODY
+  return gridDim.x;
+#else
+  return wemu::ncta();
+#endif
+}
+WROW_HD void w_syncwarp() {
+#if WROW_DEVICE_BODY
+  __syncwarp();
+#else
+  wemu::syncwarp();
+#endif
+}
+WROW_HD void w_syncthreads() {
+#if WROW_DEVICE_BODY
+  __syncthreads();
+#else
+  wemu::syncthreads();
+#endif
+}
+WROW_HD float w_shfl(float v, int src) {
+#if WROW_DEVICE_BODY
+  return __shfl_sync(0xffffffffu, v, src);
+#else
+  unsigned u;
+  memcpy(&u, &v, 4);
+  u = wemu::shfl_u32(u, src);
+  memcpy(&v, &u, 4);
+  return v;
+#endif
+}
+WROW_HD int w_shfl_i(int v, int src) {
+#if WROW_DEVICE_BODY
+  return __shfl_sync(0xffffffffu, v, src);
+#else
+  return (int)wemu::shfl_u32((unsigned)v, src);
+#endif
+}
+WROW_HD float w_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += w_shfl(v, w_lane() ^ o);
+  return v;
+}
+// warp-wide min / max of order-preserving integer encodings: one CREDUX each
+WROW_HD int w_redux_min(int v) {
+#if WROW_DEVICE_BODY
+  return __reduce_min_sync(0xffffffffu, v);
+#else
+  return wemu::redux_min(v);
+#endif
+}
+WROW_HD int w_redux_max(int v) {
+#if WROW_DEVICE_BODY
+  return __reduce_max_sync(0xffffffffu, v);
+#else
+  return wemu::redux_max(v);
+#endif
+}
+WROW_HD float w_min3(float a, float b, float c) {
+#if WROW_DEVICE_BODY
+  float r;
+  asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));  // FMNMX3
+  return r;
+#else
+  return fminf(a, fminf(b, c));
+#endif
+}
+WROW_HD float w_max3(float a, float b, float c) {
+#if WROW_DEVICE_BODY
+  float r;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+  return r;
+#else
+  return fmaxf(a, fmaxf(b, c));
+#endif
+}
+
+// ---- global memory with cache hints -------------------------------------------------------------------------------
+// raw pixels: read exactly once, straight from L2 (prefetched there by the TMA unit), no L1 allocation, evict-first in L2
+struct WPolicies {
+  unsigned long long stream, keep;  // L2 evict-first (data read once) / evict-last (data that must stay L2-resident)
+};
+WROW_HD WPolicies w_make_policies() {
+  WPolicies p{0, 0};
+#if WROW_DEVICE_BODY
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p.stream));
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p.keep));
+#endif
+  return p;
+}
+WROW_HD uint4 w_ldg_stream16(const void* p, unsigned long long pol) {
+#if WROW_DEVICE_BODY
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p), "l"(pol));
+  return v;
+#else
+  (void)pol;
+  uint4 v;
+  memcpy(&v, p, 16);
+  return v;
+#endif
+}
+// calibration rows: L2-resident, re-read by every B-scan, no reuse inside an SM
+WROW_HD float4 w_ldg_cal16(const float* p, unsigned long long pol) {
+#if WROW_DEVICE_BODY
+  float4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p), "l"(pol));
+  return v;
+#else
+  (void)pol;
+  float4 v;
+  memcpy(&v, p, 16);
+  return v;
+#endif
+}
+WROW_HD float4 w_ld_cg16(const float* p) {
+#if WROW_DEVICE_BODY
+  float4 v;
+  asm volatile("ld.global.cg.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+#else
+  float4 v;
+  memcpy(&v, p, 16);
+  return v;
+#endif
+}
+WROW_HD int w_ld_cg_i(const int* p) {
+#if WROW_DEVICE_BODY
+  return __ldcg(p);
+#else
+  return wemu::load_acquire(p);
+#endif
+}
+// dB scratch: written once, consumed from L2 a few microseconds later
+WROW_HD void w_st_keep(float* p, float v, unsigned long long pol) {
+#if WROW_DEVICE_BODY
+  asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+#else
+  (void)pol;
+  *p = v;
+#endif
+}
+WROW_HD void w_st_stream_u32(void* p, unsigned v) {
+#if WROW_DEVICE_BODY
+  __stcs(reinterpret_cast<unsigned*>(p), v);
+#else
+  memcpy(p, &v, 4);
+#endif
+}
+WROW_HD void w_st_stream_f4(float* p, float4 v) {
+#if WROW_DEVICE_BODY
+  __stcs(reinterpret_cast<float4*>(p), v);
+#else
+  memcpy(p, &v, 16);
+#endif
+}
+WROW_HD void w_discard128(const void* p) {
+#if WROW_DEVICE_BODY
+  asm volatile("discard.global.L2 [%0], 128;" ::"l"(p) : "memory");
+#else
+  (void)p;
+#endif
+}
+// TMA unit: bulk prefetch of one pixel row into L2 (SASS UBLKPF.L2); bytes a multiple of 16
+WROW_HD void w_prefetch_l2(const void* p, unsigned bytes) {
+#if WROW_DEVICE_BODY
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+#else
+  (void)p;
+  (void)bytes;
+#endif
+}
+
+// ---- scheduler atomics --------------------------------------------------------------------------------------------
+WROW_HD int w_atomic_add(int* p, int v) {
+#if WROW_DEVICE_BODY
+  return atomicAdd(p, v);
+#else
+  return wemu::atomic_add(p, v);
+#endif
+}
+WROW_HD void w_atomic_min(int* p, int v) {
+#if WROW_DEVICE_BODY
+  atomicMin(p, v);
+#else
+  wemu::atomic_min(p, v);
+#endif
+}
+WROW_HD void w_atomic_max(int* p, int v) {
+#if WROW_DEVICE_BODY
+  atomicMax(p, v);
+#else
+  wemu::atomic_max(p, v);
+#endif
+}
+// publish: everything this WARP wrote before the preceding w_syncwarp() becomes visible before the count (cumulative release)
+WROW_HD void w_release_add(int* p, int v) {
+#if WROW_DEVICE_BODY
+  __threadfence();
+  atomicAdd(p, v);  // result unused -> RED
+#else
+  wemu::atomic_add(p, v);
+#endif
+}
+WROW_HD int w_ld_acquire(const int* p) {
+#if WROW_DEVICE_BODY
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+#else
+  return wemu::load_acquire(p);
+#endif
+}
+WROW_HD int w_ld_relaxed(const int* p) {
+#if WROW_DEVICE_BODY
+  return *reinterpret_cast<const volatile int*>(p);
+#else
+  return wemu::load_acquire(p);
+#endif
+}
+WROW_HD void w_acquire_fence() {
+#if WROW_DEVICE_BODY
+  __threadfence();
+#endif
+}
+WROW_HD void w_backoff() {
+#if WROW_DEVICE_BODY
+  __nanosleep(200);
+#else
+  wemu::backoff();
+#endif
+}
+WROW_HD unsigned long long w_now_ns() {
+#if WROW_DEVICE_BODY
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+#else
+  return 0;
+#endif
+}
+WROW_HD float w_inf(bool negative) {
+  const unsigned u = negative ? 0xff800000u : 0x7f800000u;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+WROW_HD void w_trap() {
+#if WROW_DEVICE_BODY
+  __trap();
+#endif
+}
+WROW_HD unsigned w_byte_perm(unsigned a, unsigned b, unsigned s) {
+#if WROW_DEVICE_BODY
+  return __byte_perm(a, b, s);
+#else
+  unsigned long long t = ((unsigned long long)b << 32) | a;
+  unsigned r = 0;
+  for (int i = 0; i < 4; ++i) r |= (unsigned)((t >> (8 * ((s >> (4 * i)) & 7))) & 0xff) << (8 * i);
+  return r;
+#endif
+}
+WROW_HD void w_check_smem(const void* p, int bytes, int align) {
+#if !WROW_DEVICE_BODY
+  wemu::check_smem(p, bytes, align);
+#else
+  (void)p;
+  (void)bytes;
+  (void)align;
+#endif
+}
+
+}  // namespace abcoct

@@ -9,7 +9,7 @@
 #include <random>
 #include <vector>
 
-#include "../../fdoct_b200/csrc/abcoct_kernels.cu"
+#include "../../fdoct_b200/csrc/plan_registry.cuh"
 
 using namespace abcoct;
 
@@ -118,105 +118,6 @@ static double run_plan(int W, int D, int A, unsigned seed) {
   return worst;
 }
 
-// ---- dual-pair (packed f32x2) kernel: the same check with two row pairs side by side in the V2 lanes
-template <class P, bool HAS_SUB>
-static double run_plan2(int W, int D, int A, unsigned seed) {
-  const int N = P::N, T = P::T;
-  std::mt19937 rng(seed);
-  std::uniform_int_distribution<int> pix(1000, 60000);
-  std::uniform_real_distribution<float> uf(0.f, 1.f);
-  std::vector<int> idx(N);
-  std::vector<float> wq(N), win(W);
-  for (int q = 0; q < N; ++q) {
-    int i = int((double)(N - 1 - q) * (W - 1) / (N - 1) + 0.5) + (int)(3 * std::sin(q * 0.01));
-    i = std::min(std::max(i, 1), W - 1);
-    idx[q] = i;
-    wq[q] = 0.001f + 0.999f * uf(rng);
-  }
-  idx[0] = W; wq[0] = 0.f; idx[N - 1] = W; wq[N - 1] = 0.f;
-  for (int i = 0; i < W; ++i) win[i] = 0.62f - 0.48f * std::fabs(float(i) / (W - 1) - 0.5f) + 0.38f * std::cos(6.2831853f * (float(i) / (W - 1) - 0.5f));
-  std::vector<unsigned char> blob;
-  build_blob2_fn<P>(W, idx.data(), wq.data(), win.data(), blob);
-  const SmemLayout2 L = make_layout2<P>(W, HAS_SUB);
-  std::vector<unsigned char> smem(L.total(1) + 64, 0);
-  unsigned char* base = smem.data();
-  while (reinterpret_cast<uintptr_t>(base) & 15) ++base;
-  memcpy(base, blob.data(), blob.size());
-  GroupSmem2 s = resolve2<P>(base, L, 0);
-  std::vector<float> gain(4 * W), subg(4 * W);
-  for (int i = 0; i < 4 * W; ++i) {
-    gain[i] = 1.0f / (20000.f + 10000.f * uf(rng));
-    subg[i] = HAS_SUB ? (64.f + 8.f * uf(rng)) * gain[i] + 1.f : 1.f;
-  }
-  for (int row = 0; row < 4; ++row) {
-    cal_swizzle_row(gain.data() + row * W, s.gain + row * W, W);
-    if (HAS_SUB) cal_swizzle_row(subg.data() + row * W, s.subg + row * W, W);
-  }
-  std::vector<std::vector<uint16_t>> frames(A, std::vector<uint16_t>(4 * W));
-  for (auto& f : frames)
-    for (int i = 0; i < 4 * W; ++i) {
-      double ph = 0.05 * (i % W) * (1 + (i / W)) + 0.3 * (&f - &frames[0]);
-      f[i] = uint16_t(pix(rng) / 8 + 25000 + 12000 * std::sin(ph));
-    }
-  ReconArgs a{};
-  a.W = W; a.oph = 4; a.D = D; a.Dp = (D + 31) / 32 * 32; a.A = A; a.nB = 1; a.npairs = 2; a.nitems = 2;
-  a.inv_W = 1.0f / W; a.out_scale = 0.5f / A; a.db_scale = float(0.6931471805599453 * 20.0 * (1.0 / 2.303));
-  a.thr = -30.f; a.clamp55 = 0;
-  std::vector<Thread2State<P>> st(T);
-  for (auto& r : st) memset(&r, 0, sizeof(r));
-  for (int f = 0; f < A; ++f) {
-    const uint8_t* r0 = reinterpret_cast<const uint8_t*>(frames[f].data());
-    const uint8_t* const rows[4] = {r0, r0 + 2 * W, r0 + 4 * W, r0 + 6 * W};
-    std::vector<std::array<float, 4>> sm(T);
-    for (int t = 0; t < T; ++t) phase2_load<P>(t, rows, W / 8, st[t]);
-    for (int t = 0; t < T; ++t) { float q[4]; phase2_pre<P, HAS_SUB>(t, s, W, st[t], q); sm[t] = {q[0], q[1], q[2], q[3]}; }
-    float tot[4] = {0, 0, 0, 0};
-    for (int t = 0; t < T; ++t) for (int k = 0; k < 4; ++k) tot[k] += sm[t][k];
-    const V2 nm_re = v2_make(-tot[0] * a.inv_W, -tot[2] * a.inv_W), nm_im = v2_make(-tot[1] * a.inv_W, -tot[3] * a.inv_W);
-    for (int t = 0; t < T; ++t) phase2_gather<P>(t, s, st[t], nm_re, nm_im);
-    for (int t = 0; t < T; ++t) phase2_pass0<P>(t, s, st[t]);
-    for (int t = 0; t < T; ++t) phase2_pass1<P>(t, s);
-    for (int t = 0; t < T; ++t) phase2_passL<P, true>(t, s, st[t]);
-  }
-  std::vector<std::vector<float>> o(4, std::vector<float>(a.Dp, -999.f));
-  float* const out[2][2] = {{o[0].data(), o[1].data()}, {o[2].data(), o[3].data()}};
-  const int rowa[2] = {0, 2};
-  const bool valid[2][2] = {{true, true}, {true, true}};
-  float mn[2] = {1e30f, 1e30f}, mx[2] = {-1e30f, -1e30f};
-  for (int t = 0; t < T; ++t) phase2_finalise<P>(t, a, out, rowa, valid, st[t], mn, mx);
-  double worst = 0;
-  for (int row = 0; row < 4; ++row) {
-    std::vector<double> accd(D, 0.0);
-    for (int f = 0; f < A; ++f) {
-      std::vector<double> t(W), y(W), ylin(N, 0.0);
-      double mean = 0;
-      for (int i = 0; i < W; ++i) {
-        t[i] = (double)frames[f][row * W + i] * gain[row * W + i] - (subg[row * W + i] - 1.0);
-        mean += t[i];
-      }
-      mean /= W;
-      for (int i = 0; i < W; ++i) y[i] = (t[i] - mean) * win[i];
-      for (int q = 1; q < N - 1; ++q) ylin[q] = y[idx[q]] + (double)wq[q] * (y[idx[q]] - y[idx[q] - 1]);
-      for (int k = 0; k < D; ++k) {
-        std::complex<double> acc = 0;
-        for (int q = 0; q < N; ++q) acc += ylin[q] * std::polar(1.0, 2.0 * M_PI * double(((long long)q * k) % N) / N);
-        accd[k] += std::abs(acc);
-      }
-    }
-    std::vector<double> db(D);
-    for (int k = 0; k < D; ++k) db[k] = std::log(accd[k] / A + 1e-5) * (20.0 * (1.0 / 2.303));
-    db[0] = db[4]; db[1] = db[4];
-    double rmn = 1e30, rmx = -1e30;
-    for (int k = 0; k < D; ++k) {
-      worst = std::fmax(worst, std::fabs(o[row][k] - db[k]));
-      if (k >= 2) { rmn = std::fmin(rmn, db[k]); rmx = std::fmax(rmx, db[k]); }
-    }
-    (void)rmn; (void)rmx;
-  }
-  std::printf("DUAL N=%d T=%d radices=(%d,%d,%d) W=%d D=%d A=%d sub=%d  max|dB err|=%.3g\n", N, T, P::R0, P::R1, P::RL, W, D, A, (int)HAS_SUB, worst);
-  return worst;
-}
-
 int main(int argc, char** argv) {
   const bool quick = argc > 1;
   double w = 0;
@@ -227,11 +128,7 @@ int main(int argc, char** argv) {
   w = std::fmax(w, run_plan<P640, false>(640, 320, 1, 5));
   w = std::fmax(w, run_plan<P1024, false>(1024, 512, 2, 6));
   w = std::fmax(w, run_plan<P1280, true>(1280, 640, 2, 7));
-  w = std::fmax(w, run_plan2<P1024, false>(1024, 512, 2, 21));
-  w = std::fmax(w, run_plan2<P1280, true>(1280, 640, 1, 22));
   if (!quick) {
-    w = std::fmax(w, run_plan2<P2048, false>(2048, 1024, 1, 23));
-    w = std::fmax(w, run_plan2<P1920, true>(1920, 960, 1, 24));
     w = std::fmax(w, run_plan<P1920, false>(1920, 960, 1, 8));
     w = std::fmax(w, run_plan<P2048, false>(2048, 1024, 1, 9));
     w = std::fmax(w, run_plan<P2048, true>(1280, 640, 2, 10));

@@ -239,13 +239,14 @@ def test_calibration_from_frames_matches_oracle_capture():
 
 @pytest.mark.parametrize("w,h,N,D,A,variant", [(2048, 33, 2048, 1024, 1, 0), (1280, 21, 1280, 640, 2, 1), (1024, 7, 1024, 512, 1, 0),
                                                (1920, 10, 1920, 960, 3, 0)])
-def test_dual_pair_kernel_variant(w, h, N, D, A, variant, monkeypatch):
-    """The opt-in packed-f32x2 kernel (ABCOCT_KERNEL=2, recon2_kernel.cuh): odd numbers of row pairs, units that straddle
-    B-scans, averaging and the DARK variant, against the oracle."""
+def test_fallback_kernel_on_lengths_the_warp_kernel_owns(w, h, N, D, A, variant, monkeypatch):
+    """The group-per-row-pair kernel (recon_kernel.cuh, forced with ABCOCT_KERNEL=1) on transform lengths that normally go to the
+    warp-per-A-scan kernel: odd numbers of row pairs, averaging and the DARK variant, against the oracle.  Keeps the fallback
+    (which serves every other length and the general path) honest on the same inputs."""
     from fdoct_b200 import synth
     from oracle.abcoct_oracle import Oracle
 
-    monkeypatch.setenv("ABCOCT_KERNEL", "2")
+    monkeypatch.setenv("ABCOCT_KERNEL", "1")
     nB = 3
     op = oracle_params(w=w, h=h, numfftpoints=N, numdisplaypoints=D, averages=A, variant=variant, lambdamin=840.5e-9, lambdamax=859.5e-9)
     frames = synth.make_frames(nB * A, w, h, seed=61, dark=bool(variant))
@@ -257,7 +258,7 @@ def test_dual_pair_kernel_variant(w, h, N, D, A, variant, monkeypatch):
         o.set_dark(yd)
     ref8, refdb = o.process_bscans(frames)
     out8, outdb = _run_abi(op, frames, yb, yd=yd)
-    _check(out8, outdb, ref8, refdb, f"dual w{w} N{N} A{A}")
+    _check(out8, outdb, ref8, refdb, f"fallback w{w} N{N} A{A}")
 
 
 @pytest.mark.parametrize("w,h,N,extra", [(1280, 9, 1280, {}), (1024, 6, 2048, {}), (640, 5, 2560, dict(fft_multiplier=4)),
