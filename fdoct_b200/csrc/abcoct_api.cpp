@@ -623,7 +623,11 @@ int enqueue_device(abcoct_ctx* c, GpuState& g, int slot, const uint8_t* d_frames
       grid = std::min(g.sm_count, (a.nitems + c->wplan->nw - 1) / c->wplan->nw);
       const int ntiles = (c->D + 31) / 32;
       const long long warps = (long long)grid * c->wplan->nw, parts = (long long)a.nparts * (long long)nb;
-      a.nsplit = (int)std::max<long long>(1, std::min<long long>(ntiles, warps / parts));
+      // enough normalisation jobs for every warp, and - for long launches - jobs short enough (about four tiles = 16 KB of dB
+      // scratch) that a finished B-scan leaves L2 within a few microseconds instead of being written back to HBM
+      long long split = std::max<long long>((ntiles + 3) / 4, warps / parts);
+      if (const char* e = getenv("ABCOCT_NSPLIT")) split = atol(e);
+      a.nsplit = (int)std::max<long long>(1, std::min<long long>(ntiles, split));
     }
     a.gain = g.d_gain;
     a.subg = g.d_subg;

@@ -144,9 +144,21 @@ inline void wrow_permute_cal_row(const float* in, int W, float* out /* WP::WMAX 
 // loads the rows 4 q .. 4 q + 3 at the bin quads cg and cg + 4 of the tile (16-byte L2 loads, 64 contiguous bytes per row and
 // instruction) and packs the four rows of a bin into one 32-bit word, so that the eight lanes of a bin quad write one full
 // 32-byte sector of the depth-major display image per bin - no shared-memory transposition.
-template <class WP>
-WROW_HD void wrow_normalise(const ReconArgs& a, const SchedView& sv, int job) {
-  const int lane = w_lane();
+struct WNormArgs {  // by value: the job runs as a real (non-inlined) device function, one copy in the instruction cache
+  const float* scratch;
+  uint8_t* out8;
+  float* outdb;
+  const int* minv;
+  const int* maxv;
+  int oph, D, Dp, nparts, nsplit, clamp55;
+  float thr, clamp_db;
+};
+#ifdef ABC_WROW_HOST_EMU
+#define WROW_NOINLINE static __host__ __device__
+#else
+#define WROW_NOINLINE static __device__ __noinline__
+#endif
+WROW_NOINLINE void wrow_normalise(const WNormArgs a, int job, int lane) {
   const int per_b = a.nparts * a.nsplit;
   const int b = job / per_b;
   const int rem = job - b * per_b;
@@ -159,7 +171,7 @@ WROW_HD void wrow_normalise(const ReconArgs& a, const SchedView& sv, int job) {
   const int t1 = (t0 + tps) < ntiles ? (t0 + tps) : ntiles;
   if (t0 >= t1) return;
 
-  float mn = ordered_to_float(w_ld_cg_i(sv.minv + b)), mx = ordered_to_float(w_ld_cg_i(sv.maxv + b));
+  float mn = ordered_to_float(w_ld_cg_i(a.minv + b)), mx = ordered_to_float(w_ld_cg_i(a.maxv + b));
   if (a.clamp55) {  // bscandisp.at<double>(5,5) = 50.0 before the min-max (BscanFFT.cpp:1248-1253)
     mn = fminf(mn, a.clamp_db);
     mx = fmaxf(mx, a.clamp_db);
@@ -175,19 +187,24 @@ WROW_HD void wrow_normalise(const ReconArgs& a, const SchedView& sv, int job) {
   for (int rr = 0; rr < 4; ++rr) {
     const int row = 4 * q + rr;
     const bool ok = row < nrows;
-    rowp[rr] = src + (size_t)(ok ? row : 0) * a.Dp + 4 * cg;
+    rowp[rr] = src + (size_t)(ok ? row : 0) * a.Dp + 4 * cg + 32 * t0;
     valid |= ok ? (1u << rr) : 0u;
   }
   const bool has55 = a.clamp55 && part == 0 && nrows > 5;
   const bool word_ok = (a.oph & 3) == 0 && valid == 0xfu && (reinterpret_cast<uintptr_t>(a.out8) & 3) == 0;
   const bool db_vec_ok = a.outdb != nullptr && (a.oph & 3) == 0 && valid == 0xfu && (reinterpret_cast<uintptr_t>(a.outdb) & 15) == 0;
+  // output pointers of this lane's first bin (tile t0, k = 0, j = 0); they advance by whole bins (oph elements)
+  const size_t o_first = ((size_t)b * a.D + 32 * t0 + 4 * cg) * a.oph + r0 + 4 * q;
+  uint8_t* o8 = a.out8 + o_first;
+  float* odb = a.outdb != nullptr ? a.outdb + o_first : nullptr;
+  const size_t oph = (size_t)a.oph;
 
-  auto load_tile = [&](int t, float4 (&v)[2][4]) {
+  auto load_tile = [&](int i, float4 (&v)[2][4]) {  // tile t0 + i
 #pragma unroll
     for (int k = 0; k < 2; ++k)
 #pragma unroll
       for (int rr = 0; rr < 4; ++rr)
-        v[k][rr] = ((valid >> rr) & 1u) ? w_ld_cg16(rowp[rr] + 32 * t + 16 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[k][rr] = ((valid >> rr) & 1u) ? w_ld_cg16(rowp[rr] + 32 * i + 16 * k) : make_float4(0.f, 0.f, 0.f, 0.f);
   };
   auto quant = [&](float x) -> unsigned {
     // round-half-even of (max(x, thr) - mn) * 255 / (mx - mn) in [0, 255]: 1.5 * 2^23 trick, result in the low byte
@@ -201,7 +218,8 @@ WROW_HD void wrow_normalise(const ReconArgs& a, const SchedView& sv, int job) {
     const unsigned hi = w_byte_perm(quant(x2), quant(x3), 0x0040);
     return w_byte_perm(lo, hi, 0x5410);
   };
-  auto process_tile = [&](int t, float4 (&v)[2][4]) {
+  auto process_tile = [&](int i, float4 (&v)[2][4]) {
+    const int t = t0 + i;
 #pragma unroll
     for (int k = 0; k < 2; ++k) {
       const int bin0 = 32 * t + 16 * k + 4 * cg;
@@ -214,22 +232,22 @@ WROW_HD void wrow_normalise(const ReconArgs& a, const SchedView& sv, int job) {
           unsigned word = pack4(col[j][0], col[j][1], col[j][2], col[j][3]);
           if (has55 && bin == 5 && q == 1)  // element (5,5): row 5 = byte 1 of the quad 4..7
             word = (word & 0xffff00ffu) | ((quant(a.clamp_db) & 0xffu) << 8);
-          uint8_t* o = a.out8 + ((size_t)b * a.D + bin) * a.oph + r0 + 4 * q;
+          uint8_t* o = o8 + (size_t)(32 * i + 16 * k + j) * oph;
           if (word_ok) {
             w_st_stream_u32(o, word);
           } else {
 #pragma unroll
             for (int rr = 0; rr < 4; ++rr)
-              if ((valid >> rr) & 1u) o[rr] = (uint8_t)((word >> (8 * rr)) & 0xffu);
+              if ((valid >> rr) & 1u) w_st_global_u8(o + rr, (word >> (8 * rr)) & 0xffu);
           }
-          if (a.outdb != nullptr) {  // transposed dB image (rarely requested)
-            float* od = a.outdb + ((size_t)b * a.D + bin) * a.oph + r0 + 4 * q;
+          if (odb != nullptr) {  // transposed dB image (rarely requested)
+            float* od = odb + (size_t)(32 * i + 16 * k + j) * oph;
             if (db_vec_ok) {
               w_st_stream_f4(od, make_float4(col[j][0], col[j][1], col[j][2], col[j][3]));
             } else {
 #pragma unroll
               for (int rr = 0; rr < 4; ++rr)
-                if ((valid >> rr) & 1u) od[rr] = col[j][rr];
+                if ((valid >> rr) & 1u) w_st_keep(od + rr, col[j][rr]);
             }
           }
         }
@@ -239,14 +257,15 @@ WROW_HD void wrow_normalise(const ReconArgs& a, const SchedView& sv, int job) {
     if (lane < nrows) w_discard128(src + (size_t)lane * a.Dp + 32 * t);
   };
 
+  const int nt = t1 - t0;
   float4 va[2][4], vb[2][4];
-  load_tile(t0, va);
-  for (int t = t0; t < t1; t += 2) {
-    if (t + 1 < t1) load_tile(t + 1, vb);
-    process_tile(t, va);
-    if (t + 1 < t1) {
-      if (t + 2 < t1) load_tile(t + 2, va);
-      process_tile(t + 1, vb);
+  load_tile(0, va);
+  for (int i = 0; i < nt; i += 2) {
+    if (i + 1 < nt) load_tile(i + 1, vb);
+    process_tile(i, va);
+    if (i + 1 < nt) {
+      if (i + 2 < nt) load_tile(i + 2, va);
+      process_tile(i + 1, vb);
     }
   }
 }
@@ -264,25 +283,41 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
     for (int i = warp * 32 + lane; i < WP::TABLE_BYTES / 16; i += WP::NW * 32) dst[i] = src[i];
   }
   w_syncthreads();
-  const uint4* t_offs = reinterpret_cast<const uint4*>(smem + WP::T_OFFS);
-  const float4* t_pq = reinterpret_cast<const float4*>(smem + WP::T_PQ);
-  const float4* t_twa = reinterpret_cast<const float4*>(smem + WP::T_TWA);
-  const float4* t_twp = reinterpret_cast<const float4*>(smem + WP::T_TWP);
+  const uint4* t_offs = reinterpret_cast<const uint4*>(smem + WP::T_OFFS) + lane;
+  const float4* t_pq = reinterpret_cast<const float4*>(smem + WP::T_PQ) + lane;
+  const float4* t_twa = reinterpret_cast<const float4*>(smem + WP::T_TWA) + lane;
+  const float4* t_twp = reinterpret_cast<const float4*>(smem + WP::T_TWP) + lane;
   unsigned char* const wbuf = smem + WP::TABLE_BYTES + warp * WP::WBUF;
-  const WPolicies pol = w_make_policies();
   const SchedView sv = sched_view(a.sched, a.nB);
-  const int W8 = a.W >> 3;
+  const int W8m1 = (a.W >> 3) - 1;
   const unsigned rowbytes = (unsigned)a.W * 2u;
+  // samples of the padded runs (W < NCH * 256) see gain 0, i.e. t - 1 = -1 without a subtrahend row: taken out of the mean
+  const float pad_corr = HAS_SUB ? 0.f : (float)(NCH * 256 - a.W);
 
   const int nwarps = w_ncta() * WP::NW;
   const int njobs = a.nB * a.nparts * a.nsplit;
   const int per_b = a.nparts * a.nsplit;
   int myjob = w_cta() * WP::NW + warp;  // normalisation jobs are assigned statically: myjob, myjob + nwarps, ...
+  WNormArgs na;
+  na.scratch = a.scratch;
+  na.out8 = a.out8;
+  na.outdb = a.outdb;
+  na.minv = sv.minv;
+  na.maxv = sv.maxv;
+  na.oph = a.oph;
+  na.D = a.D;
+  na.Dp = a.Dp;
+  na.nparts = a.nparts;
+  na.nsplit = a.nsplit;
+  na.clamp55 = a.clamp55;
+  na.thr = a.thr;
+  na.clamp_db = a.clamp_db;
 
-  auto row_ptr = [&](int b, int row, int f) -> const uint8_t* {
-    return a.frames + ((size_t)b * a.A + f) * a.frame_stride + (size_t)row * a.row_stride;
+  auto row_ptr = [&](int item, int f) -> const uint8_t* {
+    const int b = item / a.oph;
+    return a.frames + ((size_t)b * a.A + f) * a.frame_stride + (size_t)(item - b * a.oph) * a.row_stride;
   };
-  auto claim = [&]() -> int {  // dynamic schedule: one ticket = one row of one B-scan
+  auto claim = [&]() -> int {  // dynamic schedule: one ticket = one row of one B-scan; the value lives in lane 0 until broadcast
     int t = 0;
     if (lane == 0) t = w_atomic_add(sv.ticket, 1);
     return t;
@@ -293,15 +328,62 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
   const bool lane_ok = (R == 32) || lane < R;
   const int cc = (R == 32) ? lane : (lane < R ? lane : R - 1);
 
-  // pending completion counts (lane 0): published in batches of two so that the gpu-scope fence is paid every other row
-  int pend0 = -1;
+  int pend = -1;  // (lane 0) B-scan of the finished row whose completion has not been published yet
   int cache_b = -1;
   float cache_mn = 0.f, cache_mx = 0.f;
 
-  int tk = w_shfl_i(claim(), 0);
-  if (tk < a.nitems && lane == 0) {
-    const int b = tk / a.oph;
-    w_prefetch_l2(row_ptr(b, tk - b * a.oph, 0), rowbytes);
+  // Work queue of this warp: it0 = the row being processed, it1 = the next one (its pixels and calibration rows are loaded into
+  // registers while it0 is finalised), it2 = the one after (its pixel row is pulled into L2 by the TMA unit).  Tickets are
+  // claimed one item ahead of their first use so that no warp ever waits for the atomic.
+  int it0 = w_shfl_i(claim(), 0);
+  int it1 = w_shfl_i(claim(), 0);
+
+  // ---- register-resident input of the next (item, frame): raw pixels and gain row of this lane's 8-sample runs
+  uint4 raw[NCH];
+  float4 gq[NCH][2];
+  constexpr int NCH_A = NCH / 2;  // gain runs loaded ahead of time together with the pixels; the rest follows at the row's start
+  auto issue_loads = [&](int item, int f) {
+    const int b = item / a.oph;
+    const int row = item - b * a.oph;
+    const uint8_t* rp = a.frames + ((size_t)b * a.A + f) * a.frame_stride + (size_t)row * a.row_stride;
+    const float* gp = a.gain + (size_t)row * a.calpitch + 4 * lane;
+#pragma unroll
+    for (int j = 0; j < NCH; ++j) {
+      const int run = lane + 32 * j;
+      raw[j] = w_ldg_stream16(rp + 16 * (run < W8m1 ? run : W8m1));  // padded runs re-read the last run (finite values)
+    }
+#pragma unroll
+    for (int j = 0; j < NCH_A; ++j) {
+      gq[j][0] = w_ldg_cal16(gp + (2 * j) * 128);
+      gq[j][1] = w_ldg_cal16(gp + (2 * j + 1) * 128);
+    }
+  };
+  auto issue_loads_rest = [&](int row) {
+    const float* gp = a.gain + (size_t)row * a.calpitch + 4 * lane;
+#pragma unroll
+    for (int j = NCH_A; j < NCH; ++j) {
+      gq[j][0] = w_ldg_cal16(gp + (2 * j) * 128);
+      gq[j][1] = w_ldg_cal16(gp + (2 * j + 1) * 128);
+    }
+  };
+  // (item, frame) two steps ahead of (it0, f) in this warp's sequence, for the L2 prefetch
+  auto prefetch_step2 = [&](int f, int it2) {
+    if (lane != 0) return;
+    const int nA = A1 ? 1 : a.A;
+    const int k = f + 2;
+    const int item = k < nA ? it0 : (k < 2 * nA ? it1 : it2);
+    const int fr = k < nA ? k : (k < 2 * nA ? k - nA : k - 2 * nA);
+    if (item < a.nitems && fr < nA) w_prefetch_l2(row_ptr(item, fr), rowbytes);
+  };
+  if (it0 < a.nitems) {
+    issue_loads(it0, 0);
+    if (lane == 0) {
+      const int nA = A1 ? 1 : a.A;
+      if (nA > 1)
+        w_prefetch_l2(row_ptr(it0, 1), rowbytes);
+      else if (it1 < a.nitems)
+        w_prefetch_l2(row_ptr(it1, 0), rowbytes);
+    }
   }
 
   float acc1[16], acc2[16];
@@ -310,44 +392,33 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
     for (int d = 0; d < 16; ++d) acc1[d] = acc2[d] = 0.f;
   }
 
-  while (tk < a.nitems) {
-    const int bscan = tk / a.oph;
-    const int row = tk - bscan * a.oph;
-    const int tn_raw = claim();  // the next item; consumed (broadcast) in the middle of the first frame
-    int tn = 0;
+  while (it0 < a.nitems) {
+    const int bscan = it0 / a.oph;
+    const int row = it0 - bscan * a.oph;
+    const int it2_raw = claim();  // consumed (broadcast) after the pre-processing phase of the first frame
+    int it2 = 0x7fffffff;
     int polled = 0;
     if (lane == 0 && myjob < njobs) polled = w_ld_relaxed(sv.cnt + myjob / per_b);
-    const float* gp = a.gain + (size_t)row * a.calpitch + 4 * lane;
-    const float* sp = HAS_SUB ? a.subg + (size_t)row * a.calpitch + 4 * lane : nullptr;
 
     const int nA = A1 ? 1 : a.A;
     for (int f = 0; f < nA; ++f) {
       const bool last = A1 || (f + 1 == nA);
       // ---------------------------------------------------------------- pre: pixels -> s = t - mean (registers)
-      const uint8_t* rp = row_ptr(bscan, row, f) + 16 * lane;
-      uint4 raw[NCH];
-#pragma unroll
-      for (int j = 0; j < NCH; ++j) {
-        raw[j] = make_uint4(0u, 0u, 0u, 0u);
-        if (NCH * 32 * 8 == WP::N && a.W == WP::N ? true : (lane + 32 * j) < W8) raw[j] = w_ldg_stream16(rp + 512 * j, pol.stream);
-      }
+      issue_loads_rest(row);
       float2 s[NCH][4];  // 8 samples of run j as 4 packed pairs
       float2 sum2 = make_float2(0.f, 0.f);
 #pragma unroll
       for (int j = 0; j < NCH; ++j) {
-        const bool run_ok = (lane + 32 * j) < W8;
-        float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0, q0 = g0, q1 = g0;
-        if (run_ok) {
-          g0 = w_ldg_cal16(gp + (2 * j) * 128, pol.keep);
-          g1 = w_ldg_cal16(gp + (2 * j + 1) * 128, pol.keep);
-          if constexpr (HAS_SUB) {
-            q0 = w_ldg_cal16(sp + (2 * j) * 128, pol.keep);
-            q1 = w_ldg_cal16(sp + (2 * j + 1) * 128, pol.keep);
-          }
+        float4 q0 = make_float4(1.f, 1.f, 1.f, 1.f), q1 = q0;
+        if constexpr (HAS_SUB) {
+          const float* sp = a.subg + (size_t)row * a.calpitch + 4 * lane;
+          q0 = w_ldg_cal16(sp + (2 * j) * 128);
+          q1 = w_ldg_cal16(sp + (2 * j + 1) * 128);
         }
         const unsigned w32[4] = {raw[j].x, raw[j].y, raw[j].z, raw[j].w};
-        const float2 gg[4] = {make_float2(g0.x, g0.y), make_float2(g0.z, g0.w), make_float2(g1.x, g1.y), make_float2(g1.z, g1.w)};
-        const float2 qq[4] = {make_float2(q0.x, q0.y), make_float2(q0.z, q0.w), make_float2(q1.x, q1.y), make_float2(q1.z, q1.w)};
+        const float2 gg[4] = {make_float2(gq[j][0].x, gq[j][0].y), make_float2(gq[j][0].z, gq[j][0].w), make_float2(gq[j][1].x, gq[j][1].y),
+                              make_float2(gq[j][1].z, gq[j][1].w)};
+        const float2 qq[4] = {make_float2(-q0.x, -q0.y), make_float2(-q0.z, -q0.w), make_float2(-q1.x, -q1.y), make_float2(-q1.z, -q1.w)};
 #pragma unroll
         for (int e2 = 0; e2 < 4; ++e2) {
           // u16 -> f32 without a conversion instruction: 0x4B00hhll is the float 2^23 + pixel, the subtraction is exact
@@ -357,34 +428,20 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
           memcpy(&y.y, &hi, 4);
           y = pk_sub(y, make_float2(8388608.f, 8388608.f));
           // t - 1 = y * gain - (subg + 1): the constant keeps the staged values small (t ~ 1 for a normalised interferogram)
-          float2 tv;
-          if constexpr (HAS_SUB)
-            tv = pk_fma(y, gg[e2], make_float2(-qq[e2].x, -qq[e2].y));
-          else
-            tv = pk_fma(y, gg[e2], make_float2(-1.f, -1.f));
-          if (!run_ok) tv = make_float2(0.f, 0.f);
+          const float2 tv = pk_fma(y, gg[e2], qq[e2]);
           s[j][e2] = tv;
           sum2 = pk_add(sum2, tv);
         }
       }
-      if (f == 0) tn = w_shfl_i(tn_raw, 0);
-      // prefetch (TMA unit -> L2): the next frame of this row, else the first frame of the next row
-      if (lane == 0) {
-        if (!last) {
-          w_prefetch_l2(row_ptr(bscan, row, f + 1), rowbytes);
-        } else if (tn < a.nitems) {
-          const int nb = tn / a.oph;
-          w_prefetch_l2(row_ptr(nb, tn - nb * a.oph, 0), rowbytes);
-        }
-      }
-      const float mean = w_sum(sum2.x + sum2.y) * a.inv_W;
+      float sum = sum2.x + sum2.y;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) sum += w_shfl(sum, lane ^ o);
+      const float mean = (sum + pad_corr) * a.inv_W;
       const float2 mean2 = make_float2(mean, mean);
 #pragma unroll
-      for (int j = 0; j < NCH; ++j) {
-        const bool run_ok = (lane + 32 * j) < W8;
+      for (int j = 0; j < NCH; ++j)
 #pragma unroll
-        for (int e2 = 0; e2 < 4; ++e2) s[j][e2] = run_ok ? pk_sub(s[j][e2], mean2) : make_float2(0.f, 0.f);
-      }
+        for (int e2 = 0; e2 < 4; ++e2) s[j][e2] = pk_sub(s[j][e2], mean2);
       // ---------------------------------------------------------------- stage v[i] = P[i] s[i] - Q[i] s[i-1]
       if (lane == 0) *reinterpret_cast<float4*>(wbuf + WP::ZERO_OFF) = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
@@ -392,26 +449,38 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
         // s[i-1] of the run's first sample lives in the previous lane (lane 0: in lane 31's previous run)
         const float sendv = (lane == 31) ? (j > 0 ? s[j > 0 ? j - 1 : 0][3].y : 0.f) : s[j][3].y;
         const float prev = w_shfl(sendv, (lane + 31) & 31);
-        if ((lane + 32 * j) < W8) {
-          const float4 P0 = t_pq[(j * 4 + 0) * 32 + lane], P1 = t_pq[(j * 4 + 1) * 32 + lane];
-          const float4 Q0 = t_pq[(j * 4 + 2) * 32 + lane], Q1 = t_pq[(j * 4 + 3) * 32 + lane];
-          const float sv8[8] = {s[j][0].x, s[j][0].y, s[j][1].x, s[j][1].y, s[j][2].x, s[j][2].y, s[j][3].x, s[j][3].y};
-          const float P[8] = {P0.x, P0.y, P0.z, P0.w, P1.x, P1.y, P1.z, P1.w};
-          const float Q[8] = {Q0.x, Q0.y, Q0.z, Q0.w, Q1.x, Q1.y, Q1.z, Q1.w};
-          float v[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) v[e] = fmaf(-Q[e], e == 0 ? prev : sv8[e - 1], P[e] * sv8[e]);
-          const int run = lane + 32 * j;
-          *reinterpret_cast<float4*>(wbuf + 16 * run) = make_float4(v[0], v[2], v[4], v[6]);
-          *reinterpret_cast<float4*>(wbuf + 4 * WP::PO + 16 * run) = make_float4(v[1], v[3], v[5], v[7]);
-        }
+        const float4 P0 = t_pq[(j * 4 + 0) * 32], P1 = t_pq[(j * 4 + 1) * 32];
+        const float4 Q0 = t_pq[(j * 4 + 2) * 32], Q1 = t_pq[(j * 4 + 3) * 32];
+        const float2 p01 = pk_mul(s[j][0], make_float2(P0.x, P0.y)), p23 = pk_mul(s[j][1], make_float2(P0.z, P0.w));
+        const float2 p45 = pk_mul(s[j][2], make_float2(P1.x, P1.y)), p67 = pk_mul(s[j][3], make_float2(P1.z, P1.w));
+        const float v0 = fmaf(-Q0.x, prev, p01.x), v1 = fmaf(-Q0.y, s[j][0].x, p01.y);
+        const float v2 = fmaf(-Q0.z, s[j][0].y, p23.x), v3 = fmaf(-Q0.w, s[j][1].x, p23.y);
+        const float v4 = fmaf(-Q1.x, s[j][1].y, p45.x), v5 = fmaf(-Q1.y, s[j][2].x, p45.y);
+        const float v6 = fmaf(-Q1.z, s[j][2].y, p67.x), v7 = fmaf(-Q1.w, s[j][3].x, p67.y);
+        const int run = lane + 32 * j;  // padded runs (beyond W) stage zeros: P = Q = 0 there
+        *reinterpret_cast<float4*>(wbuf + 16 * run) = make_float4(v0, v2, v4, v6);
+        *reinterpret_cast<float4*>(wbuf + 4 * WP::PO + 16 * run) = make_float4(v1, v3, v5, v7);
       }
       w_syncwarp();
+      if (f == 0) {
+        it2 = w_shfl_i(it2_raw, 0);
+        // ---- a normalisation job of this warp whose B-scan is complete?  (here nothing but the staged row is live)
+        int ready = 0;
+        if (lane == 0 && myjob < njobs && polled >= a.oph) {
+          w_acquire_fence();
+          ready = 1;
+        }
+        if (w_shfl_i(ready, 0)) {
+          wrow_normalise(na, myjob, lane);
+          myjob += nwarps;
+        }
+      }
+      prefetch_step2(f, it2);
       // ---------------------------------------------------------------- pass A: gather, radix-R, twiddle, exchange
       float2 x[R], y[R];
 #pragma unroll
       for (int a2 = 0; a2 < R / 2; ++a2) {
-        const uint4 o = t_offs[a2 * 32 + lane];
+        const uint4 o = t_offs[a2 * 32];
         x[2 * a2].x = *reinterpret_cast<const float*>(wbuf + o.x);
         x[2 * a2].y = *reinterpret_cast<const float*>(wbuf + o.y);
         x[2 * a2 + 1].x = *reinterpret_cast<const float*>(wbuf + o.z);
@@ -421,7 +490,7 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
       w_syncwarp();  // every lane has gathered: the exchange rows may overwrite the staging planes
 #pragma unroll
       for (int p = 0; p < R / 2; ++p) {
-        const float4 tw = t_twa[p * 32 + lane];
+        const float4 tw = t_twa[p * 32];
         const float2 y0 = p == 0 ? y[0] : cmul(y[2 * p], make_float2(tw.x, tw.y));
         const float2 y1 = cmul(y[2 * p + 1], make_float2(tw.z, tw.w));
         *reinterpret_cast<float4*>(wbuf + p * WP::XPITCH + 16 * lane) = make_float4(y0.x, y0.y, y1.x, y1.y);
@@ -447,13 +516,15 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
         float2 Rv;
         Rv.x = w_shfl(sv2.x, pl);
         Rv.y = w_shfl(sv2.y, pl);
-        const float4 tq = t_twp[(d >> 1) * 32 + lane];
+        const float4 tq = t_twp[(d >> 1) * 32];
         const float Tr = (d & 1) ? tq.z : tq.x, Ti = (d & 1) ? tq.w : tq.y;
         const float2 z = Z[d];
-        const float Ar = z.x + Rv.x, Ai = z.y - Rv.y, Dr = z.x - Rv.x, Di = z.y + Rv.y;
-        const float Br = fmaf(-Ti, Di, Tr * Dr), Bi = fmaf(Ti, Dr, Tr * Di);
-        const float pr = Ar + Br, pi = Ai + Bi, qr = Ar - Br, qi = Ai - Bi;
-        float a1 = fast_sqrt(fmaf(pr, pr, pi * pi)), a2 = fast_sqrt(fmaf(qr, qr, qi * qi));
+        const float2 Rc = make_float2(Rv.x, -Rv.y);
+        const float2 Av = pk_add(z, Rc), Dv = pk_sub(z, Rc);  // A = Z + conj Z', D = Z - conj Z'
+        const float2 Bt = pk_mul(Dv, make_float2(Tr, Tr));
+        const float2 Bv = make_float2(fmaf(-Ti, Dv.y, Bt.x), fmaf(Ti, Dv.x, Bt.y));  // B = T D
+        const float2 pv = pk_add(Av, Bv), qv = pk_sub(Av, Bv);
+        float a1 = fast_sqrt(fmaf(pv.x, pv.x, pv.y * pv.y)), a2 = fast_sqrt(fmaf(qv.x, qv.x, qv.y * qv.y));
         if (d == 0 && lane == 0) {  // the two self-conjugate bins: X[0] = Re Z0 + Im Z0, |X[N/4]| = |Z[N/4]| (same 1/2 scale as the rest)
           a1 = 2.f * fabsf(z.x + z.y);
           a2 = 2.f * fast_sqrt(fmaf(Rv.x, Rv.x, Rv.y * Rv.y));
@@ -473,7 +544,14 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
           }
         }
       }
-      if (!last) continue;
+      if (!last) {
+        issue_loads(it0, f + 1);
+        continue;
+      }
+      // ---------------------------------------------------------------- publish the previous row, start the next row's loads
+      // The gpu-scope fence sits where this warp has nothing in flight: the previous row's dB stores were issued a whole row ago.
+      if (lane == 0 && pend >= 0) w_release_add(sv.cnt + pend, 1);
+      if (it1 < a.nitems) issue_loads(it1, 0);
       // ---------------------------------------------------------------- finalise: dB row to the L2 scratch, min / max
       float* srow = a.scratch + ((size_t)bscan * a.oph + row) * a.Dp;
       float* s1 = srow + lane;          // bin k1 = lane + R d
@@ -497,11 +575,11 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
             ok1 = false;  // bscandb.row(4).copyTo(row(1)), row(0): BscanFFT.cpp:1239-1240
           }
           if (lane == 4 && ok1) {
-            w_st_keep(srow, db1, pol.keep);
-            w_st_keep(srow + 1, db1, pol.keep);
+            w_st_keep(srow, db1);
+            w_st_keep(srow + 1, db1);
           }
-          if (ok1) w_st_keep(s1, db1, pol.keep);
-          if (ok2) w_st_keep(lane == 0 ? srow + N2 / 2 : s2, db2, pol.keep);
+          if (ok1) w_st_keep(s1, db1);
+          if (ok2) w_st_keep(lane == 0 ? srow + N2 / 2 : s2, db2);
           const bool is55 = a.clamp55 && lane == 5 && row == 5;  // forced element: excluded from the min / max of the data
           if (ok1 && !is55) {
             mn = fminf(mn, db1);
@@ -512,18 +590,18 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
             mx = fmaxf(mx, db2);
           }
         } else if (FULLD && R == 32) {
-          w_st_keep(s1 + R * d, db1, pol.keep);
-          w_st_keep(s2 - R * d, db2, pol.keep);
+          w_st_keep(s1 + R * d, db1);
+          w_st_keep(s2 - R * d, db2);
           mn = w_min3(mn, db1, db2);
           mx = w_max3(mx, db1, db2);
         } else {
           if (ok1) {
-            w_st_keep(s1 + R * d, db1, pol.keep);
+            w_st_keep(s1 + R * d, db1);
             mn = fminf(mn, db1);
             mx = fmaxf(mx, db1);
           }
           if (ok2) {
-            w_st_keep(s2 - R * d, db2, pol.keep);
+            w_st_keep(s2 - R * d, db2);
             mn = fminf(mn, db2);
             mx = fmaxf(mx, db2);
           }
@@ -532,7 +610,7 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
       // thresholded min / max of the B-scan (BscanFFT.cpp:1247, 1254): max(., thr) commutes with min / max
       const int imn = w_redux_min(float_to_ordered(fmaxf(mn, a.thr)));
       const int imx = w_redux_max(float_to_ordered(fmaxf(mx, a.thr)));
-      w_syncwarp();  // orders every lane's scratch stores before lane 0's publication below
+      w_syncwarp();  // orders every lane's scratch stores before lane 0's publication (one row later, or in the drain)
       if (lane == 0) {
         const float fmn = ordered_to_float(imn), fmx = ordered_to_float(imx);
         if (fmn <= fmx) {
@@ -551,38 +629,15 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
             cache_mx = fmx;
           }
         }
-        if (pend0 < 0) {
-          pend0 = bscan;
-        } else {
-          if (pend0 == bscan) {
-            w_release_add(sv.cnt + bscan, 2);
-          } else {
-            w_release_add(sv.cnt + pend0, 1);
-            w_atomic_add(sv.cnt + bscan, 1);
-          }
-          pend0 = -1;
-        }
+        pend = bscan;
       }
     }
-
-    // ---- a normalisation job of this warp whose B-scan is complete?
-    {
-      int ready = 0;
-      if (lane == 0 && myjob < njobs && polled >= a.oph) {
-        w_acquire_fence();
-        ready = 1;
-      }
-      ready = w_shfl_i(ready, 0);
-      if (ready) {
-        wrow_normalise<WP>(a, sv, myjob);
-        myjob += nwarps;
-      }
-    }
-    tk = tn;
+    it0 = it1;
+    it1 = it2;
   }
 
-  // ---- drain: publish what is pending, then finish this warp's remaining normalisation jobs
-  if (lane == 0 && pend0 >= 0) w_release_add(sv.cnt + pend0, 1);
+  // ---- drain: publish the last row, then finish this warp's remaining normalisation jobs
+  if (lane == 0 && pend >= 0) w_release_add(sv.cnt + pend, 1);
   while (myjob < njobs) {
     if (lane == 0) {
       const unsigned long long t0 = w_now_ns();
@@ -592,7 +647,7 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
       }
     }
     w_syncwarp();
-    wrow_normalise<WP>(a, sv, myjob);
+    wrow_normalise(na, myjob, lane);
     myjob += nwarps;
   }
 }

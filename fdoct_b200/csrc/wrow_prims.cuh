@@ -144,42 +144,25 @@ WROW_HD float w_max3(float a, float b, float c) {
 }
 
 // ---- global memory with cache hints -------------------------------------------------------------------------------
-// raw pixels: read exactly once, straight from L2 (prefetched there by the TMA unit), no L1 allocation, evict-first in L2
-struct WPolicies {
-  unsigned long long stream, keep;  // L2 evict-first (data read once) / evict-last (data that must stay L2-resident)
-};
-WROW_HD WPolicies w_make_policies() {
-  WPolicies p{0, 0};
-#if WROW_DEVICE_BODY
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p.stream));
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p.keep));
-#endif
-  return p;
-}
-WROW_HD uint4 w_ldg_stream16(const void* p, unsigned long long pol) {
+// raw pixels: read exactly once (prefetched into L2 by the TMA unit): streaming load, evict-first in L1 and L2 (SASS LDG.E.EF)
+WROW_HD uint4 w_ldg_stream16(const void* p) {
 #if WROW_DEVICE_BODY
   uint4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
-               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-               : "l"(p), "l"(pol));
+  asm volatile("ld.global.cs.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
   return v;
 #else
-  (void)pol;
   uint4 v;
   memcpy(&v, p, 16);
   return v;
 #endif
 }
-// calibration rows: L2-resident, re-read by every B-scan, no reuse inside an SM
-WROW_HD float4 w_ldg_cal16(const float* p, unsigned long long pol) {
+// calibration rows: L2-resident, re-read by every B-scan, no reuse inside an SM (no L1 allocation)
+WROW_HD float4 w_ldg_cal16(const float* p) {
 #if WROW_DEVICE_BODY
   float4 v;
-  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
-               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "l"(p), "l"(pol));
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
   return v;
 #else
-  (void)pol;
   float4 v;
   memcpy(&v, p, 16);
   return v;
@@ -203,13 +186,19 @@ WROW_HD int w_ld_cg_i(const int* p) {
   return wemu::load_acquire(p);
 #endif
 }
-// dB scratch: written once, consumed from L2 a few microseconds later
-WROW_HD void w_st_keep(float* p, float v, unsigned long long pol) {
+// dB scratch: written once, consumed from L2 a few microseconds later and then discarded
+WROW_HD void w_st_keep(float* p, float v) {
 #if WROW_DEVICE_BODY
-  asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+  asm volatile("st.global.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 #else
-  (void)pol;
   *p = v;
+#endif
+}
+WROW_HD void w_st_global_u8(uint8_t* p, unsigned v) {  // explicit state space: the caller may have lost it (non-inlined function)
+#if WROW_DEVICE_BODY
+  asm volatile("st.global.u8 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#else
+  *p = (uint8_t)v;
 #endif
 }
 WROW_HD void w_st_stream_u32(void* p, unsigned v) {
