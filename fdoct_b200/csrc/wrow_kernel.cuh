@@ -158,6 +158,7 @@ struct WNormArgs {  // by value: the job runs as a real (non-inlined) device fun
 #else
 #define WROW_NOINLINE static __device__ __noinline__
 #endif
+template <int DEPTH>
 WROW_NOINLINE void wrow_normalise(const WNormArgs a, int job, int lane) {
   const int per_b = a.nparts * a.nsplit;
   const int b = job / per_b;
@@ -171,13 +172,6 @@ WROW_NOINLINE void wrow_normalise(const WNormArgs a, int job, int lane) {
   const int t1 = (t0 + tps) < ntiles ? (t0 + tps) : ntiles;
   if (t0 >= t1) return;
 
-  float mn = ordered_to_float(w_ld_cg_i(a.minv + b)), mx = ordered_to_float(w_ld_cg_i(a.maxv + b));
-  if (a.clamp55) {  // bscandisp.at<double>(5,5) = 50.0 before the min-max (BscanFFT.cpp:1248-1253)
-    mn = fminf(mn, a.clamp_db);
-    mx = fmaxf(mx, a.clamp_db);
-  }
-  const float range = mx - mn;
-  const float sc = range > 2.220446049250313e-16f ? 255.0f / range : 0.f;  // cv::normalize: scale = 0 for a flat image
   const float thr = a.thr;
   const int q = lane >> 2, cg = lane & 3;
   const float* src = a.scratch + ((size_t)b * a.oph + r0) * a.Dp;
@@ -199,6 +193,7 @@ WROW_NOINLINE void wrow_normalise(const WNormArgs a, int job, int lane) {
   float* odb = a.outdb != nullptr ? a.outdb + o_first : nullptr;
   const size_t oph = (size_t)a.oph;
 
+  float mn = 0.f, mx = 0.f, sc = 0.f;  // loaded after the first tiles are in flight
   auto load_tile = [&](int i, float4 (&v)[2][4]) {  // tile t0 + i
 #pragma unroll
     for (int k = 0; k < 2; ++k)
@@ -257,15 +252,40 @@ WROW_NOINLINE void wrow_normalise(const WNormArgs a, int job, int lane) {
     if (lane < nrows) w_discard128(src + (size_t)lane * a.Dp + 32 * t);
   };
 
+  // DEPTH (2 or 3) tiles in flight: nothing else is live in this function, the registers are free for load latency
   const int nt = t1 - t0;
-  float4 va[2][4], vb[2][4];
+  float4 va[2][4], vb[2][4], vc[DEPTH == 3 ? 2 : 1][4];
   load_tile(0, va);
-  for (int i = 0; i < nt; i += 2) {
-    if (i + 1 < nt) load_tile(i + 1, vb);
-    process_tile(i, va);
-    if (i + 1 < nt) {
-      if (i + 2 < nt) load_tile(i + 2, va);
-      process_tile(i + 1, vb);
+  if (DEPTH == 3 && 1 < nt) load_tile(1, vb);
+  mn = ordered_to_float(w_ld_cg_i(a.minv + b));
+  mx = ordered_to_float(w_ld_cg_i(a.maxv + b));
+  if (a.clamp55) {  // bscandisp.at<double>(5,5) = 50.0 before the min-max (BscanFFT.cpp:1248-1253)
+    mn = fminf(mn, a.clamp_db);
+    mx = fmaxf(mx, a.clamp_db);
+  }
+  sc = (mx - mn) > 2.220446049250313e-16f ? 255.0f / (mx - mn) : 0.f;  // cv::normalize: scale = 0 for a flat image
+  if constexpr (DEPTH == 3) {
+    for (int i = 0; i < nt; i += 3) {
+      if (i + 2 < nt) load_tile(i + 2, vc);
+      process_tile(i, va);
+      if (i + 1 < nt) {
+        if (i + 3 < nt) load_tile(i + 3, va);
+        process_tile(i + 1, vb);
+      }
+      if (i + 2 < nt) {
+        if (i + 4 < nt) load_tile(i + 4, vb);
+        process_tile(i + 2, vc);
+      }
+    }
+  } else {
+    (void)vc;
+    for (int i = 0; i < nt; i += 2) {
+      if (i + 1 < nt) load_tile(i + 1, vb);
+      process_tile(i, va);
+      if (i + 1 < nt) {
+        if (i + 2 < nt) load_tile(i + 2, va);
+        process_tile(i + 1, vb);
+      }
     }
   }
 }
@@ -328,7 +348,7 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
   const bool lane_ok = (R == 32) || lane < R;
   const int cc = (R == 32) ? lane : (lane < R ? lane : R - 1);
 
-  int pend = -1;  // (lane 0) B-scan of the finished row whose completion has not been published yet
+  int pend = -1, pend2 = -1;  // (lane 0) B-scans of finished rows whose completion has not been published yet
   int cache_b = -1;
   float cache_mn = 0.f, cache_mx = 0.f;
 
@@ -341,7 +361,6 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
   // ---- register-resident input of the next (item, frame): raw pixels and gain row of this lane's 8-sample runs
   uint4 raw[NCH];
   float4 gq[NCH][2];
-  constexpr int NCH_A = NCH / 2;  // gain runs loaded ahead of time together with the pixels; the rest follows at the row's start
   auto issue_loads = [&](int item, int f) {
     const int b = item / a.oph;
     const int row = item - b * a.oph;
@@ -353,15 +372,7 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
       raw[j] = w_ldg_stream16(rp + 16 * (run < W8m1 ? run : W8m1));  // padded runs re-read the last run (finite values)
     }
 #pragma unroll
-    for (int j = 0; j < NCH_A; ++j) {
-      gq[j][0] = w_ldg_cal16(gp + (2 * j) * 128);
-      gq[j][1] = w_ldg_cal16(gp + (2 * j + 1) * 128);
-    }
-  };
-  auto issue_loads_rest = [&](int row) {
-    const float* gp = a.gain + (size_t)row * a.calpitch + 4 * lane;
-#pragma unroll
-    for (int j = NCH_A; j < NCH; ++j) {
+    for (int j = 0; j < NCH; ++j) {
       gq[j][0] = w_ldg_cal16(gp + (2 * j) * 128);
       gq[j][1] = w_ldg_cal16(gp + (2 * j + 1) * 128);
     }
@@ -373,10 +384,12 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
     const int k = f + 2;
     const int item = k < nA ? it0 : (k < 2 * nA ? it1 : it2);
     const int fr = k < nA ? k : (k < 2 * nA ? k - nA : k - 2 * nA);
-    if (item < a.nitems && fr < nA) w_prefetch_l2(row_ptr(item, fr), rowbytes);
+    if (item < a.nitems && fr < nA) {
+      w_prefetch_l2(row_ptr(item, fr), rowbytes);
+      if (fr == 0) w_prefetch_l2(a.gain + (size_t)(item % a.oph) * a.calpitch, (unsigned)a.calpitch * 4u);
+    }
   };
   if (it0 < a.nitems) {
-    issue_loads(it0, 0);
     if (lane == 0) {
       const int nA = A1 ? 1 : a.A;
       if (nA > 1)
@@ -404,7 +417,7 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
     for (int f = 0; f < nA; ++f) {
       const bool last = A1 || (f + 1 == nA);
       // ---------------------------------------------------------------- pre: pixels -> s = t - mean (registers)
-      issue_loads_rest(row);
+      issue_loads(it0, f);
       float2 s[NCH][4];  // 8 samples of run j as 4 packed pairs
       float2 sum2 = make_float2(0.f, 0.f);
 #pragma unroll
@@ -471,7 +484,7 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
           ready = 1;
         }
         if (w_shfl_i(ready, 0)) {
-          wrow_normalise(na, myjob, lane);
+          wrow_normalise<(WP::NW <= 12 ? 3 : 2)>(na, myjob, lane);
           myjob += nwarps;
         }
       }
@@ -505,108 +518,111 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
       }
       w_syncwarp();  // the buffer is free for the next row's staging
       Dft<32, kFftSign, 1, 1>::run(u, Z);
-      // ---------------------------------------------------------------- split + magnitude
-      float m1[16], m2[16];
-#pragma unroll
-      for (int d = 0; d < 16; ++d) {
-        const int e = 31 - d;
-        // partner value Z[N/2 - k]: slot 31 - d of lane R - c; lane 0 pairs slot d with slot 32 - d of ITSELF (d = 0: slot 16)
-        float2 sv2 = Z[e];
-        if (lane == 0) sv2 = e < 31 ? Z[e < 31 ? e + 1 : e] : Z[16];
-        float2 Rv;
-        Rv.x = w_shfl(sv2.x, pl);
-        Rv.y = w_shfl(sv2.y, pl);
-        const float4 tq = t_twp[(d >> 1) * 32];
-        const float Tr = (d & 1) ? tq.z : tq.x, Ti = (d & 1) ? tq.w : tq.y;
-        const float2 z = Z[d];
-        const float2 Rc = make_float2(Rv.x, -Rv.y);
-        const float2 Av = pk_add(z, Rc), Dv = pk_sub(z, Rc);  // A = Z + conj Z', D = Z - conj Z'
-        const float2 Bt = pk_mul(Dv, make_float2(Tr, Tr));
-        const float2 Bv = make_float2(fmaf(-Ti, Dv.y, Bt.x), fmaf(Ti, Dv.x, Bt.y));  // B = T D
-        const float2 pv = pk_add(Av, Bv), qv = pk_sub(Av, Bv);
-        float a1 = fast_sqrt(fmaf(pv.x, pv.x, pv.y * pv.y)), a2 = fast_sqrt(fmaf(qv.x, qv.x, qv.y * qv.y));
-        if (d == 0 && lane == 0) {  // the two self-conjugate bins: X[0] = Re Z0 + Im Z0, |X[N/4]| = |Z[N/4]| (same 1/2 scale as the rest)
-          a1 = 2.f * fabsf(z.x + z.y);
-          a2 = 2.f * fast_sqrt(fmaf(Rv.x, Rv.x, Rv.y * Rv.y));
+      // ---------------------------------------------------------------- split + magnitude (+ finalise on the last frame)
+      // The dB conversion and the scratch stores are fused into the split loop: every Z register dies as soon as its
+      // pair has been formed, nothing but the running min / max is carried (no magnitude array).
+      if (last && lane == 0 && pend2 >= 0) {
+        // Publish the previous two rows.  The release fence sits where this warp has nothing in flight: their dB stores
+        // were issued a whole row ago.
+        if (pend == pend2) {
+          w_release_add(sv.cnt + pend, 2);
+        } else {
+          w_release_add(sv.cnt + pend, 1);
+          w_atomic_add(sv.cnt + pend2, 1);
         }
-        m1[d] = a1;
-        m2[d] = a2;
+        pend = pend2 = -1;
       }
-      if constexpr (!A1) {
+      float* const srow = a.scratch + ((size_t)bscan * a.oph + row) * a.Dp;
+      float* const s1 = srow + lane;         // bin k1 = lane + R d
+      float* const s2 = srow + (N2 - lane);  // bin k2 = N/2 - lane - R d
+      float mn = w_inf(false), mx = w_inf(true);
+      auto split_pass = [&](auto fin_c) {
+        constexpr bool FIN = decltype(fin_c)::value;
 #pragma unroll
         for (int d = 0; d < 16; ++d) {
-          acc1[d] += m1[d];
-          acc2[d] += m2[d];
-          if (last) {
-            m1[d] = acc1[d];
-            m2[d] = acc2[d];
-            acc1[d] = acc2[d] = 0.f;
+          const int e = 31 - d;
+          // partner value Z[N/2 - k]: slot 31 - d of lane R - c; lane 0 pairs slot d with slot 32 - d of ITSELF (d = 0: slot 16)
+          float2 sv2 = Z[e];
+          if (lane == 0) sv2 = e < 31 ? Z[e < 31 ? e + 1 : e] : Z[16];
+          float2 Rv;
+          Rv.x = w_shfl(sv2.x, pl);
+          Rv.y = w_shfl(sv2.y, pl);
+          const float4 tq = t_twp[(d >> 1) * 32];
+          const float Tr = (d & 1) ? tq.z : tq.x, Ti = (d & 1) ? tq.w : tq.y;
+          const float2 z = Z[d];
+          const float2 Rc = make_float2(Rv.x, -Rv.y);
+          const float2 Av = pk_add(z, Rc), Dv = pk_sub(z, Rc);  // A = Z + conj Z', D = Z - conj Z'
+          const float2 Bt = pk_mul(Dv, make_float2(Tr, Tr));
+          const float2 Bv = make_float2(fmaf(-Ti, Dv.y, Bt.x), fmaf(Ti, Dv.x, Bt.y));  // B = T D
+          const float2 pv = pk_add(Av, Bv), qv = pk_sub(Av, Bv);
+          float a1 = fast_sqrt(fmaf(pv.x, pv.x, pv.y * pv.y)), a2 = fast_sqrt(fmaf(qv.x, qv.x, qv.y * qv.y));
+          if (d == 0 && lane == 0) {  // the two self-conjugate bins: X[0] = Re Z0 + Im Z0, |X[N/4]| = |Z[N/4]| (same 1/2 scale as the rest)
+            a1 = 2.f * fabsf(z.x + z.y);
+            a2 = 2.f * fast_sqrt(fmaf(Rv.x, Rv.x, Rv.y * Rv.y));
+          }
+          if constexpr (!A1) {  // accumulate(magI, bscantransposed) over the frames of the B-scan (BscanFFT.cpp:1193-1209)
+            a1 += acc1[d];
+            a2 += acc2[d];
+            acc1[d] = FIN ? 0.f : a1;
+            acc2[d] = FIN ? 0.f : a2;
+          }
+          if constexpr (FIN) {
+            // /A, + 1e-5, ln, * 20 / 2.303 (BscanFFT.cpp:1221-1237)
+            const float db1 = fast_log2(fmaf(a1, a.out_scale, 1e-5f)) * a.db_scale;
+            const float db2 = fast_log2(fmaf(a2, a.out_scale, 1e-5f)) * a.db_scale;
+            const int k1 = lane + R * d;
+            int k2 = N2 - lane - R * d;
+            bool ok1 = lane_ok && (FULLD || k1 < a.D);
+            bool ok2 = lane_ok && (FULLD || k2 < a.D);
+            if (d == 0) {
+              // special bins live in slot 0 only: 0, 1 (masked), 4 (the mask source), 5 (clampupper), and lane 0's second
+              // output is bin N/4 instead of the non-existent bin N/2
+              if (lane == 0) k2 = N2 / 2;
+              ok2 = lane_ok && (lane == 0 ? (FULLD || N2 / 2 < a.D) : ok2);
+              if (lane < 2) {
+                if (a.dc01 != nullptr && ok1) a.dc01[2 * ((size_t)bscan * a.oph + row) + lane] = db1;  // kept on request only
+                ok1 = false;  // bscandb.row(4).copyTo(row(1)), row(0): BscanFFT.cpp:1239-1240
+              }
+              if (lane == 4 && ok1) {
+                w_st_keep(srow, db1);
+                w_st_keep(srow + 1, db1);
+              }
+              if (ok1) w_st_keep(s1, db1);
+              if (ok2) w_st_keep(lane == 0 ? srow + N2 / 2 : s2, db2);
+              const bool is55 = a.clamp55 && lane == 5 && row == 5;  // forced element: excluded from the min / max of the data
+              if (ok1 && !is55) {
+                mn = fminf(mn, db1);
+                mx = fmaxf(mx, db1);
+              }
+              if (ok2) {
+                mn = fminf(mn, db2);
+                mx = fmaxf(mx, db2);
+              }
+            } else if (FULLD && R == 32) {
+              w_st_keep(s1 + R * d, db1);
+              w_st_keep(s2 - R * d, db2);
+              mn = w_min3(mn, db1, db2);
+              mx = w_max3(mx, db1, db2);
+            } else {
+              if (ok1) {
+                w_st_keep(s1 + R * d, db1);
+                mn = fminf(mn, db1);
+                mx = fmaxf(mx, db1);
+              }
+              if (ok2) {
+                w_st_keep(s2 - R * d, db2);
+                mn = fminf(mn, db2);
+                mx = fmaxf(mx, db2);
+              }
+            }
           }
         }
-      }
+      };
       if (!last) {
-        issue_loads(it0, f + 1);
+        split_pass(std::false_type{});
         continue;
       }
-      // ---------------------------------------------------------------- publish the previous row, start the next row's loads
-      // The gpu-scope fence sits where this warp has nothing in flight: the previous row's dB stores were issued a whole row ago.
-      if (lane == 0 && pend >= 0) w_release_add(sv.cnt + pend, 1);
-      if (it1 < a.nitems) issue_loads(it1, 0);
-      // ---------------------------------------------------------------- finalise: dB row to the L2 scratch, min / max
-      float* srow = a.scratch + ((size_t)bscan * a.oph + row) * a.Dp;
-      float* s1 = srow + lane;          // bin k1 = lane + R d
-      float* s2 = srow + (N2 - lane);   // bin k2 = N/2 - lane - R d
-      float mn = w_inf(false), mx = w_inf(true);
-#pragma unroll
-      for (int d = 0; d < 16; ++d) {
-        const float db1 = fast_log2(fmaf(m1[d], a.out_scale, 1e-5f)) * a.db_scale;
-        const float db2 = fast_log2(fmaf(m2[d], a.out_scale, 1e-5f)) * a.db_scale;
-        const int k1 = lane + R * d;
-        int k2 = N2 - lane - R * d;
-        bool ok1 = lane_ok && (FULLD || k1 < a.D);
-        bool ok2 = lane_ok && (FULLD || k2 < a.D);
-        if (d == 0) {
-          // special bins live in slot 0 only: 0, 1 (masked), 4 (the mask source), 5 (clampupper), and lane 0's second
-          // output is bin N/4 instead of the non-existent bin N/2
-          if (lane == 0) k2 = N2 / 2;
-          ok2 = lane_ok && (lane == 0 ? (FULLD || N2 / 2 < a.D) : ok2);
-          if (lane < 2) {
-            if (a.dc01 != nullptr && ok1) a.dc01[2 * ((size_t)bscan * a.oph + row) + lane] = db1;  // kept on request only
-            ok1 = false;  // bscandb.row(4).copyTo(row(1)), row(0): BscanFFT.cpp:1239-1240
-          }
-          if (lane == 4 && ok1) {
-            w_st_keep(srow, db1);
-            w_st_keep(srow + 1, db1);
-          }
-          if (ok1) w_st_keep(s1, db1);
-          if (ok2) w_st_keep(lane == 0 ? srow + N2 / 2 : s2, db2);
-          const bool is55 = a.clamp55 && lane == 5 && row == 5;  // forced element: excluded from the min / max of the data
-          if (ok1 && !is55) {
-            mn = fminf(mn, db1);
-            mx = fmaxf(mx, db1);
-          }
-          if (ok2) {
-            mn = fminf(mn, db2);
-            mx = fmaxf(mx, db2);
-          }
-        } else if (FULLD && R == 32) {
-          w_st_keep(s1 + R * d, db1);
-          w_st_keep(s2 - R * d, db2);
-          mn = w_min3(mn, db1, db2);
-          mx = w_max3(mx, db1, db2);
-        } else {
-          if (ok1) {
-            w_st_keep(s1 + R * d, db1);
-            mn = fminf(mn, db1);
-            mx = fmaxf(mx, db1);
-          }
-          if (ok2) {
-            w_st_keep(s2 - R * d, db2);
-            mn = fminf(mn, db2);
-            mx = fmaxf(mx, db2);
-          }
-        }
-      }
+      split_pass(std::true_type{});
       // thresholded min / max of the B-scan (BscanFFT.cpp:1247, 1254): max(., thr) commutes with min / max
       const int imn = w_redux_min(float_to_ordered(fmaxf(mn, a.thr)));
       const int imx = w_redux_max(float_to_ordered(fmaxf(mx, a.thr)));
@@ -629,7 +645,10 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
             cache_mx = fmx;
           }
         }
-        pend = bscan;
+        if (pend < 0)
+          pend = bscan;
+        else
+          pend2 = bscan;
       }
     }
     it0 = it1;
@@ -637,7 +656,10 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
   }
 
   // ---- drain: publish the last row, then finish this warp's remaining normalisation jobs
-  if (lane == 0 && pend >= 0) w_release_add(sv.cnt + pend, 1);
+  if (lane == 0 && pend >= 0) {
+    w_release_add(sv.cnt + pend, 1);
+    if (pend2 >= 0) w_atomic_add(sv.cnt + pend2, 1);
+  }
   while (myjob < njobs) {
     if (lane == 0) {
       const unsigned long long t0 = w_now_ns();
@@ -647,7 +669,7 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
       }
     }
     w_syncwarp();
-    wrow_normalise(na, myjob, lane);
+    wrow_normalise<(WP::NW <= 12 ? 3 : 2)>(na, myjob, lane);
     myjob += nwarps;
   }
 }

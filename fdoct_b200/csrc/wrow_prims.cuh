@@ -257,8 +257,8 @@ WROW_HD void w_atomic_max(int* p, int v) {
 // publish: everything this WARP wrote before the preceding w_syncwarp() becomes visible before the count (cumulative release)
 WROW_HD void w_release_add(int* p, int v) {
 #if WROW_DEVICE_BODY
-  __threadfence();
-  atomicAdd(p, v);  // result unused -> RED
+  // release at gpu scope (fence.acq_rel, lighter than the fence.sc of __threadfence) + RED
+  asm volatile("red.release.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 #else
   wemu::atomic_add(p, v);
 #endif
@@ -281,7 +281,7 @@ WROW_HD int w_ld_relaxed(const int* p) {
 }
 WROW_HD void w_acquire_fence() {
 #if WROW_DEVICE_BODY
-  __threadfence();
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
 #endif
 }
 WROW_HD void w_backoff() {
