@@ -26,7 +26,6 @@ thread_local std::string g_create_error;
 
 constexpr int kTimedChunks = 512;  // timing-event pool size (chunks timed between two abcoct_timing_reset calls)
 constexpr int kSlots = 3;  // pinned-ring depth per GPU (>= 3 streams per GPU)
-constexpr int kWrowDefaultWarps = 16;  // warps per CTA of the warp-per-A-scan kernel unless ABCOCT_WROW_NW says otherwise
 
 // the images one call can produce (abcoct_outputs), bytes per pixel of each
 enum { O_U8 = 0, O_DB, O_LIN, O_BGR, O_JSUB, O_JBGR, O_COUNT };
@@ -365,7 +364,7 @@ int upload_calibration(abcoct_ctx* c) {
     if (const char* e = getenv("ABCOCT_WROW_NW")) nw = atoi(e);
     if (force != 1) {
       wp = nw ? find_wplan(c->N, nw) : nullptr;
-      if (!wp) wp = find_wplan(c->N, kWrowDefaultWarps);
+      if (!wp) wp = find_wplan(c->N, 0);
     }
   }
   c->wplan = wp;
@@ -915,13 +914,13 @@ int abcoct_create(const abcoct_params* params, const int* gpu_ids, int ngpu, abc
   // warp-per-A-scan kernel: 16-bit frames straight into the transform (no optional pre-processing stage), the reference's
   // source-indexed resampling weight (BscanFFT.cpp:1170), a transform length it has a plan for, and no gather from sample 0
   // (whose slope the reference copies from sample 1, :1161 - the fallback kernel handles that corner)
-  c->wrow_eligible = !c->general && params->weight_mode == 0 && params->bpp == 16 && find_wplan(c->N, kWrowDefaultWarps) != nullptr;
+  c->wrow_eligible = !c->general && params->weight_mode == 0 && params->bpp == 16 && find_wplan(c->N, 0) != nullptr;
   for (int q = 1; q + 1 < c->N && c->wrow_eligible; ++q) c->wrow_eligible = c->nk[q] >= 1 && c->nk[q] < c->opw;
   if (c->wrow_eligible) {
     std::vector<int> widx(c->N);
     for (int q = 0; q < c->N; ++q) widx[q] = (q == 0 || q == c->N - 1) ? -1 : c->nk[q];
     WrowTablesHost wt{c->opw, widx.data(), c->frac.data(), c->win.data()};
-    find_wplan(c->N, kWrowDefaultWarps)->build_blob(wt, c->wblob);  // the blob does not depend on the warps per CTA
+    find_wplan(c->N, 0)->build_blob(wt, c->wblob);  // the blob does not depend on the warps per CTA
   }
   std::vector<float2> twW, twM;
   if (params->fft_multiplier > 1) {

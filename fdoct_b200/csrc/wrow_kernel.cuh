@@ -58,8 +58,14 @@ struct WPlan {
   static constexpr int T_TWA = T_PQ + NCH * 4 * 32 * 16;    // float4 [R/2][32]: w^(b 2p), w^(b (2p+1))
   static constexpr int T_TWP = T_TWA + (R / 2) * 32 * 16;   // float4 [8][32]: T[c + R 2 d2], T[c + R (2 d2 + 1)]
   static constexpr int TABLE_BYTES = T_TWP + 8 * 32 * 16;
-  static constexpr int SMEM_BYTES = TABLE_BYTES + NW * WBUF;
+  // per warp: WBUF (gain row by TMA -> staged samples -> exchange rows, in turn), the raw pixel row (TMA) and its mbarrier
+  static constexpr int RAWBUF = WMAX * 2;
+  static constexpr int WSTRIDE = WBUF + RAWBUF + 64;  // + mbarrier and lane 0's bookkeeping words
+  static constexpr int SMEM_BYTES = TABLE_BYTES + NW * WSTRIDE;
+  static_assert(WMAX * 4 <= WBUF, "the calibration row must fit the warp buffer");
+  static_assert(SMEM_BYTES <= 227 * 1024, "too many warps per CTA for the shared memory");
   static constexpr int ZERO_OFF = (WMAX / 2) * 4;  // byte offset of the zero sentinel inside a warp buffer
+  static constexpr int MAXREG = cmax(32, ((65536 / (NW * 32)) / 8) * 8 > 255 ? 255 : ((65536 / (NW * 32)) / 8) * 8);  // one CTA per SM
 };
 
 // byte offset of staged sample i inside a warp buffer (two planes: even samples, then odd samples)
@@ -302,12 +308,15 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
     uint4* dst = reinterpret_cast<uint4*>(smem);
     for (int i = warp * 32 + lane; i < WP::TABLE_BYTES / 16; i += WP::NW * 32) dst[i] = src[i];
   }
+  if (lane == 0) w_mbar_init(reinterpret_cast<unsigned long long*>(smem + WP::TABLE_BYTES + warp * WP::WSTRIDE + WP::WBUF + WP::RAWBUF));
   w_syncthreads();
   const uint4* t_offs = reinterpret_cast<const uint4*>(smem + WP::T_OFFS) + lane;
   const float4* t_pq = reinterpret_cast<const float4*>(smem + WP::T_PQ) + lane;
   const float4* t_twa = reinterpret_cast<const float4*>(smem + WP::T_TWA) + lane;
   const float4* t_twp = reinterpret_cast<const float4*>(smem + WP::T_TWP) + lane;
-  unsigned char* const wbuf = smem + WP::TABLE_BYTES + warp * WP::WBUF;
+  unsigned char* const wbuf = smem + WP::TABLE_BYTES + warp * WP::WSTRIDE;
+  unsigned char* const rawbuf = wbuf + WP::WBUF;
+  unsigned long long* const mbar = reinterpret_cast<unsigned long long*>(rawbuf + WP::RAWBUF);
   const SchedView sv = sched_view(a.sched, a.nB);
   const int W8m1 = (a.W >> 3) - 1;
   const unsigned rowbytes = (unsigned)a.W * 2u;
@@ -318,20 +327,23 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
   const int njobs = a.nB * a.nparts * a.nsplit;
   const int per_b = a.nparts * a.nsplit;
   int myjob = w_cta() * WP::NW + warp;  // normalisation jobs are assigned statically: myjob, myjob + nwarps, ...
-  WNormArgs na;
-  na.scratch = a.scratch;
-  na.out8 = a.out8;
-  na.outdb = a.outdb;
-  na.minv = sv.minv;
-  na.maxv = sv.maxv;
-  na.oph = a.oph;
-  na.D = a.D;
-  na.Dp = a.Dp;
-  na.nparts = a.nparts;
-  na.nsplit = a.nsplit;
-  na.clamp55 = a.clamp55;
-  na.thr = a.thr;
-  na.clamp_db = a.clamp_db;
+  auto norm_args = [&]() {  // built from the kernel parameters (constant bank) at the call, not kept in registers
+    WNormArgs na;
+    na.scratch = a.scratch;
+    na.out8 = a.out8;
+    na.outdb = a.outdb;
+    na.minv = sv.minv;
+    na.maxv = sv.maxv;
+    na.oph = a.oph;
+    na.D = a.D;
+    na.Dp = a.Dp;
+    na.nparts = a.nparts;
+    na.nsplit = a.nsplit;
+    na.clamp55 = a.clamp55;
+    na.thr = a.thr;
+    na.clamp_db = a.clamp_db;
+    return na;
+  };
 
   auto row_ptr = [&](int item, int f) -> const uint8_t* {
     const int b = item / a.oph;
@@ -348,9 +360,56 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
   const bool lane_ok = (R == 32) || lane < R;
   const int cc = (R == 32) ? lane : (lane < R ? lane : R - 1);
 
-  int pend = -1, pend2 = -1;  // (lane 0) B-scans of finished rows whose completion has not been published yet
-  int cache_b = -1;
-  float cache_mn = 0.f, cache_mx = 0.f;
+  // Lane 0's bookkeeping lives in shared memory (it would otherwise cost every lane nine registers across the transform):
+  //   st[0], st[1]  B-scans of finished rows whose completion has not been published yet (-1: none)
+  //   st[2..4]      B-scan and bounds of the last min / max this warp pushed (skip atomics that cannot change anything)
+  //   st[5..7]      the finished row whose min / max have not been pushed yet: B-scan (-1: none), ordered min, ordered max
+  int* const st = reinterpret_cast<int*>(rawbuf + WP::RAWBUF + 16);
+  if (lane == 0) {
+    st[0] = st[1] = st[2] = st[5] = -1;
+    st[3] = st[4] = 0;
+  }
+  auto publish2 = [&]() {  // lane 0: two rows per release fence
+    const int p0 = st[0], p1 = st[1];
+    if (p1 < 0) return;
+    if (p0 == p1) {
+      w_release_add(sv.cnt + p0, 2);
+    } else {
+      w_release_add(sv.cnt + p0, 1);
+      w_atomic_add(sv.cnt + p1, 1);
+    }
+    st[0] = st[1] = -1;
+  };
+  auto housekeep = [&]() {  // lane 0
+    const int hb = st[5];
+    if (hb < 0) return;
+    const int imn = st[6], imx = st[7];
+    const float fmn = ordered_to_float(imn), fmx = ordered_to_float(imx);
+    if (fmn <= fmx) {
+      // most rows do not move the B-scan's extrema: skip the atomics when this warp already pushed tighter bounds
+      float cmn = w_inf(false), cmx = w_inf(true);
+      if (st[2] == hb) {
+        cmn = ordered_to_float(st[3]);
+        cmx = ordered_to_float(st[4]);
+      }
+      if (fmn < cmn) {
+        w_atomic_min(sv.minv + hb, imn);
+        cmn = fmn;
+      }
+      if (fmx > cmx) {
+        w_atomic_max(sv.maxv + hb, imx);
+        cmx = fmx;
+      }
+      st[2] = hb;
+      st[3] = float_to_ordered(cmn);
+      st[4] = float_to_ordered(cmx);
+    }
+    if (st[0] < 0)
+      st[0] = hb;
+    else
+      st[1] = hb;
+    st[5] = -1;
+  };
 
   // Work queue of this warp: it0 = the row being processed, it1 = the next one (its pixels and calibration rows are loaded into
   // registers while it0 is finalised), it2 = the one after (its pixel row is pulled into L2 by the TMA unit).  Tickets are
@@ -358,24 +417,32 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
   int it0 = w_shfl_i(claim(), 0);
   int it1 = w_shfl_i(claim(), 0);
 
-  // ---- register-resident input of the next (item, frame): raw pixels and gain row of this lane's 8-sample runs
+  // ---- input of one (item, frame): the pixel row and the gain row arrive in shared memory by TMA bulk copies issued one row
+  // ahead (no registers, no exposed latency); here they are read into registers with conflict-free 16-byte loads
   uint4 raw[NCH];
   float4 gq[NCH][2];
-  auto issue_loads = [&](int item, int f) {
+  unsigned tma_parity = 0;
+  auto tma_issue = [&](int item, int f) {  // lane 0, after every lane is done with the warp buffer
     const int b = item / a.oph;
     const int row = item - b * a.oph;
-    const uint8_t* rp = a.frames + ((size_t)b * a.A + f) * a.frame_stride + (size_t)row * a.row_stride;
-    const float* gp = a.gain + (size_t)row * a.calpitch + 4 * lane;
+    w_tma_arm(mbar, rowbytes + (unsigned)a.calpitch * 4u);
+    w_tma_load(rawbuf, a.frames + ((size_t)b * a.A + f) * a.frame_stride + (size_t)row * a.row_stride, rowbytes, mbar);
+    w_tma_load(wbuf, a.gain + (size_t)row * a.calpitch, (unsigned)a.calpitch * 4u, mbar);
+  };
+  auto take_loads = [&]() {
+    w_mbar_wait(mbar, tma_parity);
+    tma_parity ^= 1u;
 #pragma unroll
     for (int j = 0; j < NCH; ++j) {
       const int run = lane + 32 * j;
-      raw[j] = w_ldg_stream16(rp + 16 * (run < W8m1 ? run : W8m1));  // padded runs re-read the last run (finite values)
+      raw[j] = *reinterpret_cast<const uint4*>(rawbuf + 16 * (run < W8m1 ? run : W8m1));  // padded runs re-read the last run
     }
 #pragma unroll
     for (int j = 0; j < NCH; ++j) {
-      gq[j][0] = w_ldg_cal16(gp + (2 * j) * 128);
-      gq[j][1] = w_ldg_cal16(gp + (2 * j + 1) * 128);
+      gq[j][0] = *reinterpret_cast<const float4*>(wbuf + ((2 * j) * 32 + lane) * 16);
+      gq[j][1] = *reinterpret_cast<const float4*>(wbuf + ((2 * j + 1) * 32 + lane) * 16);
     }
+    w_syncwarp();  // every lane holds its gain values: the buffer may now be overwritten by the staged samples
   };
   // (item, frame) two steps ahead of (it0, f) in this warp's sequence, for the L2 prefetch
   auto prefetch_step2 = [&](int f, int it2) {
@@ -386,11 +453,11 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
     const int fr = k < nA ? k : (k < 2 * nA ? k - nA : k - 2 * nA);
     if (item < a.nitems && fr < nA) {
       w_prefetch_l2(row_ptr(item, fr), rowbytes);
-      if (fr == 0) w_prefetch_l2(a.gain + (size_t)(item % a.oph) * a.calpitch, (unsigned)a.calpitch * 4u);
     }
   };
   if (it0 < a.nitems) {
     if (lane == 0) {
+      tma_issue(it0, 0);
       const int nA = A1 ? 1 : a.A;
       if (nA > 1)
         w_prefetch_l2(row_ptr(it0, 1), rowbytes);
@@ -417,7 +484,7 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
     for (int f = 0; f < nA; ++f) {
       const bool last = A1 || (f + 1 == nA);
       // ---------------------------------------------------------------- pre: pixels -> s = t - mean (registers)
-      issue_loads(it0, f);
+      take_loads();
       float2 s[NCH][4];  // 8 samples of run j as 4 packed pairs
       float2 sum2 = make_float2(0.f, 0.f);
 #pragma unroll
@@ -477,6 +544,7 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
       w_syncwarp();
       if (f == 0) {
         it2 = w_shfl_i(it2_raw, 0);
+        if (lane == 0) housekeep();
         // ---- a normalisation job of this warp whose B-scan is complete?  (here nothing but the staged row is live)
         int ready = 0;
         if (lane == 0 && myjob < njobs && polled >= a.oph) {
@@ -484,7 +552,7 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
           ready = 1;
         }
         if (w_shfl_i(ready, 0)) {
-          wrow_normalise<(WP::NW <= 12 ? 3 : 2)>(na, myjob, lane);
+          wrow_normalise<(WP::NW <= 12 ? 3 : 2)>(norm_args(), myjob, lane);
           myjob += nwarps;
         }
       }
@@ -516,22 +584,20 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
 #pragma unroll
         for (int b = 0; b < 32; ++b) u[b] = *reinterpret_cast<const float2*>(xb + 16 * b);
       }
-      w_syncwarp();  // the buffer is free for the next row's staging
+      w_syncwarp();  // the buffer is free: the TMA unit fetches the next row's pixels and gain while this row is finished
+      if (lane == 0) {
+        if (!last)
+          tma_issue(it0, f + 1);
+        else if (it1 < a.nitems)
+          tma_issue(it1, 0);
+      }
       Dft<32, kFftSign, 1, 1>::run(u, Z);
       // ---------------------------------------------------------------- split + magnitude (+ finalise on the last frame)
       // The dB conversion and the scratch stores are fused into the split loop: every Z register dies as soon as its
       // pair has been formed, nothing but the running min / max is carried (no magnitude array).
-      if (last && lane == 0 && pend2 >= 0) {
-        // Publish the previous two rows.  The release fence sits where this warp has nothing in flight: their dB stores
-        // were issued a whole row ago.
-        if (pend == pend2) {
-          w_release_add(sv.cnt + pend, 2);
-        } else {
-          w_release_add(sv.cnt + pend, 1);
-          w_atomic_add(sv.cnt + pend2, 1);
-        }
-        pend = pend2 = -1;
-      }
+      // Publish the previous two rows.  The release fence sits where this warp has nothing in flight: their dB stores
+      // were issued a whole row ago.
+      if (last && lane == 0) publish2();
       float* const srow = a.scratch + ((size_t)bscan * a.oph + row) * a.Dp;
       float* const s1 = srow + lane;         // bin k1 = lane + R d
       float* const s2 = srow + (N2 - lane);  // bin k2 = N/2 - lane - R d
@@ -623,42 +689,27 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
         continue;
       }
       split_pass(std::true_type{});
-      // thresholded min / max of the B-scan (BscanFFT.cpp:1247, 1254): max(., thr) commutes with min / max
+      // thresholded min / max of the B-scan (BscanFFT.cpp:1247, 1254): max(., thr) commutes with min / max.  The atomics and the
+      // completion bookkeeping of this row are done by lane 0 in the middle of the NEXT row (housekeep), when the reduction
+      // results have long arrived.
       const int imn = w_redux_min(float_to_ordered(fmaxf(mn, a.thr)));
       const int imx = w_redux_max(float_to_ordered(fmaxf(mx, a.thr)));
-      w_syncwarp();  // orders every lane's scratch stores before lane 0's publication (one row later, or in the drain)
       if (lane == 0) {
-        const float fmn = ordered_to_float(imn), fmx = ordered_to_float(imx);
-        if (fmn <= fmx) {
-          // most rows do not move the B-scan's extrema: skip the atomics when this warp already pushed tighter bounds
-          if (cache_b != bscan) {
-            cache_b = bscan;
-            cache_mn = w_inf(false);
-            cache_mx = w_inf(true);
-          }
-          if (fmn < cache_mn) {
-            w_atomic_min(sv.minv + bscan, imn);
-            cache_mn = fmn;
-          }
-          if (fmx > cache_mx) {
-            w_atomic_max(sv.maxv + bscan, imx);
-            cache_mx = fmx;
-          }
-        }
-        if (pend < 0)
-          pend = bscan;
-        else
-          pend2 = bscan;
+        st[5] = bscan;
+        st[6] = imn;
+        st[7] = imx;
       }
     }
     it0 = it1;
     it1 = it2;
   }
 
-  // ---- drain: publish the last row, then finish this warp's remaining normalisation jobs
-  if (lane == 0 && pend >= 0) {
-    w_release_add(sv.cnt + pend, 1);
-    if (pend2 >= 0) w_atomic_add(sv.cnt + pend2, 1);
+  // ---- drain: publish the last rows, then finish this warp's remaining normalisation jobs
+  if (lane == 0) {
+    publish2();   // housekeep() needs a free slot
+    housekeep();  // the last row
+    if (st[0] >= 0) w_release_add(sv.cnt + st[0], 1);
+    if (st[1] >= 0) w_atomic_add(sv.cnt + st[1], 1);
   }
   while (myjob < njobs) {
     if (lane == 0) {
@@ -669,14 +720,14 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
       }
     }
     w_syncwarp();
-    wrow_normalise<(WP::NW <= 12 ? 3 : 2)>(na, myjob, lane);
+    wrow_normalise<(WP::NW <= 12 ? 3 : 2)>(norm_args(), myjob, lane);
     myjob += nwarps;
   }
 }
 
 #ifdef __CUDACC__
 template <class WP, bool HAS_SUB, bool A1, bool FULLD>
-__global__ void __launch_bounds__(WP::NW * 32, 1) wrow_kernel(const ReconArgs a) {
+__global__ void __maxnreg__(WP::MAXREG) wrow_kernel(const ReconArgs a) {
   extern __shared__ __align__(16) unsigned char smem[];
   wrow_body<WP, HAS_SUB, A1, FULLD>(a, smem);
 }

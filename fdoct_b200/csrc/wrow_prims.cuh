@@ -232,6 +232,55 @@ WROW_HD void w_prefetch_l2(const void* p, unsigned bytes) {
 #endif
 }
 
+// ---- TMA bulk copies global -> shared with mbarrier completion (SASS UBLKCP + SYNCS) --------------------------------
+// One mbarrier per warp; lane 0 arms it with the byte count and issues the copies, every lane waits on the phase parity.
+WROW_HD void w_mbar_init(unsigned long long* bar) {
+#if WROW_DEVICE_BODY
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#else
+  *bar = 0;
+#endif
+}
+WROW_HD void w_tma_arm(unsigned long long* bar, unsigned bytes) {  // also orders this warp's earlier generic accesses of the
+#if WROW_DEVICE_BODY                                               // destination before the async-proxy writes
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+#else
+  (void)bar;
+  (void)bytes;
+#endif
+}
+WROW_HD void w_tma_load(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+#if WROW_DEVICE_BODY
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(dst)),
+               "l"(src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+               : "memory");
+#else
+  (void)bar;
+  memcpy(dst, src, bytes);  // lock-step emulation: complete at issue; w_mbar_wait is a warp barrier
+#endif
+}
+WROW_HD void w_mbar_wait(unsigned long long* bar, unsigned parity) {
+#if WROW_DEVICE_BODY
+  unsigned ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+#else
+  (void)bar;
+  (void)parity;
+  wemu::syncwarp();
+#endif
+}
+
 // ---- scheduler atomics --------------------------------------------------------------------------------------------
 WROW_HD int w_atomic_add(int* p, int v) {
 #if WROW_DEVICE_BODY
