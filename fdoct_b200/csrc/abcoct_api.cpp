@@ -359,12 +359,13 @@ int upload_calibration(abcoct_ctx* c) {
   // ABCOCT_WROW_NW = 12 | 16 picks the occupancy point of the plan.
   const WPlanEntry* wp = nullptr;
   if (c->wrow_eligible) {
-    int force = 0, nw = 0;
+    int force = 0, nw = 0, lm = -1;
     if (const char* e = getenv("ABCOCT_KERNEL")) force = atoi(e);
     if (const char* e = getenv("ABCOCT_WROW_NW")) nw = atoi(e);
+    if (const char* e = getenv("ABCOCT_WROW_LM")) lm = atoi(e);
     if (force != 1) {
-      wp = nw ? find_wplan(c->N, nw) : nullptr;
-      if (!wp) wp = find_wplan(c->N, 0);
+      wp = find_wplan(c->N, nw, lm);
+      if (!wp) wp = find_wplan(c->N, 0, -1);
     }
   }
   c->wplan = wp;
@@ -914,13 +915,13 @@ int abcoct_create(const abcoct_params* params, const int* gpu_ids, int ngpu, abc
   // warp-per-A-scan kernel: 16-bit frames straight into the transform (no optional pre-processing stage), the reference's
   // source-indexed resampling weight (BscanFFT.cpp:1170), a transform length it has a plan for, and no gather from sample 0
   // (whose slope the reference copies from sample 1, :1161 - the fallback kernel handles that corner)
-  c->wrow_eligible = !c->general && params->weight_mode == 0 && params->bpp == 16 && find_wplan(c->N, 0) != nullptr;
+  c->wrow_eligible = !c->general && params->weight_mode == 0 && params->bpp == 16 && find_wplan(c->N, 0, -1) != nullptr;
   for (int q = 1; q + 1 < c->N && c->wrow_eligible; ++q) c->wrow_eligible = c->nk[q] >= 1 && c->nk[q] < c->opw;
   if (c->wrow_eligible) {
     std::vector<int> widx(c->N);
     for (int q = 0; q < c->N; ++q) widx[q] = (q == 0 || q == c->N - 1) ? -1 : c->nk[q];
     WrowTablesHost wt{c->opw, widx.data(), c->frac.data(), c->win.data()};
-    find_wplan(c->N, 0)->build_blob(wt, c->wblob);  // the blob does not depend on the warps per CTA
+    find_wplan(c->N, 0, -1)->build_blob(wt, c->wblob);  // the blob does not depend on the warps per CTA
   }
   std::vector<float2> twW, twM;
   if (params->fft_multiplier > 1) {

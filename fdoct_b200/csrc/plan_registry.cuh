@@ -191,6 +191,7 @@ static WPlanEntry make_wentry() {
   e.N = WP::N;
   e.R = WP::R;
   e.nw = WP::NW;
+  e.lm = WP::LM;
   e.wmax = WP::WMAX;
   e.smem_bytes = WP::SMEM_BYTES;
   e.build_blob = &wblob_fn<WP>;

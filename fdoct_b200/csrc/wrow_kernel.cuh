@@ -41,9 +41,13 @@
 
 namespace abcoct {
 
-template <int N_, int NW_>
+// LM_ (how a row's pixels and gain values reach the registers):
+//   0  16-byte global loads at the start of the row (rows pulled into L2 ahead of time by the TMA unit's bulk prefetch)
+//   1  TMA bulk copies of both rows into per-warp shared memory one row ahead (mbarrier), conflict-free 16-byte LDS
+//   2  TMA bulk copy of the gain row into the (idle) exchange buffer, pixels by global loads issued before the split step
+template <int N_, int NW_, int LM_ = 0>
 struct WPlan {
-  static constexpr int N = N_, N2 = N_ / 2, R = N_ / 64, NW = NW_;
+  static constexpr int N = N_, N2 = N_ / 2, R = N_ / 64, NW = NW_, LM = LM_;
   static_assert(N_ % 128 == 0 && R <= 32 && R >= 8, "N must be 128 * even, 512 <= N <= 2048");
   static constexpr int NCH = (N / 8 + 31) / 32;  // 8-sample runs per lane
   static constexpr int WMAX = NCH * 256;         // padded row length (calibration pitch, staging planes)
@@ -59,7 +63,7 @@ struct WPlan {
   static constexpr int T_TWP = T_TWA + (R / 2) * 32 * 16;   // float4 [8][32]: T[c + R 2 d2], T[c + R (2 d2 + 1)]
   static constexpr int TABLE_BYTES = T_TWP + 8 * 32 * 16;
   // per warp: WBUF (gain row by TMA -> staged samples -> exchange rows, in turn), the raw pixel row (TMA) and its mbarrier
-  static constexpr int RAWBUF = WMAX * 2;
+  static constexpr int RAWBUF = LM == 1 ? WMAX * 2 : 0;
   static constexpr int WSTRIDE = WBUF + RAWBUF + 64;  // + mbarrier and lane 0's bookkeeping words
   static constexpr int SMEM_BYTES = TABLE_BYTES + NW * WSTRIDE;
   static_assert(WMAX * 4 <= WBUF, "the calibration row must fit the warp buffer");
@@ -270,27 +274,65 @@ WROW_NOINLINE void wrow_normalise(const WNormArgs a, int job, int lane) {
     mx = fmaxf(mx, a.clamp_db);
   }
   sc = (mx - mn) > 2.220446049250313e-16f ? 255.0f / (mx - mn) : 0.f;  // cv::normalize: scale = 0 for a flat image
+
+  // Fast path (whole 32-row parts, whole tiles, aligned display image, no dB image): straight-line code per tile - packed
+  // arithmetic on the (x, y) / (z, w) halves of every 16-byte load, one 32-bit streaming store per bin, no per-word branches.
+  const bool fast = word_ok && odb == nullptr && 32 * t1 <= a.D;
+  const float2 mn2 = make_float2(mn, mn), sc2 = make_float2(sc, sc), magic2 = make_float2(12582912.0f, 12582912.0f);
+  const float thrm = thr - mn;  // max(x, thr) - mn == max(x - mn, thr - mn)
+  auto fast_tile = [&](int i, float4 (&v)[2][4]) {
+    uint8_t* o = o8 + (size_t)(32 * i) * oph;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+      unsigned qv[4][4];  // [row][bin] quantised values in the low byte
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        float2 lo = pk_sub(make_float2(v[k][rr].x, v[k][rr].y), mn2), hi = pk_sub(make_float2(v[k][rr].z, v[k][rr].w), mn2);
+        lo = pk_fma(make_float2(fmaxf(lo.x, thrm), fmaxf(lo.y, thrm)), sc2, magic2);
+        hi = pk_fma(make_float2(fmaxf(hi.x, thrm), fmaxf(hi.y, thrm)), sc2, magic2);
+        memcpy(&qv[rr][0], &lo.x, 4);
+        memcpy(&qv[rr][1], &lo.y, 4);
+        memcpy(&qv[rr][2], &hi.x, 4);
+        memcpy(&qv[rr][3], &hi.y, 4);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const unsigned w01 = w_byte_perm(qv[0][j], qv[1][j], 0x0040), w23 = w_byte_perm(qv[2][j], qv[3][j], 0x0040);
+        w_st_stream_u32(o + (size_t)(16 * k + j) * oph, w_byte_perm(w01, w23, 0x5410));
+      }
+    }
+    if (has55 && t0 + i == 0 && q == 1 && cg == 1)  // element (5,5), written after (and by the thread of) the word that holds it
+      w_st_global_u8(a.out8 + ((size_t)b * a.D + 5) * oph + 5, quant(a.clamp_db) & 0xffu);
+    w_syncwarp();  // every lane has consumed its loads of this tile: the lines are dead, drop them from L2 without a write-back
+    w_discard128(src + (size_t)lane * a.Dp + 32 * (t0 + i));
+  };
+  auto tile = [&](int i, float4 (&v)[2][4]) {
+    if (fast)
+      fast_tile(i, v);
+    else
+      process_tile(i, v);
+  };
   if constexpr (DEPTH == 3) {
     for (int i = 0; i < nt; i += 3) {
       if (i + 2 < nt) load_tile(i + 2, vc);
-      process_tile(i, va);
+      tile(i, va);
       if (i + 1 < nt) {
         if (i + 3 < nt) load_tile(i + 3, va);
-        process_tile(i + 1, vb);
+        tile(i + 1, vb);
       }
       if (i + 2 < nt) {
         if (i + 4 < nt) load_tile(i + 4, vb);
-        process_tile(i + 2, vc);
+        tile(i + 2, vc);
       }
     }
   } else {
     (void)vc;
     for (int i = 0; i < nt; i += 2) {
       if (i + 1 < nt) load_tile(i + 1, vb);
-      process_tile(i, va);
+      tile(i, va);
       if (i + 1 < nt) {
         if (i + 2 < nt) load_tile(i + 2, va);
-        process_tile(i + 1, vb);
+        tile(i + 1, vb);
       }
     }
   }
@@ -310,30 +352,35 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
   }
   if (lane == 0) w_mbar_init(reinterpret_cast<unsigned long long*>(smem + WP::TABLE_BYTES + warp * WP::WSTRIDE + WP::WBUF + WP::RAWBUF));
   w_syncthreads();
-  const uint4* t_offs = reinterpret_cast<const uint4*>(smem + WP::T_OFFS) + lane;
-  const float4* t_pq = reinterpret_cast<const float4*>(smem + WP::T_PQ) + lane;
-  const float4* t_twa = reinterpret_cast<const float4*>(smem + WP::T_TWA) + lane;
-  const float4* t_twp = reinterpret_cast<const float4*>(smem + WP::T_TWP) + lane;
+  // every table is read as tbl + compile-time offset: one address register for all of them
+  const unsigned char* const tbl = smem + 16 * lane;
+  auto t_offs = [&](int i) { return *reinterpret_cast<const uint4*>(tbl + WP::T_OFFS + 512 * i); };
+  auto t_pq = [&](int i) { return *reinterpret_cast<const float4*>(tbl + WP::T_PQ + 512 * i); };
+  auto t_twa = [&](int i) { return *reinterpret_cast<const float4*>(tbl + WP::T_TWA + 512 * i); };
+  auto t_twp = [&](int i) { return *reinterpret_cast<const float4*>(tbl + WP::T_TWP + 512 * i); };
   unsigned char* const wbuf = smem + WP::TABLE_BYTES + warp * WP::WSTRIDE;
   unsigned char* const rawbuf = wbuf + WP::WBUF;
   unsigned long long* const mbar = reinterpret_cast<unsigned long long*>(rawbuf + WP::RAWBUF);
-  const SchedView sv = sched_view(a.sched, a.nB);
+  // scheduler words (recon_kernel.cuh::sched_view): computed from the kernel parameters where they are used
+  auto sv_ticket = [&]() { return a.sched; };
+  auto sv_minv = [&]() { return a.sched + 32; };
+  auto sv_maxv = [&]() { return a.sched + 32 + a.nB; };
+  auto sv_cnt = [&]() { return a.sched + 32 + 2 * a.nB; };
   const int W8m1 = (a.W >> 3) - 1;
   const unsigned rowbytes = (unsigned)a.W * 2u;
   // samples of the padded runs (W < NCH * 256) see gain 0, i.e. t - 1 = -1 without a subtrahend row: taken out of the mean
   const float pad_corr = HAS_SUB ? 0.f : (float)(NCH * 256 - a.W);
 
-  const int nwarps = w_ncta() * WP::NW;
-  const int njobs = a.nB * a.nparts * a.nsplit;
-  const int per_b = a.nparts * a.nsplit;
+  auto njobs = [&]() { return a.nB * a.nparts * a.nsplit; };
+  auto per_b = [&]() { return a.nparts * a.nsplit; };
   int myjob = w_cta() * WP::NW + warp;  // normalisation jobs are assigned statically: myjob, myjob + nwarps, ...
   auto norm_args = [&]() {  // built from the kernel parameters (constant bank) at the call, not kept in registers
     WNormArgs na;
     na.scratch = a.scratch;
     na.out8 = a.out8;
     na.outdb = a.outdb;
-    na.minv = sv.minv;
-    na.maxv = sv.maxv;
+    na.minv = sv_minv();
+    na.maxv = sv_maxv();
     na.oph = a.oph;
     na.D = a.D;
     na.Dp = a.Dp;
@@ -351,7 +398,7 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
   };
   auto claim = [&]() -> int {  // dynamic schedule: one ticket = one row of one B-scan; the value lives in lane 0 until broadcast
     int t = 0;
-    if (lane == 0) t = w_atomic_add(sv.ticket, 1);
+    if (lane == 0) t = w_atomic_add(sv_ticket(), 1);
     return t;
   };
 
@@ -373,10 +420,10 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
     const int p0 = st[0], p1 = st[1];
     if (p1 < 0) return;
     if (p0 == p1) {
-      w_release_add(sv.cnt + p0, 2);
+      w_release_add(sv_cnt() + p0, 2);
     } else {
-      w_release_add(sv.cnt + p0, 1);
-      w_atomic_add(sv.cnt + p1, 1);
+      w_release_add(sv_cnt() + p0, 1);
+      w_atomic_add(sv_cnt() + p1, 1);
     }
     st[0] = st[1] = -1;
   };
@@ -393,11 +440,11 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
         cmx = ordered_to_float(st[4]);
       }
       if (fmn < cmn) {
-        w_atomic_min(sv.minv + hb, imn);
+        w_atomic_min(sv_minv() + hb, imn);
         cmn = fmn;
       }
       if (fmx > cmx) {
-        w_atomic_max(sv.maxv + hb, imx);
+        w_atomic_max(sv_maxv() + hb, imx);
         cmx = fmx;
       }
       st[2] = hb;
@@ -417,32 +464,61 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
   int it0 = w_shfl_i(claim(), 0);
   int it1 = w_shfl_i(claim(), 0);
 
-  // ---- input of one (item, frame): the pixel row and the gain row arrive in shared memory by TMA bulk copies issued one row
-  // ahead (no registers, no exposed latency); here they are read into registers with conflict-free 16-byte loads
+  // ---- input of one (item, frame), see WPlan::LM.  ahead(): issued by the previous row once it is done with the warp buffer
+  // (LM 1, 2: the TMA unit copies while that row is finished; LM 2 also starts the pixel loads into registers); take(): the
+  // values of this lane's 8-sample runs in registers.
+  constexpr int LM = WP::LM;
   uint4 raw[NCH];
   float4 gq[NCH][2];
   unsigned tma_parity = 0;
-  auto tma_issue = [&](int item, int f) {  // lane 0, after every lane is done with the warp buffer
+  auto pixel_row = [&](int item, int f) -> const uint8_t* {
     const int b = item / a.oph;
-    const int row = item - b * a.oph;
-    w_tma_arm(mbar, rowbytes + (unsigned)a.calpitch * 4u);
-    w_tma_load(rawbuf, a.frames + ((size_t)b * a.A + f) * a.frame_stride + (size_t)row * a.row_stride, rowbytes, mbar);
-    w_tma_load(wbuf, a.gain + (size_t)row * a.calpitch, (unsigned)a.calpitch * 4u, mbar);
+    return a.frames + ((size_t)b * a.A + f) * a.frame_stride + (size_t)(item - b * a.oph) * a.row_stride;
   };
-  auto take_loads = [&]() {
-    w_mbar_wait(mbar, tma_parity);
-    tma_parity ^= 1u;
+  auto ldg_pixels = [&](const uint8_t* rp) {
 #pragma unroll
     for (int j = 0; j < NCH; ++j) {
       const int run = lane + 32 * j;
-      raw[j] = *reinterpret_cast<const uint4*>(rawbuf + 16 * (run < W8m1 ? run : W8m1));  // padded runs re-read the last run
+      raw[j] = w_ldg_stream16(rp + 16 * (run < W8m1 ? run : W8m1));  // padded runs re-read the last run (finite values)
     }
+  };
+  auto ahead = [&](int item, int f) {
+    if constexpr (LM != 0) {
+      if (lane == 0) {
+        const unsigned gbytes = (unsigned)a.calpitch * 4u;
+        w_tma_arm(mbar, gbytes + (LM == 1 ? rowbytes : 0u));
+        if constexpr (LM == 1) w_tma_load(rawbuf, pixel_row(item, f), rowbytes, mbar);
+        w_tma_load(wbuf, a.gain + (size_t)(item % a.oph) * a.calpitch, gbytes, mbar);
+      }
+      if constexpr (LM == 2) ldg_pixels(pixel_row(item, f));
+    }
+  };
+  auto take = [&](int item, int f) {
+    if constexpr (LM == 0) {
+      ldg_pixels(pixel_row(item, f));
+      const float* gp = a.gain + (size_t)(item % a.oph) * a.calpitch + 4 * lane;
 #pragma unroll
-    for (int j = 0; j < NCH; ++j) {
-      gq[j][0] = *reinterpret_cast<const float4*>(wbuf + ((2 * j) * 32 + lane) * 16);
-      gq[j][1] = *reinterpret_cast<const float4*>(wbuf + ((2 * j + 1) * 32 + lane) * 16);
+      for (int j = 0; j < NCH; ++j) {
+        gq[j][0] = w_ldg_cal16(gp + (2 * j) * 128);
+        gq[j][1] = w_ldg_cal16(gp + (2 * j + 1) * 128);
+      }
+    } else {
+      w_mbar_wait(mbar, tma_parity);
+      tma_parity ^= 1u;
+      if constexpr (LM == 1) {
+#pragma unroll
+        for (int j = 0; j < NCH; ++j) {
+          const int run = lane + 32 * j;
+          raw[j] = *reinterpret_cast<const uint4*>(rawbuf + 16 * (run < W8m1 ? run : W8m1));
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < NCH; ++j) {
+        gq[j][0] = *reinterpret_cast<const float4*>(wbuf + ((2 * j) * 32 + lane) * 16);
+        gq[j][1] = *reinterpret_cast<const float4*>(wbuf + ((2 * j + 1) * 32 + lane) * 16);
+      }
+      w_syncwarp();  // every lane holds its gain values: the buffer may now be overwritten by the staged samples
     }
-    w_syncwarp();  // every lane holds its gain values: the buffer may now be overwritten by the staged samples
   };
   // (item, frame) two steps ahead of (it0, f) in this warp's sequence, for the L2 prefetch
   auto prefetch_step2 = [&](int f, int it2) {
@@ -453,11 +529,12 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
     const int fr = k < nA ? k : (k < 2 * nA ? k - nA : k - 2 * nA);
     if (item < a.nitems && fr < nA) {
       w_prefetch_l2(row_ptr(item, fr), rowbytes);
+      if (LM == 0 && fr == 0) w_prefetch_l2(a.gain + (size_t)(item % a.oph) * a.calpitch, (unsigned)a.calpitch * 4u);
     }
   };
   if (it0 < a.nitems) {
+    ahead(it0, 0);
     if (lane == 0) {
-      tma_issue(it0, 0);
       const int nA = A1 ? 1 : a.A;
       if (nA > 1)
         w_prefetch_l2(row_ptr(it0, 1), rowbytes);
@@ -478,13 +555,13 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
     const int it2_raw = claim();  // consumed (broadcast) after the pre-processing phase of the first frame
     int it2 = 0x7fffffff;
     int polled = 0;
-    if (lane == 0 && myjob < njobs) polled = w_ld_relaxed(sv.cnt + myjob / per_b);
+    if (lane == 0 && myjob < njobs()) polled = w_ld_relaxed(sv_cnt() + myjob / per_b());
 
     const int nA = A1 ? 1 : a.A;
     for (int f = 0; f < nA; ++f) {
       const bool last = A1 || (f + 1 == nA);
       // ---------------------------------------------------------------- pre: pixels -> s = t - mean (registers)
-      take_loads();
+      take(it0, f);
       float2 s[NCH][4];  // 8 samples of run j as 4 packed pairs
       float2 sum2 = make_float2(0.f, 0.f);
 #pragma unroll
@@ -529,8 +606,8 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
         // s[i-1] of the run's first sample lives in the previous lane (lane 0: in lane 31's previous run)
         const float sendv = (lane == 31) ? (j > 0 ? s[j > 0 ? j - 1 : 0][3].y : 0.f) : s[j][3].y;
         const float prev = w_shfl(sendv, (lane + 31) & 31);
-        const float4 P0 = t_pq[(j * 4 + 0) * 32], P1 = t_pq[(j * 4 + 1) * 32];
-        const float4 Q0 = t_pq[(j * 4 + 2) * 32], Q1 = t_pq[(j * 4 + 3) * 32];
+        const float4 P0 = t_pq(j * 4 + 0), P1 = t_pq(j * 4 + 1);
+        const float4 Q0 = t_pq(j * 4 + 2), Q1 = t_pq(j * 4 + 3);
         const float2 p01 = pk_mul(s[j][0], make_float2(P0.x, P0.y)), p23 = pk_mul(s[j][1], make_float2(P0.z, P0.w));
         const float2 p45 = pk_mul(s[j][2], make_float2(P1.x, P1.y)), p67 = pk_mul(s[j][3], make_float2(P1.z, P1.w));
         const float v0 = fmaf(-Q0.x, prev, p01.x), v1 = fmaf(-Q0.y, s[j][0].x, p01.y);
@@ -547,21 +624,23 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
         if (lane == 0) housekeep();
         // ---- a normalisation job of this warp whose B-scan is complete?  (here nothing but the staged row is live)
         int ready = 0;
-        if (lane == 0 && myjob < njobs && polled >= a.oph) {
+        if (lane == 0 && myjob < njobs() && polled >= a.oph) {
           w_acquire_fence();
           ready = 1;
         }
         if (w_shfl_i(ready, 0)) {
           wrow_normalise<(WP::NW <= 12 ? 3 : 2)>(norm_args(), myjob, lane);
-          myjob += nwarps;
+          myjob += w_ncta() * WP::NW;
         }
       }
       prefetch_step2(f, it2);
       // ---------------------------------------------------------------- pass A: gather, radix-R, twiddle, exchange
       float2 x[R], y[R];
+      uint4 o_next = t_offs(0);
 #pragma unroll
       for (int a2 = 0; a2 < R / 2; ++a2) {
-        const uint4 o = t_offs[a2 * 32];
+        const uint4 o = o_next;
+        if (a2 + 1 < R / 2) o_next = t_offs(a2 + 1);  // one table row ahead of its use
         x[2 * a2].x = *reinterpret_cast<const float*>(wbuf + o.x);
         x[2 * a2].y = *reinterpret_cast<const float*>(wbuf + o.y);
         x[2 * a2 + 1].x = *reinterpret_cast<const float*>(wbuf + o.z);
@@ -569,9 +648,11 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
       }
       Dft<R, kFftSign, 1, 1>::run(x, y);
       w_syncwarp();  // every lane has gathered: the exchange rows may overwrite the staging planes
+      float4 tw_next = t_twa(0);
 #pragma unroll
       for (int p = 0; p < R / 2; ++p) {
-        const float4 tw = t_twa[p * 32];
+        const float4 tw = tw_next;
+        if (p + 1 < R / 2) tw_next = t_twa(p + 1);  // one table row ahead of its use
         const float2 y0 = p == 0 ? y[0] : cmul(y[2 * p], make_float2(tw.x, tw.y));
         const float2 y1 = cmul(y[2 * p + 1], make_float2(tw.z, tw.w));
         *reinterpret_cast<float4*>(wbuf + p * WP::XPITCH + 16 * lane) = make_float4(y0.x, y0.y, y1.x, y1.y);
@@ -585,12 +666,10 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
         for (int b = 0; b < 32; ++b) u[b] = *reinterpret_cast<const float2*>(xb + 16 * b);
       }
       w_syncwarp();  // the buffer is free: the TMA unit fetches the next row's pixels and gain while this row is finished
-      if (lane == 0) {
-        if (!last)
-          tma_issue(it0, f + 1);
-        else if (it1 < a.nitems)
-          tma_issue(it1, 0);
-      }
+      if (!last)
+        ahead(it0, f + 1);
+      else if (it1 < a.nitems)
+        ahead(it1, 0);
       Dft<32, kFftSign, 1, 1>::run(u, Z);
       // ---------------------------------------------------------------- split + magnitude (+ finalise on the last frame)
       // The dB conversion and the scratch stores are fused into the split loop: every Z register dies as soon as its
@@ -613,7 +692,7 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
           float2 Rv;
           Rv.x = w_shfl(sv2.x, pl);
           Rv.y = w_shfl(sv2.y, pl);
-          const float4 tq = t_twp[(d >> 1) * 32];
+          const float4 tq = t_twp(d >> 1);
           const float Tr = (d & 1) ? tq.z : tq.x, Ti = (d & 1) ? tq.w : tq.y;
           const float2 z = Z[d];
           const float2 Rc = make_float2(Rv.x, -Rv.y);
@@ -708,20 +787,20 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
   if (lane == 0) {
     publish2();   // housekeep() needs a free slot
     housekeep();  // the last row
-    if (st[0] >= 0) w_release_add(sv.cnt + st[0], 1);
-    if (st[1] >= 0) w_atomic_add(sv.cnt + st[1], 1);
+    if (st[0] >= 0) w_release_add(sv_cnt() + st[0], 1);
+    if (st[1] >= 0) w_atomic_add(sv_cnt() + st[1], 1);
   }
-  while (myjob < njobs) {
+  while (myjob < njobs()) {
     if (lane == 0) {
       const unsigned long long t0 = w_now_ns();
-      while (w_ld_acquire(sv.cnt + myjob / per_b) < a.oph) {
+      while (w_ld_acquire(sv_cnt() + myjob / per_b()) < a.oph) {
         w_backoff();
         if (w_now_ns() - t0 > kWrowWatchdogNs) w_trap();  // a scheduling bug must surface as a launch failure, not as a hung GPU
       }
     }
     w_syncwarp();
     wrow_normalise<(WP::NW <= 12 ? 3 : 2)>(norm_args(), myjob, lane);
-    myjob += nwarps;
+    myjob += w_ncta() * WP::NW;
   }
 }
 

@@ -1,21 +1,27 @@
-// Plans of the warp-per-A-scan kernel (wrow_kernel.cuh).
+// Plans of the warp-per-A-scan kernel (wrow_kernel.cuh), transform lengths 2048 and 1920; wrow_kernels_b.cu holds 1280 / 1024.
 #include "plan_registry.cuh"
 
 namespace abcoct {
-// Transform lengths with N / 2 = 32 R, R even and <= 32: one warp holds the whole N/2-point complex transform.
-// Warps per CTA: as many as the shared memory takes (per warp: exchange / staging buffer + pixel row + mbarrier), plus a
-// 12-warp point with 168 registers per thread; abcoct_api.cpp picks (ABCOCT_WROW_NW overrides).
-static const WPlanEntry kWPlans[] = {
-    make_wentry<WPlan<2048, 15>>(), make_wentry<WPlan<2048, 14>>(), make_wentry<WPlan<2048, 12>>(),
-    make_wentry<WPlan<1920, 15>>(), make_wentry<WPlan<1920, 12>>(),
-    make_wentry<WPlan<1280, 16>>(), make_wentry<WPlan<1280, 12>>(),
-    make_wentry<WPlan<1024, 16>>(), make_wentry<WPlan<1024, 12>>(),
+// Transform lengths with N / 2 = 32 R, R even and <= 32: one warp holds the whole N/2-point complex transform.  Per length a
+// few (warps per CTA, load mode) points; the FIRST entry of a length is its default (abcoct_api.cpp; ABCOCT_WROW_NW /
+// ABCOCT_WROW_LM select another one for A/B measurements).
+static const WPlanEntry kWPlansA[] = {
+    make_wentry<WPlan<2048, 16, 0>>(), make_wentry<WPlan<2048, 16, 2>>(), make_wentry<WPlan<2048, 12, 0>>(),
+    make_wentry<WPlan<2048, 12, 1>>(), make_wentry<WPlan<2048, 12, 2>>(),
+    make_wentry<WPlan<1920, 16, 0>>(), make_wentry<WPlan<1920, 16, 2>>(), make_wentry<WPlan<1920, 12, 1>>(),
 };
-// nw > 0: that many warps per CTA exactly; nw == 0: the plan with the most warps
-const WPlanEntry* find_wplan(int N, int nw) {
-  const WPlanEntry* best = nullptr;
-  for (const WPlanEntry& e : kWPlans)
-    if (e.N == N && (nw == 0 ? (best == nullptr || e.nw > best->nw) : e.nw == nw)) best = &e;
-  return best;
+const WPlanEntry* wplans_a(int* n) {
+  *n = (int)(sizeof(kWPlansA) / sizeof(kWPlansA[0]));
+  return kWPlansA;
+}
+const WPlanEntry* wplans_b(int* n);
+const WPlanEntry* find_wplan(int N, int nw, int lm) {
+  for (int part = 0; part < 2; ++part) {
+    int n = 0;
+    const WPlanEntry* e = part ? wplans_b(&n) : wplans_a(&n);
+    for (int i = 0; i < n; ++i)
+      if (e[i].N == N && (nw == 0 || e[i].nw == nw) && (lm < 0 || e[i].lm == lm)) return &e[i];
+  }
+  return nullptr;
 }
 }  // namespace abcoct
