@@ -374,6 +374,7 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
   auto njobs = [&]() { return a.nB * a.nparts * a.nsplit; };
   auto per_b = [&]() { return a.nparts * a.nsplit; };
   int myjob = w_cta() * WP::NW + warp;  // normalisation jobs are assigned statically: myjob, myjob + nwarps, ...
+  int myjob_b = myjob < njobs() ? myjob / per_b() : 0x7fffffff;  // its B-scan (none: never polled)
   auto norm_args = [&]() {  // built from the kernel parameters (constant bank) at the call, not kept in registers
     WNormArgs na;
     na.scratch = a.scratch;
@@ -408,36 +409,44 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
   const int cc = (R == 32) ? lane : (lane < R ? lane : R - 1);
 
   // Lane 0's bookkeeping lives in shared memory (it would otherwise cost every lane nine registers across the transform):
-  //   st[0], st[1]  B-scans of finished rows whose completion has not been published yet (-1: none)
-  //   st[2..4]      B-scan and bounds of the last min / max this warp pushed (skip atomics that cannot change anything)
-  //   st[5..7]      the finished row whose min / max have not been pushed yet: B-scan (-1: none), ordered min, ordered max
+  //   st[0..3]      B-scans of finished rows whose completion has not been published yet (-1: none)
+  //   st[4..6]      B-scan and bounds of the last min / max this warp pushed (skip atomics that cannot change anything)
+  //   st[7..9]      the finished row whose min / max have not been pushed yet: B-scan (-1: none), ordered min, ordered max
+  constexpr int kPub = 4;  // rows per gpu-scope release fence (MEMBAR.ALL.GPU costs about two microseconds)
   int* const st = reinterpret_cast<int*>(rawbuf + WP::RAWBUF + 16);
   if (lane == 0) {
-    st[0] = st[1] = st[2] = st[5] = -1;
-    st[3] = st[4] = 0;
+#pragma unroll
+    for (int i = 0; i < kPub; ++i) st[i] = -1;
+    st[4] = st[7] = -1;
+    st[5] = st[6] = 0;
   }
-  auto publish2 = [&]() {  // lane 0: two rows per release fence
-    const int p0 = st[0], p1 = st[1];
-    if (p1 < 0) return;
-    if (p0 == p1) {
-      w_release_add(sv_cnt() + p0, 2);
-    } else {
-      w_release_add(sv_cnt() + p0, 1);
-      w_atomic_add(sv_cnt() + p1, 1);
+  auto publish = [&](bool all) {  // lane 0: one release fence for up to kPub rows
+    if (!all && st[kPub - 1] < 0) return;
+    bool fenced = false;
+#pragma unroll
+    for (int i = 0; i < kPub; ++i) {
+      const int pb = st[i];
+      if (pb >= 0) {
+        if (!fenced)
+          w_release_add(sv_cnt() + pb, 1);
+        else
+          w_atomic_add(sv_cnt() + pb, 1);
+        fenced = true;
+        st[i] = -1;
+      }
     }
-    st[0] = st[1] = -1;
   };
   auto housekeep = [&]() {  // lane 0
-    const int hb = st[5];
+    const int hb = st[7];
     if (hb < 0) return;
-    const int imn = st[6], imx = st[7];
+    const int imn = st[8], imx = st[9];
     const float fmn = ordered_to_float(imn), fmx = ordered_to_float(imx);
     if (fmn <= fmx) {
       // most rows do not move the B-scan's extrema: skip the atomics when this warp already pushed tighter bounds
       float cmn = w_inf(false), cmx = w_inf(true);
-      if (st[2] == hb) {
-        cmn = ordered_to_float(st[3]);
-        cmx = ordered_to_float(st[4]);
+      if (st[4] == hb) {
+        cmn = ordered_to_float(st[5]);
+        cmx = ordered_to_float(st[6]);
       }
       if (fmn < cmn) {
         w_atomic_min(sv_minv() + hb, imn);
@@ -447,15 +456,17 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
         w_atomic_max(sv_maxv() + hb, imx);
         cmx = fmx;
       }
-      st[2] = hb;
-      st[3] = float_to_ordered(cmn);
-      st[4] = float_to_ordered(cmx);
+      st[4] = hb;
+      st[5] = float_to_ordered(cmn);
+      st[6] = float_to_ordered(cmx);
     }
-    if (st[0] < 0)
-      st[0] = hb;
-    else
-      st[1] = hb;
-    st[5] = -1;
+#pragma unroll
+    for (int i = 0; i < kPub; ++i)
+      if (st[i] < 0) {
+        st[i] = hb;
+        break;
+      }
+    st[7] = -1;
   };
 
   // Work queue of this warp: it0 = the row being processed, it1 = the next one (its pixels and calibration rows are loaded into
@@ -554,8 +565,10 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
     const int row = it0 - bscan * a.oph;
     const int it2_raw = claim();  // consumed (broadcast) after the pre-processing phase of the first frame
     int it2 = 0x7fffffff;
+    // Poll the completion count of this warp's next normalisation job only once the ticket stream has moved past the job's
+    // B-scan (B-scans complete in ticket order, give or take the rows in flight)
     int polled = 0;
-    if (lane == 0 && myjob < njobs()) polled = w_ld_relaxed(sv_cnt() + myjob / per_b());
+    if (lane == 0 && myjob_b < bscan) polled = w_ld_relaxed(sv_cnt() + myjob_b);
 
     const int nA = A1 ? 1 : a.A;
     for (int f = 0; f < nA; ++f) {
@@ -624,16 +637,16 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
         if (lane == 0) housekeep();
         // ---- a normalisation job of this warp whose B-scan is complete?  (here nothing but the staged row is live)
         int ready = 0;
-        if (lane == 0 && myjob < njobs() && polled >= a.oph) {
+        if (lane == 0 && polled >= a.oph) {
           w_acquire_fence();
           ready = 1;
         }
         if (w_shfl_i(ready, 0)) {
           wrow_normalise<(WP::NW <= 12 ? 3 : 2)>(norm_args(), myjob, lane);
           myjob += w_ncta() * WP::NW;
+          myjob_b = myjob < njobs() ? myjob / per_b() : 0x7fffffff;
         }
       }
-      prefetch_step2(f, it2);
       // ---------------------------------------------------------------- pass A: gather, radix-R, twiddle, exchange
       float2 x[R], y[R];
       uint4 o_next = t_offs(0);
@@ -674,9 +687,10 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
       // ---------------------------------------------------------------- split + magnitude (+ finalise on the last frame)
       // The dB conversion and the scratch stores are fused into the split loop: every Z register dies as soon as its
       // pair has been formed, nothing but the running min / max is carried (no magnitude array).
-      // Publish the previous two rows.  The release fence sits where this warp has nothing in flight: their dB stores
-      // were issued a whole row ago.
-      if (last && lane == 0) publish2();
+      // Publish the previous rows (kPub per fence).  The release fence sits where this warp has nothing in flight: their dB
+      // stores were issued at least a whole row ago and this row's L2 prefetch is issued after it.
+      if (last && lane == 0) publish(false);
+      prefetch_step2(f, it2);
       float* const srow = a.scratch + ((size_t)bscan * a.oph + row) * a.Dp;
       float* const s1 = srow + lane;         // bin k1 = lane + R d
       float* const s2 = srow + (N2 - lane);  // bin k2 = N/2 - lane - R d
@@ -774,9 +788,9 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
       const int imn = w_redux_min(float_to_ordered(fmaxf(mn, a.thr)));
       const int imx = w_redux_max(float_to_ordered(fmaxf(mx, a.thr)));
       if (lane == 0) {
-        st[5] = bscan;
-        st[6] = imn;
-        st[7] = imx;
+        st[7] = bscan;
+        st[8] = imn;
+        st[9] = imx;
       }
     }
     it0 = it1;
@@ -785,10 +799,9 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
 
   // ---- drain: publish the last rows, then finish this warp's remaining normalisation jobs
   if (lane == 0) {
-    publish2();   // housekeep() needs a free slot
-    housekeep();  // the last row
-    if (st[0] >= 0) w_release_add(sv_cnt() + st[0], 1);
-    if (st[1] >= 0) w_atomic_add(sv_cnt() + st[1], 1);
+    publish(false);  // housekeep() needs a free slot
+    housekeep();     // the last row
+    publish(true);
   }
   while (myjob < njobs()) {
     if (lane == 0) {

@@ -6,9 +6,8 @@ namespace abcoct {
 // few (warps per CTA, load mode) points; the FIRST entry of a length is its default (abcoct_api.cpp; ABCOCT_WROW_NW /
 // ABCOCT_WROW_LM select another one for A/B measurements).
 static const WPlanEntry kWPlansA[] = {
-    make_wentry<WPlan<2048, 16, 0>>(), make_wentry<WPlan<2048, 16, 2>>(), make_wentry<WPlan<2048, 12, 0>>(),
-    make_wentry<WPlan<2048, 12, 1>>(), make_wentry<WPlan<2048, 12, 2>>(),
-    make_wentry<WPlan<1920, 16, 0>>(), make_wentry<WPlan<1920, 16, 2>>(), make_wentry<WPlan<1920, 12, 1>>(),
+    make_wentry<WPlan<2048, 16, 0>>(), make_wentry<WPlan<2048, 12, 0>>(), make_wentry<WPlan<2048, 12, 1>>(),
+    make_wentry<WPlan<1920, 16, 0>>(), make_wentry<WPlan<1920, 12, 0>>(),
 };
 const WPlanEntry* wplans_a(int* n) {
   *n = (int)(sizeof(kWPlansA) / sizeof(kWPlansA[0]));

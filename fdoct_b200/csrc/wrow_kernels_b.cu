@@ -3,8 +3,8 @@
 
 namespace abcoct {
 static const WPlanEntry kWPlansB[] = {
-    make_wentry<WPlan<1280, 16, 0>>(), make_wentry<WPlan<1280, 16, 1>>(), make_wentry<WPlan<1280, 16, 2>>(),
-    make_wentry<WPlan<1024, 16, 0>>(), make_wentry<WPlan<1024, 16, 1>>(),
+    make_wentry<WPlan<1280, 16, 0>>(), make_wentry<WPlan<1280, 12, 0>>(), make_wentry<WPlan<1280, 16, 1>>(),
+    make_wentry<WPlan<1024, 16, 0>>(), make_wentry<WPlan<1024, 12, 0>>(),
 };
 const WPlanEntry* wplans_b(int* n) {
   *n = (int)(sizeof(kWPlansB) / sizeof(kWPlansB[0]));
