@@ -554,6 +554,8 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
     }
   }
 
+  int nx_raw = claim();  // (lane 0) the ticket after it1, broadcast in the middle of the first row
+  int polled = 0;        // (lane 0) completion count of this warp's next normalisation job, polled one row ahead
   float acc1[16], acc2[16];
   if constexpr (!A1) {
 #pragma unroll
@@ -563,12 +565,7 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
   while (it0 < a.nitems) {
     const int bscan = it0 / a.oph;
     const int row = it0 - bscan * a.oph;
-    const int it2_raw = claim();  // consumed (broadcast) after the pre-processing phase of the first frame
     int it2 = 0x7fffffff;
-    // Poll the completion count of this warp's next normalisation job only once the ticket stream has moved past the job's
-    // B-scan (B-scans complete in ticket order, give or take the rows in flight)
-    int polled = 0;
-    if (lane == 0 && myjob_b < bscan) polled = w_ld_relaxed(sv_cnt() + myjob_b);
 
     const int nA = A1 ? 1 : a.A;
     for (int f = 0; f < nA; ++f) {
@@ -633,7 +630,7 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
       }
       w_syncwarp();
       if (f == 0) {
-        it2 = w_shfl_i(it2_raw, 0);
+        it2 = w_shfl_i(nx_raw, 0);  // claimed in the middle of the previous row
         if (lane == 0) housekeep();
         // ---- a normalisation job of this warp whose B-scan is complete?  (here nothing but the staged row is live)
         int ready = 0;
@@ -646,6 +643,12 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
           myjob += w_ncta() * WP::NW;
           myjob_b = myjob < njobs() ? myjob / per_b() : 0x7fffffff;
         }
+        // The next ticket and the next completion poll are issued here, far from the store burst at the end of a row, and
+        // consumed at this point of the NEXT row.  The poll is gated: only once the ticket stream has moved past the job's
+        // B-scan (B-scans complete in ticket order, give or take the rows in flight).
+        nx_raw = claim();
+        polled = 0;
+        if (lane == 0 && myjob_b < bscan) polled = w_ld_relaxed(sv_cnt() + myjob_b);
       }
       // ---------------------------------------------------------------- pass A: gather, radix-R, twiddle, exchange
       float2 x[R], y[R];
