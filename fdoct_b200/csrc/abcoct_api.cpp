@@ -620,12 +620,13 @@ int enqueue_device(abcoct_ctx* c, GpuState& g, int slot, const uint8_t* d_frames
       a.nitems = c->oph * (int)nb;
       a.nparts = (c->oph + 31) / 32;
       a.calpitch = c->wplan->wmax;
-      grid = std::min(g.sm_count, (a.nitems + c->wplan->nw - 1) / c->wplan->nw);
+      const int workers = c->wplan->nw - 1;  // the last warp of a CTA is its service warp
+      grid = std::min(g.sm_count, (a.nitems + workers - 1) / workers);
       const int ntiles = (c->D + 31) / 32;
-      const long long warps = (long long)grid * c->wplan->nw, parts = (long long)a.nparts * (long long)nb;
-      // enough normalisation jobs for every warp, and - for long launches - jobs short enough (about four tiles = 16 KB of dB
-      // scratch) that a finished B-scan leaves L2 within a few microseconds instead of being written back to HBM
-      long long split = std::max<long long>((ntiles + 3) / 4, warps / parts);
+      const long long parts = (long long)a.nparts * (long long)nb;
+      // normalisation jobs are run by one service warp per CTA: at least one job per CTA (short launches), whole 32-row
+      // parts otherwise
+      long long split = std::max<long long>(1, (grid + parts - 1) / parts);
       if (const char* e = getenv("ABCOCT_NSPLIT")) split = atol(e);
       a.nsplit = (int)std::max<long long>(1, std::min<long long>(ntiles, split));
     }

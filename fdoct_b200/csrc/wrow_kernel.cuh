@@ -64,7 +64,8 @@ struct WPlan {
   static constexpr int TABLE_BYTES = T_TWP + 8 * 32 * 16;
   // per warp: WBUF (gain row by TMA -> staged samples -> exchange rows, in turn), the raw pixel row (TMA) and its mbarrier
   static constexpr int RAWBUF = LM == 1 ? WMAX * 2 : 0;
-  static constexpr int WSTRIDE = WBUF + RAWBUF + 64;  // + mbarrier and lane 0's bookkeeping words
+  static constexpr int WSTRIDE = WBUF + RAWBUF + 128;  // + mbarrier, lane 0's bookkeeping words and the mailbox to the service warp
+  static constexpr int NWK = NW - 1;  // worker warps; the last warp of the CTA is the service warp
   static constexpr int SMEM_BYTES = TABLE_BYTES + NW * WSTRIDE;
   static_assert(WMAX * 4 <= WBUF, "the calibration row must fit the warp buffer");
   static_assert(SMEM_BYTES <= 227 * 1024, "too many warps per CTA for the shared memory");
@@ -373,8 +374,6 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
 
   auto njobs = [&]() { return a.nB * a.nparts * a.nsplit; };
   auto per_b = [&]() { return a.nparts * a.nsplit; };
-  int myjob = w_cta() * WP::NW + warp;  // normalisation jobs are assigned statically: myjob, myjob + nwarps, ...
-  int myjob_b = myjob < njobs() ? myjob / per_b() : 0x7fffffff;  // its B-scan (none: never polled)
   auto norm_args = [&]() {  // built from the kernel parameters (constant bank) at the call, not kept in registers
     WNormArgs na;
     na.scratch = a.scratch;
@@ -408,35 +407,77 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
   const bool lane_ok = (R == 32) || lane < R;
   const int cc = (R == 32) ? lane : (lane < R ? lane : R - 1);
 
-  // Lane 0's bookkeeping lives in shared memory (it would otherwise cost every lane nine registers across the transform):
-  //   st[0..3]      B-scans of finished rows whose completion has not been published yet (-1: none)
-  //   st[4..6]      B-scan and bounds of the last min / max this warp pushed (skip atomics that cannot change anything)
-  //   st[7..9]      the finished row whose min / max have not been pushed yet: B-scan (-1: none), ordered min, ordered max
-  constexpr int kPub = 4;  // rows per gpu-scope release fence (MEMBAR.ALL.GPU costs about two microseconds)
+  // Lane 0's bookkeeping and the mailbox to the service warp live in shared memory (ints at st[]):
+  //   st[0]       rows posted by this warp (written with cta-scope release: the service warp acquires it)
+  //   st[1]       rows consumed by the service warp            st[2]  this warp has finished (no more posts)
+  //   st[4..6]    B-scan and bounds of the last min / max this warp pushed (skip atomics that cannot change anything)
+  //   st[7..9]    the finished row whose min / max have not been pushed yet: B-scan (-1: none), ordered min, ordered max
+  //   st[10..17]  ring of the B-scans of the posted rows
   int* const st = reinterpret_cast<int*>(rawbuf + WP::RAWBUF + 16);
   if (lane == 0) {
-#pragma unroll
-    for (int i = 0; i < kPub; ++i) st[i] = -1;
+    st[0] = st[1] = st[2] = 0;
     st[4] = st[7] = -1;
     st[5] = st[6] = 0;
   }
-  auto publish = [&](bool all) {  // lane 0: one release fence for up to kPub rows
-    if (!all && st[kPub - 1] < 0) return;
-    bool fenced = false;
-#pragma unroll
-    for (int i = 0; i < kPub; ++i) {
-      const int pb = st[i];
-      if (pb >= 0) {
-        if (!fenced)
-          w_release_add(sv_cnt() + pb, 1);
-        else
-          w_atomic_add(sv_cnt() + pb, 1);
-        fenced = true;
-        st[i] = -1;
+  w_syncthreads();  // the service warp reads every mailbox
+
+  if (warp == WP::NW - 1) {
+    // ================================================================================================ service warp
+    // Completion counting and display normalisation for the whole CTA.  Lane l watches the mailbox of worker warp l: rows
+    // whose dB values the worker has stored are published to the other SMs with ONE gpu-scope fence for all of them (the
+    // fence is cumulative over the cta-scope release / acquire of the mailboxes), so the workers never execute a MEMBAR.GPU.
+    // A normalisation job starts as soon as the last row of its B-scan has been counted, while the dB rows are still in L2.
+    int* const mb = reinterpret_cast<int*>(smem + WP::TABLE_BYTES + (lane < WP::NWK ? lane : 0) * WP::WSTRIDE + WP::WBUF + WP::RAWBUF + 16);
+    int seen = 0;
+    int myjob = w_cta();  // jobs cta, cta + ncta, ... (B-scan major: they become ready in this order)
+    const int nj = njobs();
+    unsigned long long idle_since = 0;
+    for (;;) {
+      const int wr = lane < WP::NWK ? w_ld_acquire_cta(mb + 0) : 0;
+      const int fresh = wr - seen;
+      const bool any = w_ballot(fresh > 0) != 0u;
+      if (any) {
+        w_fence_gpu();
+        for (int k = 0; k < fresh; ++k) w_atomic_add(sv_cnt() + mb[10 + ((seen + k) & 7)], 1);  // result unused -> RED
+        if (fresh > 0) {
+          seen = wr;
+          w_st_release_cta(mb + 1, seen);  // frees the ring slots
+        }
+      }
+      bool ran = false;
+      if (myjob < nj) {
+        int c = 0;
+        if (lane == 0) c = w_ld_acquire(sv_cnt() + myjob / per_b());
+        if (w_shfl_i(c, 0) >= a.oph) {
+          wrow_normalise<3>(norm_args(), myjob, lane);
+          myjob += w_ncta();
+          ran = true;
+        }
+      }
+      if (!any && !ran) {
+        const bool done = lane < WP::NWK ? (w_ld_acquire_cta(mb + 2) != 0 && w_ld_acquire_cta(mb + 0) == seen) : true;
+        if (w_ballot(!done) == 0u && myjob >= nj) break;
+        // idle: nothing to publish, the next job's B-scan not complete.  Bounded: a scheduling bug must surface as a launch
+        // failure, not as a hung GPU.
+        const unsigned long long now = w_now_ns();
+        if (idle_since == 0) idle_since = now;
+        if (now - idle_since > kWrowWatchdogNs) w_trap();
+        w_backoff();
+      } else {
+        idle_since = 0;
       }
     }
+    return;
+  }
+
+  // ==================================================================================================== worker warps
+  auto post = [&](int b) {  // lane 0: hand a finished row to the service warp
+    const int wr = st[0];
+    while (wr - w_ld_acquire_cta(st + 1) >= 8) w_backoff();  // ring full (the service warp is inside a job): rare
+    st[10 + (wr & 7)] = b;
+    w_st_release_cta(st + 0, wr + 1);
   };
-  auto housekeep = [&]() {  // lane 0
+  auto housekeep = [&]() {  // lane 0: min / max and completion of the previous row (its stores are a whole row old)
     const int hb = st[7];
     if (hb < 0) return;
     const int imn = st[8], imx = st[9];
@@ -460,12 +501,7 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
       st[5] = float_to_ordered(cmn);
       st[6] = float_to_ordered(cmx);
     }
-#pragma unroll
-    for (int i = 0; i < kPub; ++i)
-      if (st[i] < 0) {
-        st[i] = hb;
-        break;
-      }
+    post(hb);
     st[7] = -1;
   };
 
@@ -555,7 +591,6 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
   }
 
   int nx_raw = claim();  // (lane 0) the ticket after it1, broadcast in the middle of the first row
-  int polled = 0;        // (lane 0) completion count of this warp's next normalisation job, polled one row ahead
   float acc1[16], acc2[16];
   if constexpr (!A1) {
 #pragma unroll
@@ -632,23 +667,7 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
       if (f == 0) {
         it2 = w_shfl_i(nx_raw, 0);  // claimed in the middle of the previous row
         if (lane == 0) housekeep();
-        // ---- a normalisation job of this warp whose B-scan is complete?  (here nothing but the staged row is live)
-        int ready = 0;
-        if (lane == 0 && polled >= a.oph) {
-          w_acquire_fence();
-          ready = 1;
-        }
-        if (w_shfl_i(ready, 0)) {
-          wrow_normalise<(WP::NW <= 12 ? 3 : 2)>(norm_args(), myjob, lane);
-          myjob += w_ncta() * WP::NW;
-          myjob_b = myjob < njobs() ? myjob / per_b() : 0x7fffffff;
-        }
-        // The next ticket and the next completion poll are issued here, far from the store burst at the end of a row, and
-        // consumed at this point of the NEXT row.  The poll is gated: only once the ticket stream has moved past the job's
-        // B-scan (B-scans complete in ticket order, give or take the rows in flight).
-        nx_raw = claim();
-        polled = 0;
-        if (lane == 0 && myjob_b < bscan) polled = w_ld_relaxed(sv_cnt() + myjob_b);
+        nx_raw = claim();  // the next ticket: issued here, far from the store burst at the end of a row
       }
       // ---------------------------------------------------------------- pass A: gather, radix-R, twiddle, exchange
       float2 x[R], y[R];
@@ -690,9 +709,6 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
       // ---------------------------------------------------------------- split + magnitude (+ finalise on the last frame)
       // The dB conversion and the scratch stores are fused into the split loop: every Z register dies as soon as its
       // pair has been formed, nothing but the running min / max is carried (no magnitude array).
-      // Publish the previous rows (kPub per fence).  The release fence sits where this warp has nothing in flight: their dB
-      // stores were issued at least a whole row ago and this row's L2 prefetch is issued after it.
-      if (last && lane == 0) publish(false);
       prefetch_step2(f, it2);
       float* const srow = a.scratch + ((size_t)bscan * a.oph + row) * a.Dp;
       float* const s1 = srow + lane;         // bin k1 = lane + R d
@@ -800,23 +816,11 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
     it1 = it2;
   }
 
-  // ---- drain: publish the last rows, then finish this warp's remaining normalisation jobs
+  // ---- the last row: hand it over, then tell the service warp that this worker is done
+  w_syncwarp();  // every lane's stores of the last row are ordered before lane 0's post
   if (lane == 0) {
-    publish(false);  // housekeep() needs a free slot
-    housekeep();     // the last row
-    publish(true);
-  }
-  while (myjob < njobs()) {
-    if (lane == 0) {
-      const unsigned long long t0 = w_now_ns();
-      while (w_ld_acquire(sv_cnt() + myjob / per_b()) < a.oph) {
-        w_backoff();
-        if (w_now_ns() - t0 > kWrowWatchdogNs) w_trap();  // a scheduling bug must surface as a launch failure, not as a hung GPU
-      }
-    }
-    w_syncwarp();
-    wrow_normalise<(WP::NW <= 12 ? 3 : 2)>(norm_args(), myjob, lane);
-    myjob += w_ncta() * WP::NW;
+    housekeep();
+    w_st_release_cta(st + 2, 1);
   }
 }
 

@@ -31,6 +31,7 @@ void atomic_max(int* p, int v);
 int load_acquire(const int* p);
 void check_smem(const void* p, int bytes, int align);
 void backoff();
+unsigned ballot(int pred);
 }  // namespace wemu
 #else
 #define WROW_HD __device__ __forceinline__
@@ -102,6 +103,13 @@ WROW_HD int w_shfl_i(int v, int src) {
   return __shfl_sync(0xffffffffu, v, src);
 #else
   return (int)wemu::shfl_u32((unsigned)v, src);
+#endif
+}
+WROW_HD unsigned w_ballot(bool pred) {
+#if WROW_DEVICE_BODY
+  return __ballot_sync(0xffffffffu, pred);
+#else
+  return wemu::ballot(pred ? 1 : 0);
 #endif
 }
 WROW_HD float w_sum(float v) {
@@ -319,6 +327,30 @@ WROW_HD int w_ld_acquire(const int* p) {
   return v;
 #else
   return wemu::load_acquire(p);
+#endif
+}
+// cta-scope release / acquire on SHARED-memory words: the mailboxes between the worker warps and the service warp of a CTA
+WROW_HD void w_st_release_cta(int* p, int v) {
+#if WROW_DEVICE_BODY
+  asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+#else
+  __atomic_store_n(p, v, __ATOMIC_SEQ_CST);
+#endif
+}
+WROW_HD int w_ld_acquire_cta(const int* p) {
+#if WROW_DEVICE_BODY
+  int v;
+  asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"((unsigned)__cvta_generic_to_shared(p)) : "memory");
+  return v;
+#else
+  return __atomic_load_n(p, __ATOMIC_SEQ_CST);
+#endif
+}
+// gpu-scope fence of the service warp: cumulative, i.e. it also orders the worker warps' stores that were observed through
+// the cta-scope mailboxes before the counts that follow it
+WROW_HD void w_fence_gpu() {
+#if WROW_DEVICE_BODY
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
 #endif
 }
 WROW_HD int w_ld_relaxed(const int* p) {

@@ -101,6 +101,14 @@ void atomic_max(int* p, int v) {
 int load_acquire(const int* p) { return __atomic_load_n(p, __ATOMIC_SEQ_CST); }
 void check_smem(const void*, int, int) {}
 void backoff() { std::this_thread::yield(); }
+unsigned ballot(int pred) {
+  tl->w->slot[tl->lane] = (unsigned)pred;
+  tl->w->bar.wait();
+  unsigned r = 0;
+  for (int i = 0; i < 32; ++i) r |= (tl->w->slot[i] ? 1u : 0u) << i;
+  tl->w->bar.wait();
+  return r;
+}
 }  // namespace wemu
 
 using namespace abcoct;
@@ -319,6 +327,8 @@ int main(int argc, char** argv) {
     worst = std::max(worst, run_case<WPlan<1280, 2>, false>(Case{1280, 40, 640, 1, 3, 4, 3, false, true, false}, 6));
     // whole 32-row parts, whole tiles, no dB image: the straight-line path of the normalisation jobs (with the forced element)
     worst = std::max(worst, run_case<WPlan<1280, 2>, false>(Case{1280, 64, 640, 1, 2, 5, 2, true, false, false}, 7));
+    // three worker warps per service warp, more B-scans than CTAs: mailboxes, one fence for several workers, job order
+    worst = std::max(worst, run_case<WPlan<1280, 4>, false>(Case{1280, 36, 640, 1, 5, 2, 2, false, false, false}, 8));
   }
   std::printf("worst (in units of the tolerance) = %.3f\n", worst);
   return worst <= 1.0 ? 0 : 1;

@@ -25,8 +25,9 @@ def test_thread_group_emulation_small_plans():
 
 
 def test_warp_per_ascan_kernel_lockstep_emulation():
-    """The WHOLE warp-per-A-scan kernel body (wrow_kernel.cuh: scheduler, both FFT passes, the lane pairing of the split step,
-    DC-row / clampupper special cases, completion protocol, normalisation jobs) executed by 32 host threads per warp against an
+    """The WHOLE warp-per-A-scan kernel body (wrow_kernel.cuh: ticket scheduler, both FFT passes, the lane pairing of the split
+    step, DC-row / clampupper special cases, worker -> service-warp mailboxes, completion protocol, normalisation jobs, all
+    three load modes) executed by 32 host threads per warp against an
     f64 restatement: magnitude within 1e-4 of max(|ref|, 1e-3 A-scan max), display within 1 LSB."""
     out = _run("test_wrow_host")
-    assert out.count("max rel mag err") == 7 and "worst (in units of the tolerance)" in out
+    assert out.count("max rel mag err") == 8 and "worst (in units of the tolerance)" in out
