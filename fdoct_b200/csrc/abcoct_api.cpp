@@ -624,9 +624,10 @@ int enqueue_device(abcoct_ctx* c, GpuState& g, int slot, const uint8_t* d_frames
       grid = std::min(g.sm_count, (a.nitems + workers - 1) / workers);
       const int ntiles = (c->D + 31) / 32;
       const long long parts = (long long)a.nparts * (long long)nb;
-      // normalisation jobs are run by one service warp per CTA: at least one job per CTA (short launches), whole 32-row
-      // parts otherwise
-      long long split = std::max<long long>(1, (grid + parts - 1) / parts);
+      // normalisation jobs (32 A-scans x a range of depth tiles) are handed out dynamically as soon as a B-scan is complete:
+      // about eight tiles (32 KB of dB scratch) per job keeps them short, so the scratch is consumed while it is still in
+      // L2; short launches get at least two jobs per CTA
+      long long split = std::max<long long>((ntiles + 7) / 8, (2LL * grid + parts - 1) / parts);
       if (const char* e = getenv("ABCOCT_NSPLIT")) split = atol(e);
       a.nsplit = (int)std::max<long long>(1, std::min<long long>(ntiles, split));
     }

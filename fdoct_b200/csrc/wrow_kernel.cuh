@@ -421,52 +421,96 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
   }
   w_syncthreads();  // the service warp reads every mailbox
 
+  // ---- the normalisation job queue (global words next to the row ticket): jobs are B-scan major;
+  //   sched[2] = jready: jobs [0, jready) belong to COMPLETE B-scans (a frontier, advanced by whoever sees the next B-scan's
+  //              row count reach oph); sched[1] = jnext: jobs handed out so far (atomicAdd).
+  // A job may run once its number is below jready.  Worker warps only take a job when a fresh snapshot says one is ready, and
+  // never wait for one inside the row loop (the missing row could be their own); service warps and finished workers wait.
+  auto jnext_p = [&]() { return a.sched + 1; };
+  auto jready_p = [&]() { return a.sched + 2; };
+  auto advance_frontier = [&]() {  // lane 0
+    const int jr = w_ld_acquire(jready_p());
+    if (jr >= njobs()) return jr;
+    const int fb = jr / per_b();
+    if (w_ld_acquire(sv_cnt() + fb) >= a.oph) {
+      w_fence_gpu();  // cumulative: the rows counted above are visible to whoever acquires the new frontier
+      w_atomic_max(jready_p(), (fb + 1) * per_b());
+      return (fb + 1) * per_b();
+    }
+    return jr;
+  };
+  // all lanes: wait until job j is ready (lane 0 polls and helps the frontier along), then run it.  `service` is called
+  // between polls (the service warp keeps publishing while it waits).
+  auto run_job_when_ready = [&](int j, auto&& service) {
+    const unsigned long long t_start = w_now_ns();
+    for (;;) {
+      int ok = 0;
+      if (lane == 0) ok = advance_frontier() > j ? 1 : 0;
+      if (w_shfl_i(ok, 0)) break;
+      service();
+      if (w_now_ns() - t_start > kWrowWatchdogNs) w_trap();  // a scheduling bug must surface as a launch failure, not as a hung GPU
+      w_backoff();
+    }
+    wrow_normalise<(WP::NW <= 12 ? 3 : 2)>(norm_args(), j, lane);
+  };
+  // all lanes: hand out and run jobs until none is left (service warps when idle, worker warps after their last row)
+  auto drain_jobs = [&](auto&& service) {
+    for (;;) {
+      int j = 0;
+      if (lane == 0) j = w_ld_relaxed(jnext_p()) < njobs() ? w_atomic_add(jnext_p(), 1) : 0x7fffffff;
+      j = w_shfl_i(j, 0);
+      if (j >= njobs()) break;
+      run_job_when_ready(j, service);
+    }
+  };
+
   if (warp == WP::NW - 1) {
     // ================================================================================================ service warp
-    // Completion counting and display normalisation for the whole CTA.  Lane l watches the mailbox of worker warp l: rows
-    // whose dB values the worker has stored are published to the other SMs with ONE gpu-scope fence for all of them (the
-    // fence is cumulative over the cta-scope release / acquire of the mailboxes), so the workers never execute a MEMBAR.GPU.
-    // A normalisation job starts as soon as the last row of its B-scan has been counted, while the dB rows are still in L2.
+    // Completion counting for the whole CTA.  Lane l watches the mailbox of worker warp l: rows whose dB values the worker
+    // has stored are published to the other SMs with ONE gpu-scope fence for all of them (the fence is cumulative over the
+    // cta-scope release / acquire of the mailboxes), so the workers never execute a MEMBAR.GPU.  In between it advances the
+    // job frontier and runs normalisation jobs itself.
     int* const mb = reinterpret_cast<int*>(smem + WP::TABLE_BYTES + (lane < WP::NWK ? lane : 0) * WP::WSTRIDE + WP::WBUF + WP::RAWBUF + 16);
     int seen = 0;
-    int myjob = w_cta();  // jobs cta, cta + ncta, ... (B-scan major: they become ready in this order)
-    const int nj = njobs();
-    unsigned long long idle_since = 0;
-    for (;;) {
+    auto collect = [&]() -> bool {  // all lanes; true if anything was published
       const int wr = lane < WP::NWK ? w_ld_acquire_cta(mb + 0) : 0;
       const int fresh = wr - seen;
-      const bool any = w_ballot(fresh > 0) != 0u;
+      if (w_ballot(fresh > 0) == 0u) return false;
+      w_fence_gpu();
+      for (int k = 0; k < fresh; ++k) w_atomic_add(sv_cnt() + mb[10 + ((seen + k) & 7)], 1);  // result unused -> RED
+      if (fresh > 0) {
+        seen = wr;
+        w_st_release_cta(mb + 1, seen);  // frees the ring slots
+      }
+      return true;
+    };
+    unsigned long long idle_since = 0;
+    for (;;) {
+      const bool any = collect();
+      // a ready job?  (snapshot; the hand-out itself is an atomicAdd, an overshoot waits in run_job_when_ready)
+      int j = 0x7fffffff;
+      if (lane == 0) {
+        const int jr = advance_frontier();
+        if (w_ld_relaxed(jnext_p()) < jr) j = w_atomic_add(jnext_p(), 1);
+      }
+      j = w_shfl_i(j, 0);
+      if (j < njobs()) {
+        run_job_when_ready(j, [&]() { collect(); });
+        idle_since = 0;
+        continue;
+      }
+      const bool done = lane < WP::NWK ? (w_ld_acquire_cta(mb + 2) != 0 && w_ld_acquire_cta(mb + 0) == seen) : true;
+      if (w_ballot(!done) == 0u) break;  // every worker of this CTA has finished and all their rows are published
       if (any) {
-        w_fence_gpu();
-        for (int k = 0; k < fresh; ++k) w_atomic_add(sv_cnt() + mb[10 + ((seen + k) & 7)], 1);  // result unused -> RED
-        if (fresh > 0) {
-          seen = wr;
-          w_st_release_cta(mb + 1, seen);  // frees the ring slots
-        }
-      }
-      bool ran = false;
-      if (myjob < nj) {
-        int c = 0;
-        if (lane == 0) c = w_ld_acquire(sv_cnt() + myjob / per_b());
-        if (w_shfl_i(c, 0) >= a.oph) {
-          wrow_normalise<3>(norm_args(), myjob, lane);
-          myjob += w_ncta();
-          ran = true;
-        }
-      }
-      if (!any && !ran) {
-        const bool done = lane < WP::NWK ? (w_ld_acquire_cta(mb + 2) != 0 && w_ld_acquire_cta(mb + 0) == seen) : true;
-        if (w_ballot(!done) == 0u && myjob >= nj) break;
-        // idle: nothing to publish, the next job's B-scan not complete.  Bounded: a scheduling bug must surface as a launch
-        // failure, not as a hung GPU.
+        idle_since = 0;
+      } else {
         const unsigned long long now = w_now_ns();
         if (idle_since == 0) idle_since = now;
         if (now - idle_since > kWrowWatchdogNs) w_trap();
         w_backoff();
-      } else {
-        idle_since = 0;
       }
     }
+    drain_jobs([&]() {});  // the tail: the last B-scans complete when the last rows have been published
     return;
   }
 
@@ -597,10 +641,17 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
     for (int d = 0; d < 16; ++d) acc1[d] = acc2[d] = 0.f;
   }
 
+  int myjob = -1;  // a job this warp owns but whose B-scan was not complete yet when it was handed out (overshoot)
   while (it0 < a.nitems) {
     const int bscan = it0 / a.oph;
     const int row = it0 - bscan * a.oph;
     int it2 = 0x7fffffff;
+    // (lane 0) snapshot of the job queue, consumed after the pre-processing phase: no wait, a few microseconds stale
+    int jn_snap = 0, jr_snap = 0;
+    if (lane == 0) {
+      jn_snap = w_ld_relaxed(jnext_p());
+      jr_snap = w_ld_relaxed(jready_p());
+    }
 
     const int nA = A1 ? 1 : a.A;
     for (int f = 0; f < nA; ++f) {
@@ -667,6 +718,27 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
       if (f == 0) {
         it2 = w_shfl_i(nx_raw, 0);  // claimed in the middle of the previous row
         if (lane == 0) housekeep();
+        // ---- a normalisation job?  (here nothing but the staged row is live)  At most one per row; never waited for.
+        int j = -1;
+        if (lane == 0) {
+          if (myjob >= 0) {
+            if (jr_snap > myjob) j = myjob;
+          } else if (jn_snap < jr_snap && jn_snap < njobs()) {
+            const int t = w_atomic_add(jnext_p(), 1);
+            if (t < njobs()) {
+              if (t < jr_snap)
+                j = t;
+              else
+                myjob = t;  // overshoot: owned, run at a later row once the frontier has passed it
+            }
+          }
+          if (j >= 0) {
+            myjob = -1;
+            w_acquire_fence();
+          }
+        }
+        j = w_shfl_i(j, 0);
+        if (j >= 0) wrow_normalise<(WP::NW <= 12 ? 3 : 2)>(norm_args(), j, lane);
         nx_raw = claim();  // the next ticket: issued here, far from the store burst at the end of a row
       }
       // ---------------------------------------------------------------- pass A: gather, radix-R, twiddle, exchange
@@ -822,6 +894,10 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
     housekeep();
     w_st_release_cta(st + 2, 1);
   }
+  // ---- the tail: an owned job first, then help with whatever is left
+  myjob = w_shfl_i(myjob, 0);
+  if (myjob >= 0) run_job_when_ready(myjob, [&]() {});
+  drain_jobs([&]() {});
 }
 
 #ifdef __CUDACC__
