@@ -1105,8 +1105,12 @@ int abcoct_set_calibration_from_frames(abcoct_ctx* c, int which, const void* fra
       for (double& v : acc) v *= s;
     }
     if (c->p.lowpassfilter && which >= 2) host_lpfilter(acc, c->oph, c->opw);  // BscanDark.cpp:1070-1074, 1145-1149, 1218-1222
-  } else if (nframes != 1) {
-    return fail(c, ABCOCT_ERR_INVALID, "the pi-shifted frame is a copy of ONE frame (BscanFFT.cpp:1081)");
+  } else {
+    if (nframes != 1) return fail(c, ABCOCT_ERR_INVALID, "the pi-shifted frame is a copy of ONE frame (BscanFFT.cpp:1081)");
+    // BscanFFT.cpp:1092-1096: the copy is normalised to [0, 1] like data_y is (:1126-1129) - no 0.0001 floor, no division by n
+    if (c->p.rowwisenormalize)
+      for (int r = 0; r < c->oph; ++r) host_normalize(&acc[(size_t)r * c->opw], &acc[(size_t)r * c->opw] + c->opw, 0.0, 1.0);
+    if (!c->p.donotnormalize) host_normalize(acc.data(), acc.data() + n, 0.0, 1.0);
   }
   std::vector<double>& dst = which == 0 ? c->yb : which == 1 ? c->yp : which == 2 ? c->yd : which == 3 ? c->yr : c->ys;
   bool& have = which == 0 ? c->have_yb : which == 1 ? c->have_yp : which == 2 ? c->have_yd : which == 3 ? c->have_yr : c->have_ys;
@@ -1314,13 +1318,22 @@ int abcoct_process_bscans_ex(abcoct_ctx* c, const void* frames, size_t nframes, 
     pd.busy = false;
     return ABCOCT_OK;
   };
+  // on any error: wait for everything already enqueued - the header promises that inputs may be freed on return
+  auto bail = [&](int rc) -> int {
+    for (GpuState& g : c->gpus) {
+      cudaSetDevice(g.dev);
+      for (int s = 0; s < kSlots; ++s) cudaStreamSynchronize(g.stream[s]);
+    }
+    cudaGetLastError();
+    return rc;
+  };
   size_t chunk = 0;
   for (size_t b0 = 0; b0 < nB; b0 += slotB, ++chunk) {
     const size_t nb = std::min(slotB, nB - b0);
     const size_t gi = chunk % ngpu;
     const int s = (int)((chunk / ngpu) % kSlots);
     int rc = drain(gi, s);
-    if (rc) return rc;
+    if (rc) return bail(rc);
     GpuState& g = c->gpus[gi];
     CU(c, cudaSetDevice(g.dev));
     cudaStream_t st = g.stream[s];
@@ -1340,7 +1353,7 @@ int abcoct_process_bscans_ex(abcoct_ctx* c, const void* frames, size_t nframes, 
     OutPtrs dev;
     for (int k = 0; k < O_COUNT; ++k) dev.p[k] = host.p[k] ? g.d_o[k][s] : nullptr;
     rc = enqueue_device(c, g, s, g.d_in[s], nb, dense, frame_dev, dev, st, false);
-    if (rc) return rc;
+    if (rc) return bail(rc);
     for (int k = 0; k < O_COUNT; ++k)
       if (host.p[k]) {
         void* dst = out_pinned ? static_cast<void*>(static_cast<uint8_t*>(host.p[k]) + b0 * out_px * kOutBpp[k]) : g.h_o[k][s];

@@ -606,7 +606,7 @@ __device__ __forceinline__ void normalise_part(const ReconArgs& a, const SchedVi
   const float thr = a.thr;
   const float* src = a.scratch + ((size_t)b * a.oph + r0) * a.Dp;
   const bool has55 = a.clamp55 && r0 <= 5 && 5 < r0 + nrows;
-  const bool vec_ok = (a.oph & 15) == 0 && nrows == NR && (NR % 16) == 0;
+  const bool vec_ok = (a.oph & 15) == 0 && nrows == NR && (NR % 16) == 0 && (reinterpret_cast<uintptr_t>(a.out8) & 15) == 0;
   const int c4 = tid & 7, q0 = tid >> 3;
   const int ntiles = (a.D + kNormBins - 1) / kNormBins;
 
@@ -848,7 +848,6 @@ __global__ void __launch_bounds__(P::T* G, 1) recon_kernel(const ReconArgs a) {
           }
         }
       }
-      if (f == 0 && tid == kPublishTid && npend == kPublishBatch) publish();
       // prefetch while this frame is transformed: next frame of the item, else the first frame of the next item
       if (!last) {
         prefetch_rows(pair, bscan, f + 1);
@@ -856,6 +855,9 @@ __global__ void __launch_bounds__(P::T* G, 1) recon_kernel(const ReconArgs a) {
         prefetch_rows(npair, nbscan, 0);
       }
       group_sync<P::T>(g);  // staged samples and row sums visible; the calibration rows have been consumed
+      // Publish AFTER the barrier: it orders the other warps' scratch stores and min / max atomics of the finished items before
+      // the publisher's gpu-scope fence (a count published before it could be seen ahead of the data it covers).
+      if (f == 0 && tid == kPublishTid && npend == kPublishBatch) publish();
       if (!IN_F32 && last && npair >= 0 && tid == 0) issue_calibration(npair);
       if constexpr (P::NWARPS > 1 && !IN_F32) {
         sa = 0.f;

@@ -113,10 +113,11 @@ int abcoct_set_background(abcoct_ctx* ctx, const double* yb, size_t ld);
 int abcoct_set_pishift(abcoct_ctx* ctx, const double* yp, size_t ld);
 int abcoct_set_dark(abcoct_ctx* ctx, const double* yd, size_t ld);
 /* The capture done on keys b / p / o / r / t (BscanFFT.cpp:1041-1062, 1081; BscanDark.cpp:1045-1225): data_y of
- * `nframes` raw frames (after median, binning, convertTo, smoothmovavg) is accumulated, then - except for the pi-shifted
- * frame, which is a plain copy of one frame - normalised to [0.0001, 1] row-wise (rowwisenormalize) and / or globally
- * (!donotnormalize), else divided by nframes, with the reference's `if (rowwise) ...; if (!donotnormalize) ...; else /n`
- * structure; the DARK captures are low-pass filtered when `lowpassfilter` is set.  Runs on the host (once per key press).
+ * `nframes` raw frames (after median, binning, convertTo, smoothmovavg) is accumulated, then normalised to [0.0001, 1]
+ * row-wise (rowwisenormalize) and / or globally (!donotnormalize), else divided by nframes, with the reference's
+ * `if (rowwise) ...; if (!donotnormalize) ...; else /n` structure; the DARK captures are low-pass filtered when
+ * `lowpassfilter` is set.  The pi-shifted frame (which = 1) is a copy of ONE frame, normalised to [0, 1] row-wise / globally
+ * under the same two switches (BscanFFT.cpp:1081, 1092-1096).  Runs on the host (once per key press).
  *   which: 0 background data_yb, 1 pishift data_yp, 2 dark data_yd, 3 reference arm data_yr, 4 sample arm data_ys. */
 int abcoct_set_calibration_from_frames(abcoct_ctx* ctx, int which, const void* frames, size_t nframes,
                                        size_t stride_bytes);
@@ -150,7 +151,10 @@ int abcoct_process_bscans(abcoct_ctx* ctx, const void* frames, size_t nframes, s
 
 /* Same computation with every buffer already resident on GPU `gpu_index` (index into gpu_ids).
  * Asynchronous on `cuda_stream` (a cudaStream_t; NULL = the context's own stream, then the call
- * synchronises before returning). */
+ * synchronises before returning).  d_frames must be 16-byte aligned with a 16-byte multiple row stride; the output
+ * pointers may have any alignment (aligned ones take the vector-store path).  The asynchronous calls of ONE context share
+ * its scratch / scheduler buffers: enqueue them on a single stream at a time (or order the streams with events), and do
+ * not change the calibration while such work is in flight unless you synchronise first. */
 int abcoct_process_bscans_device(abcoct_ctx* ctx, int gpu_index, const void* d_frames, size_t nframes,
                                  size_t stride_bytes, uint8_t* d_bscan_u8, float* d_bscan_db,
                                  void* cuda_stream);

@@ -288,6 +288,19 @@ class Oracle:
             out = lpfilter(out)
         return out
 
+    def calib_capture_pishift(self, frame) -> np.ndarray:
+        """Key p: data_y.copyTo(data_yp) of ONE frame (after median, binning, convertTo, smoothmovavg), then normalised like
+        data_y itself - normalizerows(.., 0, 1) / normalize(.., 0, 1, NORM_MINMAX) - BscanFFT.cpp:1081, 1092-1096."""
+        p = self.p
+        y = bin_frame(frame, p).astype(np.float64)
+        if p.movavgn > 0:
+            y = smoothmovavg(y, p.movavgn)
+        if p.rowwisenormalize:
+            y = normalizerows(y, 0, 1)
+        if not p.donotnormalize:
+            y = cv2.normalize(y, None, 0, 1, cv2.NORM_MINMAX)
+        return y
+
     # per-frame stages ------------------------------------------------------------
     def linearised(self, mraw: np.ndarray, dump: dict | None = None) -> np.ndarray:
         """Everything up to data_ylin (f64, oph x N): BscanFFT.cpp:953-1177."""

@@ -294,7 +294,7 @@ def test_stage_parity_linearised(w, h, N, extra):
 def test_calibration_captures_match_oracle():
     """Every capture kind and normalise branch, read back with abcoct_get_calibration, against the oracle's capture."""
     from fdoct_b200 import api, synth
-    from oracle.abcoct_oracle import Oracle, bin_frame, smoothmovavg
+    from oracle.abcoct_oracle import Oracle
 
     w, h = 640, 10
     bf = synth.make_background_frames(3, w, h, seed=91, dark=True)
@@ -311,11 +311,9 @@ def test_calibration_captures_match_oracle():
                 ref = o.calib_capture(bf, lowpass=op.lowpassfilter and which >= 2)
                 tol = 2e-6 if (op.lowpassfilter and which >= 2) else 1e-12  # lpfilter is an f32 FFT in the reference
                 assert np.abs(got - ref).max() <= tol * np.abs(ref).max(), (extra, which, np.abs(got - ref).max())
-            ctx.set_calibration_from_frames(1, bf[:1])  # key 'p': data_y.copyTo(data_yp), no normalisation (BscanFFT.cpp:1081)
-            yp = bin_frame(bf[0], op).astype(np.float64)
-            if op.movavgn > 0:
-                yp = smoothmovavg(yp, op.movavgn)
-            assert np.abs(ctx.get_calibration(1) - yp).max() <= 1e-12 * yp.max()
+            ctx.set_calibration_from_frames(1, bf[:1])  # key 'p': copy of one frame, normalised to [0, 1] (BscanFFT.cpp:1081-1096)
+            yp = o.calib_capture_pishift(bf[0])
+            assert np.abs(ctx.get_calibration(1) - yp).max() <= 1e-12 * np.abs(yp).max(), extra
 
 
 @pytest.mark.parametrize("extra", [dict(), dict(lowpassfilter=True), dict(movavgn=1, rowwisenormalize=True)])
