@@ -39,7 +39,7 @@ int list_plans(int* out, int cap) {
 __global__ void sched_init_kernel(int* sched, int nB) {
   const SchedView v = sched_view(sched, nB);
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < 32) sched[i] = 0;
+  if (i < kSchedHeader) sched[i] = 0;
   if (i < nB) {
     v.minv[i] = float_to_ordered(__int_as_float(0x7f800000));  // +inf
     v.maxv[i] = float_to_ordered(__int_as_float(0xff800000));  // -inf
@@ -47,7 +47,7 @@ __global__ void sched_init_kernel(int* sched, int nB) {
   }
 }
 cudaError_t launch_sched_init(int* sched, int nB, cudaStream_t st) {
-  const int n = nB > 32 ? nB : 32;
+  const int n = nB > kSchedHeader ? nB : kSchedHeader;
   sched_init_kernel<<<(n + 127) / 128, 128, 0, st>>>(sched, nB);
   return cudaGetLastError();
 }

@@ -67,8 +67,10 @@ struct ReconArgs {
   int nsplit;       // depth-tile ranges a normalisation part is split into (small launches: more, shorter jobs)
 };
 
-// Scheduler / per-B-scan state in global memory (ints): [0] item ticket, then nB each of
-// minv, maxv (order-preserving int encodings) and cnt (row pairs finished and published).
+// Scheduler / per-B-scan state in global memory (ints).  Header of kSchedHeader ints - three 128-byte lines so that the hot
+// words never share a line: [0] item ticket, [32] normalisation jobs handed out, [64] job frontier (wrow_kernel.cuh) - then nB
+// each of minv, maxv (order-preserving int encodings) and cnt (rows / row pairs finished and published).
+constexpr int kSchedHeader = 96;
 constexpr int kNormBins = 32;   // depth bins per transposition tile
 struct SchedView {
   int* ticket;
@@ -79,12 +81,12 @@ struct SchedView {
 __host__ __device__ inline SchedView sched_view(int* base, int nB) {
   SchedView v;
   v.ticket = base;
-  v.minv = base + 32;
+  v.minv = base + kSchedHeader;
   v.maxv = v.minv + nB;
   v.cnt = v.maxv + nB;
   return v;
 }
-__host__ __device__ inline size_t sched_ints(int nB) { return 32 + 3 * (size_t)nB; }
+__host__ __device__ inline size_t sched_ints(int nB) { return kSchedHeader + 3 * (size_t)nB; }
 
 
 // ------------------------------------------------------------------------------------------- shared memory map

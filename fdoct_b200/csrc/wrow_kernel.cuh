@@ -364,9 +364,9 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
   unsigned long long* const mbar = reinterpret_cast<unsigned long long*>(rawbuf + WP::RAWBUF);
   // scheduler words (recon_kernel.cuh::sched_view): computed from the kernel parameters where they are used
   auto sv_ticket = [&]() { return a.sched; };
-  auto sv_minv = [&]() { return a.sched + 32; };
-  auto sv_maxv = [&]() { return a.sched + 32 + a.nB; };
-  auto sv_cnt = [&]() { return a.sched + 32 + 2 * a.nB; };
+  auto sv_minv = [&]() { return a.sched + kSchedHeader; };
+  auto sv_maxv = [&]() { return a.sched + kSchedHeader + a.nB; };
+  auto sv_cnt = [&]() { return a.sched + kSchedHeader + 2 * a.nB; };
   const int W8m1 = (a.W >> 3) - 1;
   const unsigned rowbytes = (unsigned)a.W * 2u;
   // samples of the padded runs (W < NCH * 256) see gain 0, i.e. t - 1 = -1 without a subtrahend row: taken out of the mean
@@ -422,12 +422,12 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
   w_syncthreads();  // the service warp reads every mailbox
 
   // ---- the normalisation job queue (global words next to the row ticket): jobs are B-scan major;
-  //   sched[2] = jready: jobs [0, jready) belong to COMPLETE B-scans (a frontier, advanced by whoever sees the next B-scan's
-  //              row count reach oph); sched[1] = jnext: jobs handed out so far (atomicAdd).
+  //   sched[64] = jready: jobs [0, jready) belong to COMPLETE B-scans (a frontier, advanced by whoever sees the next B-scan's
+  //              row count reach oph); sched[32] = jnext: jobs handed out so far (atomicAdd).
   // A job may run once its number is below jready.  Worker warps only take a job when a fresh snapshot says one is ready, and
   // never wait for one inside the row loop (the missing row could be their own); service warps and finished workers wait.
-  auto jnext_p = [&]() { return a.sched + 1; };
-  auto jready_p = [&]() { return a.sched + 2; };
+  auto jnext_p = [&]() { return a.sched + 32; };
+  auto jready_p = [&]() { return a.sched + 64; };
   auto advance_frontier = [&]() {  // lane 0
     const int jr = w_ld_acquire(jready_p());
     if (jr >= njobs()) return jr;

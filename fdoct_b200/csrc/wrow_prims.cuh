@@ -367,7 +367,7 @@ WROW_HD void w_acquire_fence() {
 }
 WROW_HD void w_backoff() {
 #if WROW_DEVICE_BODY
-  __nanosleep(200);
+  __nanosleep(1000);  // pollers must not crowd the L2 lines that the workers' tickets and counts live in
 #else
   wemu::backoff();
 #endif

@@ -197,7 +197,7 @@ static double run_case(const Case& cs, unsigned seed) {
   std::vector<int> sched(sched_ints(nB));
   {
     SchedView v = sched_view(sched.data(), nB);
-    for (int i = 0; i < 32; ++i) sched[i] = 0;
+    for (int i = 0; i < kSchedHeader; ++i) sched[i] = 0;
     for (int b = 0; b < nB; ++b) {
       v.minv[b] = float_to_ordered(w_inf(false));
       v.maxv[b] = float_to_ordered(w_inf(true));
