@@ -83,6 +83,37 @@ def test_ini_positional_parser(name, flavour):
         assert p.bandpassfilter == 1 and p.lowpassfilter == 0
 
 
+# The reference's own shipped configuration files (build/*.ini, copied verbatim as fixtures): expected values read off the files.
+REF_INI = {
+    #                  flavour          bpp  w     h    binx biny avg N     D    movavg median mult rown nonorm
+    "BscanFFT":        (api.INI_BSCANFFT, 8, 320, 240, 2, 2, 10, 2560, 320, 0, 0, 4, 0, 1),
+    "BscanFFTspin":    (api.INI_BSCANFFT, 8, 1280, 960, 2, 2, 10, 2560, 320, 0, 0, 4, 0, 1),
+    "BscanFFTspinj":   (api.INI_SPINJ, 16, 720, 480, 1, 1, 10, 2880, 360, 0, 0, 4, 0, 1),
+    "BscanFFTspinjnt": (api.INI_SPINJNT, 16, 720, 480, 1, 1, 10, 2880, 360, 0, 0, 4, 0, 1),
+    "BscanDark":       (api.INI_DARK, 16, 1280, 960, 2, 2, 10, 2560, 320, 0, 0, 4, 0, 1),
+    "BscanFFTpeak":    (api.INI_PEAK, 8, 1280, 960, 2, 2, 10, 2560, 320, 0, 0, 4, 0, 1),
+    "BscanFFTwebcam":  (api.INI_WEBCAM, 8, 640, 480, 1, 1, 10, 640, 320, 0, 0, 1, 0, 1),
+}
+
+
+@pytest.mark.parametrize("name", sorted(REF_INI))
+def test_ini_parser_on_the_reference_shipped_files(name):
+    """abcoct_params_from_ini on the seven .ini files the reference ships (positional layouts of BscanFFT.cpp:395-484 and its
+    variants): every field the reconstruction block reads."""
+    exp = REF_INI[name]
+    p = api.params_from_ini(os.path.join(GOLDEN, "ref_ini", name + ".ini"), exp[0])
+    got = (p.bpp, p.w, p.h, p.binx, p.biny, p.averages, p.numfftpoints, p.numdisplaypoints, p.movavgn, p.mediann, p.fft_multiplier,
+           p.rowwisenormalize, p.donotnormalize)
+    assert got == exp[1:], (name, got)
+    assert p.lambdamin == 840.5e-9 and p.lambdamax == 859.5e-9
+    assert p.variant == (1 if exp[0] == api.INI_DARK else 0)
+    if exp[0] == api.INI_SPINJNT:
+        assert (p.bscanbinx, p.bscanbiny, p.output_rebin, p.clamp_db) == (1, 1, 1, 30.0)
+    if exp[0] == api.INI_DARK:
+        assert p.bandpassfilter == 1  # the shipped file stops there: lowpassfilter keeps its default
+        assert p.lowpassfilter == 0
+
+
 def test_ini_wrong_flavour_misparses_like_the_reference():
     """BscanFFTsim reads BscanFFT.ini, whose offsets shift every later field by two."""
     p = api.params_from_ini(os.path.join(GOLDEN, "bscanfft.ini"), api.INI_SIM)
