@@ -92,44 +92,84 @@ def make_inputs(wl, nframes, n_unique=4):
 
 
 # --------------------------------------------------------------------------------------------- CPU reference leg
-def _cpu_worker(args):
-    """One worker process: oracle over its own B-scans. Returns A-scans processed."""
+_CPU_SHARED = {}  # inputs of the worker processes: set BEFORE the pool forks, so nothing is pickled per call
+
+
+def _cpu_worker(nbscans):
+    """One worker process: the oracle over `nbscans` B-scans of the shared sample. Returns A-scans processed."""
     import cv2
 
     from oracle.abcoct_oracle import Oracle
 
-    wl, frames, yb, yd = args
+    wl, frames, yb, yd = _CPU_SHARED["wl"], _CPU_SHARED["frames"], _CPU_SHARED["yb"], _CPU_SHARED["yd"]
     cv2.setNumThreads(1)
     o = Oracle(oracle_params(wl))
     o.set_background(yb)
     if yd is not None:
         o.set_dark(yd)
-    o.process_bscans(frames)
-    return frames.shape[0] * wl["h"]
+    n = nbscans * wl["A"]
+    o.process_bscans(frames[:n])
+    return n * wl["h"]
+
+
+def _cpu_sample(wl, uniq, bscans):
+    A = wl["A"]
+    return np.concatenate([uniq] * ((bscans * A + len(uniq) - 1) // len(uniq)))[: bscans * A]
 
 
 def time_cpu_reference(wl, uniq, yb, yd, cores, bscans_per_core):
-    """All host cores, one oracle process per core over disjoint B-scans; returns (A-scans/s, sample description)."""
+    """All host cores, one oracle process per core, `bscans_per_core` B-scans each (inputs inherited by fork); returns
+    (A-scans/s, seconds, sample description)."""
     import multiprocessing as mp
 
-    A = wl["A"]
-    per = np.concatenate([uniq] * ((bscans_per_core * A + len(uniq) - 1) // len(uniq)))[: bscans_per_core * A]
-    jobs = [(wl, per, yb, yd)] * cores
+    _CPU_SHARED.update(wl=wl, frames=_cpu_sample(wl, uniq, bscans_per_core), yb=yb, yd=yd)
     ctx = mp.get_context("fork")
     with ctx.Pool(cores) as pool:
-        pool.map(_cpu_worker, [(wl, per[:A], yb, yd)] * cores)  # warm the workers (imports, cv2 init)
+        pool.map(_cpu_worker, [1] * cores)  # warm the workers (imports, cv2 init)
         t0 = time.perf_counter()
-        n = sum(pool.map(_cpu_worker, jobs))
+        n = sum(pool.map(_cpu_worker, [bscans_per_core] * cores, chunksize=1))
         dt = time.perf_counter() - t0
-    return n / dt, dt, f"{cores} processes x {bscans_per_core} B-scans ({per.shape[0]} frames of {wl['h']} A-scans each)"
+    return n / dt, dt, f"{cores} processes x {bscans_per_core} B-scans ({bscans_per_core * wl['A']} frames of {wl['h']} A-scans each)"
 
 
-def calibrate_cpu_sample(wl, uniq, yb, yd, target_s):
-    """Pick how many B-scans per core make about `target_s` seconds of CPU work (one timed B-scan on this host)."""
+def time_cpu_single_process(wl, uniq, yb, yd, bscans):
+    """The reference-like mode: ONE process, OpenCV's own internal threads (what the reference binary does)."""
+    import cv2
+
+    from oracle.abcoct_oracle import Oracle
+
+    cv2.setNumThreads(-1)
+    o = Oracle(oracle_params(wl))
+    o.set_background(yb)
+    if yd is not None:
+        o.set_dark(yd)
+    frames = _cpu_sample(wl, uniq, bscans)
+    o.process_bscans(frames[: wl["A"]])
     t0 = time.perf_counter()
-    _cpu_worker((wl, uniq[: wl["A"]], yb, yd))
+    o.process_bscans(frames)
+    dt = time.perf_counter() - t0
+    return {"value": frames.shape[0] * wl["h"] / dt, "unit": "A-scans/s", "bscans": bscans, "seconds": dt,
+            "cv2_threads": int(cv2.getNumThreads())}
+
+
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def calibrate_cpu_sample(wl, uniq, yb, yd, target_s, lo=16, hi=64):
+    """B-scans per core: about `target_s` seconds of CPU work, never fewer than `lo` (a short sample under-measures the CPU:
+    worker start-up and the first-call costs of cv2 would dominate)."""
+    _CPU_SHARED.update(wl=wl, frames=_cpu_sample(wl, uniq, 1), yb=yb, yd=yd)
+    t0 = time.perf_counter()
+    _cpu_worker(1)
     one = max(time.perf_counter() - t0, 1e-3)
-    return int(max(1, min(64, round(target_s / one))))
+    return int(max(lo, min(hi, round(target_s / one))))
 
 
 # --------------------------------------------------------------------------------------------- clocks
@@ -186,21 +226,43 @@ class ClockSampler:
                 "power_w_max": max(r[2] for r in rows) if rows else None, "samples": in_region, "reasons": reasons}
 
 
-def measured_traffic(workload, nframes):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the fused kernel from the committed ncu capture
-    (profiles/r01_traffic.json), or None when this workload / batch was not captured."""
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "r02_traffic.json")
+
+
+def measured_traffic(workload, nframes, live=True):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the fused kernel.  Measured in this run by a one-launch
+    ncu pass over a child bench process (counters only - no timing is taken from it); when ncu is not available here the
+    number recorded by the last profiled run (profiles/r02_traffic.json) is reported instead.  Returns (bytes, source)."""
+    if live:
+        try:
+            cmd = ["ncu", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k",
+                   "regex:wrow_kernel|recon_kernel", "-s", "3", "-c", "1", "--csv", sys.executable, os.path.abspath(__file__),
+                   "--workload", workload, "--frames", str(nframes), "--steps", "1", "--warmup", "3", "--no-cpu", "--no-traffic",
+                   "--e2e-steps", "1"]
+            out = subprocess.run(cmd, capture_output=True, text=True, timeout=240).stdout
+            vals = {}
+            import csv as _csv
+
+            for r in _csv.reader(out.splitlines()):
+                if len(r) > 10 and r[0].isdigit():
+                    scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(r[-2], 1)
+                    vals[r[-3]] = float(r[-1].replace(",", "")) * scale
+            if len(vals) == 2:
+                return int(sum(vals.values())), "ncu, one launch, this run"
+        except Exception:  # noqa: BLE001
+            pass
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+        with open(TRAFFIC_FILE) as f:
             t = json.load(f)[workload][str(nframes)]
-        return int(t["dram_read"]) + int(t["dram_write"])
-    except Exception:
-        return None
+        return int(t["dram_read"]) + int(t["dram_write"]), "profiles/r02_traffic.json (recorded ncu capture; ncu unavailable in this run)"
+    except Exception:  # noqa: BLE001
+        return None, "not measured"
 
 
 def ncu_summary(workload):
     """Secondary-roof evidence of the committed ncu capture (issue slots, FMA pipe, shared-memory wavefronts), if any."""
     try:
-        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+        with open(TRAFFIC_FILE) as f:
             return json.load(f)[workload]["ncu"]
     except Exception:
         return None
@@ -220,7 +282,7 @@ def run_reference(args, wl, rank):
         return
     cores = os.cpu_count() or 1
     _, uniq, yb, yd = make_inputs(wl, max(wl["A"], 4))
-    per_core = calibrate_cpu_sample(wl, uniq, yb, yd, target_s=args.cpu_seconds / max(1, args.steps + args.warmup))
+    per_core = calibrate_cpu_sample(wl, uniq, yb, yd, target_s=10 * args.cpu_seconds / max(1, args.steps + args.warmup))
     vals = []
     for i in range(args.warmup + args.steps):
         v, dt, sample = time_cpu_reference(wl, uniq, yb, yd, cores, per_core)
@@ -236,8 +298,9 @@ def run_reference(args, wl, rank):
         "vs_baseline": None, "dtype": "f64/f32 (OpenCV)", "data": "synthetic",
         "config": {"workload": wl["desc"], "name": args.workload, "sample_per_step": sample},
         "bscans_per_s": value / (wl["h"] * wl["A"]),
-        "cpu_baseline": {"value": value, "unit": "A-scans/s", "cores": cores, "kind": "port",
-                         "sample": sample + f"; oracle = Python restatement calling OpenCV {cv2.__version__} kernels"},
+        "cpu_baseline": {"value": value, "unit": "A-scans/s", "cores": cores, "kind": "port", "cpu": cpu_model(),
+                         "sample": sample + f"; oracle = Python restatement calling OpenCV {cv2.__version__} kernels",
+                         "single_process": time_cpu_single_process(wl, uniq, yb, yd, 4)},
         "e2e": {"value": value, "unit": "A-scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -350,6 +413,7 @@ def run_ours(args, wl, rank, world, local_rank):
         value = ascans_step * args.steps / (dev_ms * 1e-3)
         e2e_value = ascans_step * e2e_steps / (e2e_ms * 1e-3)
         peak, peak_src = measured_hbm_peak()
+        traffic, traffic_src = (None, "skipped") if args.no_traffic else measured_traffic(args.workload, nframes, live=world == 1)
         bytes_per_ascan = 2 * w + D / A  # u16 pixels in + u8 display pixels out, dB output off
         ascans_per_launch = nframes * h / max(nchunks // max(args.steps, 1), 1)
         achieved = bytes_per_ascan * ascans_per_launch / (recon_launch_ms * 1e-3) / 1e9 if recon_launch_ms > 0 else None
@@ -367,10 +431,12 @@ def run_ours(args, wl, rank, world, local_rank):
             "e2e": {"value": e2e_value, "unit": "A-scans/s", "h2d_bytes_per_step": int(frames.nbytes) * world,
                     "d2h_bytes_per_step": int(nB * D * h) * world, "steps": e2e_steps, "matches_device_leg": ok},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": measured_traffic(args.workload, nframes),
+                         "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src,
                          "algorithmic_bytes_per_launch": bytes_per_ascan * ascans_per_launch,
                          "secondary_roofs_ncu": ncu_summary(args.workload),
-                         "kernel": "recon_kernel (fused reconstruction)", "bytes_per_ascan": bytes_per_ascan,
+                         "kernel": ("wrow_kernel (fused reconstruction + display normalisation, one warp per A-scan)" if info.fft_threads == 32 and info.fft_radix[2] == 32
+                                    else "recon_kernel (fused reconstruction + display normalisation, thread group per row pair)"),
+                         "bytes_per_ascan": bytes_per_ascan,
                          "ascans_per_launch": ascans_per_launch, "launch_ms": recon_launch_ms, "peak_source": peak_src,
                          "whole_step_frac": bytes_per_ascan * value / world / 1e9 / peak},
             "plan": {"fft_threads": info.fft_threads, "radix": list(info.fft_radix), "groups_per_cta": info.groups_per_cta,
@@ -382,8 +448,9 @@ def run_ours(args, wl, rank, world, local_rank):
             cores = os.cpu_count() or 1
             per_core = calibrate_cpu_sample(wl, uniq, yb, yd, target_s=args.cpu_seconds)
             v, dt, sample = time_cpu_reference(wl, uniq, yb, yd, cores, per_core)
-            line["cpu_baseline"] = {"value": v, "unit": "A-scans/s", "cores": cores, "kind": "port",
-                                    "sample": sample + f"; {dt:.1f} s; oracle = Python restatement calling the reference's OpenCV kernels (cv2)"}
+            line["cpu_baseline"] = {"value": v, "unit": "A-scans/s", "cores": cores, "kind": "port", "cpu": cpu_model(),
+                                    "sample": sample + f"; {dt:.1f} s; oracle = Python restatement calling the reference's OpenCV kernels (cv2)",
+                                    "single_process": time_cpu_single_process(wl, uniq, yb, yd, 4)}
         print(json.dumps(line), flush=True)
     pin_in.free()
     pin_out.free()
@@ -403,6 +470,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work per timed CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-traffic", action="store_true", help="skip the one-launch ncu pass that measures roofline.traffic")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

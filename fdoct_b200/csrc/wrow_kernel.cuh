@@ -451,7 +451,7 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
       if (w_now_ns() - t_start > kWrowWatchdogNs) w_trap();  // a scheduling bug must surface as a launch failure, not as a hung GPU
       w_backoff();
     }
-    wrow_normalise<(WP::NW <= 12 ? 3 : 2)>(norm_args(), j, lane);
+    wrow_normalise<3>(norm_args(), j, lane);
   };
   // all lanes: hand out and run jobs until none is left (service warps when idle, worker warps after their last row)
   auto drain_jobs = [&](auto&& service) {
@@ -723,7 +723,7 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
         if (lane == 0) {
           if (myjob >= 0) {
             if (jr_snap > myjob) j = myjob;
-          } else if (jn_snap < jr_snap && jn_snap < njobs()) {
+          } else if (jn_snap + w_ncta() < jr_snap && jn_snap < njobs()) {  // only when the service warps have a backlog
             const int t = w_atomic_add(jnext_p(), 1);
             if (t < njobs()) {
               if (t < jr_snap)

@@ -292,7 +292,11 @@ WROW_HD void w_mbar_wait(unsigned long long* bar, unsigned parity) {
 // ---- scheduler atomics --------------------------------------------------------------------------------------------
 WROW_HD int w_atomic_add(int* p, int v) {
 #if WROW_DEVICE_BODY
-  return atomicAdd(p, v);
+  // plain PTX: the compiler's warp-aggregation of atomicAdd (vote + leader + broadcast) would wait for the result on the
+  // spot, and these tickets are deliberately consumed a row later
+  int r;
+  asm volatile("atom.relaxed.gpu.global.add.s32 %0, [%1], %2;" : "=r"(r) : "l"(p), "r"(v) : "memory");
+  return r;
 #else
   return wemu::atomic_add(p, v);
 #endif

@@ -2,7 +2,8 @@
 
 Tolerances (BASELINE.json north_star):
   * index / weight tables ............ bit-exact (int32 equal, f64 equal)
-  * magnitude ........................ <= 1e-4 relative to max(|ref|, 3e-3 * A-scan max) against the oracle (OpenCV f32 DFT), AND
+  * magnitude ........................ <= 1e-4 relative to max(|ref|, 1e-3 * A-scan max) against the oracle (OpenCV f32 DFT; the one
+                                       full-size N = 2048 comparison uses 2e-3, see test_full_size_properties_c5), AND
                                        no further from an exact f64 evaluation than the reference's own f32 path is
                                        (tests/test_parity_gpu.py::test_accuracy_vs_exact_f64).  The floor is where two correct f32 FFTs stop
                                        agreeing to 1e-4 of the value: measured on B200 (profiles/r01_precision_probe.txt), OpenCV's f32 DFT
