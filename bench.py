@@ -236,7 +236,7 @@ def measured_traffic(workload, nframes, live=True):
     if live:
         try:
             cmd = ["ncu", "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k",
-                   "regex:wrow_kernel|recon_kernel", "-s", "3", "-c", "1", "--csv", sys.executable, os.path.abspath(__file__),
+                   "regex:wres_kernel|wrow_kernel|recon_kernel", "-s", "3", "-c", "1", "--csv", sys.executable, os.path.abspath(__file__),
                    "--workload", workload, "--frames", str(nframes), "--steps", "1", "--warmup", "3", "--no-cpu", "--no-traffic",
                    "--e2e-steps", "1"]
             out = subprocess.run(cmd, capture_output=True, text=True, timeout=240).stdout
@@ -434,8 +434,9 @@ def run_ours(args, wl, rank, world, local_rank):
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic, "traffic_source": traffic_src,
                          "algorithmic_bytes_per_launch": bytes_per_ascan * ascans_per_launch,
                          "secondary_roofs_ncu": ncu_summary(args.workload),
-                         "kernel": ("wrow_kernel (fused reconstruction + display normalisation, one warp per A-scan)" if info.fft_threads == 32 and info.fft_radix[2] == 32
-                                    else "recon_kernel (fused reconstruction + display normalisation, thread group per row pair)"),
+                         "kernel": ["recon_kernel (fused reconstruction + display normalisation, thread group per row pair, dB scratch in L2)",
+                                    "wrow_kernel (fused reconstruction + display normalisation, one warp per A-scan, dB scratch in L2)",
+                                    "wres_kernel (fused reconstruction + display normalisation, one warp per A-scan, dB rows resident in shared memory)"][info.kernel_kind],
                          "bytes_per_ascan": bytes_per_ascan,
                          "ascans_per_launch": ascans_per_launch, "launch_ms": recon_launch_ms, "peak_source": peak_src,
                          "whole_step_frac": bytes_per_ascan * value / world / 1e9 / peak},

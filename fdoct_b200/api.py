@@ -48,6 +48,7 @@ class Info(C.Structure):
         ("groups_per_cta", C.c_uint32), ("ctas_per_sm", C.c_uint32), ("smem_bytes", C.c_uint32),
         ("regs_per_thread", C.c_uint32), ("ngpu", C.c_uint32), ("sm_count", C.c_uint32),
         ("kernel_launches", C.c_uint64), ("last_recon_ms", C.c_double), ("last_norm_ms", C.c_double),
+        ("kernel_kind", C.c_uint32), ("slots_per_warp", C.c_uint32),
     ]
 
 

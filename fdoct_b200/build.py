@@ -13,8 +13,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libabcoct.so")
-SOURCES = ["wrow_kernels.cu", "wrow_kernels_b.cu", "plans_large.cu", "plans_small.cu", "abcoct_kernels.cu", "prep_kernels.cu", "post_kernels.cu", "abcoct_api.cpp"]
-HEADERS = ["fft_regs.cuh", "plan.h", "recon_kernel.cuh", "wrow_kernel.cuh", "wrow_prims.cuh", "kernels.h", "plan_registry.cuh",
+SOURCES = ["wres_kernels.cu", "wrow_kernels.cu", "wrow_kernels_b.cu", "plans_large.cu", "plans_small.cu", "abcoct_kernels.cu", "prep_kernels.cu", "post_kernels.cu", "abcoct_api.cpp"]
+HEADERS = ["fft_regs.cuh", "plan.h", "recon_kernel.cuh", "wrow_kernel.cuh", "wres_kernel.cuh", "wrow_prims.cuh", "kernels.h", "plan_registry.cuh",
            os.path.join("..", "..", "include", "abcoct.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 

@@ -92,7 +92,7 @@ struct abcoct_ctx {
   // warp-per-A-scan kernel (wrow_kernel.cuh): eligible configurations and the plan in use (nullptr: recon_kernel.cuh)
   bool wrow_eligible = false;
   const WPlanEntry* wplan = nullptr;
-  std::vector<unsigned char> blob1, wblob;
+  std::vector<unsigned char> blob1, wblob, rblob;  // table blobs of the group kernel, the scratch warp kernel, the resident-row kernel
   const std::vector<unsigned char>* blob_loaded = nullptr;  // which blob d_tables holds
   std::vector<int> gidx;      // the kernel's remapped gather indices / weights (debug tap)
   std::vector<float> gwq;
@@ -354,16 +354,25 @@ int upload_calibration(abcoct_ctx* c) {
       CU(c, cudaMemcpy(g.d_yd, fd.data(), n * 4, cudaMemcpyHostToDevice));
     }
   }
-  // which kernel: the warp-per-A-scan kernel wherever it applies (wrow_kernel.cuh); ABCOCT_KERNEL=1 forces the group-per-row-pair
-  // kernel (recon_kernel.cuh, the fallback for every other transform length and for the general path) for A/B measurements,
-  // ABCOCT_WROW_NW = 12 | 16 picks the occupancy point of the plan.
+  // which kernel: the resident-row kernel wherever it applies (wres_kernel.cuh: one warp per A-scan, dB rows stay in shared
+  // memory); for A/B measurements ABCOCT_KERNEL=2 forces the warp-per-A-scan kernel with the global dB scratch (wrow_kernel.cuh)
+  // and ABCOCT_KERNEL=1 the group-per-row-pair kernel (recon_kernel.cuh, the fallback for every other transform length and for
+  // the general path); ABCOCT_WRES_NW / ABCOCT_WROW_NW pick another occupancy point of a plan.
   const WPlanEntry* wp = nullptr;
   if (c->wrow_eligible) {
-    int force = 0, nw = 0, lm = -1;
+    int force = 0, nw = 0, lm = -1, rnw = 0;
     if (const char* e = getenv("ABCOCT_KERNEL")) force = atoi(e);
     if (const char* e = getenv("ABCOCT_WROW_NW")) nw = atoi(e);
     if (const char* e = getenv("ABCOCT_WROW_LM")) lm = atoi(e);
-    if (force != 1) {
+    if (const char* e = getenv("ABCOCT_WRES_NW")) rnw = atoi(e);
+    if (force == 0 && !c->rblob.empty()) {
+      wp = find_rplan(c->N, rnw);
+      if (!wp) wp = find_rplan(c->N, 0);
+      // progress of the slot protocol: a team's rounds k - K and k must never lie in the same B-scan (wres_kernel.cuh)
+      const long long nbb = (c->oph + 3) / 4;
+      if (wp && nbb > (long long)wp->slots * wp->teams * c->gpus[0].sm_count) wp = nullptr;
+    }
+    if (!wp && force != 1) {
       wp = find_wplan(c->N, nw, lm);
       if (!wp) wp = find_wplan(c->N, 0, -1);
     }
@@ -397,7 +406,7 @@ int upload_calibration(abcoct_ctx* c) {
       CU(c, cudaMemcpy(g.d_subg, ps.data(), ps.size() * 4, cudaMemcpyHostToDevice));
     }
   }
-  const std::vector<unsigned char>& blob = wp ? c->wblob : c->blob1;
+  const std::vector<unsigned char>& blob = wp ? (wp->resident ? c->rblob : c->wblob) : c->blob1;
   if (c->blob_loaded != &blob || c->gpus[0].d_tables == nullptr) {
     for (GpuState& g : c->gpus) {
       CU(c, cudaSetDevice(g.dev));
@@ -442,7 +451,8 @@ int ensure_scratch(abcoct_ctx* c, GpuState& g, int slot, size_t nB) {
   g.d_sched[slot] = nullptr;
   g.d_jmm[slot] = nullptr;
   g.scratch_bscans[slot] = 0;
-  CU(c, cudaMalloc(&g.d_scratch[slot], nB * c->oph * (size_t)scratch_pitch(c) * sizeof(float)));
+  const bool resident = c->wplan && c->wplan->resident;  // the resident-row kernel keeps the dB rows in shared memory: no scratch
+  CU(c, cudaMalloc(&g.d_scratch[slot], resident ? 256 : nB * c->oph * (size_t)scratch_pitch(c) * sizeof(float)));
   CU(c, cudaMalloc(&g.d_sched[slot], sched_ints((int)nB) * sizeof(int)));
   CU(c, cudaMalloc(&g.d_jmm[slot], 2 * nB * sizeof(int)));
   CU(c, cudaMalloc(&g.d_dc01[slot], 2 * nB * c->oph * sizeof(float)));
@@ -622,6 +632,10 @@ int enqueue_device(abcoct_ctx* c, GpuState& g, int slot, const uint8_t* d_frames
       a.calpitch = c->wplan->wmax;
       const int workers = c->wplan->nw - 1;  // the last warp of a CTA is its service warp
       grid = std::min(g.sm_count, (a.nitems + workers - 1) / workers);
+      if (c->wplan->resident) {  // static schedule: blocks of 4 A-scans over teams of 4 warps
+        const long long blocks = (long long)((c->oph + 3) / 4) * (long long)nb;
+        grid = (int)std::min<long long>(g.sm_count, (blocks + c->wplan->teams - 1) / c->wplan->teams);
+      }
       const int ntiles = (c->D + 31) / 32;
       const long long parts = (long long)a.nparts * (long long)nb;
       // normalisation jobs (32 A-scans x a range of depth tiles) are handed out dynamically as soon as a B-scan is complete:
@@ -924,6 +938,7 @@ int abcoct_create(const abcoct_params* params, const int* gpu_ids, int ngpu, abc
     for (int q = 0; q < c->N; ++q) widx[q] = (q == 0 || q == c->N - 1) ? -1 : c->nk[q];
     WrowTablesHost wt{c->opw, widx.data(), c->frac.data(), c->win.data()};
     find_wplan(c->N, 0, -1)->build_blob(wt, c->wblob);  // the blob does not depend on the warps per CTA
+    if (const WPlanEntry* rp = find_rplan(c->N, 0)) rp->build_blob(wt, c->rblob);  // nor on the warps / slots of a resident plan
   }
   std::vector<float2> twW, twM;
   if (params->fft_multiplier > 1) {
@@ -1455,6 +1470,8 @@ int abcoct_get_info(const abcoct_ctx* c, abcoct_info* o) {
   o->kernel_launches = c->launches;
   o->last_recon_ms = c->last_recon_ms;
   o->last_norm_ms = c->last_norm_ms;
+  o->kernel_kind = c->wplan ? (c->wplan->resident ? 2u : 1u) : 0u;
+  o->slots_per_warp = c->wplan ? (uint32_t)c->wplan->slots : 0u;
   return ABCOCT_OK;
 }
 

@@ -8,6 +8,7 @@
 #include "plan.h"
 #include "recon_kernel.cuh"
 #include "wrow_kernel.cuh"
+#include "wres_kernel.cuh"
 
 namespace abcoct {
 
@@ -29,12 +30,15 @@ struct PlanEntry {
 // One compiled plan of the warp-per-A-scan kernel (wrow_kernel.cuh).
 struct WPlanEntry {
   int N, R, nw, lm, wmax, smem_bytes;  // lm: WPlan::LM, how pixel / gain rows reach the registers
+  // resident-row kernel (wres_kernel.cuh): dB rows stay in shared memory (`slots` per warp, `teams` of 4 warps per CTA), no scratch
+  int resident = 0, slots = 0, teams = 0;
   void (*build_blob)(const WrowTablesHost& t, std::vector<unsigned char>& blob);
   void (*permute_cal_row)(const float* in, int W, float* out);  // one calibration row into the kernel's layout (wmax floats)
   cudaError_t (*launch)(const ReconArgs& a, bool has_sub, int grid, cudaStream_t st);  // picks A1 / FULLD from the arguments
   cudaError_t (*attrs)(bool has_sub, bool a1, bool fulld, int* regs);
 };
 const WPlanEntry* find_wplan(int N, int nw, int lm);  // nw == 0 / lm < 0: the default plan of that length
+const WPlanEntry* find_rplan(int N, int nw);         // resident-row plan of that length (nw == 0: the default), or nullptr
 
 const PlanEntry* find_plan(int N);
 int list_plans(int* out, int cap);

@@ -201,4 +201,55 @@ static WPlanEntry make_wentry() {
   return e;
 }
 
+// ------------------------------------------------------------------------------------------------ resident-row plans (wres_kernel.cuh)
+template <class RP, bool HAS_SUB, bool A1, bool FULLD>
+static cudaError_t rlaunch_one(const ReconArgs& a, int grid, cudaStream_t st) {
+  wres_kernel<RP, HAS_SUB, A1, FULLD><<<grid, RP::NW * 32, RP::SMEM_BYTES, st>>>(a);
+  return cudaGetLastError();
+}
+template <class RP, bool HAS_SUB, bool A1, bool FULLD>
+static cudaError_t rattrs_one(int* regs) {
+  const void* f = (const void*)wres_kernel<RP, HAS_SUB, A1, FULLD>;
+  cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, RP::SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  cudaFuncAttributes fa;
+  e = cudaFuncGetAttributes(&fa, f);
+  if (e == cudaSuccess && regs) *regs = fa.numRegs;
+  return e;
+}
+template <class RP, bool S, bool A, bool D>
+struct RLaunchF {
+  static cudaError_t run(const ReconArgs& a, int grid, cudaStream_t st) { return rlaunch_one<RP, S, A, D>(a, grid, st); }
+};
+template <class RP, bool S, bool A, bool D>
+struct RAttrsF {
+  static cudaError_t run(int* regs) { return rattrs_one<RP, S, A, D>(regs); }
+};
+template <class RP>
+static cudaError_t rlaunch_fn(const ReconArgs& a, bool has_sub, int grid, cudaStream_t st) {
+  return wdispatch<RP, RLaunchF, const ReconArgs&, int, cudaStream_t>(has_sub, a.A == 1, a.D == RP::N2, a, grid, st);
+}
+template <class RP>
+static cudaError_t rattrs_fn(bool has_sub, bool a1, bool fulld, int* regs) {
+  return wdispatch<RP, RAttrsF, int*>(has_sub, a1, fulld, regs);
+}
+template <class RP>
+static WPlanEntry make_rentry() {
+  WPlanEntry e;
+  e.N = RP::N;
+  e.R = RP::R;
+  e.nw = RP::NW;
+  e.lm = 0;
+  e.wmax = RP::WMAX;
+  e.smem_bytes = RP::SMEM_BYTES;
+  e.resident = 1;
+  e.slots = RP::K;
+  e.teams = RP::NT;
+  e.build_blob = &wblob_fn<RP>;
+  e.permute_cal_row = &wrow_permute_cal_row<RP>;
+  e.launch = &rlaunch_fn<RP>;
+  e.attrs = &rattrs_fn<RP>;
+  return e;
+}
+
 }  // namespace abcoct

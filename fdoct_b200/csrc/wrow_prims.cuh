@@ -376,6 +376,49 @@ WROW_HD void w_backoff() {
   wemu::backoff();
 #endif
 }
+// ---- primitives of the resident-row kernel (wres_kernel.cuh) ---------------------------------------------------------
+// tables that do not fit the shared memory of a plan: read through L1 (the same 16 KB for every warp of the SM)
+WROW_HD float4 w_ldg_tbl16(const void* p) {
+#if WROW_DEVICE_BODY
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+#else
+  float4 v;
+  memcpy(&v, p, 16);
+  return v;
+#endif
+}
+// display image, 4 A-scans of one depth bin: a partial sector - default policy, so that L2 merges the eight writers of a sector
+WROW_HD void w_st_global_u32(void* p, unsigned v) {
+#if WROW_DEVICE_BODY
+  asm volatile("st.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#else
+  memcpy(p, &v, 4);
+#endif
+}
+WROW_HD void w_st_global_f4(float* p, float4 v) {
+#if WROW_DEVICE_BODY
+  asm volatile("st.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+#else
+  memcpy(p, &v, 16);
+#endif
+}
+// team counters in shared memory: add with cta-scope release (the rows / quarters counted are visible to whoever acquires)
+WROW_HD void w_red_release_cta(int* p, int v) {
+#if WROW_DEVICE_BODY
+  asm volatile("red.release.cta.shared::cta.add.s32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+#else
+  __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST);
+#endif
+}
+WROW_HD void w_backoff_short() {
+#if WROW_DEVICE_BODY
+  __nanosleep(200);
+#else
+  wemu::backoff();
+#endif
+}
 WROW_HD unsigned long long w_now_ns() {
 #if WROW_DEVICE_BODY
   unsigned long long t;

@@ -213,6 +213,8 @@ typedef struct abcoct_info {
   uint32_t ngpu, sm_count;
   uint64_t kernel_launches;        /* kernels launched by this ctx so far                     */
   double last_recon_ms, last_norm_ms; /* mean per-chunk kernel times of the last abcoct_timing_read */
+  uint32_t kernel_kind;            /* fused kernel in use: 0 thread group per row pair, 1 warp per A-scan + dB scratch, 2 warp per A-scan, dB rows resident in shared memory */
+  uint32_t slots_per_warp;         /* kernel_kind 2: dB row slots per warp                    */
 } abcoct_info;
 int abcoct_get_info(const abcoct_ctx* ctx, abcoct_info* out);
 

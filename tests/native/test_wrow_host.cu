@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "../../fdoct_b200/csrc/wrow_kernel.cuh"
+#include "../../fdoct_b200/csrc/wres_kernel.cuh"
 
 // ------------------------------------------------------------------------------------------------ the emulator
 namespace wemu {
@@ -113,6 +114,11 @@ unsigned ballot(int pred) {
 
 using namespace abcoct;
 
+template <class T, class = void>
+struct is_resident : std::false_type {};
+template <class T>
+struct is_resident<T, std::void_t<decltype(T::TR)>> : std::true_type {};
+
 template <class WP, bool HAS_SUB, bool A1, bool FULLD>
 static void run_grid(const ReconArgs& a, int ncta) {
   std::vector<wemu::Cta> ctas(ncta);
@@ -135,7 +141,10 @@ static void run_grid(const ReconArgs& a, int ncta) {
         x = wemu::Ctx{l, w, c, ncta, WP::NW, &warps[(size_t)c * WP::NW + w], &ctas[c]};
         th.emplace_back([&a, &x] {
           wemu::tl = &x;
-          wrow_body<WP, HAS_SUB, A1, FULLD>(a, x.c->smem);
+          if constexpr (is_resident<WP>::value)
+            wres_body<WP, HAS_SUB, A1, FULLD>(a, x.c->smem);
+          else
+            wrow_body<WP, HAS_SUB, A1, FULLD>(a, x.c->smem);
         });
       }
   for (auto& t : th) t.join();
@@ -329,6 +338,15 @@ int main(int argc, char** argv) {
     worst = std::max(worst, run_case<WPlan<1280, 2>, false>(Case{1280, 64, 640, 1, 2, 5, 2, true, false, false}, 7));
     // three worker warps per service warp, more B-scans than CTAs: mailboxes, one fence for several workers, job order
     worst = std::max(worst, run_case<WPlan<1280, 4>, false>(Case{1280, 36, 640, 1, 5, 2, 2, false, false, false}, 8));
+  }
+  // ---- resident-row kernel (wres_kernel.cuh): teams of 4 warps, dB rows in shared-memory slots, static schedule
+  //   one team, several rounds per team (slot reuse), partial last block (oph % 4 != 0), forced element, dB image, DC rows
+  worst = std::max(worst, run_case<RPlan<1280, 4, 2>, true>(Case{1280, 9, 500, 2, 2, 1, 2, true, true, true}, 11));
+  if (!quick) {
+    worst = std::max(worst, run_case<RPlan<2048, 4, 2, true>, false>(Case{2048, 8, 1024, 1, 3, 1, 1, false, true, true}, 12));   // P / Q from global
+    worst = std::max(worst, run_case<RPlan<1920, 8, 2>, false>(Case{1920, 12, 960, 1, 4, 1, 2, false, false, false}, 13));       // two teams per CTA, word stores
+    worst = std::max(worst, run_case<RPlan<1280, 8, 3>, false>(Case{1280, 38, 640, 1, 3, 1, 2, true, true, false}, 14));         // three slots, byte stores
+    worst = std::max(worst, run_case<RPlan<1024, 4, 2>, false>(Case{1000, 32, 512, 3, 2, 1, 4, true, false, false}, 15));        // averages, R = 16
   }
   std::printf("worst (in units of the tolerance) = %.3f\n", worst);
   return worst <= 1.0 ? 0 : 1;

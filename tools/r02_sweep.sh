@@ -8,7 +8,7 @@ M=gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,lts__t_secto
 while read -r name wl envs; do
   [ -z "$name" ] && continue
   v=$(env $envs python bench.py --workload $wl --steps 10 --warmup 3 --no-cpu --e2e-steps 1 2>gpurun_out/sweep_${name}.err | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('%.4e frac %.3f regs %d ok %s'%(d['value'],d['roofline']['frac'],d['plan']['regs_per_thread'],d['e2e']['matches_device_leg']))")
-  env $envs ncu --metrics $M --clock-control none -k regex:'wrow_kernel|recon_kernel' -s 3 -c 1 --csv python bench.py --workload $wl --steps 2 --warmup 3 --no-cpu --e2e-steps 1 2>/dev/null | python -c "
+  env $envs ncu --metrics $M --clock-control none -k regex:'wres_kernel|wrow_kernel|recon_kernel' -s 3 -c 1 --csv python bench.py --workload $wl --steps 2 --warmup 3 --no-cpu --e2e-steps 1 2>/dev/null | python -c "
 import sys,csv
 rows=[r for r in csv.reader(sys.stdin) if len(r)>10 and r[0].isdigit()]
 print(' '.join('%s=%s'%(r[-3].split('__')[-1][:28],r[-1]) for r in rows))" > gpurun_out/sweep_${name}.ncu 2>&1
