@@ -441,7 +441,8 @@ def run_ours(args, wl, rank, world, local_rank):
                          "ascans_per_launch": ascans_per_launch, "launch_ms": recon_launch_ms, "peak_source": peak_src,
                          "whole_step_frac": bytes_per_ascan * value / world / 1e9 / peak},
             "plan": {"fft_threads": info.fft_threads, "radix": list(info.fft_radix), "groups_per_cta": info.groups_per_cta,
-                     "smem_bytes": info.smem_bytes, "regs_per_thread": info.regs_per_thread, "sm_count": info.sm_count},
+                     "smem_bytes": info.smem_bytes, "regs_per_thread": info.regs_per_thread, "sm_count": info.sm_count,
+                     "kernel_kind": info.kernel_kind, "slots_per_warp": info.slots_per_warp},
             "clocks": clocks,
         }
         line["config"]["cpu_affinity"] = affinity

@@ -354,10 +354,11 @@ int upload_calibration(abcoct_ctx* c) {
       CU(c, cudaMemcpy(g.d_yd, fd.data(), n * 4, cudaMemcpyHostToDevice));
     }
   }
-  // which kernel: the resident-row kernel wherever it applies (wres_kernel.cuh: one warp per A-scan, dB rows stay in shared
-  // memory); for A/B measurements ABCOCT_KERNEL=2 forces the warp-per-A-scan kernel with the global dB scratch (wrow_kernel.cuh)
-  // and ABCOCT_KERNEL=1 the group-per-row-pair kernel (recon_kernel.cuh, the fallback for every other transform length and for
-  // the general path); ABCOCT_WRES_NW / ABCOCT_WROW_NW pick another occupancy point of a plan.
+  // which kernel: the warp-per-A-scan kernel wherever it applies (wrow_kernel.cuh).  For A/B measurements ABCOCT_KERNEL=1 forces
+  // the group-per-row-pair kernel (recon_kernel.cuh, the fallback for every other transform length and for the general path) and
+  // ABCOCT_KERNEL=3 the resident-row kernel (wres_kernel.cuh: dB rows parked in tensor memory, no global scratch - 1.3x instead
+  // of 2.9x the algorithmic DRAM traffic, but measured slower: its 4-byte stores into the depth-major image are partial-sector
+  // writes); ABCOCT_WROW_NW / ABCOCT_WRES_NW pick another occupancy point of a plan.
   const WPlanEntry* wp = nullptr;
   if (c->wrow_eligible) {
     int force = 0, nw = 0, lm = -1, rnw = 0;
@@ -365,14 +366,14 @@ int upload_calibration(abcoct_ctx* c) {
     if (const char* e = getenv("ABCOCT_WROW_NW")) nw = atoi(e);
     if (const char* e = getenv("ABCOCT_WROW_LM")) lm = atoi(e);
     if (const char* e = getenv("ABCOCT_WRES_NW")) rnw = atoi(e);
-    if (force == 0 && !c->rblob.empty()) {
+    if (force == 3 && !c->rblob.empty()) {  // opt-in: measured slower than the scratch kernel
       wp = find_rplan(c->N, rnw);
       if (!wp) wp = find_rplan(c->N, 0);
       // progress of the slot protocol: a team's rounds k - K and k must never lie in the same B-scan (wres_kernel.cuh)
       const long long nbb = (c->oph + 3) / 4;
       if (wp && nbb > (long long)wp->slots * wp->teams * c->gpus[0].sm_count) wp = nullptr;
     }
-    if (!wp && force != 1) {
+    if (!wp && force != 1) {  // 0 / 2
       wp = find_wplan(c->N, nw, lm);
       if (!wp) wp = find_wplan(c->N, 0, -1);
     }
@@ -644,6 +645,8 @@ int enqueue_device(abcoct_ctx* c, GpuState& g, int slot, const uint8_t* d_frames
       long long split = std::max<long long>((ntiles + 7) / 8, (2LL * grid + parts - 1) / parts);
       if (const char* e = getenv("ABCOCT_NSPLIT")) split = atol(e);
       a.nsplit = (int)std::max<long long>(1, std::min<long long>(ntiles, split));
+      a.hints = 0;
+      if (const char* e = getenv("ABCOCT_HINTS")) a.hints = atoi(e);
     }
     a.gain = g.d_gain;
     a.subg = g.d_subg;

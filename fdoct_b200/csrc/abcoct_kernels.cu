@@ -44,6 +44,7 @@ __global__ void sched_init_kernel(int* sched, int nB) {
     v.minv[i] = float_to_ordered(__int_as_float(0x7f800000));  // +inf
     v.maxv[i] = float_to_ordered(__int_as_float(0xff800000));  // -inf
     v.cnt[i] = 0;
+    sched[kSchedHeader + 3 * nB + 32 * i] = 0;  // the resident-row kernel's row count (one line per B-scan)
   }
 }
 cudaError_t launch_sched_init(int* sched, int nB, cudaStream_t st) {

@@ -65,6 +65,8 @@ struct ReconArgs {
   // warp-per-A-scan kernel (wrow_kernel.cuh) only
   int calpitch;     // floats per calibration row in its permuted layout
   int nsplit;       // depth-tile ranges a normalisation part is split into (small launches: more, shorter jobs)
+  int hints;        // A/B switches (ABCOCT_HINTS).  L2 policies of the scratch kernel: 1 pixel-row prefetch evict_first, 2 scratch stores
+                    // evict_last, 4 pixel loads evict_first (measured: no effect).  Resident-row kernel: 8 = every warp writes its own row's bytes
 };
 
 // Scheduler / per-B-scan state in global memory (ints).  Header of kSchedHeader ints - three 128-byte lines so that the hot
@@ -86,7 +88,8 @@ __host__ __device__ inline SchedView sched_view(int* base, int nB) {
   v.cnt = v.maxv + nB;
   return v;
 }
-__host__ __device__ inline size_t sched_ints(int nB) { return kSchedHeader + 3 * (size_t)nB; }
+// + one 128-byte line per B-scan: the row counts of the resident-row kernel (wres_kernel.cuh), polled from every SM
+__host__ __device__ inline size_t sched_ints(int nB) { return kSchedHeader + 3 * (size_t)nB + 32 * (size_t)nB; }
 
 
 // ------------------------------------------------------------------------------------------- shared memory map

@@ -2,24 +2,27 @@
 // and the dB values of a row never leave the SM - one HBM read of the raw pixels and one HBM write of the display pixels per
 // A-scan, nothing else.
 //
-// Why (round-2 measurement, profiles/r02a_*): the warp-per-A-scan kernel with a global dB scratch (wrow_kernel.cuh) moved
+// Why (round-2 measurement, profiles/r02a_*): the warp-per-A-scan kernel with a global dB scratch (wrow_kernel.cuh) moves
 // 15.8 GB through DRAM per 1024-frame launch against 5.4 GB algorithmic - the L2 does not keep 4 KB per A-scan of freshly written
-// scratch for the 10 - 25 us until the B-scan's global min / max are known, so the scratch was written back and fetched again,
-// and a third of all stall samples were waits on global memory.  Here
-//   * a row's dB values go into a shared-memory slot of the warp that computed them (K slots per warp) and stay there until
-//     the B-scan is complete; the only global traffic of the completion protocol is one RED per row (count) and the occasional
-//     min / max atomic - no fence over bulk data, no service warp, no scratch, no discard;
-//   * four consecutive warps form a TEAM that owns 4 adjacent A-scans (a block): when the B-scan is complete each warp of the team
-//     normalises a quarter of the depth bins of all 4 rows (threshold, global min-max, round-half-even, BscanFFT.cpp:1243-1255)
-//     and writes 4 display pixels of a bin with one 32-bit store into the depth-major image;
+// scratch for the 10 - 40 us until the B-scan's global min / max are known (L2 policies make no difference, measured), so the
+// scratch is written back and fetched again, and a third of all stall samples are waits on global memory.  Here
+//   * the kernel issues no MMA, so the SM's 256 KB of TENSOR MEMORY are free: a finished row's 32 dB values per lane are parked
+//     in 32 TMEM columns of the warp's own lane quarter (tcgen05.st; K = 4 - 5 rows per warp) and come back into the same
+//     registers (tcgen05.ld) when the B-scan is complete - no shared memory, no global scratch, no fence over bulk data;
+//   * four consecutive warps form a TEAM that owns 4 adjacent A-scans (a block).  When the B-scan is complete each warp quantises
+//     its own row (threshold, global min-max, round-half-even, BscanFFT.cpp:1243-1255) into a small byte tile [bin][4] in shared
+//     memory; when all four rows are there each warp writes a quarter of the bins, 4 display pixels per 32-bit store, into the
+//     depth-major image;
 //   * blocks are assigned statically (block g -> team g mod nteams): every row costs the same, no ticket atomics, and all rows of
-//     a B-scan are in flight at the same time, so a B-scan completes about one row time after its first row.
+//     a B-scan are in flight at the same time, so a B-scan completes about one row time after its first row;
+//   * the completion protocol in global memory is one RED per row (count) plus the occasional min / max atomic.
 // The row pipeline itself (pre-processing, staging, the two in-register FFT passes, split, dB) is the one of wrow_kernel.cuh.
 //
-// Slot protocol (per team, shared-memory counters, monotone): wr[s] counts rows written into slot s (all rounds), nd[s] counts
-// quarters normalised out of slot s.  Round k of a team uses slot s = k mod K.  A warp may write its row of round k when
-// nd[s] >= 4 floor(k / K) (the block of round k - K is fully normalised); it may normalise its quarter of round j when
-// wr[j mod K] >= 4 (j / K + 1) and the B-scan's row count has reached oph.  Progress needs K * nteams >= blocks per B-scan
+// Protocol (per warp: rounds k = 0, 1, ...; TMEM slot k mod K).  jS = next round this warp has to STAGE (TMEM -> bytes in the
+// team's tile jS & 1), possible when the B-scan of that round is complete and the tile's previous user (round jS - 2) has been
+// written out by all four warps; jW = next round whose quarter this warp has to WRITE, possible when all four rows of it are
+// staged.  Both are tried, without waiting, twice per row (where no register is live).  The only wait: before the dB values of
+// round k go into their slot, round k - K must have been staged (jS > k - K).  Progress needs K * nteams >= blocks per B-scan
 // (otherwise round k - K and round k of a team could lie in the same, incomplete B-scan): checked on the host.
 #pragma once
 #include <cstdint>
@@ -33,13 +36,13 @@
 
 namespace abcoct {
 
-template <int N_, int NW_, int K_, bool PQG_ = false>
+template <int N_, int NW_>
 struct RPlan {
-  static constexpr int N = N_, N2 = N_ / 2, R = N_ / 64, NW = NW_, K = K_, LM = 0;
-  static constexpr bool PQG = PQG_;  // the P / Q staging coefficients are read from global memory through L1 instead of shared memory
+  static constexpr int N = N_, N2 = N_ / 2, R = N_ / 64, NW = NW_, LM = 0;
   static constexpr int TR = 4, NT = NW_ / TR;  // rows per block = warps per team; teams per CTA
+  static constexpr int K = 16 / NT;            // TMEM slots per warp: 512 columns / 32 per row, shared by the NT warps of a lane quarter
   static_assert(N_ % 128 == 0 && R <= 32 && R >= 8, "N must be 128 * even, 512 <= N <= 2048");
-  static_assert(NW_ % TR == 0 && K_ >= 2 && K_ <= 4, "whole teams, 2 .. 4 slots per warp");
+  static_assert(NW_ % TR == 0 && NT >= 1 && NT <= 8 && K >= 2, "whole teams, at least 2 slots per warp");
   static constexpr int NCH = (N / 8 + 31) / 32;
   static constexpr int WMAX = NCH * 256;
   static constexpr int PO = WMAX / 2 + 4;
@@ -47,85 +50,23 @@ struct RPlan {
   static constexpr int XPITCH = 33 * 16;
   static constexpr int XCH_BYTES = (R / 2) * XPITCH;
   static constexpr int WBUF = ((cmax(STAGE_BYTES, XCH_BYTES) + 15) / 16) * 16;
-  // table blob (global); its first TABLE_SMEM bytes are the shared-memory image
+  // table blob = shared-memory image
   static constexpr int T_OFFS = 0;
   static constexpr int T_TWA = T_OFFS + (R / 2) * 32 * 16;
   static constexpr int T_TWP = T_TWA + (R / 2) * 32 * 16;
   static constexpr int T_PQ = T_TWP + 8 * 32 * 16;
   static constexpr int TABLE_BYTES = T_PQ + NCH * 4 * 32 * 16;
-  static constexpr int TABLE_SMEM = PQG ? T_PQ : TABLE_BYTES;
-  static constexpr int SLOT_BYTES = N2 * 4;  // one row of dB values (bins 0 .. N/2 - 1)
-  static constexpr int CTL_BYTES = 128;      // per team: wr[K] at int 0, nd[K] at int 4, per-warp {B-scan, min, max} at int 8 + 4 wi
-  static constexpr int OFF_WBUF = TABLE_SMEM;
-  static constexpr int OFF_SLOTS = OFF_WBUF + NW * WBUF;
-  static constexpr int OFF_CTL = OFF_SLOTS + NW * K * SLOT_BYTES;
-  static constexpr int SMEM_BYTES = OFF_CTL + NT * CTL_BYTES;
-  static_assert(SMEM_BYTES <= 227 * 1024, "too many warps / slots for the shared memory");
+  static constexpr int TILE_BYTES = N2 * 4;  // display bytes of a block: [bin][4 rows]
+  static constexpr int CTL_BYTES = 128;      // per team: staged[2] at int 0, done[2] at int 2, per-warp {B-scan, min, max} at int 8 + 4 wi
+  static constexpr int OFF_WBUF = TABLE_BYTES;
+  static constexpr int OFF_TILES = OFF_WBUF + NW * WBUF;
+  static constexpr int OFF_CTL = OFF_TILES + NT * 2 * TILE_BYTES;
+  static constexpr int OFF_TMEM = OFF_CTL + NT * CTL_BYTES;  // the TMEM base address written by tcgen05.alloc; + 4: frontier, + 8: time of the last poll
+  static constexpr int SMEM_BYTES = OFF_TMEM + 16;
+  static_assert(SMEM_BYTES <= 227 * 1024, "too many warps for the shared memory");
   static constexpr int ZERO_OFF = (WMAX / 2) * 4;
   static constexpr int MAXREG = cmax(32, ((65536 / (NW * 32)) / 8) * 8 > 255 ? 255 : ((65536 / (NW * 32)) / 8) * 8);
 };
-
-// ------------------------------------------------------------------------------------------------- normalisation of a block
-struct RNormArgs {
-  uint8_t* out8;
-  float* outdb;
-  int oph, D, clamp55;
-  float thr, clamp_db;
-};
-// Quarter q of the depth bins of the 4 rows r0 .. r0 + 3 of B-scan b; row i lives at rows + i * rowpitch (bytes, shared memory).
-// Lane = bin inside a 32-bin tile: four conflict-free 4-byte shared loads, one 32-bit store per bin.
-WROW_NOINLINE void wres_normalise(const RNormArgs a, const unsigned char* rows, int rowpitch, int b, int r0, int q, float mn, float mx,
-                                  int lane) {
-  const int nrows = (a.oph - r0) < 4 ? (a.oph - r0) : 4;
-  const int ntiles = (a.D + 31) >> 5;
-  const int tq = (ntiles + 3) >> 2;
-  const int t0 = q * tq;
-  const int t1 = (t0 + tq) < ntiles ? (t0 + tq) : ntiles;
-  if (a.clamp55) {  // bscandisp.at<double>(5,5) = 50.0 before the min-max (BscanFFT.cpp:1248-1253)
-    mn = fminf(mn, a.clamp_db);
-    mx = fmaxf(mx, a.clamp_db);
-  }
-  const float sc = (mx - mn) > 2.220446049250313e-16f ? 255.0f / (mx - mn) : 0.f;  // cv::normalize: scale = 0 for a flat image
-  const float thr = a.thr;
-  auto quant = [&](float x) -> unsigned {  // round-half-even of (max(x, thr) - mn) * 255 / (mx - mn): 1.5 * 2^23 trick, low byte
-    float r = fmaf(fmaxf(x, thr) - mn, sc, 12582912.0f);
-    unsigned u;
-    memcpy(&u, &r, 4);
-    return u;
-  };
-  const bool word_ok = nrows == 4 && (a.oph & 3) == 0 && (reinterpret_cast<uintptr_t>(a.out8) & 3) == 0;
-  const bool db_vec_ok = a.outdb != nullptr && nrows == 4 && (a.oph & 3) == 0 && (reinterpret_cast<uintptr_t>(a.outdb) & 15) == 0;
-  const bool has55 = a.clamp55 && r0 == 4 && nrows >= 2;  // element (5,5): row 5 is byte 1 of the block 4 .. 7
-  const float* p0 = reinterpret_cast<const float*>(rows) + lane;
-  const float* p1 = reinterpret_cast<const float*>(rows + (nrows > 1 ? 1 : 0) * rowpitch) + lane;
-  const float* p2 = reinterpret_cast<const float*>(rows + (nrows > 2 ? 2 : 0) * rowpitch) + lane;
-  const float* p3 = reinterpret_cast<const float*>(rows + (nrows > 3 ? 3 : 0) * rowpitch) + lane;
-  const size_t oph = (size_t)a.oph;
-  const size_t o_base = (size_t)b * a.D * oph + r0;
-  for (int t = t0; t < t1; ++t) {
-    const int bin = 32 * t + lane;
-    if (bin >= a.D) continue;
-    const float x0 = p0[32 * t], x1 = p1[32 * t], x2 = p2[32 * t], x3 = p3[32 * t];
-    const unsigned w01 = w_byte_perm(quant(x0), quant(x1), 0x0040), w23 = w_byte_perm(quant(x2), quant(x3), 0x0040);
-    unsigned word = w_byte_perm(w01, w23, 0x5410);
-    if (has55 && bin == 5) word = (word & 0xffff00ffu) | ((quant(a.clamp_db) & 0xffu) << 8);
-    uint8_t* o = a.out8 + o_base + (size_t)bin * oph;
-    if (word_ok) {
-      w_st_global_u32(o, word);
-    } else {
-      for (int i = 0; i < nrows; ++i) w_st_global_u8(o + i, (word >> (8 * i)) & 0xffu);
-    }
-    if (a.outdb != nullptr) {  // transposed dB image (on request)
-      float* od = a.outdb + o_base + (size_t)bin * oph;
-      if (db_vec_ok) {
-        w_st_global_f4(od, make_float4(x0, x1, x2, x3));
-      } else {
-        const float xs[4] = {x0, x1, x2, x3};
-        for (int i = 0; i < nrows; ++i) w_st_keep(od + i, xs[i]);
-      }
-    }
-  }
-}
 
 // ------------------------------------------------------------------------------------------------- the kernel body
 template <class RP, bool HAS_SUB, bool A1, bool FULLD>
@@ -135,34 +76,49 @@ WROW_HD void wres_body(const ReconArgs& a, unsigned char* smem) {
   {  // tables: global (L2-resident) -> shared, once per persistent CTA; team counters start at zero
     const uint4* src = reinterpret_cast<const uint4*>(a.idxT);
     uint4* dst = reinterpret_cast<uint4*>(smem);
-    for (int i = warp * 32 + lane; i < RP::TABLE_SMEM / 16; i += RP::NW * 32) dst[i] = src[i];
+    for (int i = warp * 32 + lane; i < RP::TABLE_BYTES / 16; i += RP::NW * 32) dst[i] = src[i];
     int* ctl0 = reinterpret_cast<int*>(smem + RP::OFF_CTL);
-    for (int i = warp * 32 + lane; i < RP::NT * RP::CTL_BYTES / 4; i += RP::NW * 32) ctl0[i] = (i & 31) >= 8 && ((i & 3) == 0) ? -1 : 0;
+    for (int i = warp * 32 + lane; i < RP::NT * RP::CTL_BYTES / 4; i += RP::NW * 32) ctl0[i] = ((i & 31) >= 8 && (i & 3) == 0) ? -1 : 0;
+    if (warp == 0 && lane < 4) reinterpret_cast<int*>(smem + RP::OFF_TMEM)[lane] = 0;
   }
-  w_syncthreads();
+  const unsigned tmem_base = w_tmem_alloc512(reinterpret_cast<unsigned*>(smem + RP::OFF_TMEM));  // includes the CTA barrier
   const unsigned char* const tbl = smem + 16 * lane;
-  const unsigned char* const gtbl = reinterpret_cast<const unsigned char*>(a.idxT) + 16 * lane;
   auto t_offs = [&](int i) { return *reinterpret_cast<const uint4*>(tbl + RP::T_OFFS + 512 * i); };
-  auto t_pq = [&](int i) {
-    if constexpr (RP::PQG)
-      return w_ldg_tbl16(gtbl + RP::T_PQ + 512 * i);
-    else
-      return *reinterpret_cast<const float4*>(tbl + RP::T_PQ + 512 * i);
-  };
+  auto t_pq = [&](int i) { return *reinterpret_cast<const float4*>(tbl + RP::T_PQ + 512 * i); };
   auto t_twa = [&](int i) { return *reinterpret_cast<const float4*>(tbl + RP::T_TWA + 512 * i); };
   auto t_twp = [&](int i) { return *reinterpret_cast<const float4*>(tbl + RP::T_TWP + 512 * i); };
   unsigned char* const wbuf = smem + RP::OFF_WBUF + warp * RP::WBUF;
   const int team = warp >> 2, wi = warp & 3;
-  unsigned char* const myslots = smem + RP::OFF_SLOTS + (size_t)warp * K * RP::SLOT_BYTES;          // slot s: + s * SLOT_BYTES
-  const unsigned char* const teamslots = smem + RP::OFF_SLOTS + (size_t)(team * 4) * K * RP::SLOT_BYTES;  // row i, slot s: + (i K + s) SLOT_BYTES
+  // this warp's TMEM slots: lane quarter wi (the hardware rule: warp w reaches lanes 32 (w % 4) ..), 32 columns per slot
+  const unsigned tslot0 = tmem_base + ((unsigned)(32 * wi) << 16) + (unsigned)(team * K * 32);
+  unsigned char* const tiles = smem + RP::OFF_TILES + team * 2 * RP::TILE_BYTES;  // tile p: + p * TILE_BYTES
   int* const ctl = reinterpret_cast<int*>(smem + RP::OFF_CTL + team * RP::CTL_BYTES);
-  int* const wr = ctl;
-  int* const nd = ctl + 4;
+  int* const staged = ctl;    // [2] rows staged into tile p, all rounds
+  int* const done = ctl + 2;  // [2] quarters written out of tile p, all rounds
   int* const mm = ctl + 8 + 4 * wi;  // {B-scan of the bounds below (-1: none), ordered min, ordered max} pushed by this warp so far
 
   auto sv_minv = [&]() { return a.sched + kSchedHeader; };
   auto sv_maxv = [&]() { return a.sched + kSchedHeader + a.nB; };
-  auto sv_cnt = [&]() { return a.sched + kSchedHeader + 2 * a.nB; };
+  auto sv_cnt = [&](int b) { return a.sched + kSchedHeader + 3 * a.nB + 32 * b; };  // one 128-byte line per B-scan
+  // completion frontier of this CTA: B-scans [0, *frontier) are known to be complete.  It is advanced by whichever warp needs it,
+  // at most one global poll per kPollNs and CTA - thousands of warps polling the counters themselves made the counts crawl
+  int* const frontier = reinterpret_cast<int*>(smem + RP::OFF_TMEM) + 1;
+  unsigned* const tpoll = reinterpret_cast<unsigned*>(smem + RP::OFF_TMEM) + 2;
+  constexpr unsigned kPollNs = 400;
+  auto bscan_complete = [&](int b) -> bool {  // lane 0
+    int f = w_ld_acquire_cta(frontier);
+    if (f > b) return true;
+    const unsigned now = w_now_ns32(), last = *reinterpret_cast<volatile unsigned*>(tpoll);
+    if (now - last < kPollNs) return false;
+    if (w_cas_smem(tpoll, last, now) != last) return false;  // somebody else polls
+    const int f0 = f;
+    while (f < a.nB && f < f0 + 4 && w_ld_relaxed(sv_cnt(f)) >= a.oph) ++f;
+    if (f == f0) return false;
+    (void)w_ld_acquire(sv_cnt(f - 1));  // acquire: the min / max atomics of the rows counted are visible from here on ...
+    w_acquire_fence();                  // ... for every B-scan below the new frontier
+    w_max_release_smem(frontier, f);    // ... and for whoever acquires the frontier
+    return f > b;
+  };
   const int W8m1 = (a.W >> 3) - 1;
   const unsigned rowbytes = (unsigned)a.W * 2u;
   const float pad_corr = HAS_SUB ? 0.f : (float)(NCH * 256 - a.W);
@@ -186,64 +142,116 @@ WROW_HD void wres_body(const ReconArgs& a, unsigned char* smem) {
   auto row_ptr = [&](const RowId& r, int f) -> const uint8_t* {
     return a.frames + ((size_t)r.b * a.A + f) * a.frame_stride + (size_t)(r.r0 + wi) * a.row_stride;
   };
-  auto norm_args = [&]() {
-    RNormArgs na;
-    na.out8 = a.out8;
-    na.outdb = a.outdb;
-    na.oph = a.oph;
-    na.D = a.D;
-    na.clamp55 = a.clamp55;
-    na.thr = a.thr;
-    na.clamp_db = a.clamp_db;
-    return na;
-  };
 
-  // ---- normalisation of this warp's quarter of round j (all lanes)
-  int jn = 0;  // first round whose quarter this warp has not normalised yet
-  auto ready = [&](int j) -> bool {  // lane 0: all 4 rows of round j are in their slots and the B-scan is complete
-    if (w_ld_acquire_cta(wr + (j % K)) < 4 * (j / K + 1)) return false;
-    return w_ld_acquire(sv_cnt() + block_of(j).b) >= a.oph;
+  // ---- stage: this warp's row of round jS, TMEM -> display bytes in the team's tile (all lanes; conditions checked by lane 0)
+  int jS = 0, jW = 0;
+  const bool direct = (a.hints & 8) != 0;  // A/B: every warp writes the display bytes of its own row itself (no team tile, 1-byte stores)
+  RowId sblk = block_of(0);  // block of round jS
+  auto can_stage = [&]() -> bool {  // lane 0
+    if (!direct && w_ld_acquire_cta(done + (jS & 1)) < 4 * (jS >> 1)) return false;  // the tile's previous block has been written out
+    return bscan_complete(sblk.b);  // every row of the B-scan has been counted
   };
-  auto normalise_round = [&](int j) {  // all lanes; ready(j) has been observed by lane 0
-    const RowId r = block_of(j);
-    int imn = 0, imx = 0;
-    if (lane == 0) {
-      imn = w_ld_cg_i(sv_minv() + r.b);
-      imx = w_ld_cg_i(sv_maxv() + r.b);
+  auto stage_next = [&]() {  // all lanes
+    const int row = sblk.r0 + wi;
+    if (row < a.oph) {
+      int imn = 0, imx = 0;
+      if (lane == 0) {
+        imn = w_ld_cg_i(sv_minv() + sblk.b);
+        imx = w_ld_cg_i(sv_maxv() + sblk.b);
+      }
+      float mn = ordered_to_float(w_shfl_i(imn, 0)), mx = ordered_to_float(w_shfl_i(imx, 0));
+      if (a.clamp55) {  // bscandisp.at<double>(5,5) = 50.0 before the min-max (BscanFFT.cpp:1248-1253)
+        mn = fminf(mn, a.clamp_db);
+        mx = fmaxf(mx, a.clamp_db);
+      }
+      const float sc = (mx - mn) > 2.220446049250313e-16f ? 255.0f / (mx - mn) : 0.f;  // cv::normalize: scale = 0 for a flat image
+      const float thr = a.thr;
+      auto quant = [&](float x) -> unsigned {  // round-half-even of (max(x, thr) - mn) * 255 / (mx - mn): 1.5 * 2^23 trick, low byte
+        float r = fmaf(fmaxf(x, thr) - mn, sc, 12582912.0f);
+        unsigned u;
+        memcpy(&u, &r, 4);
+        return u & 0xffu;
+      };
+      unsigned char* const tile = tiles + (jS & 1) * RP::TILE_BYTES + wi;
+      const bool lane_okS = (R == 32) || lane < R;
+      const bool is55row = a.clamp55 && row == 5;
+      float* const od = a.outdb != nullptr ? a.outdb + (size_t)sblk.b * a.D * a.oph + row : nullptr;
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        float v[16];
+        w_tmem_ld16(tslot0 + (unsigned)((jS % K) * 32 + 16 * h), v);
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const int d = 8 * h + (i >> 1);
+          int bin = (i & 1) ? N2 - lane - R * d : lane + R * d;
+          if ((i & 1) && d == 0 && lane == 0) bin = N2 / 2;
+          if (lane_okS && bin < a.D) {
+            unsigned q = quant(v[i]);
+            if (is55row && bin == 5) q = quant(a.clamp_db);  // the forced element
+            if (direct)
+              w_st_global_u8(a.out8 + ((size_t)sblk.b * a.D + bin) * a.oph + row, q);
+            else
+              w_st_shared_u8(tile + 4 * bin, q);
+            if (od != nullptr) w_st_keep(od + (size_t)bin * a.oph, v[i]);  // transposed dB image (on request)
+          }
+        }
+      }
     }
-    imn = w_shfl_i(imn, 0);
-    imx = w_shfl_i(imx, 0);
-    wres_normalise(norm_args(), teamslots + (size_t)(j % K) * RP::SLOT_BYTES, K * RP::SLOT_BYTES, r.b, r.r0, wi, ordered_to_float(imn),
-                   ordered_to_float(imx), lane);
-    w_syncwarp();  // every lane has read its values: the slots of round j may be overwritten once all four quarters are counted
-    if (lane == 0) w_red_release_cta(nd + (j % K), 1);
+    w_syncwarp();
+    if (lane == 0 && !direct) w_red_release_cta(staged + (jS & 1), 1);
+    ++jS;
+    if (direct) jW = jS;
+    sblk = block_of(jS);
   };
-  auto try_normalise = [&](int kmax) {  // at most one pending round, never waits
+  // ---- write: this warp's quarter of the bins of round jW, 4 display pixels per store
+  auto can_write = [&]() -> bool { return w_ld_acquire_cta(staged + (jW & 1)) >= 4 * ((jW >> 1) + 1); };  // lane 0
+  auto write_next = [&]() {  // all lanes
+    const RowId r = block_of(jW);
+    const int nrows = (a.oph - r.r0) < 4 ? (a.oph - r.r0) : 4;
+    const int ntiles = (a.D + 31) >> 5;
+    const int tq = (ntiles + 3) >> 2;
+    const int t0 = wi * tq;
+    const int t1 = (t0 + tq) < ntiles ? (t0 + tq) : ntiles;
+    const bool word_ok = nrows == 4 && (a.oph & 3) == 0 && (reinterpret_cast<uintptr_t>(a.out8) & 3) == 0;
+    const unsigned char* const tile = tiles + (jW & 1) * RP::TILE_BYTES;
+    uint8_t* const o_base = a.out8 + (size_t)r.b * a.D * a.oph + r.r0;
+    for (int t = t0; t < t1; ++t) {
+      const int bin = 32 * t + lane;
+      if (bin < a.D) {
+        const unsigned word = *reinterpret_cast<const unsigned*>(tile + 4 * bin);
+        uint8_t* o = o_base + (size_t)bin * a.oph;
+        if (word_ok) {
+          w_st_global_u32(o, word);
+        } else {
+          for (int i = 0; i < nrows; ++i) w_st_global_u8(o + i, (word >> (8 * i)) & 0xffu);
+        }
+      }
+    }
+    w_syncwarp();
+    if (lane == 0) w_red_release_cta(done + (jW & 1), 1);
+    ++jW;
+  };
+  auto service = [&](int kmax) -> int {  // at most one stage and one write of rounds < kmax; never waits
     int go = 0;
-    if (lane == 0) go = (jn < kmax && ready(jn)) ? 1 : 0;
-    if (w_shfl_i(go, 0)) {
-      normalise_round(jn);
-      ++jn;
-    }
+    if (lane == 0) go = ((jS < kmax && can_stage()) ? 1 : 0) | ((jW < jS && can_write()) ? 2 : 0);
+    go = w_shfl_i(go, 0);
+    if (go & 1) stage_next();
+    if (go & 2) write_next();
+    return go;
   };
-  auto wait_until = [&](auto&& cond) {  // all lanes; lane 0 polls
-    const unsigned long long t_start = w_now_ns();
-    for (;;) {
-      int ok = 0;
-      if (lane == 0) ok = cond() ? 1 : 0;
-      if (w_shfl_i(ok, 0)) break;
-      if (w_now_ns() - t_start > kWrowWatchdogNs) w_trap();  // a protocol bug must surface as a launch failure, not as a hung GPU
-      w_backoff_short();
+  auto acquire_slot = [&](int k) {  // before the dB values of round k go into TMEM slot k mod K: round k - K must have been staged
+    unsigned spins = 0;
+    unsigned long long t_start = 0;
+    while (jS <= k - K) {
+      if (service(k) == 0) {
+        if ((++spins & 255u) == 0u) {  // a protocol bug must surface as a launch failure, not as a hung GPU
+          const unsigned long long now = w_now_ns();
+          if (t_start == 0) t_start = now;
+          if (now - t_start > kWrowWatchdogNs) w_trap();
+        }
+        w_backoff_short();
+      }
     }
-  };
-  auto acquire_slot = [&](int k) {  // before this warp's row of round k goes into slot k mod K
-    if (k < K) return;
-    while (jn <= k - K) {  // my own quarter of the round that occupies the slot
-      wait_until([&]() { return ready(jn); });
-      normalise_round(jn);
-      ++jn;
-    }
-    wait_until([&]() { return w_ld_acquire_cta(nd + (k % K)) >= 4 * (k / K); });
   };
 
   // partner lane of the split step and the validity of this lane's outputs
@@ -294,14 +302,12 @@ WROW_HD void wres_body(const ReconArgs& a, unsigned char* smem) {
     const RowId rid = block_of(k);
     const int bscan = rid.b;
     const int row = rid.r0 + wi;
-    const int s_k = k % K;
-    if (row >= a.oph) {  // the last block of a B-scan may be partial: this warp has no row, but it keeps the slot protocol
-      try_normalise(k);
+    if (row >= a.oph) {  // the last block of a B-scan may be partial: this warp has no row, but it keeps the team protocol going
+      service(k);
       acquire_slot(k);
-      if (lane == 0) w_red_release_cta(wr + s_k, 1);
       continue;
     }
-    float* const slot = reinterpret_cast<float*>(myslots + (size_t)s_k * RP::SLOT_BYTES);
+    const unsigned tslot = tslot0 + (unsigned)((k % K) * 32);
 
     for (int f = 0; f < nA; ++f) {
       const bool last = A1 || (f + 1 == nA);
@@ -364,8 +370,8 @@ WROW_HD void wres_body(const ReconArgs& a, unsigned char* smem) {
       }
       w_syncwarp();
       prefetch_step(k, f, 2);
-      // ---- nothing but the staged row is live here: the cheap place to normalise a finished round (never waits)
-      if (f == 0) try_normalise(k);
+      // ---- nothing but the staged row is live here: the cheap place to finish earlier rounds (never waits)
+      if (f == 0) service(k);
       // ---------------------------------------------------------------- pass A: gather, radix-R, twiddle, exchange
       {
         float2 x[R], y[R];
@@ -392,9 +398,12 @@ WROW_HD void wres_body(const ReconArgs& a, unsigned char* smem) {
         }
       }
       w_syncwarp();
-      // ---- between the passes no register is live either: take the slot of this round here (waits only when the team or the
-      // B-scan of round k - K is late)
-      if (last) acquire_slot(k);
+      // ---- between the passes no register is live either: a second chance, and the TMEM slot of this round is taken here
+      // (with K slots per warp that waits only when some warp of the GPU is K - 1 rounds behind)
+      if (last) {
+        service(k);
+        acquire_slot(k);
+      }
       // ---------------------------------------------------------------- pass B: radix-32 over the lanes of pass A
       float2 u[32], Z[32];
       {
@@ -406,6 +415,7 @@ WROW_HD void wres_body(const ReconArgs& a, unsigned char* smem) {
       Dft<32, kFftSign, 1, 1>::run(u, Z);
       // ---------------------------------------------------------------- split + magnitude (+ finalise on the last frame)
       float mn = w_inf(false), mx = w_inf(true);
+      float dbv[16];  // the dB values of 8 split steps: value 2 d' = bin lane + R d, value 2 d' + 1 = bin N/2 - lane - R d
       auto split_pass = [&](auto fin_c) {
         constexpr bool FIN = decltype(fin_c)::value;
 #pragma unroll
@@ -437,7 +447,7 @@ WROW_HD void wres_body(const ReconArgs& a, unsigned char* smem) {
           }
           if constexpr (FIN) {
             // /A, + 1e-5, ln, * 20 / 2.303 (BscanFFT.cpp:1221-1237)
-            const float db1 = fast_log2(fmaf(a1, a.out_scale, 1e-5f)) * a.db_scale;
+            float db1 = fast_log2(fmaf(a1, a.out_scale, 1e-5f)) * a.db_scale;
             const float db2 = fast_log2(fmaf(a2, a.out_scale, 1e-5f)) * a.db_scale;
             const int k1 = lane + R * d;
             int k2 = N2 - lane - R * d;
@@ -446,16 +456,10 @@ WROW_HD void wres_body(const ReconArgs& a, unsigned char* smem) {
             if (d == 0) {
               if (lane == 0) k2 = N2 / 2;
               ok2 = lane_ok && (lane == 0 ? (FULLD || N2 / 2 < a.D) : ok2);
-              if (lane < 2) {
-                if (a.dc01 != nullptr && ok1) a.dc01[2 * ((size_t)bscan * a.oph + row) + lane] = db1;  // kept on request only
-                ok1 = false;  // bscandb.row(4).copyTo(row(1)), row(0): BscanFFT.cpp:1239-1240
-              }
-              if (lane == 4 && ok1) {
-                slot[0] = db1;
-                slot[1] = db1;
-              }
-              if (ok1) slot[k1] = db1;
-              if (ok2) slot[k2] = db2;
+              if (lane < 2 && a.dc01 != nullptr && ok1) a.dc01[2 * ((size_t)bscan * a.oph + row) + lane] = db1;  // kept on request only
+              // bscandb.row(4).copyTo(row(1)), row(0): BscanFFT.cpp:1239-1240 - bins 0 and 1 (lanes 0, 1) take the value of bin 4
+              const float db4 = w_shfl(db1, 4);
+              if (lane < 2) db1 = db4;
               const bool is55 = a.clamp55 && lane == 5 && row == 5;  // forced element: excluded from the min / max of the data
               if (ok1 && !is55) {
                 mn = fminf(mn, db1);
@@ -466,22 +470,21 @@ WROW_HD void wres_body(const ReconArgs& a, unsigned char* smem) {
                 mx = fmaxf(mx, db2);
               }
             } else if (FULLD && R == 32) {
-              slot[k1] = db1;
-              slot[k2] = db2;
               mn = w_min3(mn, db1, db2);
               mx = w_max3(mx, db1, db2);
             } else {
               if (ok1) {
-                slot[k1] = db1;
                 mn = fminf(mn, db1);
                 mx = fmaxf(mx, db1);
               }
               if (ok2) {
-                slot[k2] = db2;
                 mn = fminf(mn, db2);
                 mx = fmaxf(mx, db2);
               }
             }
+            dbv[2 * (d & 7)] = db1;
+            dbv[2 * (d & 7) + 1] = db2;
+            if ((d & 7) == 7) w_tmem_st16(tslot + (unsigned)(16 * (d >> 3)), dbv);  // 16 values -> 16 TMEM columns of this lane
           }
         }
       };
@@ -493,9 +496,10 @@ WROW_HD void wres_body(const ReconArgs& a, unsigned char* smem) {
       // thresholded min / max of the B-scan (BscanFFT.cpp:1247, 1254): max(., thr) commutes with min / max
       const int imn = w_redux_min(float_to_ordered(fmaxf(mn, a.thr)));
       const int imx = w_redux_max(float_to_ordered(fmaxf(mx, a.thr)));
-      w_syncwarp();  // every lane's dB values are in the slot before lane 0 counts the row
+      w_tmem_st_wait();  // the row is in tensor memory before it is counted
       if (lane == 0) {
         const float fmn = ordered_to_float(imn), fmx = ordered_to_float(imx);
+        bool pushed = false;
         if (fmn <= fmx) {
           // most rows do not move the B-scan's extrema: skip the atomics when this warp already pushed tighter bounds
           float cmn = w_inf(false), cmx = w_inf(true);
@@ -506,26 +510,42 @@ WROW_HD void wres_body(const ReconArgs& a, unsigned char* smem) {
           if (fmn < cmn) {
             w_atomic_min(sv_minv() + bscan, imn);
             cmn = fmn;
+            pushed = true;
           }
           if (fmx > cmx) {
             w_atomic_max(sv_maxv() + bscan, imx);
             cmx = fmx;
+            pushed = true;
           }
           mm[0] = bscan;
           mm[1] = float_to_ordered(cmn);
           mm[2] = float_to_ordered(cmx);
         }
-        w_red_release_cta(wr + s_k, 1);
-        w_release_add(sv_cnt() + bscan, 1);  // release at gpu scope: this lane's min / max atomics are visible before the count
+        // the count: released at gpu scope only when this row pushed a bound (the atomics must be visible before the count);
+        // otherwise nothing of this row lives in global memory and a relaxed RED does
+        if (pushed)
+          w_release_add(sv_cnt(bscan), 1);
+        else
+          w_red_relaxed(sv_cnt(bscan), 1);
       }
     }
   }
-  // ---- the tail: the rounds this warp has not normalised yet
-  while (jn < nk) {
-    wait_until([&]() { return ready(jn); });
-    normalise_round(jn);
-    ++jn;
+  // ---- the tail: the rounds this warp has not staged / written yet
+  {
+    unsigned spins = 0;
+    unsigned long long t_start = 0;
+    while (jW < nk) {
+      if (service(nk) == 0) {
+        if ((++spins & 255u) == 0u) {
+          const unsigned long long now = w_now_ns();
+          if (t_start == 0) t_start = now;
+          if (now - t_start > kWrowWatchdogNs) w_trap();
+        }
+        w_backoff_short();
+      }
+    }
   }
+  w_tmem_free512(tmem_base);  // includes the CTA barrier: every warp has read its last row back
 }
 
 #ifdef __CUDACC__

@@ -4,9 +4,9 @@
 
 namespace abcoct {
 static const WPlanEntry kRPlans[] = {
-    make_rentry<RPlan<2048, 12, 2, true>>(),
-    make_rentry<RPlan<1920, 12, 2, false>>(),
-    make_rentry<RPlan<1280, 16, 2, false>>(), make_rentry<RPlan<1280, 12, 3, false>>(),
+    make_rentry<RPlan<2048, 16>>(),
+    make_rentry<RPlan<1920, 16>>(),
+    make_rentry<RPlan<1280, 16>>(),
 };
 const WPlanEntry* find_rplan(int N, int nw) {
   for (const WPlanEntry& e : kRPlans)

@@ -369,6 +369,10 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
   auto sv_cnt = [&]() { return a.sched + kSchedHeader + 2 * a.nB; };
   const int W8m1 = (a.W >> 3) - 1;
   const unsigned rowbytes = (unsigned)a.W * 2u;
+  // L2 policies (ReconArgs::hints): the raw pixel rows pass through L2 once (prefetch + one read) and must not push out the dB
+  // scratch, which is read back 10 - 25 us after it was written
+  const unsigned long long pol_in = w_policy((a.hints & 1) ? 1 : 0), pol_scr = w_policy((a.hints & 2) ? 2 : 0);
+  const bool ld_hint = (a.hints & 4) != 0;
   // samples of the padded runs (W < NCH * 256) see gain 0, i.e. t - 1 = -1 without a subtrahend row: taken out of the mean
   const float pad_corr = HAS_SUB ? 0.f : (float)(NCH * 256 - a.W);
 
@@ -570,7 +574,8 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
 #pragma unroll
     for (int j = 0; j < NCH; ++j) {
       const int run = lane + 32 * j;
-      raw[j] = w_ldg_stream16(rp + 16 * (run < W8m1 ? run : W8m1));  // padded runs re-read the last run (finite values)
+      const void* pp = rp + 16 * (run < W8m1 ? run : W8m1);  // padded runs re-read the last run (finite values)
+      raw[j] = ld_hint ? w_ldg_stream16_pol(pp, pol_in) : w_ldg_stream16(pp);
     }
   };
   auto ahead = [&](int item, int f) {
@@ -619,7 +624,7 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
     const int item = k < nA ? it0 : (k < 2 * nA ? it1 : it2);
     const int fr = k < nA ? k : (k < 2 * nA ? k - nA : k - 2 * nA);
     if (item < a.nitems && fr < nA) {
-      w_prefetch_l2(row_ptr(item, fr), rowbytes);
+      w_prefetch_l2_pol(row_ptr(item, fr), rowbytes, pol_in);
       if (LM == 0 && fr == 0) w_prefetch_l2(a.gain + (size_t)(item % a.oph) * a.calpitch, (unsigned)a.calpitch * 4u);
     }
   };
@@ -628,9 +633,9 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
     if (lane == 0) {
       const int nA = A1 ? 1 : a.A;
       if (nA > 1)
-        w_prefetch_l2(row_ptr(it0, 1), rowbytes);
+        w_prefetch_l2_pol(row_ptr(it0, 1), rowbytes, pol_in);
       else if (it1 < a.nitems)
-        w_prefetch_l2(row_ptr(it1, 0), rowbytes);
+        w_prefetch_l2_pol(row_ptr(it1, 0), rowbytes, pol_in);
     }
   }
 
@@ -834,11 +839,11 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
                 ok1 = false;  // bscandb.row(4).copyTo(row(1)), row(0): BscanFFT.cpp:1239-1240
               }
               if (lane == 4 && ok1) {
-                w_st_keep(srow, db1);
-                w_st_keep(srow + 1, db1);
+                w_st_keep_pol(srow, db1, pol_scr);
+                w_st_keep_pol(srow + 1, db1, pol_scr);
               }
-              if (ok1) w_st_keep(s1, db1);
-              if (ok2) w_st_keep(lane == 0 ? srow + N2 / 2 : s2, db2);
+              if (ok1) w_st_keep_pol(s1, db1, pol_scr);
+              if (ok2) w_st_keep_pol(lane == 0 ? srow + N2 / 2 : s2, db2, pol_scr);
               const bool is55 = a.clamp55 && lane == 5 && row == 5;  // forced element: excluded from the min / max of the data
               if (ok1 && !is55) {
                 mn = fminf(mn, db1);
@@ -849,18 +854,18 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
                 mx = fmaxf(mx, db2);
               }
             } else if (FULLD && R == 32) {
-              w_st_keep(s1 + R * d, db1);
-              w_st_keep(s2 - R * d, db2);
+              w_st_keep_pol(s1 + R * d, db1, pol_scr);
+              w_st_keep_pol(s2 - R * d, db2, pol_scr);
               mn = w_min3(mn, db1, db2);
               mx = w_max3(mx, db1, db2);
             } else {
               if (ok1) {
-                w_st_keep(s1 + R * d, db1);
+                w_st_keep_pol(s1 + R * d, db1, pol_scr);
                 mn = fminf(mn, db1);
                 mx = fmaxf(mx, db1);
               }
               if (ok2) {
-                w_st_keep(s2 - R * d, db2);
+                w_st_keep_pol(s2 - R * d, db2, pol_scr);
                 mn = fminf(mn, db2);
                 mx = fmaxf(mx, db2);
               }

@@ -32,6 +32,7 @@ int load_acquire(const int* p);
 void check_smem(const void* p, int bytes, int align);
 void backoff();
 unsigned ballot(int pred);
+unsigned* tmem();  // per-CTA emulation of the tensor memory: [128 lanes][512 columns] 32-bit words
 }  // namespace wemu
 #else
 #define WROW_HD __device__ __forceinline__
@@ -240,6 +241,122 @@ WROW_HD void w_prefetch_l2(const void* p, unsigned bytes) {
 #endif
 }
 
+// ---- tensor memory (TMEM) as a row store -----------------------------------------------------------------------------
+// The kernel issues no MMA, so the 256 KB of tensor memory of the SM (128 lanes x 512 columns x 32 bit) are free: a warp parks
+// the 32 dB values that each lane holds for a finished A-scan in 32 columns of its own lane quarter (tcgen05.st, shape 32x32b:
+// thread i of warp w reaches lane 32 (w % 4) + i) and reads them back into the same registers when the B-scan is complete.
+// Address = lane << 16 | column.  Allocation: the whole 512 columns, by warp 0 of the (only) CTA of the SM.
+WROW_HD unsigned w_tmem_alloc512(unsigned* smem_word) {  // all threads of the CTA
+#if WROW_DEVICE_BODY
+  if ((threadIdx.x >> 5) == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(smem_word)), "r"(512u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  return *reinterpret_cast<volatile unsigned*>(smem_word);
+#else
+  (void)smem_word;
+  wemu::syncthreads();
+  return 0u;
+#endif
+}
+WROW_HD void w_tmem_free512(unsigned base) {  // all threads of the CTA, after their last access
+#if WROW_DEVICE_BODY
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if ((threadIdx.x >> 5) == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(512u) : "memory");
+#else
+  (void)base;
+  wemu::syncthreads();
+#endif
+}
+WROW_HD void w_tmem_st16(unsigned taddr, const float (&v)[16]) {  // whole warp; 16 consecutive columns of this thread's lane
+#if WROW_DEVICE_BODY
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])), "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])),
+      "r"(__float_as_uint(v[5])), "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7])), "r"(__float_as_uint(v[8])), "r"(__float_as_uint(v[9])),
+      "r"(__float_as_uint(v[10])), "r"(__float_as_uint(v[11])), "r"(__float_as_uint(v[12])), "r"(__float_as_uint(v[13])),
+      "r"(__float_as_uint(v[14])), "r"(__float_as_uint(v[15]))
+      : "memory");
+#else
+  unsigned* t = wemu::tmem() + (size_t)(((taddr >> 16) & 127u) + (unsigned)wemu::lane()) * 512u + (taddr & 511u);
+  for (int i = 0; i < 16; ++i) memcpy(t + i, &v[i], 4);
+#endif
+}
+WROW_HD void w_tmem_st_wait() {
+#if WROW_DEVICE_BODY
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+#endif
+}
+WROW_HD void w_tmem_ld16(unsigned taddr, float (&v)[16]) {  // whole warp; returns when the values are in the registers
+#if WROW_DEVICE_BODY
+  unsigned r[16];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n\t"
+      "tcgen05.wait::ld.sync.aligned;"  // same statement: the registers are defined only after the wait
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+#pragma unroll
+  for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+#else
+  const unsigned* t = wemu::tmem() + (size_t)(((taddr >> 16) & 127u) + (unsigned)wemu::lane()) * 512u + (taddr & 511u);
+  for (int i = 0; i < 16; ++i) memcpy(&v[i], t + i, 4);
+#endif
+}
+WROW_HD void w_st_shared_u8(unsigned char* p, unsigned v) {
+  *p = (unsigned char)v;
+}
+
+// ---- L2 cache policies (createpolicy): which = 0 evict_normal, 1 evict_first, 2 evict_last -----------------------------
+WROW_HD unsigned long long w_policy(int which) {
+#if WROW_DEVICE_BODY
+  unsigned long long pn, pf, pl;
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pn));
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pf));
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pl));
+  return which == 1 ? pf : (which == 2 ? pl : pn);
+#else
+  return (unsigned long long)which;
+#endif
+}
+WROW_HD void w_prefetch_l2_pol(const void* p, unsigned bytes, unsigned long long pol) {
+#if WROW_DEVICE_BODY
+  asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(p), "r"(bytes), "l"(pol) : "memory");
+#else
+  (void)p;
+  (void)bytes;
+  (void)pol;
+#endif
+}
+WROW_HD void w_st_keep_pol(float* p, float v, unsigned long long pol) {
+#if WROW_DEVICE_BODY
+  asm volatile("st.global.L2::cache_hint.f32 [%0], %1, %2;" ::"l"(p), "f"(v), "l"(pol) : "memory");
+#else
+  (void)pol;
+  *p = v;
+#endif
+}
+WROW_HD uint4 w_ldg_stream16_pol(const void* p, unsigned long long pol) {
+#if WROW_DEVICE_BODY
+  uint4 v;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(p), "l"(pol));
+  return v;
+#else
+  (void)pol;
+  uint4 v;
+  memcpy(&v, p, 16);
+  return v;
+#endif
+}
+
 // ---- TMA bulk copies global -> shared with mbarrier completion (SASS UBLKCP + SYNCS) --------------------------------
 // One mbarrier per warp; lane 0 arms it with the byte count and issues the copies, every lane waits on the phase parity.
 WROW_HD void w_mbar_init(unsigned long long* bar) {
@@ -410,6 +527,54 @@ WROW_HD void w_red_release_cta(int* p, int v) {
   asm volatile("red.release.cta.shared::cta.add.s32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
 #else
   __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST);
+#endif
+}
+WROW_HD void w_red_relaxed(int* p, int v) {
+#if WROW_DEVICE_BODY
+  asm volatile("red.relaxed.gpu.global.add.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+#else
+  wemu::atomic_add(p, v);
+#endif
+}
+// shared-memory words of the per-CTA completion frontier (wres_kernel.cuh)
+WROW_HD unsigned w_cas_smem(unsigned* p, unsigned expect, unsigned desired) {
+#if WROW_DEVICE_BODY
+  unsigned old;
+  asm volatile("atom.relaxed.cta.shared::cta.cas.b32 %0, [%1], %2, %3;" : "=r"(old) : "r"((unsigned)__cvta_generic_to_shared(p)), "r"(expect), "r"(desired) : "memory");
+  return old;
+#else
+  __atomic_compare_exchange_n(p, &expect, desired, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST);
+  return expect;
+#endif
+}
+WROW_HD void w_max_release_smem(int* p, int v) {
+#if WROW_DEVICE_BODY
+  asm volatile("red.release.cta.shared::cta.max.s32 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(p)), "r"(v) : "memory");
+#else
+  int cur = __atomic_load_n(p, __ATOMIC_SEQ_CST);
+  while (v > cur && !__atomic_compare_exchange_n(p, &cur, v, false, __ATOMIC_SEQ_CST, __ATOMIC_SEQ_CST)) {
+  }
+#endif
+}
+WROW_HD unsigned w_now_ns32() {
+#if WROW_DEVICE_BODY
+  unsigned t;
+  asm volatile("mov.u32 %0, %%globaltimer_lo;" : "=r"(t));
+  return t;
+#else
+  static unsigned fake = 0;
+  return __atomic_add_fetch(&fake, 1000u, __ATOMIC_SEQ_CST);
+#endif
+}
+WROW_HD void w_sleep_ns(unsigned ns) {
+#if WROW_DEVICE_BODY
+  while (ns > 0u) {  // nanosleep takes at most about a millisecond; the argument here is a few microseconds
+    const unsigned step = ns > 500000u ? 500000u : ns;
+    __nanosleep(step);
+    ns -= step;
+  }
+#else
+  (void)ns;
 #endif
 }
 WROW_HD void w_backoff_short() {

@@ -261,6 +261,38 @@ def test_fallback_kernel_on_lengths_the_warp_kernel_owns(w, h, N, D, A, variant,
     _check(out8, outdb, ref8, refdb, f"fallback w{w} N{N} A{A}")
 
 
+@pytest.mark.parametrize("w,h,N,D,A,variant,clamp", [(2048, 36, 2048, 1024, 1, 0, 0), (1280, 21, 1280, 600, 2, 1, 1), (1920, 64, 1920, 960, 1, 0, 1)])
+def test_resident_row_kernel_tmem(w, h, N, D, A, variant, clamp, monkeypatch):
+    """The opt-in resident-row kernel (wres_kernel.cuh, ABCOCT_KERNEL=3): finished dB rows parked in TENSOR MEMORY (tcgen05.st / ld)
+    until the B-scan's min / max are known, teams of 4 warps, static schedule - against the oracle, with partial last blocks
+    (h % 4 != 0), averaging, the DARK variant, D < N/2, the forced element and the dB image."""
+    from fdoct_b200 import api, synth
+    from oracle.abcoct_oracle import Oracle
+
+    monkeypatch.setenv("ABCOCT_KERNEL", "3")
+    nB = 7
+    op = oracle_params(w=w, h=h, numfftpoints=N, numdisplaypoints=D, averages=A, variant=variant, clampupper=bool(clamp), lambdamin=840.5e-9,
+                       lambdamax=859.5e-9)
+    frames = synth.make_frames(nB * A, w, h, seed=71, dark=bool(variant))
+    yb = synth.make_background_frames(2, w, h, seed=72, dark=bool(variant)).mean(axis=0)
+    yd = synth.make_dark_frames(2, w, h, seed=73).mean(axis=0) if variant else None
+    o = Oracle(op)
+    o.set_background(yb)
+    if variant:
+        o.set_dark(yd)
+    ref8, refdb = o.process_bscans(frames)
+    with api.Context(abi_params(op)) as ctx:
+        ctx.set_background(yb)
+        if yd is not None:
+            ctx.set_dark(yd)
+        out8, outdb = ctx.process_bscans(frames, want_db=True)
+        out8b, _ = ctx.process_bscans(frames)  # without the dB image
+        kind = ctx.info().kernel_kind
+    assert kind == 2, "the resident-row kernel was not selected"
+    _check(out8, outdb, ref8, refdb, f"resident w{w} N{N} A{A}")
+    assert np.array_equal(out8, out8b)
+
+
 @pytest.mark.parametrize("w,h,N,extra", [(1280, 9, 1280, {}), (1024, 6, 2048, {}), (640, 5, 2560, dict(fft_multiplier=4)),
                                          (1280, 8, 640, dict(binx=2, biny=2, movavgn=1)), (1280, 6, 1280, dict(variant=1))])
 def test_stage_parity_linearised(w, h, N, extra):
