@@ -276,6 +276,106 @@ def measured_hbm_peak():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+
+# --------------------------------------------------------------------------------------------- multi-GPU volume leg
+def volume_leg(api, torch, dist, dev, rank, world, local_rank, per_gpu):
+    """BASELINE config 4 in the shape `north_star` names: a triggered-capture volume of 1920x1200 frames, `per_gpu` B-scans per
+    GPU (125 -> 1000 B-scans on 8 GPUs), host buffers in, host display B-scans out, FINAL HOST GATHER INSIDE the timed region.
+    Three measurements (all ranks take part; rank 0 returns the dict):
+      ranks_gather   one process per GPU through fdoct_b200.shard.process_sharded: every rank reconstructs its shard from pinned
+                     host memory, the display images are gathered to rank 0 over a host (gloo) group
+      one_context    ONE abcoct context spanning all GPUs (abcoct_create(ngpu = world), one feeder thread per GPU) on rank 0:
+                     the whole volume in one pinned host buffer, all outputs into one host array - the gather is implicit
+      copy_ceiling   the same bytes, H2D and D2H concurrently on every GPU, no kernel: what the box's host side can feed
+    and a self-check: every rank's shard and the one-context output are identical (all shards hold the same frames)."""
+    from fdoct_b200 import shard
+
+    wl = WORKLOADS["c4"]
+    w, h, D, A = wl["w"], wl["h"], wl["D"], wl["A"]
+    frames, uniq, yb, yd = make_inputs(wl, per_gpu)
+    gloo = dist.new_group(backend="gloo")
+    ctx = api.Context(abi_params(api, wl), gpu_ids=[local_rank])
+    ctx.set_background(yb)
+    pin_in = api.PinnedArray(frames.shape, np.uint16)
+    pin_in.array[...] = frames
+    pin_out = api.PinnedArray((per_gpu, D, h), np.uint8)
+
+    def fn(fr):
+        ctx.process_bscans(fr, out8=pin_out.array)
+        return pin_out.array
+
+    src = shard.FrameSource(per_gpu * world, lambda lo, hi: pin_in.array)  # every rank's shard = its own pinned copy
+    fn(pin_in.array)  # warm-up (allocates the ring)
+    t = torch.zeros(3, dtype=torch.float64, device=dev)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        dist.barrier(group=gloo)
+
+    sync_all()
+    t0 = time.perf_counter()
+    whole = shard.process_sharded(fn, src, A, (D, h), rank=rank, world=world, group=gloo)
+    dist.barrier(group=gloo)
+    t[0] = time.perf_counter() - t0
+
+    # copy ceiling: the shard's input up, the shard's output down, concurrently on two streams, no kernel
+    d_in = torch.empty(frames.nbytes, dtype=torch.uint8, device=dev)
+    d_out = torch.empty(per_gpu * D * h, dtype=torch.uint8, device=dev)
+    h_in = torch.from_numpy(pin_in.array.view(np.uint8).reshape(-1))
+    h_out = torch.from_numpy(pin_out.array.reshape(-1))
+    keep = pin_out.array.copy()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for timed in (False, True):
+        sync_all()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(s1):
+            d_in.copy_(h_in, non_blocking=True)
+        with torch.cuda.stream(s2):
+            h_out.copy_(d_out, non_blocking=True)
+        sync_all()
+        if timed:
+            t[1] = time.perf_counter() - t0
+    same_shards = True
+    ctx.close()
+
+    # one context over all GPUs, on rank 0 (the other ranks wait)
+    one_ok = None
+    if rank == 0:
+        big_in = api.PinnedArray((per_gpu * world,) + frames.shape[1:], np.uint16)
+        for r in range(world):
+            big_in.array[r * per_gpu:(r + 1) * per_gpu] = frames
+        big_out = api.PinnedArray((per_gpu * world, D, h), np.uint8)
+        with api.Context(abi_params(api, wl), gpu_ids=list(range(world))) as mctx:
+            mctx.set_background(yb)
+            mctx.process_bscans(big_in.array, out8=big_out.array)  # warm-up
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            mctx.process_bscans(big_in.array, out8=big_out.array)
+            t[2] = time.perf_counter() - t0
+        one_ok = all(np.array_equal(big_out.array[r * per_gpu:(r + 1) * per_gpu], keep) for r in range(world))
+        same_shards = all(np.array_equal(whole[r * per_gpu:(r + 1) * per_gpu], keep) for r in range(world))
+        big_in.free()
+        big_out.free()
+    dist.barrier(group=gloo)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    pin_in.free()
+    pin_out.free()
+    if rank != 0:
+        return None
+    t_rg, t_cp, t_one = [float(x) for x in t.cpu()]
+    ascans = per_gpu * world * A * h
+    in_b, out_b = int(frames.nbytes) * world, per_gpu * D * h * world
+    ceiling = ascans / t_cp
+    return {"workload": wl["desc"], "bscans_total": per_gpu * world, "bscans_per_gpu": per_gpu, "host_bytes_in": in_b, "host_bytes_out": out_b,
+            "ranks_gather": {"value": ascans / t_rg, "unit": "A-scans/s", "seconds": t_rg,
+                             "note": "torchrun ranks via shard.process_sharded, gloo gather of the display images to rank 0 inside the timed region"},
+            "one_context": {"value": ascans / t_one, "unit": "A-scans/s", "seconds": t_one,
+                            "note": "one abcoct context over all GPUs (one feeder thread per GPU), one pinned host buffer in, one out"},
+            "copy_ceiling": {"value": ceiling, "unit": "A-scans/s", "seconds": t_cp, "h2d_gbs": in_b / t_cp / 1e9, "d2h_gbs": out_b / t_cp / 1e9,
+                             "note": "same bytes, cudaMemcpyAsync H2D + D2H concurrently on every GPU, no kernel"},
+            "one_context_frac_of_ceiling": (ascans / t_one) / ceiling, "ranks_gather_frac_of_ceiling": (ascans / t_rg) / ceiling,
+            "outputs_identical": bool(one_ok and same_shards)}
+
 # --------------------------------------------------------------------------------------------- main arms
 def run_reference(args, wl, rank):
     if rank != 0:
@@ -408,6 +508,10 @@ def run_ours(args, wl, rank, world, local_rank):
     dev_ms, e2e_ms, recon_launch_ms = [float(x) for x in t.cpu()]
     info = ctx.info()
 
+    volume = None
+    if world > 1 and not args.no_volume:
+        volume = volume_leg(api, torch, dist, dev, rank, world, local_rank, args.volume_bscans)
+
     if rank == 0:
         ascans_step = nframes * h * world
         value = ascans_step * args.steps / (dev_ms * 1e-3)
@@ -446,6 +550,8 @@ def run_ours(args, wl, rank, world, local_rank):
             "clocks": clocks,
         }
         line["config"]["cpu_affinity"] = affinity
+        if volume is not None:
+            line["volume"] = volume
         if not args.no_cpu and world == 1:  # the CPU baseline is a single-GPU-run figure (rank 0 at N = 1 only)
             cores = os.cpu_count() or 1
             per_core = calibrate_cpu_sample(wl, uniq, yb, yd, target_s=args.cpu_seconds)
@@ -473,6 +579,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU work per timed CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-traffic", action="store_true", help="skip the one-launch ncu pass that measures roofline.traffic")
+    ap.add_argument("--no-volume", action="store_true", help="multi-GPU runs: skip the C4 volume leg (sharded volume + host gather, one context over all GPUs, copy ceiling)")
+    ap.add_argument("--volume-bscans", type=int, default=125, help="B-scans per GPU in the volume leg (125 x 8 GPUs = the 1000-B-scan volume of BASELINE config 4)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
+#include <mutex>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -102,7 +104,7 @@ struct abcoct_ctx {
   int G = 1, smem = 0, regs = 0;
   std::vector<GpuState> gpus;
   std::string err;
-  uint64_t launches = 0;
+  std::atomic<uint64_t> launches{0};  // bumped by the per-GPU feeder threads of a multi-GPU context
   double last_recon_ms = 0, last_norm_ms = 0;
 };
 
@@ -114,6 +116,8 @@ int fail(abcoct_ctx* c, int code, const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(buf, sizeof buf, fmt, ap);
   va_end(ap);
+  static std::mutex err_mutex;  // the feeder threads of a multi-GPU context may fail at the same time
+  std::lock_guard<std::mutex> lock(err_mutex);
   if (c)
     c->err = buf;
   else
@@ -1345,46 +1349,72 @@ int abcoct_process_bscans_ex(abcoct_ctx* c, const void* frames, size_t nframes, 
     cudaGetLastError();
     return rc;
   };
-  size_t chunk = 0;
-  for (size_t b0 = 0; b0 < nB; b0 += slotB, ++chunk) {
-    const size_t nb = std::min(slotB, nB - b0);
-    const size_t gi = chunk % ngpu;
-    const int s = (int)((chunk / ngpu) % kSlots);
-    int rc = drain(gi, s);
-    if (rc) return bail(rc);
+  // One feeder per GPU: chunks gi, gi + ngpu, ... go through that GPU's slot ring (copy in, kernels, copy out, all on the slot's
+  // stream).  With several GPUs every feeder is its own host thread - a single loop would serialise the staging copies and the
+  // enqueue calls of all GPUs (round 1: 2.5x at 8 GPUs).
+  auto feed = [&](size_t gi) -> int {
     GpuState& g = c->gpus[gi];
     CU(c, cudaSetDevice(g.dev));
-    cudaStream_t st = g.stream[s];
-    const uint8_t* src = static_cast<const uint8_t*>(frames) + b0 * c->A * frame_in;
-    const size_t nfr = nb * c->A;
-    if (in_pinned) {
-      CU(c, cudaMemcpyAsync(g.d_in[s], src, nfr * frame_dev, cudaMemcpyHostToDevice, st));
-    } else {
-      // pageable (or pitched) caller memory: stage through the pinned ring
-      if (stride_bytes == dense) {
-        staging_copy(g.h_in[s], src, nfr * frame_dev);
+    size_t k = 0;
+    for (size_t chunk = gi; chunk * slotB < nB; chunk += ngpu, ++k) {
+      const size_t b0 = chunk * slotB;
+      const size_t nb = std::min(slotB, nB - b0);
+      const int s = (int)(k % kSlots);
+      int rc = drain(gi, s);
+      if (rc) return rc;
+      cudaStream_t st = g.stream[s];
+      const uint8_t* src = static_cast<const uint8_t*>(frames) + b0 * c->A * frame_in;
+      const size_t nfr = nb * c->A;
+      if (in_pinned) {
+        CU(c, cudaMemcpyAsync(g.d_in[s], src, nfr * frame_dev, cudaMemcpyHostToDevice, st));
       } else {
-        for (size_t r = 0; r < nfr * c->p.h; ++r) memcpy(g.h_in[s] + r * dense, src + r * stride_bytes, dense);
+        // pageable (or pitched) caller memory: stage through the pinned ring
+        if (stride_bytes == dense) {
+          staging_copy(g.h_in[s], src, nfr * frame_dev);
+        } else {
+          for (size_t r = 0; r < nfr * c->p.h; ++r) memcpy(g.h_in[s] + r * dense, src + r * stride_bytes, dense);
+        }
+        CU(c, cudaMemcpyAsync(g.d_in[s], g.h_in[s], nfr * frame_dev, cudaMemcpyHostToDevice, st));
       }
-      CU(c, cudaMemcpyAsync(g.d_in[s], g.h_in[s], nfr * frame_dev, cudaMemcpyHostToDevice, st));
+      OutPtrs dev;
+      for (int q = 0; q < O_COUNT; ++q) dev.p[q] = host.p[q] ? g.d_o[q][s] : nullptr;
+      rc = enqueue_device(c, g, s, g.d_in[s], nb, dense, frame_dev, dev, st, false);
+      if (rc) return rc;
+      for (int q = 0; q < O_COUNT; ++q)
+        if (host.p[q]) {
+          void* dst = out_pinned ? static_cast<void*>(static_cast<uint8_t*>(host.p[q]) + b0 * out_px * kOutBpp[q]) : g.h_o[q][s];
+          CU(c, cudaMemcpyAsync(dst, g.d_o[q][s], nb * out_px * kOutBpp[q], cudaMemcpyDeviceToHost, st));
+        }
+      CU(c, cudaEventRecord(g.slot_done[s], st));
+      pend[gi * kSlots + s] = Pending{b0, nb, true};
     }
-    OutPtrs dev;
-    for (int k = 0; k < O_COUNT; ++k) dev.p[k] = host.p[k] ? g.d_o[k][s] : nullptr;
-    rc = enqueue_device(c, g, s, g.d_in[s], nb, dense, frame_dev, dev, st, false);
-    if (rc) return bail(rc);
-    for (int k = 0; k < O_COUNT; ++k)
-      if (host.p[k]) {
-        void* dst = out_pinned ? static_cast<void*>(static_cast<uint8_t*>(host.p[k]) + b0 * out_px * kOutBpp[k]) : g.h_o[k][s];
-        CU(c, cudaMemcpyAsync(dst, g.d_o[k][s], nb * out_px * kOutBpp[k], cudaMemcpyDeviceToHost, st));
-      }
-    CU(c, cudaEventRecord(g.slot_done[s], st));
-    pend[gi * kSlots + s] = Pending{b0, nb, true};
-  }
-  for (size_t gi = 0; gi < ngpu; ++gi)
     for (int s = 0; s < kSlots; ++s) {
       int rc = drain(gi, s);
       if (rc) return rc;
     }
+    return ABCOCT_OK;
+  };
+  int rc_all = ABCOCT_OK;
+  if (ngpu == 1) {
+    rc_all = feed(0);
+  } else {
+    std::vector<int> rcs(ngpu, ABCOCT_OK);
+    std::vector<std::thread> th;
+    for (size_t gi = 1; gi < ngpu; ++gi) {
+      try {
+        th.emplace_back([&, gi] { rcs[gi] = feed(gi); });
+      } catch (...) {  // no thread to be had: this thread feeds that GPU after its own
+        rcs[gi] = -12345;
+      }
+    }
+    rcs[0] = feed(0);
+    for (std::thread& t : th) t.join();
+    for (size_t gi = 1; gi < ngpu; ++gi)
+      if (rcs[gi] == -12345) rcs[gi] = feed(gi);
+    for (int r : rcs)
+      if (r && !rc_all) rc_all = r;
+  }
+  if (rc_all) return bail(rc_all);
   return ABCOCT_OK;
 }
 

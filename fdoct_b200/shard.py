@@ -28,6 +28,20 @@ def frame_range(bscan_range: tuple[int, int], averages: int) -> tuple[int, int]:
     return bscan_range[0] * averages, bscan_range[1] * averages
 
 
+class FrameSource:
+    """A batch of frames that is not one array in this process: `getter(lo, hi)` returns frames [lo, hi) (e.g. a slice of a
+    memory-mapped volume, or - in bench.py - the rank's own pinned copy of its shard).  Only slicing is supported."""
+
+    def __init__(self, nframes: int, getter):
+        self.nframes, self.getter = int(nframes), getter
+
+    def __getitem__(self, sl):
+        lo, hi, step = sl.indices(self.nframes)
+        if step != 1:
+            raise ValueError("contiguous slices only")
+        return self.getter(lo, hi)
+
+
 def process_sharded(process_fn, frames: np.ndarray, averages: int, out_shape_per_bscan: tuple[int, int], *, rank: int,
                     world: int, group=None, dst: int = 0):
     """Run `process_fn(frames_slice) -> uint8 [nb, D, oph]` on this rank's B-scans and gather on `dst`.
@@ -35,8 +49,9 @@ def process_sharded(process_fn, frames: np.ndarray, averages: int, out_shape_per
     `frames` is the WHOLE batch (every rank sees the same host array / memory map, only its slice is touched);
     `group` must be a host-capable (gloo) process group when world > 1.  Returns the full [nB, D, oph] array on
     `dst`, None elsewhere."""
-    nB = frames.shape[0] // averages
-    if frames.shape[0] != nB * averages:
+    nframes = frames.nframes if isinstance(frames, FrameSource) else frames.shape[0]
+    nB = nframes // averages
+    if nframes != nB * averages:
         raise ValueError("nframes must be a multiple of averages")
     parts = partition(nB, world)
     lo, hi = frame_range(parts[rank], averages)

@@ -286,7 +286,7 @@ def test_resident_row_kernel_tmem(w, h, N, D, A, variant, clamp, monkeypatch):
         if yd is not None:
             ctx.set_dark(yd)
         out8, outdb = ctx.process_bscans(frames, want_db=True)
-        out8b, _ = ctx.process_bscans(frames)  # without the dB image
+        out8b = ctx.process_bscans(frames)  # without the dB image
         kind = ctx.info().kernel_kind
     assert kind == 2, "the resident-row kernel was not selected"
     _check(out8, outdb, ref8, refdb, f"resident w{w} N{N} A{A}")

@@ -68,3 +68,30 @@ def test_sharded_gather_matches_single_process(world, nB, A):
     rng = np.random.default_rng(5)
     frames = rng.integers(0, 65535, size=(nB * A, 6, 16), dtype=np.uint16)
     assert np.array_equal(got, _fake_process(frames, A, 8, 6))
+
+
+def test_frame_source_shards_like_an_array():
+    """FrameSource (frames that are not one array in this process, e.g. bench.py's per-rank pinned shard) partitions exactly like
+    an ndarray: same slices asked for, same result for world = 1."""
+    import numpy as np
+
+    from fdoct_b200 import shard
+
+    frames = np.arange(12 * 2 * 3, dtype=np.uint16).reshape(12, 2, 3)
+    asked = []
+
+    def getter(lo, hi):
+        asked.append((lo, hi))
+        return frames[lo:hi]
+
+    def fn(fr):
+        return np.full((fr.shape[0] // 2, 4, 2), fr[0, 0, 0] % 251, np.uint8)
+
+    a = shard.process_sharded(fn, frames, 2, (4, 2), rank=0, world=1)
+    b = shard.process_sharded(fn, shard.FrameSource(12, getter), 2, (4, 2), rank=0, world=1)
+    assert np.array_equal(a, b) and asked == [(0, 12)]
+    for world in (2, 3, 5):
+        for r, (lo, hi) in enumerate(shard.partition(6, world)):
+            asked.clear()
+            shard.FrameSource(12, getter)[slice(*shard.frame_range((lo, hi), 2))]
+            assert asked == [(2 * lo, 2 * hi)]
