@@ -33,7 +33,7 @@ class Params(C.Structure):
         ("fft_multiplier", C.c_uint32), ("rowwisenormalize", C.c_uint8), ("donotnormalize", C.c_uint8),
         ("variant", C.c_uint8), ("weight_mode", C.c_uint8), ("bscanthreshold", C.c_double),
         ("clampupper", C.c_uint8), ("bandpassfilter", C.c_uint8), ("lowpassfilter", C.c_uint8), ("output_rebin", C.c_uint8),
-        ("bscanbinx", C.c_uint8), ("bscanbiny", C.c_uint8), ("reserved", C.c_uint8 * 2),
+        ("bscanbinx", C.c_uint8), ("bscanbiny", C.c_uint8), ("channelnum", C.c_uint8), ("reserved", C.c_uint8 * 1),
         ("clamp_db", C.c_double),
     ]
 
@@ -237,7 +237,7 @@ class Context:
 
     def set_calibration_from_frames(self, which: int, frames: np.ndarray):
         frames = np.ascontiguousarray(frames)
-        assert frames.ndim == 3 and frames.dtype == (np.uint8 if self.params.bpp == 8 else np.uint16)
+        self._check_frames(frames)
         self._check(lib().abcoct_set_calibration_from_frames(self._h, which, frames.ctypes.data, frames.shape[0], 0))
 
     def set_threshold(self, thr: float):
@@ -267,12 +267,19 @@ class Context:
         return nk, fr, win
 
     # the hot path ----------------------------------------------------------------------
+    def _check_frames(self, frames: np.ndarray):
+        """(nframes, h, w) uint8 / uint16, or (nframes, h, w, 3) uint8 interleaved BGR when channelnum >= 3 (BscanFFTwebcam.cpp:1021)."""
+        assert frames.flags.c_contiguous
+        assert frames.dtype == (np.uint8 if self.params.bpp == 8 else np.uint16), frames.dtype
+        if self.params.channelnum >= 3:
+            assert frames.ndim == 4 and frames.shape[1:] == (self.params.h, self.params.w, 3), frames.shape
+        else:
+            assert frames.ndim == 3 and frames.shape[1:] == (self.params.h, self.params.w), frames.shape
+
     def process_bscans(self, frames: np.ndarray, want_db: bool = False, out8: np.ndarray | None = None,
                        outdb: np.ndarray | None = None):
         """Host-buffer call (abcoct_process_bscans). frames: (nframes, h, w) uint16, C-contiguous."""
-        assert frames.ndim == 3 and frames.flags.c_contiguous
-        assert frames.dtype == (np.uint8 if self.params.bpp == 8 else np.uint16), frames.dtype
-        assert frames.shape[1:] == (self.params.h, self.params.w), frames.shape
+        self._check_frames(frames)
         nframes = frames.shape[0]
         nB = nframes // max(self.A, 1)
         if out8 is None:
@@ -300,9 +307,7 @@ class Context:
 
     def process_bscans_ex(self, frames: np.ndarray, want=("bscan_u8",)) -> dict:
         """abcoct_process_bscans_ex: returns {name: array} for the requested images (see OUTPUT_KINDS); bscan_u8 always."""
-        assert frames.ndim == 3 and frames.flags.c_contiguous
-        assert frames.dtype == (np.uint8 if self.params.bpp == 8 else np.uint16), frames.dtype
-        assert frames.shape[1:] == (self.params.h, self.params.w), frames.shape
+        self._check_frames(frames)
         nframes = frames.shape[0]
         nB = nframes // max(self.A, 1)
         res, o = {}, Outputs()

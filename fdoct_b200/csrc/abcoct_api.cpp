@@ -98,7 +98,9 @@ struct abcoct_ctx {
   const std::vector<unsigned char>* blob_loaded = nullptr;  // which blob d_tables holds
   std::vector<int> gidx;      // the kernel's remapped gather indices / weights (debug tap)
   std::vector<float> gwq;
-  int px_bytes = 2;
+  int px_bytes = 2;      // bytes per pixel of the CALLER's frames: 1, 2, or 3 (interleaved BGR, channelnum >= 3)
+  bool bgr = false;      // BscanFFTwebcam.cpp:1021-1037: sum of the three channels * 0.00130718954
+  float px_scale = 1.f;  // factor between the integer pixel (sum) and data_y
   std::vector<int> radW, radM;
   const PlanEntry* plan = nullptr;
   int G = 1, smem = 0, regs = 0;
@@ -191,10 +193,15 @@ int validate(const abcoct_params& p, std::string& why, int& code) {
   if (p.binx > 1 && p.w % p.binx) return bad("w is not a multiple of the x binning factor (cv::resize would round the size)");
   if (p.biny > 1 && p.h % p.biny) return bad("h is not a multiple of the y binning factor (cv::resize would round the size)");
   if (p.mediann < 0 || p.movavgn < 0) return bad("mediann / movavgn must be >= 0");
+  if (p.channelnum >= 3 && p.bpp != 8) return bad("channelnum >= 3 (sum of the BGR channels) needs 8-bit frames");
+  if (p.channelnum >= 3 && p.mediann != 0)
+    return bad("channelnum >= 3 with mediann > 0: cv::medianBlur throws on the CV_64F channel sum in the reference (BscanFFTwebcam.cpp:1045)");
   code = ABCOCT_ERR_UNSUPPORTED;
   if (p.mediann != 0 && p.mediann != 3 && p.mediann != 5)
     return bad("medianBlur kernel sizes other than 3 and 5 are not built (OpenCV itself only takes 3 / 5 for 16-bit frames)");
   if (p.movavgn > 64) return bad("movavgn > 64 is not built");
+  if (p.channelnum >= 3 && (p.binx > 1 || p.biny > 1))
+    return bad("channelnum >= 3 with binning (INTER_AREA on the CV_64F channel sum, BscanFFTwebcam.cpp:1049) is not built");
   if (p.output_rebin && (p.bscanbinx > 1 || p.bscanbiny > 1 || p.binx > 1 || p.biny > 1))
     return bad("BscanFFTspinjnt's output re-binning of the linear B-scan (INTER_AREA down, x multiplyfactor, INTER_CUBIC up; "
                "BscanFFTspinjnt.cpp:1856-1862, active whenever any binning factor exceeds 1) is not built");
@@ -481,6 +488,9 @@ int ensure_prep(abcoct_ctx* c, GpuState& g, int slot, size_t nframes) {
   g.d_med[slot] = g.d_bin[slot] = nullptr;
   g.d_rows[slot] = g.d_fmm[slot] = nullptr;
   g.prep_frames[slot] = 0;
+  if (c->bgr) {  // the channel sums (<= 765) as 16-bit frames; reuses the median buffer slot (mediann is 0 with channelnum >= 3)
+    CU(c, cudaMalloc(&g.d_med[slot], nframes * c->p.h * c->p.w * 2));
+  }
   if (c->p.mediann > 0) CU(c, cudaMalloc(&g.d_med[slot], nframes * c->p.h * c->p.w * c->px_bytes));
   if (c->p.binx > 1 || c->p.biny > 1) CU(c, cudaMalloc(&g.d_bin[slot], nframes * c->oph * c->opw * c->px_bytes));
   CU(c, cudaMalloc(&g.d_rows[slot], nframes * c->oph * (size_t)c->M * sizeof(float)));
@@ -497,6 +507,15 @@ int run_prep(abcoct_ctx* c, GpuState& g, int slot, const uint8_t* d_frames, size
   const void* src = d_frames;
   size_t rs = row_stride / pb, fs = frame_stride / pb;
   int n = 0;
+  int bpp = (int)c->p.bpp;
+  if (c->bgr) {  // BscanFFTwebcam.cpp:1021-1037
+    CU(c, launch_bgr_sum(d_frames, static_cast<uint16_t*>(g.d_med[slot]), (int)c->p.w, (int)c->p.h, row_stride, frame_stride, (int)nframes, st));
+    src = g.d_med[slot];
+    rs = c->p.w;
+    fs = (size_t)c->p.w * c->p.h;
+    bpp = 16;
+    ++n;
+  }
   if (c->p.mediann > 0) {
     CU(c, launch_median(src, g.d_med[slot], (int)c->p.bpp, c->p.mediann, (int)c->p.w, (int)c->p.h, rs, fs, (int)nframes, st));
     src = g.d_med[slot];
@@ -515,7 +534,8 @@ int run_prep(abcoct_ctx* c, GpuState& g, int slot, const uint8_t* d_frames, size
   h.binned = src;  // without binning the row kernel reads the caller's (or the median's) frames through their strides
   h.row_stride = rs;
   h.frame_stride = fs;
-  h.bpp = (int)c->p.bpp;
+  h.bpp = bpp;
+  h.px_scale = c->px_scale;
   h.opw = c->opw;
   h.oph = c->oph;
   h.nframes = (int)nframes;
@@ -818,7 +838,7 @@ int abcoct_params_from_ini(const char* path, int flavour, abcoct_params* o) {
   }
   std::ifstream in(path);
   if (!in.is_open()) return ABCOCT_ERR_IO;  // "Unable to open ini file, using defaults." BscanFFT.cpp:484
-  enum F { SKIP, BPP, W, H, BIN, BINX, BINY, OBINX, OBINY, AVG, NFFT, MOVAVG, NDISP, LMIN, LMAX, MEDIAN, MULT, ROWNORM, NONORM, BANDPASS, LOWPASS };
+  enum F { SKIP, BPP, W, H, BIN, BINX, BINY, OBINX, OBINY, AVG, NFFT, MOVAVG, NDISP, LMIN, LMAX, MEDIAN, MULT, ROWNORM, NONORM, BANDPASS, LOWPASS, CHANNEL };
   std::vector<F> order = {SKIP /*camgain*/, SKIP /*camtime*/, BPP, W, H};
   const bool offsets = flavour == ABCOCT_INI_BSCANFFT || flavour == ABCOCT_INI_SPINJ || flavour == ABCOCT_INI_SPINJNT;
   if (offsets) {
@@ -835,6 +855,7 @@ int abcoct_params_from_ini(const char* path, int flavour, abcoct_params* o) {
                              SKIP /*saveinterferograms*/, MOVAVG, NDISP, LMIN, LMAX, MEDIAN, MULT});
   if (flavour != ABCOCT_INI_SIM) order.insert(order.end(), {ROWNORM, NONORM});
   if (flavour == ABCOCT_INI_DARK) order.insert(order.end(), {BANDPASS, LOWPASS});
+  if (flavour == ABCOCT_INI_WEBCAM) order.push_back(CHANNEL);  // BscanFFTwebcam.cpp:508
   std::string tok;
   for (int i = 0; i < 3; ++i)  // "first three lines of ini file are comments" BscanFFT.cpp:420-423
     if (!(in >> tok)) return ABCOCT_OK;
@@ -870,6 +891,7 @@ int abcoct_params_from_ini(const char* path, int flavour, abcoct_params* o) {
       case NONORM: o->donotnormalize = iv != 0; stop = !numeric; break;
       case BANDPASS: o->bandpassfilter = iv != 0; stop = !numeric; break;
       case LOWPASS: o->lowpassfilter = iv != 0; stop = !numeric; break;
+      case CHANNEL: o->channelnum = (uint8_t)std::min(255L, std::max(0L, iv)); stop = !numeric; break;
     }
     if (stop) break;  // an istream in the fail state ignores every later extraction
   }
@@ -901,8 +923,13 @@ int abcoct_create(const abcoct_params* params, const int* gpu_ids, int ngpu, abc
   c->A = params->averages;
   c->plan = find_plan(c->N);
   c->px_bytes = params->bpp == 8 ? 1 : 2;
+  c->bgr = params->channelnum >= 3;
+  if (c->bgr) {
+    c->px_bytes = 3;
+    c->px_scale = (float)0.00130718954;  // 1 / 255 / 3, BscanFFTwebcam.cpp:1036
+  }
   c->general = params->bpp == 8 || params->binx > 1 || params->biny > 1 || params->mediann > 0 || params->movavgn > 0 ||
-               params->fft_multiplier > 1 || params->rowwisenormalize || !params->donotnormalize;
+               params->fft_multiplier > 1 || params->rowwisenormalize || !params->donotnormalize;  // (8-bit covers channelnum >= 3)
   if (params->fft_multiplier > 1) {
     c->radW = factor_radices(c->opw);
     c->radM = factor_radices(c->M);
@@ -1109,7 +1136,13 @@ int abcoct_set_calibration_from_frames(abcoct_ctx* c, int which, const void* fra
       fr = med.data();
       rs = w;
     }
-    if (pb == 1)  // resize(..., INTER_AREA), BscanFFT.cpp:958
+    if (c->bgr) {  // BscanFFTwebcam.cpp:1021-1037: CV_64F sum of the three channels, then * 0.00130718954 (no binning, validated)
+      for (int y = 0; y < h; ++y)
+        for (int x = 0; x < w; ++x) {
+          const uint8_t* px = fr + (size_t)y * stride_bytes + 3 * (size_t)x;
+          one[(size_t)y * w + x] = ((double)px[0] + (double)px[1] + (double)px[2]) * 0.00130718954;
+        }
+    } else if (pb == 1)  // resize(..., INTER_AREA), BscanFFT.cpp:958
       host_bin(fr, rs, one.data(), c->opw, c->oph, (int)c->p.binx, (int)c->p.biny);
     else
       host_bin(reinterpret_cast<const uint16_t*>(fr), rs, one.data(), c->opw, c->oph, (int)c->p.binx, (int)c->p.biny);

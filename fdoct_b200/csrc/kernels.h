@@ -50,6 +50,7 @@ struct PrepArgsHost {
   const void* binned;  // integer pixels after median + binning: frames of oph rows of opw pixels
   size_t row_stride, frame_stride;  // of `binned`, in pixels
   int bpp, opw, oph, nframes, movavgn;
+  float px_scale;      // data_y = pixel * px_scale (1, or 1 / 765 for the webcam channel sum)
   const float* yd;     // nullable (DARK variant)
   int rowwise, global_norm;
   float* frame_minmax;  // [nframes][2], needed when global_norm
@@ -62,6 +63,9 @@ struct PrepArgsHost {
 };
 cudaError_t launch_median(const void* in, void* out, int bpp, int k, int w, int h, size_t row_stride_elems, size_t frame_stride_elems,
                           int nframes, cudaStream_t st);
+// BscanFFTwebcam.cpp:1021-1037: interleaved 8-bit BGR frames (strides in bytes) -> dense 16-bit frames of channel sums
+cudaError_t launch_bgr_sum(const void* in, uint16_t* out, int w, int h, size_t row_stride_bytes, size_t frame_stride_bytes, int nframes,
+                           cudaStream_t st);
 cudaError_t launch_bin(const void* in, void* out, int bpp, int opw, int oph, int bx, int by, size_t row_stride_elems,
                        size_t frame_stride_elems, int nframes, cudaStream_t st);
 cudaError_t launch_rowprep(const PrepArgsHost& h, cudaStream_t st, int* launched);

@@ -150,6 +150,7 @@ struct PrepArgs {
   int bpp;              // 8 or 16
   int opw, oph, nframes;
   int movavgn;          // smoothmovavg half width (0 = off)
+  float px_scale;       // data_y = pixel * px_scale (BscanFFTwebcam.cpp:1036: 1 / 765 for the channel sum; 1 otherwise - exact)
   const float* yd;      // nullable: dark frame (DARK variant)
   int rowwise;          // normalizerows(data_y, 0, 1)
   int global_norm;      // normalize(data_y, 0, 1, NORM_MINMAX) over the frame: 0 off, 1 = reduce pass, 2 = apply pass
@@ -195,10 +196,10 @@ __device__ bool rowprep_one(const PrepArgs& a, int row, int f, float* x, float* 
   // convertTo(data_y, CV_64F)  (BscanFFT.cpp:987); integers up to 65535 are exact in f32
   if (a.bpp == 8) {
     const uint8_t* src = static_cast<const uint8_t*>(a.binned) + pix;
-    for (int j = threadIdx.x; j < W; j += blockDim.x) x[j] = (float)src[j];
+    for (int j = threadIdx.x; j < W; j += blockDim.x) x[j] = (float)src[j] * a.px_scale;
   } else {
     const uint16_t* src = static_cast<const uint16_t*>(a.binned) + pix;
-    for (int j = threadIdx.x; j < W; j += blockDim.x) x[j] = (float)src[j];
+    for (int j = threadIdx.x; j < W; j += blockDim.x) x[j] = (float)src[j] * a.px_scale;
   }
   __syncthreads();
   if (a.movavgn > 0) {  // smoothmovavg, BscanFFT.cpp:247-304: 2n+1 taps, centre counted twice, missing taps -> centre
@@ -294,12 +295,12 @@ __device__ __forceinline__ void rowpair_fast(const PrepArgs& a, const PX* src0, 
         const uint4 p = __ldg(reinterpret_cast<const uint4*>(srcs[r]) + ch);
         const unsigned w32[4] = {p.x, p.y, p.z, p.w};
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = (float)((k & 1) ? (w32[k >> 1] >> 16) : (w32[k >> 1] & 0xffffu));
+        for (int k = 0; k < 8; ++k) v[k] = (float)((k & 1) ? (w32[k >> 1] >> 16) : (w32[k >> 1] & 0xffffu)) * a.px_scale;
       } else {
         const uint2 p = __ldg(reinterpret_cast<const uint2*>(srcs[r]) + ch);
         const unsigned w32[2] = {p.x, p.y};
 #pragma unroll
-        for (int k = 0; k < 8; ++k) v[k] = (float)((w32[k >> 2] >> (8 * (k & 3))) & 0xffu);
+        for (int k = 0; k < 8; ++k) v[k] = (float)((w32[k >> 2] >> (8 * (k & 3))) & 0xffu) * a.px_scale;
       }
       float b[8], s[8], d[8];
       *reinterpret_cast<float4*>(b) = __ldg(reinterpret_cast<const float4*>(rows[r]) + 2 * ch);
@@ -431,6 +432,22 @@ cudaError_t launch_lerp_rows(const float* rows, const int* idx, const float* wq,
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------ webcam channel sum
+// BscanFFTwebcam.cpp:1021-1037 (channelnum >= 3): mraw = (B + G + R) * 0.00130718954 as CV_64F.  The integer sum (<= 765) is
+// exact in 16 bits; the scale is applied where the pixel becomes a float (PrepArgs::px_scale).
+__global__ void bgr_sum_kernel(const uint8_t* __restrict__ in, uint16_t* __restrict__ out, int w, int h, size_t row_stride, size_t frame_stride) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, f = blockIdx.z;
+  if (x >= w) return;
+  const uint8_t* p = in + (size_t)f * frame_stride + (size_t)y * row_stride + 3 * (size_t)x;
+  out[((size_t)f * h + y) * w + x] = (uint16_t)((unsigned)p[0] + (unsigned)p[1] + (unsigned)p[2]);
+}
+cudaError_t launch_bgr_sum(const void* in, uint16_t* out, int w, int h, size_t row_stride_bytes, size_t frame_stride_bytes, int nframes,
+                           cudaStream_t st) {
+  dim3 grid((w + 127) / 128, h, nframes), block(128);
+  bgr_sum_kernel<<<grid, block, 0, st>>>(static_cast<const uint8_t*>(in), out, w, h, row_stride_bytes, frame_stride_bytes);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------ launchers
 cudaError_t launch_median(const void* in, void* out, int bpp, int k, int w, int h, size_t row_stride_elems, size_t frame_stride_elems,
                           int nframes, cudaStream_t st) {
@@ -476,7 +493,7 @@ size_t rowprep_smem_bytes(int opw, int M, int m, int movavgn) {
 // returns the number of kernels launched (through *launched)
 cudaError_t launch_rowprep(const PrepArgsHost& h, cudaStream_t st, int* launched) {
   PrepArgs a{};
-  a.binned = h.binned; a.row_stride = h.row_stride; a.frame_stride = h.frame_stride; a.bpp = h.bpp; a.opw = h.opw; a.oph = h.oph; a.nframes = h.nframes; a.movavgn = h.movavgn;
+  a.binned = h.binned; a.row_stride = h.row_stride; a.frame_stride = h.frame_stride; a.bpp = h.bpp; a.opw = h.opw; a.oph = h.oph; a.nframes = h.nframes; a.movavgn = h.movavgn; a.px_scale = h.px_scale;
   a.yd = h.yd; a.rowwise = h.rowwise; a.frame_minmax = h.frame_minmax; a.yb = h.yb; a.yp = h.yp; a.win = h.win;
   a.m = h.m; a.M = h.M; a.bandpass = h.bandpass; a.twW = h.twW; a.twM = h.twM; a.out = h.out;
   a.rlW.n = h.opw; a.rlW.count = h.nradW;

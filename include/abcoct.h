@@ -74,7 +74,11 @@ typedef struct abcoct_params {
                                 BscanFFTspinjnt.cpp:835, 1856-1862).  Set by the ABCOCT_INI_SPINJNT parser.  That stage is NOT built:
                                 abcoct_create answers ABCOCT_ERR_UNSUPPORTED instead of returning the un-rebinned image.       */
   uint8_t bscanbinx, bscanbiny; /* BscanFFTspinjnt.cpp:795-797; only looked at when output_rebin is set                       */
-  uint8_t reserved[2];
+  uint8_t channelnum;        /* BscanFFTwebcam.cpp:412, 1016-1037: 0..2 = the caller passes the selected 8-bit plane (bpp = 8);
+                                >= 3: frames are interleaved 8-bit BGR (3 bytes per pixel, what cap.read gives) and the library
+                                sums the channels, scaled by 0.00130718954 like the reference's CV_64F mraw.  Needs bpp = 8,
+                                mediann = 0 (cv::medianBlur throws on CV_64F in the reference) and no binning (not built)      */
+  uint8_t reserved[1];
   double clamp_db;           /* 50.0 (BscanFFT.cpp:1252), 30.0 in BscanFFTspinjnt.cpp:1886                 */
 } abcoct_params;
 

@@ -80,6 +80,7 @@ class Params:
     clamp_db: float = 50.0  # BscanFFT.cpp:1252 (30.0 in BscanFFTspinjnt.cpp:1886)
     bandpassfilter: bool = False  # BscanDark.cpp:218-236, only inside zeropadrowwise
     lowpassfilter: bool = False  # BscanDark.cpp:1070-1074: lpfilter on the captured calibration frames
+    channelnum: int = 0  # BscanFFTwebcam.cpp:412, 1019: >= 3 sums the three channels of a BGR frame, scaled by 1/765, into a CV_64F mraw
 
     @property
     def opw(self) -> int:
@@ -219,6 +220,14 @@ def lpfilter(sm: np.ndarray) -> np.ndarray:
 
 def bin_frame(mraw: np.ndarray, p: Params) -> np.ndarray:
     """medianBlur + INTER_AREA binning on the integer frame, BscanFFT.cpp:953-958 (x/y: BscanFFTspinjnt.cpp:1553)."""
+    if p.channelnum >= 3:  # BscanFFTwebcam.cpp:1021-1037: mraw (h x w x 3, u8) -> CV_64F sum of the channels * 0.00130718954
+        assert mraw.ndim == 3 and mraw.shape[2] == 3 and mraw.dtype == np.uint8
+        s64 = mraw[:, :, 0].astype(np.float64)
+        s64 = s64 + mraw[:, :, 1].astype(np.float64)
+        s64 = s64 + mraw[:, :, 2].astype(np.float64)
+        mraw = s64 * 0.00130718954
+        if p.mediann > 0:
+            raise ValueError("cv::medianBlur does not take CV_64F: the reference throws with mediann > 0 and channelnum >= 3")
     m = cv2.medianBlur(mraw, p.mediann) if p.mediann > 0 else mraw
     if p.binx == 1 and p.biny == 1:
         return m.copy()

@@ -81,6 +81,7 @@ def test_ini_positional_parser(name, flavour):
     assert p.variant == (1 if flavour == api.INI_DARK else 0)
     if flavour == api.INI_DARK:
         assert p.bandpassfilter == 1 and p.lowpassfilter == 0
+    assert p.channelnum == (2 if flavour == api.INI_WEBCAM else 0)
 
 
 # The reference's own shipped configuration files (build/*.ini, copied verbatim as fixtures): expected values read off the files.
@@ -112,6 +113,8 @@ def test_ini_parser_on_the_reference_shipped_files(name):
     if exp[0] == api.INI_DARK:
         assert p.bandpassfilter == 1  # the shipped file stops there: lowpassfilter keeps its default
         assert p.lowpassfilter == 0
+    if exp[0] == api.INI_WEBCAM:
+        assert p.channelnum == 3  # BscanFFTwebcam.cpp:508, the last field: the shipped file asks for the SUM of the three channels
 
 
 def test_ini_wrong_flavour_misparses_like_the_reference():

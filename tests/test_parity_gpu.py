@@ -293,6 +293,41 @@ def test_resident_row_kernel_tmem(w, h, N, D, A, variant, clamp, monkeypatch):
     assert np.array_equal(out8, out8b)
 
 
+@pytest.mark.parametrize("movavgn,capture", [(0, False), (1, True)])
+def test_webcam_channel_sum(movavgn, capture):
+    """BscanFFTwebcam.cpp:1021-1037 (channelnum >= 3): interleaved 8-bit BGR frames, mraw = (B + G + R) * 0.00130718954 as CV_64F.
+    The library takes the BGR frames as they come from cap.read, sums the channels on the GPU and folds the scale into the
+    conversion; the background is either set in data_y units or captured from BGR frames (key b) like the reference does."""
+    from fdoct_b200 import api, synth
+    from oracle.abcoct_oracle import Oracle
+
+    w, h, N, D, A, nB = 640, 12, 640, 320, 2, 3
+    op = oracle_params(w=w, h=h, bpp=8, numfftpoints=N, numdisplaypoints=D, averages=A, movavgn=movavgn, channelnum=3,
+                       lambdamin=840.5e-9, lambdamax=859.5e-9)
+    rng = np.random.default_rng(5)
+
+    def to_bgr(fr16):  # split a 0 .. 765 interferogram into three unequal 8-bit channels
+        tot = np.clip(fr16.astype(np.int64) * 700 // 65535, 0, 765)
+        b = np.minimum(tot // 3 + rng.integers(0, 3, tot.shape), 255)
+        g = np.minimum((tot - b) // 2, 255)
+        r = np.clip(tot - b - g, 0, 255)
+        return np.ascontiguousarray(np.stack([b, g, r], axis=-1).astype(np.uint8))
+
+    frames = to_bgr(synth.make_frames(nB * A, w, h, seed=91))
+    bframes = to_bgr(synth.make_background_frames(A, w, h, seed=92))
+    o = Oracle(op)
+    yb = o.calib_capture(bframes)
+    o.set_background(yb)
+    ref8, refdb = o.process_bscans(frames)
+    with api.Context(abi_params(op)) as ctx:
+        if capture:
+            ctx.set_calibration_from_frames(0, bframes)
+        else:
+            ctx.set_background(yb)
+        out8, outdb = ctx.process_bscans(frames, want_db=True)
+    _check(out8, outdb, ref8, refdb, f"webcam channel sum movavg{movavgn}")
+
+
 @pytest.mark.parametrize("w,h,N,extra", [(1280, 9, 1280, {}), (1024, 6, 2048, {}), (640, 5, 2560, dict(fft_multiplier=4)),
                                          (1280, 8, 640, dict(binx=2, biny=2, movavgn=1)), (1280, 6, 1280, dict(variant=1))])
 def test_stage_parity_linearised(w, h, N, extra):
