@@ -237,61 +237,6 @@ std::vector<int> factor_radices(int n) {  // greedy, largest first; every entry 
   return r;
 }
 
-// Host restatement of the integer stages in front of the calibration captures (median + INTER_AREA binning,
-// BscanFFT.cpp:953-958): calibration happens once per key press, so it stays on the CPU.
-template <class T>
-void host_median(const T* in, size_t row_stride, T* out, int w, int h, int k) {
-  const int R = k / 2;
-  std::vector<T> v(k * k);
-  for (int y = 0; y < h; ++y)
-    for (int x = 0; x < w; ++x) {
-      int n = 0;
-      for (int dy = -R; dy <= R; ++dy)
-        for (int dx = -R; dx <= R; ++dx) {
-          const int yy = std::min(std::max(y + dy, 0), h - 1), xx = std::min(std::max(x + dx, 0), w - 1);
-          v[n++] = in[(size_t)yy * row_stride + xx];
-        }
-      std::nth_element(v.begin(), v.begin() + n / 2, v.end());
-      out[(size_t)y * w + x] = v[n / 2];
-    }
-}
-template <class T>
-void host_bin(const T* in, size_t row_stride, double* out, int opw, int oph, int bx, int by) {
-  for (int y = 0; y < oph; ++y)
-    for (int x = 0; x < opw; ++x) {
-      unsigned sum = 0;
-      for (int dy = 0; dy < by; ++dy)
-        for (int dx = 0; dx < bx; ++dx) sum += in[(size_t)(y * by + dy) * row_stride + (size_t)x * bx + dx];
-      unsigned r;
-      if (bx == 1 && by == 1) {
-        r = sum;
-      } else if (bx == 2 && by == 2) {
-        r = (sum + 2u) >> 2;
-      } else {
-        const float scale = 1.f / (float)(bx * by);
-        r = (unsigned)std::lrintf((float)sum * scale);  // round half to even (default rounding mode)
-      }
-      out[(size_t)y * opw + x] = (double)r;
-    }
-}
-
-// smoothmovavg, BscanFFT.cpp:247-304 (2n+1 taps, centre counted twice, missing taps replaced by the centre sample)
-void host_movavg(std::vector<double>& m, int rows, int cols, int n) {
-  std::vector<double> out(cols);
-  for (int r = 0; r < rows; ++r) {
-    double* x = &m[(size_t)r * cols];
-    for (int j = 0; j < cols; ++j) {
-      double s = 0.0;
-      for (int k = -n; k <= n; ++k) {
-        const int jj = j + k;
-        s = s + ((jj > -1 && jj < cols) ? x[jj] : x[j]);
-      }
-      s = s + x[j];
-      out[j] = s / 2 / (n + 1);
-    }
-    std::copy(out.begin(), out.end(), x);
-  }
-}
 // cv::normalize(src, dst, a, b, NORM_MINMAX) over [first, last): dst = src * scale + (a - min * scale)
 void host_normalize(double* first, double* last, double a, double b) {
   const auto mm = std::minmax_element(first, last);
@@ -1121,33 +1066,57 @@ int abcoct_set_calibration_from_frames(abcoct_ctx* c, int which, const void* fra
   if (stride_bytes == 0) stride_bytes = (size_t)w * pb;
   if (stride_bytes % pb) return fail(c, ABCOCT_ERR_INVALID, "stride_bytes must be a multiple of the pixel size");
   const size_t n = (size_t)c->oph * c->opw;
-  std::vector<double> acc(n, 0.0), one(n);  // accumulate(data_y, baccum), BscanFFT.cpp:1043
-  std::vector<uint8_t> med;
-  if (c->p.mediann > 0) med.resize((size_t)w * h * pb);
-  const uint8_t* base = static_cast<const uint8_t*>(frames);
-  for (size_t f = 0; f < nframes; ++f) {
-    const uint8_t* fr = base + f * h * stride_bytes;
-    size_t rs = stride_bytes / pb;
-    if (c->p.mediann > 0) {  // medianBlur while the numbers are still integers, BscanFFT.cpp:953-954
-      if (pb == 1)
-        host_median(fr, rs, med.data(), w, h, c->p.mediann);
-      else
-        host_median(reinterpret_cast<const uint16_t*>(fr), rs, reinterpret_cast<uint16_t*>(med.data()), w, h, c->p.mediann);
-      fr = med.data();
+  std::vector<double> acc(n, 0.0);
+  {
+    // accumulate(data_y, baccum) over the frames (BscanFFT.cpp:1041-1046) on the GPU, with the very kernels of the processing path
+    // for the integer stages (channel sum, medianBlur, INTER_AREA binning) and an f64 kernel for convertTo + smoothmovavg + the sum
+    GpuState& g = c->gpus[0];
+    CU(c, cudaSetDevice(g.dev));
+    cudaStream_t st = g.stream[0];
+    const size_t in_bytes = nframes * (size_t)h * stride_bytes;
+    const int ipb = c->bgr ? 2 : pb;  // bytes per pixel after the channel sum
+    uint8_t *d_in = nullptr, *d_a = nullptr, *d_b = nullptr;
+    double* d_acc = nullptr;
+    auto cleanup = [&]() {
+      cudaFree(d_in);
+      cudaFree(d_a);
+      cudaFree(d_b);
+      cudaFree(d_acc);
+    };
+    cudaError_t e = cudaMalloc(&d_in, in_bytes);
+    if (e == cudaSuccess) e = cudaMalloc(&d_acc, n * sizeof(double));
+    if (e == cudaSuccess && (c->bgr || c->p.mediann > 0)) e = cudaMalloc(&d_a, nframes * (size_t)w * h * ipb);
+    if (e == cudaSuccess && (c->p.binx > 1 || c->p.biny > 1)) e = cudaMalloc(&d_b, nframes * n * ipb);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_in, frames, in_bytes, cudaMemcpyHostToDevice, st);
+    const void* src = d_in;
+    size_t rs = stride_bytes / pb, fs = (size_t)h * stride_bytes / pb;
+    int bpp = (int)c->p.bpp;
+    if (e == cudaSuccess && c->bgr) {  // BscanFFTwebcam.cpp:1021-1037 (mediann == 0 and no binning, validated at create)
+      e = launch_bgr_sum(d_in, reinterpret_cast<uint16_t*>(d_a), w, h, stride_bytes, (size_t)h * stride_bytes, (int)nframes, st);
+      src = d_a;
       rs = w;
+      fs = (size_t)w * h;
+      bpp = 16;
     }
-    if (c->bgr) {  // BscanFFTwebcam.cpp:1021-1037: CV_64F sum of the three channels, then * 0.00130718954 (no binning, validated)
-      for (int y = 0; y < h; ++y)
-        for (int x = 0; x < w; ++x) {
-          const uint8_t* px = fr + (size_t)y * stride_bytes + 3 * (size_t)x;
-          one[(size_t)y * w + x] = ((double)px[0] + (double)px[1] + (double)px[2]) * 0.00130718954;
-        }
-    } else if (pb == 1)  // resize(..., INTER_AREA), BscanFFT.cpp:958
-      host_bin(fr, rs, one.data(), c->opw, c->oph, (int)c->p.binx, (int)c->p.biny);
-    else
-      host_bin(reinterpret_cast<const uint16_t*>(fr), rs, one.data(), c->opw, c->oph, (int)c->p.binx, (int)c->p.biny);
-    if (c->p.movavgn > 0) host_movavg(one, c->oph, c->opw, c->p.movavgn);  // BscanFFT.cpp:990-991
-    for (size_t i = 0; i < n; ++i) acc[i] += one[i];
+    if (e == cudaSuccess && c->p.mediann > 0) {  // medianBlur while the numbers are still integers, BscanFFT.cpp:953-954
+      e = launch_median(src, d_a, bpp, c->p.mediann, w, h, rs, fs, (int)nframes, st);
+      src = d_a;
+      rs = w;
+      fs = (size_t)w * h;
+    }
+    if (e == cudaSuccess && (c->p.binx > 1 || c->p.biny > 1)) {  // resize(..., INTER_AREA), BscanFFT.cpp:958
+      e = launch_bin(src, d_b, bpp, c->opw, c->oph, (int)c->p.binx, (int)c->p.biny, rs, fs, (int)nframes, st);
+      src = d_b;
+      rs = c->opw;
+      fs = n;
+    }
+    if (e == cudaSuccess)  // convertTo + smoothmovavg (BscanFFT.cpp:987-991) + accumulate, f64
+      e = launch_cal_accum(src, bpp, rs, fs, (int)nframes, c->opw, c->oph, c->p.movavgn, c->bgr ? 0.00130718954 : 1.0, d_acc, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(acc.data(), d_acc, n * sizeof(double), cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cleanup();
+    if (e != cudaSuccess) return fail(c, ABCOCT_ERR_CUDA, "calibration capture: %s", cudaGetErrorString(e));
+    c->launches += 1 + (c->bgr ? 1 : 0) + (c->p.mediann > 0 ? 1 : 0) + ((c->p.binx > 1 || c->p.biny > 1) ? 1 : 0);
   }
   if (which != 1) {
     // BscanFFT.cpp:1050-1057: if (rowwisenormalize) normalizerows(.., 0.0001, 1); if (!donotnormalize) normalize(.., 0.0001, 1); else / n

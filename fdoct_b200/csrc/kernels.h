@@ -68,6 +68,9 @@ cudaError_t launch_bgr_sum(const void* in, uint16_t* out, int w, int h, size_t r
                            cudaStream_t st);
 cudaError_t launch_bin(const void* in, void* out, int bpp, int opw, int oph, int bx, int by, size_t row_stride_elems,
                        size_t frame_stride_elems, int nframes, cudaStream_t st);
+// calibration captures: sum over the frames of the binned pixels as f64 (+ smoothmovavg), BscanFFT.cpp:1041-1046
+cudaError_t launch_cal_accum(const void* px, int bpp, size_t row_stride_elems, size_t frame_stride_elems, int nframes, int opw, int oph,
+                             int movavgn, double px_scale, double* acc, cudaStream_t st);
 cudaError_t launch_rowprep(const PrepArgsHost& h, cudaStream_t st, int* launched);
 size_t rowprep_smem_bytes(int opw, int M, int m, int movavgn);
 cudaError_t launch_lerp_rows(const float* rows, const int* idx, const float* wq, float* ylin, int M, int N, int oph, cudaStream_t st);

@@ -448,6 +448,44 @@ cudaError_t launch_bgr_sum(const void* in, uint16_t* out, int w, int h, size_t r
   return cudaGetLastError();
 }
 
+// ------------------------------------------------------------------------------------------------ calibration captures
+// accumulate(data_y, baccum) over the frames of a capture (keys b / p / o / r / t, BscanFFT.cpp:1041-1046): data_y is the binned
+// integer pixel converted to CV_64F (x px_scale for the webcam channel sum) and smoothed by smoothmovavg (BscanFFT.cpp:247-304, f64,
+// same order of additions as the reference: taps -n .. n with missing taps replaced by the centre, centre once more, / 2 / (n + 1)).
+// One thread per binned pixel, frames in order: bit-identical to the host loop it replaces.
+template <class T>
+__global__ void cal_accum_kernel(const T* __restrict__ px, size_t rs, size_t fs, int nframes, int opw, int oph, int movavgn, double px_scale,
+                                 double* __restrict__ acc) {
+  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+  if (x >= opw || y >= oph) return;
+  double a = 0.0;
+  for (int f = 0; f < nframes; ++f) {
+    const T* row = px + (size_t)f * fs + (size_t)y * rs;
+    const double c = (double)row[x] * px_scale;
+    double v = c;
+    if (movavgn > 0) {
+      double s = 0.0;
+      for (int k = -movavgn; k <= movavgn; ++k) {
+        const int jj = x + k;
+        s = s + ((jj > -1 && jj < opw) ? (double)row[jj] * px_scale : c);
+      }
+      s = s + c;
+      v = s / 2 / (movavgn + 1);
+    }
+    a += v;
+  }
+  acc[(size_t)y * opw + x] = a;
+}
+cudaError_t launch_cal_accum(const void* px, int bpp, size_t row_stride_elems, size_t frame_stride_elems, int nframes, int opw, int oph,
+                             int movavgn, double px_scale, double* acc, cudaStream_t st) {
+  dim3 grid((opw + 127) / 128, oph), block(128);
+  if (bpp == 8)
+    cal_accum_kernel<uint8_t><<<grid, block, 0, st>>>(static_cast<const uint8_t*>(px), row_stride_elems, frame_stride_elems, nframes, opw, oph, movavgn, px_scale, acc);
+  else
+    cal_accum_kernel<uint16_t><<<grid, block, 0, st>>>(static_cast<const uint16_t*>(px), row_stride_elems, frame_stride_elems, nframes, opw, oph, movavgn, px_scale, acc);
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------ launchers
 cudaError_t launch_median(const void* in, void* out, int bpp, int k, int w, int h, size_t row_stride_elems, size_t frame_stride_elems,
                           int nframes, cudaStream_t st) {
