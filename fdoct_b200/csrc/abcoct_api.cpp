@@ -59,6 +59,9 @@ struct GpuState {
   void* d_bin[kSlots] = {};
   float* d_rows[kSlots] = {};
   float* d_fmm[kSlots] = {};
+  int* d_gidx = nullptr;  // generic kernel: gather indices, weights, exp(+2 pi i k / N)
+  float* d_gwq = nullptr;
+  float2* d_twN = nullptr;
   size_t prep_frames[kSlots] = {};
   // per-slot device + pinned staging for the host-buffer API
   uint8_t* d_in[kSlots] = {};
@@ -91,6 +94,8 @@ struct abcoct_ctx {
   bool have_yr = false, have_ys = false;
   bool have_yb = false, have_yp = false, have_yd = false, cal_dirty = true, has_sub = false;
   bool general = false;  // any optional pre-processing stage is on: frames go through prep_kernels.cu first
+  bool generic = false;  // no fused plan for this N / row width / D: generic_recon_kernel on the prepared rows (implies general)
+  std::vector<int> radN;
   // warp-per-A-scan kernel (wrow_kernel.cuh): eligible configurations and the plan in use (nullptr: recon_kernel.cuh)
   bool wrow_eligible = false;
   const WPlanEntry* wplan = nullptr;
@@ -170,6 +175,13 @@ void build_window(int opw, std::vector<double>& win) {
   }
 }
 
+// Configurations the fused kernels are not compiled for - a transform length without a plan, rows that are not a multiple of
+// 8 samples, display rows above N / 2 - run on the generic kernel (prep_kernels.cu: generic_recon_kernel); cv::dft and colRange
+// take all of them (BscanFFT.cpp:1185, 1193).
+bool needs_generic(const abcoct_params& p) {
+  return !find_plan((int)p.numfftpoints) || (p.w / p.binx) % 8 != 0 || p.numdisplaypoints > p.numfftpoints / 2;
+}
+
 int validate(const abcoct_params& p, std::string& why, int& code) {
   code = ABCOCT_ERR_INVALID;
   auto bad = [&](const char* s) {
@@ -186,7 +198,7 @@ int validate(const abcoct_params& p, std::string& why, int& code) {
   if (opw < 8 || oph < 1) return bad("binned frame too small");
   if (p.numfftpoints < p.fft_multiplier * opw)
     return bad("numfftpoints < fft_multiplier * (w / binx): the reference reads past fractionalk (BscanFFT.cpp:1170)");
-  if (p.numdisplaypoints > p.numfftpoints / 2) return bad("numdisplaypoints > numfftpoints / 2 (bins above N/2 mirror the lower half)");
+  if (p.numdisplaypoints > p.numfftpoints) return bad("numdisplaypoints > numfftpoints (colRange(0, numdisplaypoints) throws, BscanFFT.cpp:1193)");
   if (p.numdisplaypoints < 6) return bad("numdisplaypoints < 6 (rows 4 and 5 are addressed, BscanFFT.cpp:1239, 1252)");
   if (p.clampupper && oph < 6) return bad("clampupper needs at least 6 A-scans (element (5,5), BscanFFT.cpp:1252)");
   if (p.variant > 1 || p.weight_mode > 1) return bad("variant / weight_mode out of range");
@@ -215,13 +227,19 @@ int validate(const abcoct_params& p, std::string& why, int& code) {
       while (r % f == 0) r /= f;
     if (r != 1) return bad("increasefftpointsmultiplier must be of the form 2^a 3^b 5^c");
   }
-  if (opw % 8) return bad("w / binx must be a multiple of 8");
-  if (!find_plan((int)p.numfftpoints)) {
-    why = "numfftpoints has no compiled FFT plan; available:";
-    int ns[64];
-    int n = list_plans(ns, 64);
-    for (int i = 0; i < n && i < 64; ++i) why += " " + std::to_string(ns[i]);
-    return 1;
+  if (needs_generic(p)) {  // any N = 2^a 3^b 5^c, any row width, D up to N: the shared-memory Stockham kernel (prep_kernels.cu)
+    unsigned r = p.numfftpoints;
+    for (unsigned f : {2u, 3u, 5u})
+      while (r % f == 0) r /= f;
+    if (r != 1) {
+      why = "numfftpoints must be of the form 2^a 3^b 5^c (cv::getOptimalDFTSize lengths); fused plans exist for:";
+      int ns[64];
+      int n = list_plans(ns, 64);
+      for (int i = 0; i < n && i < 64; ++i) why += " " + std::to_string(ns[i]);
+      return 1;
+    }
+    if (generic_smem_bytes((int)p.numfftpoints, (int)p.numdisplaypoints) > 227 * 1024)
+      return bad("numfftpoints too long for the shared-memory transform (two complex rows and two accumulators must fit in 227 KB)");
   }
   code = 0;
   return 0;
@@ -309,6 +327,13 @@ int upload_calibration(abcoct_ctx* c) {
       CU(c, cudaMemcpy(g.d_yp, fp.data(), n * 4, cudaMemcpyHostToDevice));
       CU(c, cudaMemcpy(g.d_yd, fd.data(), n * 4, cudaMemcpyHostToDevice));
     }
+  }
+  if (c->generic) {  // generic_recon_kernel reads the prepared rows only: no swizzled calibration, no table blob, no plan attributes
+    c->smem = (int)generic_smem_bytes(c->N, c->D);
+    c->G = 1;
+    c->regs = 0;
+    c->cal_dirty = false;
+    return ABCOCT_OK;
   }
   // which kernel: the warp-per-A-scan kernel wherever it applies (wrow_kernel.cuh).  For A/B measurements ABCOCT_KERNEL=1 forces
   // the group-per-row-pair kernel (recon_kernel.cuh, the fallback for every other transform length and for the general path) and
@@ -564,6 +589,7 @@ int enqueue_device(abcoct_ctx* c, GpuState& g, int slot, const uint8_t* d_frames
     const size_t per_bscan = (size_t)c->A * c->oph * c->M * sizeof(float);
     chunkB = std::min(chunkB, std::max<size_t>(1, ((size_t)1 << 30) / per_bscan));
   }
+  if (c->generic) chunkB = std::min<size_t>(chunkB, 65535);  // one grid row / plane per B-scan
   int rc = ensure_scratch(c, g, slot, chunkB);
   if (rc) return rc;
   if (c->general) {
@@ -593,6 +619,42 @@ int enqueue_device(abcoct_ctx* c, GpuState& g, int slot, const uint8_t* d_frames
     a.npairs = (c->oph + 1) / 2;
     if ((size_t)a.npairs * nb > 0x7fff0000u) return fail(c, ABCOCT_ERR_INVALID, "too many A-scan pairs in one chunk");
     a.nitems = a.npairs * (int)nb;
+    if (c->generic) {  // any transform length / row width / D up to N: two launches on the prepared rows
+      GenericHost gh{};
+      gh.rows = g.d_rows[slot];
+      gh.M = c->M; gh.N = c->N; gh.D = c->D; gh.Dp = a.Dp; gh.oph = c->oph; gh.A = c->A; gh.nB = (int)nb;
+      gh.idx = g.d_gidx;
+      gh.wq = g.d_gwq;
+      gh.nrad = (int)c->radN.size();
+      for (size_t i = 0; i < c->radN.size(); ++i) gh.rad[i] = c->radN[i];
+      gh.tw = g.d_twN;
+      gh.scratch = g.d_scratch[slot];
+      gh.minv = g.d_jmm[slot];  // free until the lock-in kernels run (they reset it themselves)
+      gh.maxv = g.d_jmm[slot] + nb;
+      gh.dc01 = need_db ? g.d_dc01[slot] : nullptr;
+      gh.out8 = d_out8 + b0 * c->D * c->oph;
+      gh.outdb = d_outdb ? d_outdb + b0 * c->D * c->oph : nullptr;
+      gh.out_scale = 0.5f / (float)c->A;
+      gh.db_scale_ln = (float)(20.0 * (1.0 / 2.303));
+      gh.thr = (float)c->p.bscanthreshold;
+      gh.clamp_db = (float)c->p.clamp_db;
+      gh.clamp55 = c->p.clampupper ? 1 : 0;
+      a.out8 = gh.out8;
+      a.outdb = gh.outdb;
+      a.dc01 = gh.dc01;
+      a.db_scale = (float)(0.6931471805599453 * (20.0 * (1.0 / 2.303)));
+      a.thr = gh.thr;
+      const bool timed = time_it && g.tev_used + 3 <= g.tev.size();
+      if (timed) CU(c, cudaEventRecord(g.tev[g.tev_used], st));
+      int nl = 0;
+      CU(c, launch_generic(gh, st, &nl));
+      if (timed) {
+        CU(c, cudaEventRecord(g.tev[g.tev_used + 1], st));
+        CU(c, cudaEventRecord(g.tev[g.tev_used + 2], st));
+        g.tev_used += 3;
+      }
+      c->launches += nl;
+    } else {
     a.nparts = (c->oph + c->plan->d.T - 1) / c->plan->d.T;
     int grid = 0;
     if (c->wplan) {  // one item per row, normalisation parts of 32 A-scans split into depth-tile ranges for short launches
@@ -645,6 +707,7 @@ int enqueue_device(abcoct_ctx* c, GpuState& g, int slot, const uint8_t* d_frames
       g.tev_used += 3;
     }
     c->launches += 2;
+    }
     // consumers of the finished B-scans (post_kernels.cu), same stream
     float* lin = d_outlin ? d_outlin + b0 * px : nullptr;
     const float inv = (float)(1.0 / (0.6931471805599453 * (20.0 * (1.0 / 2.303))));
@@ -875,6 +938,12 @@ int abcoct_create(const abcoct_params* params, const int* gpu_ids, int ngpu, abc
   }
   c->general = params->bpp == 8 || params->binx > 1 || params->biny > 1 || params->mediann > 0 || params->movavgn > 0 ||
                params->fft_multiplier > 1 || params->rowwisenormalize || !params->donotnormalize;  // (8-bit covers channelnum >= 3)
+  c->generic = needs_generic(*params);
+  if (c->generic) {
+    c->general = true;  // rowprep_kernel prepares f32 rows for every configuration, generic_recon_kernel consumes them
+    c->plan = nullptr;
+    c->radN = factor_radices(c->N);
+  }
   if (params->fft_multiplier > 1) {
     c->radW = factor_radices(c->opw);
     c->radM = factor_radices(c->M);
@@ -901,7 +970,9 @@ int abcoct_create(const abcoct_params* params, const int* gpu_ids, int ngpu, abc
   c->gidx = idx;
   c->gwq = wq;
   std::vector<unsigned char>& blob = c->blob1;
-  if (c->general) {  // the fused kernel sees rows of M apodised samples: no window / mean term left to apply there
+  if (c->generic) {
+    // gidx / gwq go to the device as they are
+  } else if (c->general) {  // the fused kernel sees rows of M apodised samples: no window / mean term left to apply there
     std::vector<float> zero(c->M, 0.f);
     c->plan->build_blob(c->M, idx.data(), wq.data(), zero.data(), blob);
   } else {
@@ -910,7 +981,7 @@ int abcoct_create(const abcoct_params* params, const int* gpu_ids, int ngpu, abc
   // warp-per-A-scan kernel: 16-bit frames straight into the transform (no optional pre-processing stage), the reference's
   // source-indexed resampling weight (BscanFFT.cpp:1170), a transform length it has a plan for, and no gather from sample 0
   // (whose slope the reference copies from sample 1, :1161 - the fallback kernel handles that corner)
-  c->wrow_eligible = !c->general && params->weight_mode == 0 && params->bpp == 16 && find_wplan(c->N, 0, -1) != nullptr;
+  c->wrow_eligible = !c->general && !c->generic && params->weight_mode == 0 && params->bpp == 16 && find_wplan(c->N, 0, -1) != nullptr;
   for (int q = 1; q + 1 < c->N && c->wrow_eligible; ++q) c->wrow_eligible = c->nk[q] >= 1 && c->nk[q] < c->opw;
   if (c->wrow_eligible) {
     std::vector<int> widx(c->N);
@@ -926,6 +997,12 @@ int abcoct_create(const abcoct_params* params, const int* gpu_ids, int ngpu, abc
     twM.resize(c->M);
     for (int k = 0; k < c->opw; ++k) twW[k] = make_float2((float)std::cos(tau * k / c->opw), (float)-std::sin(tau * k / c->opw));
     for (int k = 0; k < c->M; ++k) twM[k] = make_float2((float)std::cos(tau * k / c->M), (float)std::sin(tau * k / c->M));
+  }
+  std::vector<float2> twN;
+  if (c->generic) {
+    const double tau = 6.283185307179586476925286766559;
+    twN.resize(c->N);
+    for (int k = 0; k < c->N; ++k) twN[k] = make_float2((float)std::cos(tau * k / c->N), (float)std::sin(tau * k / c->N));
   }
 
   c->gpus.resize(ngpu);
@@ -961,6 +1038,13 @@ int abcoct_create(const abcoct_params* params, const int* gpu_ids, int ngpu, abc
         ok = ok && cudaMalloc(&g.d_twW, twW.size() * 8) == cudaSuccess && cudaMalloc(&g.d_twM, twM.size() * 8) == cudaSuccess;
         ok = ok && cudaMemcpy(g.d_twW, twW.data(), twW.size() * 8, cudaMemcpyHostToDevice) == cudaSuccess;
         ok = ok && cudaMemcpy(g.d_twM, twM.data(), twM.size() * 8, cudaMemcpyHostToDevice) == cudaSuccess;
+      }
+      if (c->generic) {
+        ok = ok && cudaMalloc(&g.d_gidx, idx.size() * 4) == cudaSuccess && cudaMalloc(&g.d_gwq, wq.size() * 4) == cudaSuccess &&
+             cudaMalloc(&g.d_twN, twN.size() * 8) == cudaSuccess;
+        ok = ok && cudaMemcpy(g.d_gidx, idx.data(), idx.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+        ok = ok && cudaMemcpy(g.d_gwq, wq.data(), wq.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess;
+        ok = ok && cudaMemcpy(g.d_twN, twN.data(), twN.size() * 8, cudaMemcpyHostToDevice) == cudaSuccess;
       }
     }
     if (!ok) {
@@ -1006,6 +1090,9 @@ void abcoct_destroy(abcoct_ctx* c) {
     cudaFree(g.d_win);
     cudaFree(g.d_twW);
     cudaFree(g.d_twM);
+    cudaFree(g.d_gidx);
+    cudaFree(g.d_gwq);
+    cudaFree(g.d_twN);
     for (int s2 = 0; s2 < kSlots; ++s2) {
       cudaFree(g.d_med[s2]);
       cudaFree(g.d_bin[s2]);
@@ -1492,10 +1579,15 @@ int abcoct_get_info(const abcoct_ctx* c, abcoct_info* o) {
   o->N = c->N;
   o->D = c->D;
   o->averages = c->A;
-  o->fft_threads = c->wplan ? 32 : c->plan->d.T;
-  o->fft_radix[0] = c->wplan ? c->wplan->R : c->plan->d.R0;
-  o->fft_radix[1] = c->wplan ? 1 : c->plan->d.R1;
-  o->fft_radix[2] = c->wplan ? 32 : c->plan->d.RL;
+  if (c->generic) {  // run-time radix list of the shared-memory Stockham transform (first three passes reported)
+    o->fft_threads = 256;
+    for (size_t i = 0; i < 3; ++i) o->fft_radix[i] = i < c->radN.size() ? c->radN[i] : 1;
+  } else {
+    o->fft_threads = c->wplan ? 32 : c->plan->d.T;
+    o->fft_radix[0] = c->wplan ? c->wplan->R : c->plan->d.R0;
+    o->fft_radix[1] = c->wplan ? 1 : c->plan->d.R1;
+    o->fft_radix[2] = c->wplan ? 32 : c->plan->d.RL;
+  }
   o->groups_per_cta = c->G;
   o->ctas_per_sm = 1;
   o->smem_bytes = c->smem;
@@ -1505,7 +1597,7 @@ int abcoct_get_info(const abcoct_ctx* c, abcoct_info* o) {
   o->kernel_launches = c->launches;
   o->last_recon_ms = c->last_recon_ms;
   o->last_norm_ms = c->last_norm_ms;
-  o->kernel_kind = c->wplan ? (c->wplan->resident ? 2u : 1u) : 0u;
+  o->kernel_kind = c->generic ? 3u : c->wplan ? (c->wplan->resident ? 2u : 1u) : 0u;
   o->slots_per_warp = c->wplan ? (uint32_t)c->wplan->slots : 0u;
   return ABCOCT_OK;
 }

@@ -75,6 +75,26 @@ cudaError_t launch_rowprep(const PrepArgsHost& h, cudaStream_t st, int* launched
 size_t rowprep_smem_bytes(int opw, int M, int m, int movavgn);
 cudaError_t launch_lerp_rows(const float* rows, const int* idx, const float* wq, float* ylin, int M, int N, int oph, cudaStream_t st);
 
+// ---- any transform length N = 2^a 3^b 5^c, any row width, D up to N (prep_kernels.cu): gather-lerp + Stockham DFT + magnitude +
+// accumulate + dB into the scratch, then normalise + transpose; runs on the rows prepared by launch_rowprep
+struct GenericHost {
+  const float* rows;
+  int M, N, D, Dp, oph, A, nB;
+  const int* idx;
+  const float* wq;
+  int nrad, rad[12];
+  const float2* tw;  // exp(+2 pi i k / N)
+  float* scratch;
+  int *minv, *maxv;
+  float* dc01;
+  uint8_t* out8;
+  float* outdb;
+  float out_scale, db_scale_ln, thr, clamp_db;
+  int clamp55;
+};
+size_t generic_smem_bytes(int N, int D);
+cudaError_t launch_generic(const GenericHost& h, cudaStream_t st, int* launched);
+
 // ---- consumers of a finished B-scan (post_kernels.cu)
 cudaError_t post_init_device();  // once per device: the JET table
 // linear bscan (BscanFFT.cpp:1220-1222) from the dB image [nB][px] and the unmasked DC rows dc01 [nB][oph][2]

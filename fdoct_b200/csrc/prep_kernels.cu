@@ -416,6 +416,151 @@ __global__ void __launch_bounds__(256) rowprep_kernel(const PrepArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------ any transform length
+// cv::dft takes any N (BscanFFT.cpp:1185); the fused kernels are compiled for twelve lengths, rows that are multiples of 8 samples
+// and D <= N / 2.  Everything else (N = 2^a 3^b 5^c, any row width, D up to N) runs here, on the rows prepared by rowprep_kernel:
+// one CTA per pair of A-scans of one B-scan - gather-lerp (BscanFFT.cpp:1151-1177) of both rows into one complex buffer, the
+// shared-memory Stockham transform above (run-time radices), two-for-one split, magnitude (:1189-1190), accumulation over the
+// frames (:1193-1209), dB + DC-row mask (:1221-1240) into the dB scratch and the B-scan's thresholded min / max; a second kernel
+// normalises and transposes (:1243-1255).  Slow (a few 1e7 A-scans/s) and exact to the same tolerances; never used for the
+// BASELINE configurations.
+struct GenericArgs {
+  const float* rows;  // [nB * A][oph][M] prepared rows
+  int M, N, D, Dp, oph, A, nB;
+  const int* idx;     // [N] source sample (1 .. M - 1), M = never written (zero)
+  const float* wq;    // [N] lerp weights (the reference's quirk already applied)
+  RadixList rl;
+  const float2* tw;   // exp(+2 pi i k / N)
+  float* scratch;     // [nB][oph][Dp]
+  int *minv, *maxv;   // [nB] order-preserving ints
+  float* dc01;        // nullable [nB][oph][2]
+  float out_scale, db_scale_ln, thr;
+  int clamp55;
+};
+__global__ void __launch_bounds__(256) generic_recon_kernel(const GenericArgs a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ float red[8];
+  const int N = a.N, b = blockIdx.y, r0 = 2 * blockIdx.x;
+  const bool has1 = r0 + 1 < a.oph;
+  float2* bufa = reinterpret_cast<float2*>(smem_raw);
+  float2* bufb = bufa + fft_buf_slots(N);
+  float* acc0 = reinterpret_cast<float*>(bufb + fft_buf_slots(N));
+  float* acc1 = acc0 + a.D;
+  for (int k = threadIdx.x; k < a.D; k += blockDim.x) acc0[k] = acc1[k] = 0.f;
+  for (int f = 0; f < a.A; ++f) {
+    const float* y0 = a.rows + (((size_t)b * a.A + f) * a.oph + r0) * a.M;
+    const float* y1 = y0 + (has1 ? a.M : 0);
+    __syncthreads();  // the buffers of the previous frame have been consumed
+    for (int q = threadIdx.x; q < N; q += blockDim.x) {
+      const int i = a.idx[q];
+      float2 v = make_float2(0.f, 0.f);
+      if (i < a.M) {  // data_ylin = y[i] + w (y[i] - y[i-1]); columns 0 and N - 1 are never written (BscanFFT.cpp:1164-1171)
+        const float w = a.wq[q];
+        v.x = fmaf(w, y0[i] - y0[i - 1], y0[i]);
+        v.y = has1 ? fmaf(w, y1[i] - y1[i - 1], y1[i]) : 0.f;
+      }
+      bufa[fpad(q)] = v;
+    }
+    __syncthreads();
+    const float2* Z = block_fft<+1>(bufa, bufb, a.rl, a.tw);  // unscaled inverse DFT of row0 + i row1 (BscanFFT.cpp:1185)
+    for (int k = threadIdx.x; k < a.D; k += blockDim.x) {
+      const float2 z = Z[fpad(k)], zc = Z[fpad(k == 0 ? 0 : N - k)];
+      // X0[k] = (Z[k] + conj Z[N-k]) / 2, X1[k] = (Z[k] - conj Z[N-k]) / (2 i); the 1 / 2 lives in out_scale
+      const float ar = z.x + zc.x, ai = z.y - zc.y, br = z.x - zc.x, bi = z.y + zc.y;
+      acc0[k] += sqrtf(fmaf(ar, ar, ai * ai));
+      acc1[k] += sqrtf(fmaf(br, br, bi * bi));
+    }
+  }
+  __syncthreads();
+  // /A, + 1e-5, ln, * 20 / 2.303 (BscanFFT.cpp:1221-1237); rows 0 and 1 take the value of row 4 (:1239-1240)
+  float mn = __int_as_float(0x7f800000), mx = __int_as_float(0xff800000);
+  for (int rr = 0; rr < (has1 ? 2 : 1); ++rr) {
+    const float* acc = rr ? acc1 : acc0;
+    const int row = r0 + rr;
+    float* srow = a.scratch + ((size_t)b * a.oph + row) * a.Dp;
+    const float db4 = logf(fmaf(acc[4], a.out_scale, 1e-5f)) * a.db_scale_ln;
+    for (int k = threadIdx.x; k < a.D; k += blockDim.x) {
+      float db = logf(fmaf(acc[k], a.out_scale, 1e-5f)) * a.db_scale_ln;
+      if (k < 2) {
+        if (a.dc01) a.dc01[2 * ((size_t)b * a.oph + row) + k] = db;
+        db = db4;
+      }
+      srow[k] = db;
+      if (!(a.clamp55 && k == 5 && row == 5)) {  // the forced element is excluded from the min / max of the data
+        mn = fminf(mn, db);
+        mx = fmaxf(mx, db);
+      }
+    }
+  }
+  mn = block_reduce(mn, red, 1);
+  mx = block_reduce(mx, red, 2);
+  if (threadIdx.x == 0 && mn <= mx) {  // max(., thr) commutes with min / max (BscanFFT.cpp:1247, 1254)
+    atomicMin(a.minv + b, f2ord(fmaxf(mn, a.thr)));
+    atomicMax(a.maxv + b, f2ord(fmaxf(mx, a.thr)));
+  }
+}
+// threshold, global min-max normalise, round-half-even to u8 (BscanFFT.cpp:1243-1255), transposed to depth-major; 32 x 32 tiles
+__global__ void generic_norm_kernel(const float* __restrict__ scratch, const int* __restrict__ minv, const int* __restrict__ maxv,
+                                    uint8_t* __restrict__ out8, float* __restrict__ outdb, int oph, int D, int Dp, float thr, int clamp55,
+                                    float clamp_db) {
+  __shared__ float tile[32][33];
+  const int b = blockIdx.z, bin0 = 32 * blockIdx.x, row0 = 32 * blockIdx.y;
+  float mn = ord2f(minv[b]), mx = ord2f(maxv[b]);
+  if (clamp55) {  // bscandisp.at<double>(5,5) = 50.0 before the min-max (BscanFFT.cpp:1248-1253)
+    mn = fminf(mn, clamp_db);
+    mx = fmaxf(mx, clamp_db);
+  }
+  const float sc = (mx - mn) > 2.220446049250313e-16f ? 255.0f / (mx - mn) : 0.f;  // cv::normalize: scale = 0 for a flat image
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int row = row0 + j, bin = bin0 + threadIdx.x;
+    tile[j][threadIdx.x] = (row < oph && bin < D) ? scratch[((size_t)b * oph + row) * Dp + bin] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const int bin = bin0 + j, row = row0 + threadIdx.x;
+    if (bin < D && row < oph) {
+      const float x = tile[threadIdx.x][j];
+      const float v = (clamp55 && bin == 5 && row == 5) ? clamp_db : x;
+      const float r = fmaf(fmaxf(v, thr) - mn, sc, 12582912.0f);  // round-half-even: 1.5 * 2^23 trick, result in the low byte
+      const size_t o = ((size_t)b * D + bin) * oph + row;
+      out8[o] = (uint8_t)(__float_as_uint(r) & 0xffu);
+      if (outdb) outdb[o] = x;
+    }
+  }
+}
+__global__ void generic_minmax_reset_kernel(int* minv, int* maxv, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    minv[i] = f2ord(__int_as_float(0x7f800000));
+    maxv[i] = f2ord(__int_as_float(0xff800000));
+  }
+}
+size_t generic_smem_bytes(int N, int D) { return 2 * (size_t)fft_buf_slots(N) * sizeof(float2) + 2 * (size_t)D * sizeof(float); }
+cudaError_t launch_generic(const GenericHost& h, cudaStream_t st, int* launched) {
+  GenericArgs a{};
+  a.rows = h.rows; a.M = h.M; a.N = h.N; a.D = h.D; a.Dp = h.Dp; a.oph = h.oph; a.A = h.A; a.nB = h.nB; a.idx = h.idx; a.wq = h.wq;
+  a.tw = h.tw; a.scratch = h.scratch; a.minv = h.minv; a.maxv = h.maxv; a.dc01 = h.dc01; a.out_scale = h.out_scale;
+  a.db_scale_ln = h.db_scale_ln; a.thr = h.thr; a.clamp55 = h.clamp55;
+  a.rl.n = h.N; a.rl.count = h.nrad;
+  int nc = h.N, stp = 1;
+  for (int i = 0; i < h.nrad && i < 12; ++i) {
+    a.rl.r[i] = h.rad[i];
+    a.rl.nc[i] = nc;
+    a.rl.s[i] = stp;
+    nc /= h.rad[i];
+    stp *= h.rad[i];
+  }
+  const size_t smem = generic_smem_bytes(h.N, h.D);
+  cudaError_t e = cudaFuncSetAttribute(generic_recon_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return e;
+  generic_minmax_reset_kernel<<<(h.nB + 127) / 128, 128, 0, st>>>(h.minv, h.maxv, h.nB);
+  generic_recon_kernel<<<dim3((h.oph + 1) / 2, h.nB), 256, smem, st>>>(a);
+  generic_norm_kernel<<<dim3((h.D + 31) / 32, (h.oph + 31) / 32, h.nB), dim3(32, 8), 0, st>>>(h.scratch, h.minv, h.maxv, h.out8, h.outdb, h.oph,
+                                                                                                h.D, h.Dp, h.thr, h.clamp55, h.clamp_db);
+  if (launched) *launched = 3;
+  return cudaGetLastError();
+}
+
 // ------------------------------------------------------------------------------------------------ debug tap
 // data_ylin (BscanFFT.cpp:1151-1177) from prepared rows, for the stage-level parity test only: idx / wq are the kernel's
 // remapped gather tables (idx >= 1, idx == M -> the never-written end points, weight quirk already applied).

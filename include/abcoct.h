@@ -96,7 +96,11 @@ int abcoct_params_from_ini(const char* path, int ini_flavour, abcoct_params* out
  * block keeps between frames (data_yb/yp/yd, bscantransposed, indextemp).  gpu_ids == NULL means
  * device 0..ngpu-1.  Rejects what is undefined behaviour in the reference: numfftpoints <
  * fft_multiplier * (w / binx) (BscanFFT.cpp:1170 reads past fractionalk), numdisplaypoints >
- * numfftpoints / 2 or < 6 (rows 4 and 5 are addressed at :1239, :1252). */
+ * numfftpoints (colRange throws, :1193) or < 6 (rows 4 and 5 are addressed at :1239, :1252).
+ * Transform lengths with a fused plan (abcoct_list_plans), rows that are a multiple of 8 samples and
+ * numdisplaypoints <= numfftpoints / 2 run in the fused kernels; every other numfftpoints = 2^a 3^b 5^c,
+ * row width and numdisplaypoints <= numfftpoints runs on the generic kernel (abcoct_info.kernel_kind 3),
+ * same results, a fraction of the throughput.  Other lengths: ABCOCT_ERR_UNSUPPORTED. */
 int abcoct_create(const abcoct_params* params, const int* gpu_ids, int ngpu, abcoct_ctx** out);
 void abcoct_destroy(abcoct_ctx* ctx);
 const char* abcoct_last_error(const abcoct_ctx* ctx); /* ctx may be NULL: error of the last failed create */
@@ -217,7 +221,7 @@ typedef struct abcoct_info {
   uint32_t ngpu, sm_count;
   uint64_t kernel_launches;        /* kernels launched by this ctx so far                     */
   double last_recon_ms, last_norm_ms; /* mean per-chunk kernel times of the last abcoct_timing_read */
-  uint32_t kernel_kind;            /* fused kernel in use: 0 thread group per row pair, 1 warp per A-scan + dB scratch, 2 warp per A-scan, dB rows resident in shared memory */
+  uint32_t kernel_kind;            /* fused kernel in use: 0 thread group per row pair, 1 warp per A-scan + dB scratch, 2 warp per A-scan, dB rows resident in tensor memory, 3 generic (any N = 2^a 3^b 5^c, any row width, D <= N; run-time radices) */
   uint32_t slots_per_warp;         /* kernel_kind 2: dB row slots per warp                    */
 } abcoct_info;
 int abcoct_get_info(const abcoct_ctx* ctx, abcoct_info* out);

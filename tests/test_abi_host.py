@@ -144,14 +144,26 @@ def test_create_rejects_reference_undefined_behaviour():
     assert rc == api.ERR_INVALID and "1170" in msg
     rc, _ = _create_rc(w=1280, h=8, numfftpoints=1280, numdisplaypoints=4)
     assert rc == api.ERR_INVALID
-    rc, _ = _create_rc(w=1280, h=8, numfftpoints=1280, numdisplaypoints=1000)  # D > N/2
+    rc, _ = _create_rc(w=1280, h=8, numfftpoints=1280, numdisplaypoints=1281)  # D > N: colRange throws (BscanFFT.cpp:1193)
     assert rc == api.ERR_INVALID
     rc, _ = _create_rc(w=1280, h=8, numfftpoints=1280, numdisplaypoints=640, lambdamin=860e-9, lambdamax=840e-9)
     assert rc == api.ERR_INVALID
 
 
+def test_create_accepts_what_cv_dft_accepts():
+    """cv::dft takes any length and colRange any D <= N (BscanFFT.cpp:1185, 1193): transform lengths without a fused plan, rows
+    that are not a multiple of 8 samples and display rows above N / 2 pass validation (generic kernel); ERR_CUDA = no GPU here."""
+    for kw in (dict(w=1280, h=8, numfftpoints=1280, numdisplaypoints=1000),  # D > N/2
+               dict(w=1280, h=8, numfftpoints=1280, numdisplaypoints=1280),  # D = N
+               dict(w=1000, h=8, numfftpoints=2000, numdisplaypoints=512),  # 2^4 5^3
+               dict(w=1284, h=8, numfftpoints=3072, numdisplaypoints=512),  # row width 4 mod 8, 2^10 3
+               dict(w=750, h=8, numfftpoints=3000, numdisplaypoints=100, fft_multiplier=2)):
+        rc, msg = _create_rc(**kw)
+        assert rc in (api.OK, api.ERR_CUDA), (kw, rc, msg)
+
+
 def test_create_reports_unsupported_not_silently_wrong():
-    rc, msg = _create_rc(w=1280, h=8, numfftpoints=1344, numdisplaypoints=512)  # no compiled plan for 1344
+    rc, msg = _create_rc(w=1280, h=8, numfftpoints=1344, numdisplaypoints=512)  # 1344 = 2^6 3 7: neither a plan nor 2^a 3^b 5^c
     assert rc == api.ERR_UNSUPPORTED and "1280" in msg
     rc, msg = _create_rc(w=1280, h=8, numfftpoints=1280, numdisplaypoints=512, mediann=7)  # OpenCV: 3 / 5 only for 16-bit
     assert rc == api.ERR_UNSUPPORTED and "median" in msg

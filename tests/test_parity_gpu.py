@@ -133,6 +133,31 @@ def test_against_oracle(w, h, N, D, A, nB, variant, extra):
     _check(out8, outdb, ref8, refdb, f"w{w} N{N} A{A}")
 
 
+GENERIC = [
+    # any N = 2^a 3^b 5^c, any row width, D up to N (abcoct_info.kernel_kind 3): what cv::dft / colRange accept (BscanFFT.cpp:1185, 1193)
+    (1000, 7, 2000, 1000, 1, 2, 0, {}),  # 2^4 5^3
+    (1500, 6, 3000, 700, 2, 2, 1, {}),  # 2^3 3 5^3, averaged, DARK
+    (1284, 5, 3072, 512, 1, 3, 0, {"pishift": True}),  # row width 4 mod 8, 2^10 3
+    (1283, 9, 2048, 1024, 1, 2, 0, {}),  # odd row width on a length that has a fused plan
+    (1280, 6, 1280, 1280, 1, 2, 0, {}),  # D = N: the mirrored upper half is displayed too
+    (2048, 7, 2048, 1500, 3, 1, 0, {"clampupper": True, "bscanthreshold": 12.0}),  # D > N / 2
+    (243, 6, 243, 100, 1, 2, 0, {}),  # odd transform length 3^5
+    (750, 8, 3000, 600, 1, 2, 0, {"fft_multiplier": 2, "movavgn": 1}),  # Fourier upsample in front of it
+    (4000, 3, 6000, 2000, 1, 1, 0, {}),  # longer than every fused plan
+]
+
+
+@pytest.mark.parametrize("w,h,N,D,A,nB,variant,extra", GENERIC)
+def test_generic_lengths_against_oracle(w, h, N, D, A, nB, variant, extra):
+    from fdoct_b200 import api
+
+    test_against_oracle(w, h, N, D, A, nB, variant, extra)
+    op = oracle_params(w=w, h=max(h, 6) if extra.get("clampupper") else h, numfftpoints=N, numdisplaypoints=D, averages=A, variant=variant,
+                       lambdamin=840.5e-9, lambdamax=859.5e-9, **{k: v for k, v in extra.items() if k != "pishift"})
+    with api.Context(abi_params(op)) as ctx:
+        assert ctx.info().kernel_kind == 3
+
+
 @pytest.mark.parametrize("w,h,N,D", [(1024, 128, 1024, 512), (2048, 128, 2048, 1024), (4096, 64, 4096, 2048), (1280, 96, 1280, 640),
                                      (128, 64, 128, 64), (256, 64, 256, 128), (512, 64, 512, 256), (640, 64, 640, 320), (240, 64, 256, 128)])
 def test_accuracy_vs_exact_f64(w, h, N, D):
