@@ -54,6 +54,24 @@ import numpy as np
 PI = 3.141592653589793  # BscanFFT.cpp:609
 
 
+def aligned_empty(shape, dtype, align: int = 64) -> np.ndarray:
+    """An array whose data pointer is `align`-byte aligned, like every cv::Mat buffer (cv::fastMalloc, CV_MALLOC_ALIGN = 64).
+    cv2's IPP-backed kernels (magnitude, dft) pick their peel / vector split from the pointer alignment and differ by one f32 ulp
+    between alignments (measured: cv2.magnitude into a destination at 4 mod 16 bytes), so the f32 stages run on buffers aligned
+    the way the C++ reference's are."""
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape)) * dtype.itemsize
+    raw = np.empty(n + align, dtype=np.uint8)
+    off = (-raw.ctypes.data) % align
+    return raw[off : off + n].view(dtype).reshape(shape)
+
+
+def aligned_copy(a: np.ndarray) -> np.ndarray:
+    out = aligned_empty(a.shape, a.dtype)
+    out[...] = a
+    return out
+
+
 @dataclasses.dataclass
 class Params:
     """Mirror of ``abcoct_params`` (include/abcoct.h) / the .ini fields the block reads."""
@@ -185,7 +203,7 @@ def zeropadrowwise(sm: np.ndarray, sn: int, bandpassfilter: bool = False) -> np.
     numcols = sm.shape[1]
     newnumcols = numcols * sn
     orig = sm.astype(np.float32)  # :209
-    ft = cv2.dft(orig, flags=cv2.DFT_SCALE | cv2.DFT_COMPLEX_OUTPUT | cv2.DFT_ROWS)  # :211
+    ft = cv2.dft(aligned_copy(orig), aligned_empty(orig.shape + (2,), np.float32), flags=cv2.DFT_SCALE | cv2.DFT_COMPLEX_OUTPUT | cv2.DFT_ROWS)  # :211
     ft = _swap_halves(ft)  # :215-227
     if bandpassfilter:
         cols = ft.shape[1]
@@ -199,14 +217,14 @@ def zeropadrowwise(sm: np.ndarray, sn: int, bandpassfilter: bool = False) -> np.
     pad = int(math.floor((newnumcols - numcols) / 2))
     ftzp = cv2.copyMakeBorder(ft, 0, 0, pad, pad, cv2.BORDER_CONSTANT, value=0.0)  # :229
     ftzp = _swap_halves(ftzp)  # :233-239
-    inv = cv2.dft(ftzp, flags=cv2.DFT_INVERSE | cv2.DFT_REAL_OUTPUT | cv2.DFT_ROWS)  # :241
+    inv = cv2.dft(aligned_copy(ftzp), aligned_empty(ftzp.shape[:2], np.float32), flags=cv2.DFT_INVERSE | cv2.DFT_REAL_OUTPUT | cv2.DFT_ROWS)  # :241
     return inv.astype(np.float64)  # :242
 
 
 def lpfilter(sm: np.ndarray) -> np.ndarray:
     """BscanDark.cpp:119-167: row-wise FFT-domain low-pass (keeps the centre 20 % of the shifted spectrum). Returns f64."""
     orig = sm.astype(np.float32)
-    ft = cv2.dft(orig, flags=cv2.DFT_SCALE | cv2.DFT_COMPLEX_OUTPUT | cv2.DFT_ROWS)
+    ft = cv2.dft(aligned_copy(orig), aligned_empty(orig.shape + (2,), np.float32), flags=cv2.DFT_SCALE | cv2.DFT_COMPLEX_OUTPUT | cv2.DFT_ROWS)
     ft = _swap_halves(ft)
     cols = ft.shape[1]
     dcl = cols // 2 - int(math.floor(cols / 10))
@@ -214,7 +232,7 @@ def lpfilter(sm: np.ndarray) -> np.ndarray:
     ft[:, 0:dcl] = 0
     ft[:, dcr : dcr + dcl] = 0
     ft = _swap_halves(ft)
-    inv = cv2.dft(ft, flags=cv2.DFT_INVERSE | cv2.DFT_REAL_OUTPUT | cv2.DFT_ROWS)
+    inv = cv2.dft(aligned_copy(ft), aligned_empty(ft.shape[:2], np.float32), flags=cv2.DFT_INVERSE | cv2.DFT_REAL_OUTPUT | cv2.DFT_ROWS)
     return inv.astype(np.float64)
 
 
@@ -353,10 +371,11 @@ class Oracle:
     def magnitude(self, ylin: np.ndarray) -> np.ndarray:
         """Row inverse DFT (unscaled, f32) + magnitude: BscanFFT.cpp:1181-1190. Returns f32 oph x N."""
         re = ylin.astype(np.float32)  # Mat_<float>(data_ylin)
-        c = np.zeros(re.shape + (2,), dtype=np.float32)
+        c = aligned_empty(re.shape + (2,), np.float32)
         c[..., 0] = re
-        c = cv2.dft(c, flags=cv2.DFT_ROWS | cv2.DFT_INVERSE)
-        return cv2.magnitude(np.ascontiguousarray(c[..., 0]), np.ascontiguousarray(c[..., 1]))
+        c[..., 1] = 0
+        c = cv2.dft(c, aligned_empty(c.shape, np.float32), flags=cv2.DFT_ROWS | cv2.DFT_INVERSE)
+        return cv2.magnitude(aligned_copy(c[..., 0]), aligned_copy(c[..., 1]), aligned_empty(re.shape, np.float32))
 
     def finalise(self, acc: np.ndarray, averages: int):
         """BscanFFT.cpp:1220-1255. Returns (bscan linear f64, bscandb f64, bscandisp u8), all D x oph."""

@@ -1,0 +1,136 @@
+// Harness around the reference's OWN processing block, compiled verbatim.  TEST INFRASTRUCTURE ONLY.
+//
+// oracle/build_ref.py cuts these line ranges out of /root/reference/BscanFFT.cpp into oracle/_ref/frag_*.inc at build time (checked
+// against anchor strings, deleted again after the compile; the repository holds none of the reference's text):
+//   frag_normalizerows  BscanFFT.cpp:88-97      normalizerows()
+//   frag_helpers        BscanFFT.cpp:173-305    makeonlypositive(), zeropadrowwise(), smoothmovavg()
+//   frag_tables         BscanFFT.cpp:615-698    lambda -> k tables (nearestkindex, fractionalk)
+//   frag_window         BscanFFT.cpp:936-944    Bartlett-Hann window
+//   frag_ingest1        BscanFFT.cpp:953-958    medianBlur + INTER_AREA binning
+//   frag_ingest2        BscanFFT.cpp:987-991    convertTo(CV_64F) + smoothmovavg
+//   frag_block          BscanFFT.cpp:1125-1255  normalise, (y - yp) / yb, mean, window, upsample, gather-lerp, DFT, magnitude,
+//                                               accumulate, dB, DC mask, threshold, clamp, min-max, u8  (+ one closing brace)
+// and, compiled a second time with -DREF_DARK into abcoct_ref_dark, the same ranges of /root/reference/BscanDark.cpp
+// (82-91, 111-314 incl. lpfilter and the band-pass in zeropadrowwise, 614-697, 929-937, 946-951, 980-984,
+// 1268-1393: the block with the dark-frame subtraction `data_y = data_y - data_yd`).
+// Everything in THIS file is the scaffolding main() has around those ranges: the declarations (same names and types as
+// BscanFFT.cpp:349-613), the frame loop, and the state the key handler would set (data_yb / data_yp, BscanFFT.cpp:1027-1033, 1081).
+// The OpenCV calls inside the fragments run in OpenCV itself, through cv2 (oracle/cvshim).
+#include "opencv2/opencv.hpp"
+
+using namespace cv;  // BscanFFT.cpp:86
+
+#include "_ref/frag_normalizerows.inc"
+#include "_ref/frag_helpers.inc"
+
+namespace py = pybind11;
+
+static py::dict run_block(py::dict prm, py::array frames, py::object yb_in, py::object yp_in, py::object yd_in) {
+  // ---- declarations, BscanFFT.cpp:357-613 (names and types as there; camera / file / GUI state left out)
+  unsigned int w = prm["w"].cast<unsigned>(), h = prm["h"].cast<unsigned>(), opw, oph;
+  uint indextemp;
+  uint averagestoggle = prm["averages"].cast<unsigned>();
+  int binvalue = prm["binvalue"].cast<int>();
+  int numfftpoints = prm["numfftpoints"].cast<int>();
+  int numdisplaypoints = prm["numdisplaypoints"].cast<int>();
+  bool saveframes = 0;
+  int movavgn = prm["movavgn"].cast<int>();
+  bool clampupper = prm["clampupper"].cast<bool>();
+  bool jlockin = 0;
+#ifdef REF_DARK
+  bool jthresholding = 0;                                 // BscanDark.cpp
+  bool bandpassfilter = prm["bandpassfilter"].cast<bool>();  // BscanDark.cpp:396
+  Mat jmask, jmaskt;
+#endif
+  double lambdamin = prm["lambdamin"].cast<double>(), lambdamax = prm["lambdamax"].cast<double>();
+  int mediann = prm["mediann"].cast<int>();
+  uint increasefftpointsmultiplier = prm["fft_multiplier"].cast<unsigned>();
+  double bscanthreshold = prm["bscanthreshold"].cast<double>();
+  bool rowwisenormalize = prm["rowwisenormalize"].cast<bool>();
+  bool donotnormalize = prm["donotnormalize"].cast<bool>();
+  bool zeroisactive = 1;
+  Mat m, opm, bscan, bscanlog, bscandb, bscandisp, bscantemp, bscantransposed;
+  Mat tempmat;
+  Mat mraw;
+  Mat statusimg = Mat::zeros(cv::Size(600, 300), CV_64F);
+  Mat secrowofstatusimgRHS = statusimg(Rect(300, 50, 300, 50));
+  char textbuffer[80];
+  opw = w / binvalue;  // :545
+  oph = h / binvalue;  // :546
+  Mat data_y(oph, opw, CV_64F);
+  Mat data_ylin(oph, numfftpoints, CV_64F);
+  Mat data_yb(oph, opw, CV_64F);
+  Mat data_yp(oph, opw, CV_64F);
+  Mat barthannwin(1, opw, CV_64F);
+  data_yb = Mat::zeros(Size(opw, oph), CV_64F);  // :562
+  data_yp = Mat::zeros(Size(opw, oph), CV_64F);  // :563
+#ifdef REF_DARK
+  Mat data_yd(oph, opw, CV_64F);
+  data_yd = Mat::zeros(Size(opw, oph), CV_64F);
+  if (!yd_in.is_none()) Mat(yd_in).copyTo(data_yd);  // key 'o' (BscanDark.cpp)
+#endif
+  Mat bscansave0[100];
+  Mat bscansave1[100];
+  Mat jscansave;
+  Mat positivediff;
+  Mat magI;
+  Scalar meanval;
+  Mat lambdas, k, klinear;
+  Mat diffk, slopes, fractionalk, nearestkindex;
+  double kmin, kmax;
+  double pi = 3.141592653589793;  // :609
+
+#include "_ref/frag_tables.inc"
+
+  indextemp = 0;                                                         // :931
+  bscantransposed = Mat::zeros(Size(numdisplaypoints, oph), CV_64F);    // :932
+#include "_ref/frag_window.inc"
+
+  // what keys 'b' / 'p' leave behind (:1027-1033, :1081): the caller's calibration frames
+  if (!yb_in.is_none()) Mat(yb_in).copyTo(data_yb);
+  if (!yp_in.is_none()) Mat(yp_in).copyTo(data_yp);
+
+  py::list disp, db;
+  py::object last_ylin = py::none();
+  const py::ssize_t nframes = frames.shape(0);
+  for (py::ssize_t fi = 0; fi < nframes; ++fi) {
+    mraw = Mat(py::reinterpret_borrow<py::object>(frames[py::int_(fi)]));  // GetQHYCCDLiveFrame(..., mraw.data), :949
+    {
+#include "_ref/frag_ingest1.inc"
+#include "_ref/frag_ingest2.inc"
+#include "_ref/frag_block.inc"
+      }  // closes `if (indextemp >= averagestoggle)` (the J0 lock-in display and the key handler follow in the reference)
+    }
+    if (indextemp == 0) {  // a B-scan was completed by this frame
+      disp.append(ops().attr("copy")(bscandisp.arr));
+      db.append(ops().attr("copy")(bscandb.arr));
+      bscantransposed = Mat::zeros(Size(numdisplaypoints, oph), CV_64F);  // :1482
+    }
+  }
+  py::dict out;
+  out["bscandisp"] = disp;
+  out["bscandb"] = db;
+  out["nearestkindex"] = ops().attr("copy")(nearestkindex.arr);
+  out["fractionalk"] = ops().attr("copy")(fractionalk.arr);
+  out["barthannwin"] = ops().attr("copy")(barthannwin.arr);
+  out["data_ylin"] = ops().attr("copy")(data_ylin.arr);
+  (void)kmin, (void)kmax, (void)zeroisactive, (void)saveframes, (void)jlockin, (void)textbuffer, (void)clampupper, (void)yd_in;
+  return out;
+}
+
+#ifdef REF_DARK
+PYBIND11_MODULE(abcoct_ref_dark, mod) {
+  mod.doc() = "the reference's processing block (BscanDark.cpp), compiled verbatim against oracle/cvshim";
+  mod.def("lpfilter", [](py::object a) {  // BscanDark.cpp:119-167, applied to the captured calibration frames (:1070-1074)
+    Mat mm(ops().attr("copy")(a));
+    lpfilter(mm);
+    return mm.arr;
+  });
+#else
+PYBIND11_MODULE(abcoct_ref, mod) {
+  mod.doc() = "the reference's processing block (BscanFFT.cpp), compiled verbatim against oracle/cvshim";
+#endif
+  mod.def("run_block", &run_block, py::arg("params"), py::arg("frames"), py::arg("yb") = py::none(), py::arg("yp") = py::none(),
+          py::arg("yd") = py::none());
+  mod.def("opencv_version", []() { return ops().attr("opencv_version")().cast<std::string>(); });
+}

@@ -30,4 +30,4 @@ def test_warp_per_ascan_kernel_lockstep_emulation():
     three load modes) executed by 32 host threads per warp against an
     f64 restatement: magnitude within 1e-4 of max(|ref|, 1e-3 A-scan max), display within 1 LSB."""
     out = _run("test_wrow_host")
-    assert out.count("max rel mag err") == 8 and "worst (in units of the tolerance)" in out
+    assert out.count("max rel mag err") >= 8 and "worst (in units of the tolerance)" in out

@@ -1,0 +1,155 @@
+"""The pin of the oracle: oracle/abcoct_oracle.py against the reference's OWN processing block, compiled verbatim.
+
+oracle/build_ref.py cuts the block (and the helper functions, the table precompute, the window loop and the frame ingest) out of
+/root/reference/BscanFFT.cpp and BscanDark.cpp at build time and compiles them unmodified against oracle/cvshim, a stand-in for the
+OpenCV C++ headers that forwards every OpenCV call to the same OpenCV kernels through cv2.  The modules live in oracle/_ref/ (git-
+ignored, built by __graft_entry__.build() wherever /root/reference exists, shipped to the GPU box as built files).
+
+Bar: bit-exact.  Both sides run the same OpenCV kernels on the same inputs, so every difference would be a difference in the
+restatement: tables, display bytes and the f64 dB image must be IDENTICAL."""
+import os
+
+import numpy as np
+import pytest
+
+from util import GOLDEN, oracle_params
+
+from oracle import build_ref
+
+
+def _ref(name="abcoct_ref"):
+    build_ref.build()  # no-op when up to date or when the reference is not on this machine
+    mod = build_ref.load(name)
+    if mod is None:
+        pytest.skip("oracle/_ref is not built (no /root/reference on this machine and no shipped module)")
+    return mod
+
+
+def ref_params(p):
+    assert p.binx == p.biny
+    return dict(w=p.w, h=p.h, averages=p.averages, binvalue=p.binx, numfftpoints=p.numfftpoints, numdisplaypoints=p.numdisplaypoints,
+                movavgn=p.movavgn, clampupper=p.clampupper, lambdamin=p.lambdamin, lambdamax=p.lambdamax, mediann=p.mediann,
+                fft_multiplier=p.fft_multiplier, bscanthreshold=p.bscanthreshold, rowwisenormalize=p.rowwisenormalize,
+                donotnormalize=p.donotnormalize, bandpassfilter=p.bandpassfilter)
+
+
+FFT_CASES = [
+    dict(w=128, h=8, numfftpoints=128, numdisplaypoints=64),
+    dict(w=256, h=12, numfftpoints=256, numdisplaypoints=100, averages=3),
+    dict(w=640, h=9, numfftpoints=1280, numdisplaypoints=300, fft_multiplier=2, movavgn=1),
+    dict(w=256, h=16, numfftpoints=256, numdisplaypoints=128, binx=2, biny=2, mediann=3),
+    dict(w=512, h=10, numfftpoints=512, numdisplaypoints=256, mediann=5, movavgn=2, averages=2),
+    dict(w=320, h=10, numfftpoints=512, numdisplaypoints=200, rowwisenormalize=True),
+    dict(w=320, h=10, numfftpoints=512, numdisplaypoints=200, donotnormalize=False, clampupper=True, bscanthreshold=5.0),
+    dict(w=300, h=7, numfftpoints=1000, numdisplaypoints=1000, fft_multiplier=3),  # D = N, odd multiplier
+    dict(w=1280, h=6, numfftpoints=2048, numdisplaypoints=1024, pishift=True),
+    dict(w=250, h=6, numfftpoints=250, numdisplaypoints=125, bpp=8),
+    dict(w=2048, h=4, numfftpoints=2048, numdisplaypoints=1024),  # the north_star configuration's row shape
+]
+
+
+@pytest.mark.parametrize("kw", FFT_CASES)
+def test_oracle_equals_compiled_bscanfft_block(kw):
+    from fdoct_b200 import synth
+    from oracle.abcoct_oracle import Oracle
+
+    ref = _ref()
+    kw = dict(kw)
+    pishift = kw.pop("pishift", False)
+    p = oracle_params(lambdamin=840.5e-9, lambdamax=859.5e-9, **kw)
+    nB = 2
+    frames = synth.make_frames(nB * p.averages, p.w, p.h, seed=4242 + p.w)
+    if p.bpp == 8:
+        frames = (frames >> 8).astype(np.uint8)
+    for strict in (True, False):
+        o = Oracle(p, strict=strict)
+        bgf = synth.make_background_frames(2, p.w, p.h, seed=77)
+        yb = o.calib_mean_of_frames((bgf >> 8).astype(np.uint8) if p.bpp == 8 else bgf)
+        o.set_background(yb)
+        yp = None
+        if pishift:
+            yp = 0.05 * yb
+            o.set_pishift(yp)
+        o8, odb = o.process_bscans(frames)
+        if strict:
+            r = ref.run_block(ref_params(p), frames, np.ascontiguousarray(yb), None if yp is None else np.ascontiguousarray(yp))
+            assert np.array_equal(r["nearestkindex"].ravel(), o.t["nearestkindex"])
+            assert np.array_equal(r["fractionalk"].ravel(), o.t["fractionalk"])
+            assert np.array_equal(r["barthannwin"].ravel(), np.asarray(o.win).ravel())
+            r8, rdb = np.stack(r["bscandisp"]), np.stack(r["bscandb"])
+            assert r8.shape == o8.shape == (nB, p.numdisplaypoints, p.oph)
+            assert np.array_equal(r8, o8), "display bytes differ from the compiled reference block"
+            assert np.array_equal(rdb, odb), f"dB image differs from the compiled reference block by {np.abs(rdb - odb).max():.3g}"
+        else:  # the vectorised mode (the CPU baseline): f64 sums in another order flip single f32 ulps in front of the f32 DFT
+            assert np.abs(np.stack(r["bscandb"]) - odb).max() <= 1e-4 and np.abs(r8.astype(int) - o8.astype(int)).max() <= 1
+
+
+DARK_CASES = [
+    dict(w=256, h=8, numfftpoints=256, numdisplaypoints=128),
+    dict(w=1280, h=6, numfftpoints=1280, numdisplaypoints=640, averages=4),
+    dict(w=640, h=8, numfftpoints=2560, numdisplaypoints=500, fft_multiplier=4, bandpassfilter=True),
+    dict(w=640, h=8, numfftpoints=1280, numdisplaypoints=500, fft_multiplier=2, movavgn=1, mediann=3),
+    dict(w=320, h=10, numfftpoints=512, numdisplaypoints=200, rowwisenormalize=True),
+    dict(w=320, h=10, numfftpoints=512, numdisplaypoints=200, donotnormalize=False, binx=2, biny=2),
+]
+
+
+@pytest.mark.parametrize("kw", DARK_CASES)
+def test_oracle_equals_compiled_bscandark_block(kw):
+    from fdoct_b200 import synth
+    from oracle.abcoct_oracle import Oracle, dark_background
+
+    ref = _ref("abcoct_ref_dark")
+    p = oracle_params(variant=1, lambdamin=840.5e-9, lambdamax=859.5e-9, **kw)
+    nB = 2
+    frames = synth.make_frames(nB * p.averages, p.w, p.h, seed=99 + p.w, dark=True)
+    o = Oracle(p, strict=True)
+    yd = o.calib_mean_of_frames(synth.make_dark_frames(2, p.w, p.h, seed=5))
+    yr = o.calib_mean_of_frames(synth.make_background_frames(2, p.w, p.h, seed=6, dark=True))
+    yb = dark_background(yr, yd, yd + 0.02 * (yr - yd))
+    o.set_dark(yd)
+    o.set_background(yb)
+    o8, odb = o.process_bscans(frames)
+    r = ref.run_block(ref_params(p), frames, np.ascontiguousarray(yb), None, np.ascontiguousarray(yd))
+    assert np.array_equal(r["nearestkindex"].ravel(), o.t["nearestkindex"])
+    assert np.array_equal(r["fractionalk"].ravel(), o.t["fractionalk"])
+    assert np.array_equal(np.stack(r["bscandisp"]), o8)
+    assert np.array_equal(np.stack(r["bscandb"]), odb)
+
+
+def test_oracle_lpfilter_equals_compiled():
+    """lpfilter (BscanDark.cpp:119-167), applied to the captured calibration frames."""
+    from oracle.abcoct_oracle import lpfilter
+
+    ref = _ref("abcoct_ref_dark")
+    rng = np.random.default_rng(3)
+    for cols in (128, 250, 1280):
+        a = rng.uniform(100.0, 4000.0, size=(5, cols))
+        assert np.array_equal(ref.lpfilter(a), lpfilter(a))
+
+
+def test_reference_generated_golden_vectors():
+    """tests/golden/ref_*.npz were written by the compiled reference block itself (tests/golden/make_ref_golden.py); the oracle must
+    reproduce them bit for bit - this is the check that also runs where oracle/_ref cannot be built."""
+    from oracle.abcoct_oracle import Oracle
+
+    names = sorted(f for f in os.listdir(GOLDEN) if f.startswith("ref_") and f.endswith(".npz"))
+    assert names, "no reference-generated fixtures"
+    for name in names:
+        z = np.load(os.path.join(GOLDEN, name), allow_pickle=False)
+        kw = {k[2:]: z[k].item() for k in z.files if k.startswith("p_")}
+        p = oracle_params(**kw)
+        o = Oracle(p, strict=True)
+        if "yd" in z.files:
+            o.set_dark(z["yd"])
+        o.set_background(z["yb"])
+        o8, odb = o.process_bscans(z["frames"])
+        assert np.array_equal(o8, z["bscandisp"]), name
+        assert np.array_equal(odb, z["bscandb"]), name
+        assert np.array_equal(o.t["nearestkindex"], z["nearestkindex"]) and np.array_equal(o.t["fractionalk"], z["fractionalk"])
+        # the product library's host-side precompute (abcoct_build_tables, no GPU needed) against the reference's own tables
+        from fdoct_b200 import api
+        from util import abi_params
+
+        nk, fr, win = api.build_tables(abi_params(p))
+        assert np.array_equal(nk, z["nearestkindex"]) and np.array_equal(fr, z["fractionalk"]) and np.array_equal(win, z["barthannwin"])

@@ -43,6 +43,26 @@ def test_golden_wang128():
     _check(out8, outdb, z["disp"][None], z["db"][None], "wang128")
 
 
+REF_GOLDEN = sorted(f[:-4] for f in os.listdir(GOLDEN) if f.startswith("ref_") and f.endswith(".npz"))
+
+
+@pytest.mark.parametrize("name", REF_GOLDEN)
+def test_golden_from_the_compiled_reference_block(name):
+    """Fixtures written by the reference's own block compiled verbatim (tests/golden/make_ref_golden.py, oracle/build_ref.py): the
+    CUDA path against outputs that never went through the oracle."""
+    assert REF_GOLDEN
+    z = np.load(os.path.join(GOLDEN, name + ".npz"))
+    kw = {k[2:]: z[k].item() for k in z.files if k.startswith("p_")}
+    op = oracle_params(**kw)
+    out8, outdb = _run_abi(op, z["frames"], z["yb"], yd=z["yd"] if "yd" in z.files else None)
+    _check(out8, outdb, z["bscandisp"], z["bscandb"], name)
+    from fdoct_b200 import api
+
+    with api.Context(abi_params(op)) as ctx:
+        nk, fr, win = ctx.tables()
+    assert np.array_equal(nk, z["nearestkindex"]) and np.array_equal(fr, z["fractionalk"]) and np.array_equal(win, z["barthannwin"])
+
+
 @pytest.mark.parametrize("name", ["synth_fft_1280x32", "synth_dark_1280x16_a4", "synth_fft_1024x17_n2048_clamp"])
 def test_golden_synth(name):
     z = np.load(os.path.join(GOLDEN, name + ".npz"))
