@@ -14,10 +14,11 @@ generator Matlab files/wangOCTimg2.m).  One JSON line is printed by rank 0:
                host display B-scans out, H2D + D2H inside the timed region)
   roofline     fused reconstruction kernel: algorithmic bytes per launch / mean launch duration (CUDA events on the
                launching stream, inside the timed region) against the measured HBM peak (MEASURED_PEAKS.json)
-  cpu_baseline the oracle (the reference's OpenCV arithmetic via cv2) timed on this box's host cores on a bounded sample
+  cpu_baseline the reference's own processing block compiled verbatim (oracle/_ref, kind "reference"; the oracle port when that
+               module is absent, kind "port") timed on this box's host cores on a bounded sample
 
 `--impl reference` times that CPU implementation only (all host cores, one process per core, disjoint B-scans).
-The oracle is used here ONLY as the thing timed in those two legs; the product path never touches it.
+oracle/ is used here ONLY as the thing timed in those two legs; the product path never touches it.
 """
 from __future__ import annotations
 
@@ -95,20 +96,56 @@ def make_inputs(wl, nframes, n_unique=4):
 _CPU_SHARED = {}  # inputs of the worker processes: set BEFORE the pool forks, so nothing is pickled per call
 
 
-def _cpu_worker(nbscans):
-    """One worker process: the oracle over `nbscans` B-scans of the shared sample. Returns A-scans processed."""
+def cpu_reference_module(wl):
+    """oracle/_ref: the reference's own processing block compiled verbatim (oracle/build_ref.py) - BscanFFT.cpp for variant 0,
+    BscanDark.cpp for variant 1.  None when it was not built / shipped: the CPU legs then time the oracle port."""
+    try:
+        from oracle import build_ref
+
+        return build_ref.load("abcoct_ref_dark" if wl["variant"] == 1 else "abcoct_ref")
+    except Exception:
+        return None
+
+
+def cpu_kind(wl):
     import cv2
 
+    if cpu_reference_module(wl) is not None:
+        src = "BscanDark.cpp" if wl["variant"] == 1 else "BscanFFT.cpp"
+        return "reference", f"the reference's processing block ({src}) compiled verbatim, OpenCV {cv2.__version__} kernels through cv2"
+    return "port", f"oracle = Python restatement calling OpenCV {cv2.__version__} kernels"
+
+
+def cpu_process(wl, frames, yb, yd):
+    """`frames` through the reference's CPU implementation of the path: oracle/_ref when present, else the oracle port."""
+    mod = cpu_reference_module(wl)
+    if mod is not None:
+        prm = dict(w=wl["w"], h=wl["h"], averages=wl["A"], binvalue=1, numfftpoints=wl["N"], numdisplaypoints=wl["D"], movavgn=0,
+                   clampupper=False, lambdamin=LMIN, lambdamax=LMAX, mediann=0, fft_multiplier=wl.get("m", 1), bscanthreshold=-30.0,
+                   rowwisenormalize=False, donotnormalize=True, bandpassfilter=False)
+        ybc = np.ascontiguousarray(yb, dtype=np.float64)
+        ydc = None if yd is None else np.ascontiguousarray(yd, dtype=np.float64)
+        step = 8 * wl["A"]  # the module returns every B-scan it made: bounded chunks keep a worker's memory flat (the one-off
+        for i in range(0, len(frames), step):  # table precompute it repeats per call is ~1e-3 of a chunk)
+            mod.run_block(prm, frames[i:i + step], ybc, None, ydc)
+        return
     from oracle.abcoct_oracle import Oracle
 
-    wl, frames, yb, yd = _CPU_SHARED["wl"], _CPU_SHARED["frames"], _CPU_SHARED["yb"], _CPU_SHARED["yd"]
-    cv2.setNumThreads(1)
     o = Oracle(oracle_params(wl))
     o.set_background(yb)
     if yd is not None:
         o.set_dark(yd)
+    o.process_bscans(frames)
+
+
+def _cpu_worker(nbscans):
+    """One worker process: the reference block over `nbscans` B-scans of the shared sample. Returns A-scans processed."""
+    import cv2
+
+    wl, frames, yb, yd = _CPU_SHARED["wl"], _CPU_SHARED["frames"], _CPU_SHARED["yb"], _CPU_SHARED["yd"]
+    cv2.setNumThreads(1)
     n = nbscans * wl["A"]
-    o.process_bscans(frames[:n])
+    cpu_process(wl, frames[:n], yb, yd)
     return n * wl["h"]
 
 
@@ -136,17 +173,11 @@ def time_cpu_single_process(wl, uniq, yb, yd, bscans):
     """The reference-like mode: ONE process, OpenCV's own internal threads (what the reference binary does)."""
     import cv2
 
-    from oracle.abcoct_oracle import Oracle
-
     cv2.setNumThreads(-1)
-    o = Oracle(oracle_params(wl))
-    o.set_background(yb)
-    if yd is not None:
-        o.set_dark(yd)
     frames = _cpu_sample(wl, uniq, bscans)
-    o.process_bscans(frames[: wl["A"]])
+    cpu_process(wl, frames[: wl["A"]], yb, yd)
     t0 = time.perf_counter()
-    o.process_bscans(frames)
+    cpu_process(wl, frames, yb, yd)
     dt = time.perf_counter() - t0
     return {"value": frames.shape[0] * wl["h"] / dt, "unit": "A-scans/s", "bscans": bscans, "seconds": dt,
             "cv2_threads": int(cv2.getNumThreads())}
@@ -398,8 +429,8 @@ def run_reference(args, wl, rank):
         "vs_baseline": None, "dtype": "f64/f32 (OpenCV)", "data": "synthetic",
         "config": {"workload": wl["desc"], "name": args.workload, "sample_per_step": sample},
         "bscans_per_s": value / (wl["h"] * wl["A"]),
-        "cpu_baseline": {"value": value, "unit": "A-scans/s", "cores": cores, "kind": "port", "cpu": cpu_model(),
-                         "sample": sample + f"; oracle = Python restatement calling OpenCV {cv2.__version__} kernels",
+        "cpu_baseline": {"value": value, "unit": "A-scans/s", "cores": cores, "kind": cpu_kind(wl)[0], "cpu": cpu_model(),
+                         "sample": sample + "; " + cpu_kind(wl)[1],
                          "single_process": time_cpu_single_process(wl, uniq, yb, yd, 4)},
         "e2e": {"value": value, "unit": "A-scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -556,8 +587,8 @@ def run_ours(args, wl, rank, world, local_rank):
             cores = os.cpu_count() or 1
             per_core = calibrate_cpu_sample(wl, uniq, yb, yd, target_s=args.cpu_seconds)
             v, dt, sample = time_cpu_reference(wl, uniq, yb, yd, cores, per_core)
-            line["cpu_baseline"] = {"value": v, "unit": "A-scans/s", "cores": cores, "kind": "port", "cpu": cpu_model(),
-                                    "sample": sample + f"; {dt:.1f} s; oracle = Python restatement calling the reference's OpenCV kernels (cv2)",
+            line["cpu_baseline"] = {"value": v, "unit": "A-scans/s", "cores": cores, "kind": cpu_kind(wl)[0], "cpu": cpu_model(),
+                                    "sample": sample + f"; {dt:.1f} s; " + cpu_kind(wl)[1],
                                     "single_process": time_cpu_single_process(wl, uniq, yb, yd, 4)}
         print(json.dumps(line), flush=True)
     pin_in.free()

@@ -31,14 +31,16 @@ re-implemented: the same OpenCV kernels are called through
 ``opencv-python-headless`` (4.13.0 in this image; the reference pins no OpenCV
 version - README.md:18 just installs ``libopencv-dev``).
 
-PARITY UNPINNED: the reference ships no tests, no golden outputs and cannot be
-built here (no OpenCV C++ headers, no camera SDKs).  The pin we create is
-"cv2 4.13.0 running this restatement" plus a physics known-answer test on the
-reference's own fixtures ``Matlab files/imgi.png`` / ``backg.png`` (peak depth
-predicted by the generator ``Matlab files/wangOCTimg.m``); see
-``tests/test_oracle.py`` and ``tests/golden/make_golden.py``.
+PINNED (round 2): the reference ships no tests and no golden outputs and its executables cannot be built here (no
+OpenCV C++ headers, no camera SDKs) - but its processing block can.  oracle/build_ref.py cuts the block, the helper
+functions, the table precompute, the window loop and the frame ingest out of /root/reference/BscanFFT.cpp and
+BscanDark.cpp and compiles them verbatim against oracle/cvshim (a stand-in for the OpenCV headers that forwards every
+OpenCV call to the same kernels through cv2) into oracle/_ref/.  ``strict=True`` of this module equals those modules
+BIT FOR BIT (tables, display bytes, f64 dB image) on every configuration of tests/test_oracle_pinned.py, and reproduces
+the vectors they wrote (tests/golden/ref_*.npz).  Also kept: the physics known-answer test on the reference's own
+fixtures ``Matlab files/imgi.png`` / ``backg.png`` (tests/test_oracle.py).
 
-Two execution modes give the same numbers to <= 1e-12 relative (f64):
+Two execution modes give the same f64 intermediates to <= 1e-12 relative (single f32 ulps can flip behind the f32 DFT):
 ``strict=True`` issues the per-row OpenCV calls exactly like the reference's C++
 loops; ``strict=False`` vectorises those loops with NumPy so that the CPU
 baseline is not handicapped by the Python interpreter.
