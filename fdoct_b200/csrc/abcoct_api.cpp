@@ -94,6 +94,10 @@ struct abcoct_ctx {
   bool have_yr = false, have_ys = false;
   bool have_yb = false, have_yp = false, have_yd = false, cal_dirty = true, has_sub = false;
   bool general = false;  // any optional pre-processing stage is on: frames go through prep_kernels.cu first
+  // BscanFFTspinjnt.cpp:1856-1862 with bscanbinx = bscanbiny = binvaluey = 1 < binvaluex: both resizes are copies, what is left is
+  // bscan *= multiplyfactor (= binvaluex, :835) before the log, i.e. + (20 / 2.303) ln(multiplyfactor) dB on the dB image; the display
+  // image sees the threshold and the clamp value lowered by the same amount (min-max normalisation is shift invariant)
+  float db_shift = 0.f;
   bool generic = false;  // no fused plan for this N / row width / D: generic_recon_kernel on the prepared rows (implies general)
   std::vector<int> radN;
   // warp-per-A-scan kernel (wrow_kernel.cuh): eligible configurations and the plan in use (nullptr: recon_kernel.cuh)
@@ -214,9 +218,12 @@ int validate(const abcoct_params& p, std::string& why, int& code) {
   if (p.movavgn > 64) return bad("movavgn > 64 is not built");
   if (p.channelnum >= 3 && (p.binx > 1 || p.biny > 1))
     return bad("channelnum >= 3 with binning (INTER_AREA on the CV_64F channel sum, BscanFFTwebcam.cpp:1049) is not built");
-  if (p.output_rebin && (p.bscanbinx > 1 || p.bscanbiny > 1 || p.binx > 1 || p.biny > 1))
-    return bad("BscanFFTspinjnt's output re-binning of the linear B-scan (INTER_AREA down, x multiplyfactor, INTER_CUBIC up; "
-               "BscanFFTspinjnt.cpp:1856-1862, active whenever any binning factor exceeds 1) is not built");
+  if (p.output_rebin && (p.bscanbinx > 1 || p.bscanbiny > 1 || p.biny > 1))
+    return bad("BscanFFTspinjnt's output re-binning of the linear B-scan with a real resampling step (INTER_AREA down by bscanbinx/y, "
+               "INTER_CUBIC up by bscanbinx * binvaluey and bscanbiny; BscanFFTspinjnt.cpp:1856-1862) is not built: the bicubic "
+               "overshoot goes negative next to every bright A-scan and the reference's own log() turns that into NaN; only the "
+               "shipped shape (bscanbinx = bscanbiny = binvaluey = 1, where both resizes are copies and the block multiplies the "
+               "B-scan by multiplyfactor) is supported");
   if (p.fft_multiplier > 1) {
     unsigned r = opw;
     for (unsigned f : {2u, 3u, 5u})
@@ -560,6 +567,8 @@ int enqueue_device(abcoct_ctx* c, GpuState& g, int slot, const uint8_t* d_frames
   OutPtrs o = o_in;
   const size_t px = (size_t)c->D * c->oph;
   const bool want_j = o.p[O_JSUB] || o.p[O_JBGR];
+  if (want_j && c->db_shift != 0.f)
+    return fail(c, ABCOCT_ERR_UNSUPPORTED, "the J0 lock-in outputs together with BscanFFTspinjnt's multiplyfactor are not built");
   if (want_j) {
     if (c->jscan.empty()) return fail(c, ABCOCT_ERR_STATE, "jsub output requested but no jscan is set (abcoct_set_jscan)");
     if (c->jscan_dirty) {
@@ -636,8 +645,8 @@ int enqueue_device(abcoct_ctx* c, GpuState& g, int slot, const uint8_t* d_frames
       gh.outdb = d_outdb ? d_outdb + b0 * c->D * c->oph : nullptr;
       gh.out_scale = 0.5f / (float)c->A;
       gh.db_scale_ln = (float)(20.0 * (1.0 / 2.303));
-      gh.thr = (float)c->p.bscanthreshold;
-      gh.clamp_db = (float)c->p.clamp_db;
+      gh.thr = (float)c->p.bscanthreshold - c->db_shift;
+      gh.clamp_db = (float)c->p.clamp_db - c->db_shift;
       gh.clamp55 = c->p.clampupper ? 1 : 0;
       a.out8 = gh.out8;
       a.outdb = gh.outdb;
@@ -690,8 +699,8 @@ int enqueue_device(abcoct_ctx* c, GpuState& g, int slot, const uint8_t* d_frames
     a.inv_W = 1.0f / (float)c->opw;
     a.out_scale = 0.5f / (float)c->A;
     a.db_scale = (float)(0.6931471805599453 * (20.0 * (1.0 / 2.303)));
-    a.thr = (float)c->p.bscanthreshold;
-    a.clamp_db = (float)c->p.clamp_db;
+    a.thr = (float)c->p.bscanthreshold - c->db_shift;
+    a.clamp_db = (float)c->p.clamp_db - c->db_shift;
     a.clamp55 = c->p.clampupper ? 1 : 0;
     if (!c->wplan) grid = std::min(g.sm_count, (a.nitems + c->G - 1) / c->G);
     CU(c, launch_sched_init(a.sched, (int)nb, st));
@@ -707,6 +716,11 @@ int enqueue_device(abcoct_ctx* c, GpuState& g, int slot, const uint8_t* d_frames
       g.tev_used += 3;
     }
     c->launches += 2;
+    }
+    if (c->db_shift != 0.f && (a.outdb || a.dc01)) {  // the dB image (and the unmasked DC rows) of bscan * multiplyfactor
+      int nl = 0;
+      CU(c, launch_add_const(a.outdb, nb * px, a.dc01, 2 * nb * (size_t)c->oph, c->db_shift, g.sm_count, st, &nl));
+      c->launches += nl;
     }
     // consumers of the finished B-scans (post_kernels.cu), same stream
     float* lin = d_outlin ? d_outlin + b0 * px : nullptr;
@@ -938,6 +952,8 @@ int abcoct_create(const abcoct_params* params, const int* gpu_ids, int ngpu, abc
   }
   c->general = params->bpp == 8 || params->binx > 1 || params->biny > 1 || params->mediann > 0 || params->movavgn > 0 ||
                params->fft_multiplier > 1 || params->rowwisenormalize || !params->donotnormalize;  // (8-bit covers channelnum >= 3)
+  if (params->output_rebin && params->binx > 1)
+    c->db_shift = (float)(20.0 * (1.0 / 2.303) * std::log((double)(params->bscanbinx * params->bscanbiny * params->binx * params->biny)));
   c->generic = needs_generic(*params);
   if (c->generic) {
     c->general = true;  // rowprep_kernel prepares f32 rows for every configuration, generic_recon_kernel consumes them

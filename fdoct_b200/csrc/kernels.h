@@ -104,5 +104,7 @@ cudaError_t launch_lin_from_db(const float* db, const float* dc01, float* lin, i
 // exists, else (lin == nullptr) the dB image + dc01 and the linear value is derived on the fly; jscan [px], mm [2 nB] ints
 cudaError_t launch_jsub(const float* lin, const float* db, const float* dc01, const float* jscan, int* mm, uint8_t* out, int oph,
                         size_t px, int nB, float db_scale, float inv_db_scale, float thr, int sm_count, cudaStream_t st, int* launched);
+// x += v over two arrays (either may be NULL): the dB offset of BscanFFTspinjnt's multiplyfactor (BscanFFTspinjnt.cpp:1860)
+cudaError_t launch_add_const(float* a, size_t na, float* b, size_t nb, float v, int sm_count, cudaStream_t st, int* launched);
 cudaError_t launch_jet(const uint8_t* in, uint8_t* out, size_t n, int sm_count, cudaStream_t st);  // applyColorMap(., COLORMAP_JET)
 }  // namespace abcoct

@@ -6,6 +6,7 @@
 //     ln(.) * 20 / 2.303, max(., bscanthreshold), global min-max normalise, convertTo(CV_8UC1, 255)
 //   * applyColorMap(., COLORMAP_JET) (BscanFFT.cpp:1268, 1284): u8 -> BGR through OpenCV's own 256-entry table
 // All of it is elementwise work plus one min/max per B-scan: HBM-bound streaming kernels, grid = B-scans x chunks.
+#include <algorithm>
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -217,6 +218,23 @@ bool vec_ok(size_t px, const void* a, const void* b, const void* c) {
   return px % 4 == 0 && ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) & 15) == 0;
 }
 }  // namespace
+
+__global__ void __launch_bounds__(256) add_const_kernel(float* __restrict__ x, size_t n, float v) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) x[i] += v;
+}
+cudaError_t launch_add_const(float* a, size_t na, float* b, size_t nb, float v, int sm_count, cudaStream_t st, int* launched) {
+  int n = 0;
+  if (a && na) {
+    add_const_kernel<<<(unsigned)std::min<size_t>((na + 255) / 256, (size_t)sm_count * 8), 256, 0, st>>>(a, na, v);
+    ++n;
+  }
+  if (b && nb) {
+    add_const_kernel<<<(unsigned)std::min<size_t>((nb + 255) / 256, (size_t)sm_count * 8), 256, 0, st>>>(b, nb, v);
+    ++n;
+  }
+  if (launched) *launched = n;
+  return cudaGetLastError();
+}
 
 cudaError_t launch_lin_from_db(const float* db, const float* dc01, float* lin, int oph, size_t px, int nB, float inv_db_scale,
                                int sm_count, cudaStream_t st, int* launched) {

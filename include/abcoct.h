@@ -71,8 +71,10 @@ typedef struct abcoct_params {
   uint8_t output_rebin;      /* 1 = the caller is BscanFFTspinjnt, whose block re-bins the LINEAR B-scan before the log whenever
                                 any of binx / biny / bscanbinx / bscanbiny exceeds 1 (resize INTER_AREA down by bscanbinx/y, times
                                 multiplyfactor, resize INTER_CUBIC up by bscanbinx * binvaluey and bscanbiny,
-                                BscanFFTspinjnt.cpp:835, 1856-1862).  Set by the ABCOCT_INI_SPINJNT parser.  That stage is NOT built:
-                                abcoct_create answers ABCOCT_ERR_UNSUPPORTED instead of returning the un-rebinned image.       */
+                                BscanFFTspinjnt.cpp:835, 1856-1862).  Set by the ABCOCT_INI_SPINJNT parser.  Built for the shape the
+                                shipped ini gives (binx > 1, biny = bscanbinx = bscanbiny = 1): both resizes are copies there and the
+                                block is bscan *= multiplyfactor.  With a real resampling step the reference's own output is NaN
+                                wherever the bicubic overshoot is negative; abcoct_create answers ABCOCT_ERR_UNSUPPORTED.         */
   uint8_t bscanbinx, bscanbiny; /* BscanFFTspinjnt.cpp:795-797; only looked at when output_rebin is set                       */
   uint8_t channelnum;        /* BscanFFTwebcam.cpp:412, 1016-1037: 0..2 = the caller passes the selected 8-bit plane (bpp = 8);
                                 >= 3: frames are interleaved 8-bit BGR (3 bytes per pixel, what cap.read gives) and the library

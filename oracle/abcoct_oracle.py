@@ -100,6 +100,9 @@ class Params:
     clamp_db: float = 50.0  # BscanFFT.cpp:1252 (30.0 in BscanFFTspinjnt.cpp:1886)
     bandpassfilter: bool = False  # BscanDark.cpp:218-236, only inside zeropadrowwise
     lowpassfilter: bool = False  # BscanDark.cpp:1070-1074: lpfilter on the captured calibration frames
+    output_rebin: bool = False  # BscanFFTspinjnt.cpp:1856-1862: re-bin the LINEAR B-scan before the log (that variant only)
+    bscanbinx: int = 1  # BscanFFTspinjnt.cpp:795
+    bscanbiny: int = 1  # BscanFFTspinjnt.cpp:797
     channelnum: int = 0  # BscanFFTwebcam.cpp:412, 1019: >= 3 sums the three channels of a BGR frame, scaled by 1/765, into a CV_64F mraw
 
     @property
@@ -384,6 +387,13 @@ class Oracle:
         p = self.p
         bscan = acc.T * (1.0 / averages)  # :1220-1221
         bscan = bscan + 0.00001  # :1222
+        if p.output_rebin and (p.bscanbinx > 1 or p.bscanbiny > 1 or p.binx > 1 or p.biny > 1):  # BscanFFTspinjnt.cpp:1856
+            multiplyfactor = p.bscanbinx * p.bscanbiny * p.binx * p.biny  # :835 (int)
+            bscanbinned = cv2.resize(np.ascontiguousarray(bscan), None, fx=1.0 / p.bscanbinx, fy=1.0 / p.bscanbiny,
+                                     interpolation=cv2.INTER_AREA)  # :1859
+            # :1860 - int * Mat is a MatExpr scaling (one multiplication per element); fx carries binvaluey, the reference's quirk
+            bscan = cv2.resize(bscanbinned * float(multiplyfactor), None, fx=p.bscanbinx * p.biny, fy=p.bscanbiny,
+                               interpolation=cv2.INTER_CUBIC)
         bscanlog = cv2.log(bscan)  # :1235
         bscandb = bscanlog * (20.0 * (1.0 / 2.303))  # :1237
         bscandb[1] = bscandb[4]  # :1239

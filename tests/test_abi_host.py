@@ -171,18 +171,25 @@ def test_create_reports_unsupported_not_silently_wrong():
     assert rc == api.ERR_UNSUPPORTED
     rc, msg = _create_rc(w=1281, h=8, numfftpoints=1280, numdisplaypoints=512, binx=2, biny=2)  # cv::resize would round the size
     assert rc == api.ERR_INVALID
-    # BscanFFTspinjnt re-bins the linear B-scan at the output whenever any binning factor exceeds 1 (BscanFFTspinjnt.cpp:1856-1862):
-    # not built, so the shipped-shape ini (binvaluex = 2) must be refused for that variant rather than silently reconstructed without it
+    # BscanFFTspinjnt re-bins the linear B-scan at the output whenever any binning factor exceeds 1 (BscanFFTspinjnt.cpp:1856-1862).
+    # The shipped shape (binvaluex = 2, everything else 1) reduces to bscan *= multiplyfactor and is built; a real resampling step
+    # (bscanbinx / bscanbiny / binvaluey > 1) is refused rather than silently reconstructed without it
     p = api.params_from_ini(os.path.join(GOLDEN, "spinjnt.ini"), api.INI_SPINJNT)
-    assert (p.output_rebin, p.bscanbinx, p.bscanbiny, p.binx) == (1, 1, 1, 2)
+    assert (p.output_rebin, p.bscanbinx, p.bscanbiny, p.binx, p.biny) == (1, 1, 1, 2, 1)
     h = C.c_void_p()
-    assert api.lib().abcoct_create(C.byref(p), None, 1, C.byref(h)) == api.ERR_UNSUPPORTED
-    assert "1856" in api.lib().abcoct_last_error(None).decode()
-    p.binx = 1
-    p.w = 1280
+    rc = api.lib().abcoct_create(C.byref(p), None, 1, C.byref(h))
+    assert rc in (api.OK, api.ERR_CUDA)  # ERR_CUDA: no GPU on the CPU test box - validation passed
+    if rc == api.OK:
+        api.lib().abcoct_destroy(h)
     p.bscanbinx = 2
     assert api.lib().abcoct_create(C.byref(p), None, 1, C.byref(h)) == api.ERR_UNSUPPORTED
-    p.bscanbinx = 1  # no binning anywhere: the re-binning block is skipped by the reference too, nothing left to refuse
+    assert "1856" in api.lib().abcoct_last_error(None).decode()
+    p.bscanbinx = 1
+    p.biny = 2
+    p.h = 2 * (p.h // 2)
+    assert api.lib().abcoct_create(C.byref(p), None, 1, C.byref(h)) == api.ERR_UNSUPPORTED
+    p.biny = 1
+    p.binx = 1  # no binning anywhere: the re-binning block is skipped by the reference too
     rc = api.lib().abcoct_create(C.byref(p), None, 1, C.byref(h))
     assert rc in (api.OK, api.ERR_CUDA)  # ERR_CUDA: no GPU on the CPU test box - validation passed
     if rc == api.OK:

@@ -218,3 +218,25 @@ def test_golden_consumers_regression():
     assert np.abs(jsub.astype(int) - z["jsub"].astype(int)).max() <= 1 and (jsub != z["jsub"]).mean() < 1e-3
     assert np.array_equal(colormap_jet(z["out8"]), z["bgr"]) and np.array_equal(colormap_jet(z["jsub"]), z["jbgr"])
     assert z["jsub"].min() == 0 and z["jsub"].max() == 255
+
+
+def test_spinjnt_output_rebinning_shapes():
+    """BscanFFTspinjnt.cpp:1856-1862.  Shipped shape (binvaluex = 2, the other three factors 1): both cv::resize calls are copies,
+    the block is `bscan *= multiplyfactor`, a constant dB offset.  With a real resampling step the bicubic overshoot next to bright
+    A-scans is negative and the reference's own log() gives NaN - why abcoct_create refuses those shapes (ABCOCT_ERR_UNSUPPORTED)."""
+    import dataclasses
+
+    from fdoct_b200 import synth
+    from oracle.abcoct_oracle import Oracle, Params
+
+    w, h = 512, 12
+    base = Params(w=w, h=h, binx=2, biny=1, numfftpoints=256, numdisplaypoints=128, lambdamin=840.5e-9, lambdamax=859.5e-9)
+    frames = synth.make_frames(2, w, h, seed=5)
+    outs = {}
+    for name, kw in (("plain", {}), ("shipped", dict(output_rebin=True)), ("resampled", dict(output_rebin=True, bscanbinx=2))):
+        o = Oracle(dataclasses.replace(base, **kw))
+        o.set_background(o.calib_mean_of_frames(synth.make_background_frames(2, w, h, seed=6)))
+        with np.errstate(invalid="ignore"):
+            outs[name] = o.process_bscans(frames)[1]
+    assert np.allclose(outs["shipped"] - outs["plain"], 20.0 / 2.303 * np.log(2.0), atol=1e-9)
+    assert outs["resampled"].shape == outs["plain"].shape and np.isnan(outs["resampled"]).any()

@@ -1,5 +1,6 @@
 """GPU parity tests proper: the CUDA path, called through the C ABI, against the oracle and the committed
 golden fixtures.  Everything here needs a B200 (`-m gpu`)."""
+import dataclasses
 import os
 
 import numpy as np
@@ -151,6 +152,33 @@ def test_against_oracle(w, h, N, D, A, nB, variant, extra):
     ref8, refdb = o.process_bscans(frames)
     out8, outdb = _run_abi(op, frames, yb, yp=yp, yd=yd)
     _check(out8, outdb, ref8, refdb, f"w{w} N{N} A{A}")
+
+
+@pytest.mark.parametrize("clamp", [False, True])
+def test_spinjnt_multiplyfactor_shipped_shape(clamp):
+    """BscanFFTspinjnt.cpp:1856-1862 in the shape its shipped ini gives (binvaluex = 2, bscanbinx = bscanbiny = binvaluey = 1): both
+    resizes are copies and the linear B-scan is multiplied by multiplyfactor = 2 before the log; clamp value 30 dB (:1886)."""
+    from fdoct_b200 import api, synth
+    from oracle.abcoct_oracle import Oracle
+
+    w, h, N, D = 2560, 9, 1280, 640
+    op = oracle_params(w=w, h=h, binx=2, biny=1, numfftpoints=N, numdisplaypoints=D, lambdamin=840.5e-9, lambdamax=859.5e-9,
+                       output_rebin=True, clampupper=clamp, clamp_db=30.0, bscanthreshold=12.0 if clamp else -30.0)
+    frames = synth.make_frames(3, w, h, seed=321)
+    o = Oracle(op)
+    yb = o.calib_mean_of_frames(synth.make_background_frames(2, w, h, seed=322))
+    o.set_background(yb)
+    ref8, refdb, reflin = o.process_bscans(frames, want_linear=True)
+    plain = Oracle(dataclasses.replace(op, output_rebin=False))
+    plain.set_background(yb)
+    _, plaindb = plain.process_bscans(frames)
+    assert np.allclose(refdb - plaindb, 20.0 / 2.303 * np.log(2.0), atol=1e-9)  # what the block does to the dB image
+    with api.Context(abi_params(op)) as ctx:
+        ctx.set_background(yb)
+        r = ctx.process_bscans_ex(frames, want=("bscan_u8", "bscan_db", "bscan_lin"))
+    _check(r["bscan_u8"], r["bscan_db"], ref8, refdb, "spinjnt multiplyfactor")
+    err = mag_err(r["bscan_lin"].astype(np.float64)[:, 2:] - 2e-5, reflin[:, 2:] - 2e-5)
+    assert err <= MAG_RTOL, err
 
 
 GENERIC = [

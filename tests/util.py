@@ -49,7 +49,8 @@ def abi_params(op):
         movavgn=op.movavgn, fft_multiplier=op.fft_multiplier, rowwisenormalize=int(op.rowwisenormalize),
         donotnormalize=int(op.donotnormalize), variant=op.variant, weight_mode=op.weight_mode,
         bscanthreshold=op.bscanthreshold, clampupper=int(op.clampupper), clamp_db=op.clamp_db,
-        bandpassfilter=int(op.bandpassfilter), lowpassfilter=int(op.lowpassfilter), channelnum=int(op.channelnum))
+        bandpassfilter=int(op.bandpassfilter), lowpassfilter=int(op.lowpassfilter), channelnum=int(op.channelnum),
+        output_rebin=int(op.output_rebin), bscanbinx=op.bscanbinx, bscanbiny=op.bscanbiny)
 
 
 def db_to_mag(db):
