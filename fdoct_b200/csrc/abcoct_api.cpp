@@ -59,6 +59,11 @@ struct GpuState {
   void* d_bin[kSlots] = {};
   float* d_rows[kSlots] = {};
   float* d_fmm[kSlots] = {};
+  // normalised-calibration regime (single_row_regime): calibration, window and lerp weights as doubles, f64 rows per slot
+  double *d_yb64 = nullptr, *d_yp64 = nullptr, *d_yd64 = nullptr, *d_win64 = nullptr, *d_gwq64 = nullptr;
+  double* d_rows64[kSlots] = {};
+  float* d_pre32[kSlots] = {};
+  long long* d_fmm64[kSlots] = {};
   int* d_gidx = nullptr;  // generic kernel: gather indices, weights, exp(+2 pi i k / N)
   float* d_gwq = nullptr;
   float2* d_twN = nullptr;
@@ -107,6 +112,7 @@ struct abcoct_ctx {
   const std::vector<unsigned char>* blob_loaded = nullptr;  // which blob d_tables holds
   std::vector<int> gidx;      // the kernel's remapped gather indices / weights (debug tap)
   std::vector<float> gwq;
+  bool single = false;        // single_row_regime(p): f64 row preparation + f64 lerp, one row per transform
   int px_bytes = 2;      // bytes per pixel of the CALLER's frames: 1, 2, or 3 (interleaved BGR, channelnum >= 3)
   bool bgr = false;      // BscanFFTwebcam.cpp:1021-1037: sum of the three channels * 0.00130718954
   float px_scale = 1.f;  // factor between the integer pixel (sum) and data_y
@@ -182,8 +188,14 @@ void build_window(int opw, std::vector<double>& win) {
 // Configurations the fused kernels are not compiled for - a transform length without a plan, rows that are not a multiple of
 // 8 samples, display rows above N / 2 - run on the generic kernel (prep_kernels.cu: generic_recon_kernel); cv::dft and colRange
 // take all of them (BscanFFT.cpp:1185, 1193).
+// Also there: the normalised-calibration regime (rowwisenormalize / !donotnormalize, BscanFFT.cpp:1126-1129, 1044-1047).  The
+// captured data_yb is stretched to [1e-4, 1], 1 / data_yb spans four decades and neighbouring rows differ by orders of magnitude;
+// the fused kernels pack two rows into one complex transform, whose f32 rounding noise then follows the LARGER row (measured
+// 1.9e-4 of the smaller one against the reference's 0.7e-4).  The generic kernel transforms one row at a time there, so every
+// A-scan keeps its own noise floor like cv::dft's rows do and the 1e-4 bound holds.
+bool single_row_regime(const abcoct_params& p) { return p.rowwisenormalize || !p.donotnormalize; }
 bool needs_generic(const abcoct_params& p) {
-  return !find_plan((int)p.numfftpoints) || (p.w / p.binx) % 8 != 0 || p.numdisplaypoints > p.numfftpoints / 2;
+  return !find_plan((int)p.numfftpoints) || (p.w / p.binx) % 8 != 0 || p.numdisplaypoints > p.numfftpoints / 2 || single_row_regime(p);
 }
 
 int validate(const abcoct_params& p, std::string& why, int& code) {
@@ -333,6 +345,15 @@ int upload_calibration(abcoct_ctx* c) {
       CU(c, cudaMemcpy(g.d_yb, fb.data(), n * 4, cudaMemcpyHostToDevice));
       CU(c, cudaMemcpy(g.d_yp, fp.data(), n * 4, cudaMemcpyHostToDevice));
       CU(c, cudaMemcpy(g.d_yd, fd.data(), n * 4, cudaMemcpyHostToDevice));
+      if (c->single) {  // the f64 row preparation reads the calibration frames as they are
+        std::vector<double> zero(n, 0.0);
+        if (!g.d_yb64) CU(c, cudaMalloc(&g.d_yb64, n * 8));
+        if (!g.d_yp64) CU(c, cudaMalloc(&g.d_yp64, n * 8));
+        if (!g.d_yd64) CU(c, cudaMalloc(&g.d_yd64, n * 8));
+        CU(c, cudaMemcpy(g.d_yb64, c->yb.data(), n * 8, cudaMemcpyHostToDevice));
+        CU(c, cudaMemcpy(g.d_yp64, c->have_yp ? c->yp.data() : zero.data(), n * 8, cudaMemcpyHostToDevice));
+        CU(c, cudaMemcpy(g.d_yd64, dark ? c->yd.data() : zero.data(), n * 8, cudaMemcpyHostToDevice));
+      }
     }
   }
   if (c->generic) {  // generic_recon_kernel reads the prepared rows only: no swizzled calibration, no table blob, no plan attributes
@@ -462,6 +483,12 @@ int ensure_prep(abcoct_ctx* c, GpuState& g, int slot, size_t nframes) {
   cudaFree(g.d_bin[slot]);
   cudaFree(g.d_rows[slot]);
   cudaFree(g.d_fmm[slot]);
+  cudaFree(g.d_rows64[slot]);
+  cudaFree(g.d_pre32[slot]);
+  cudaFree(g.d_fmm64[slot]);
+  g.d_rows64[slot] = nullptr;
+  g.d_pre32[slot] = nullptr;
+  g.d_fmm64[slot] = nullptr;
   g.d_med[slot] = g.d_bin[slot] = nullptr;
   g.d_rows[slot] = g.d_fmm[slot] = nullptr;
   g.prep_frames[slot] = 0;
@@ -472,6 +499,13 @@ int ensure_prep(abcoct_ctx* c, GpuState& g, int slot, size_t nframes) {
   if (c->p.binx > 1 || c->p.biny > 1) CU(c, cudaMalloc(&g.d_bin[slot], nframes * c->oph * c->opw * c->px_bytes));
   CU(c, cudaMalloc(&g.d_rows[slot], nframes * c->oph * (size_t)c->M * sizeof(float)));
   CU(c, cudaMalloc(&g.d_fmm[slot], nframes * 2 * sizeof(float)));
+  if (c->single) {
+    if (c->p.fft_multiplier > 1)
+      CU(c, cudaMalloc(&g.d_pre32[slot], nframes * c->oph * (size_t)c->opw * sizeof(float)));
+    else
+      CU(c, cudaMalloc(&g.d_rows64[slot], nframes * c->oph * (size_t)c->opw * sizeof(double)));
+    CU(c, cudaMalloc(&g.d_fmm64[slot], nframes * 2 * sizeof(long long)));
+  }
   g.prep_frames[slot] = nframes;
   return ABCOCT_OK;
 }
@@ -507,7 +541,35 @@ int run_prep(abcoct_ctx* c, GpuState& g, int slot, const uint8_t* d_frames, size
     fs = (size_t)c->opw * c->oph;
     ++n;
   }
+  int n64 = 0;
+  if (c->single) {  // normalised-calibration regime: every stage up to the apodised row in f64 (rowprep64_kernel)
+    PrepArgs64Host q{};
+    q.binned = src;
+    q.row_stride = rs;
+    q.frame_stride = fs;
+    q.bpp = bpp;
+    q.opw = c->opw;
+    q.oph = c->oph;
+    q.nframes = (int)nframes;
+    q.movavgn = c->p.movavgn;
+    q.px_scale = c->bgr ? 0.00130718954 : 1.0;
+    q.yd = (c->p.variant == 1 && c->have_yd) ? g.d_yd64 : nullptr;
+    q.yb = g.d_yb64;
+    q.yp = c->have_yp ? g.d_yp64 : nullptr;
+    q.win = g.d_win64;
+    q.rowwise = c->p.rowwisenormalize;
+    q.global_norm = c->p.donotnormalize ? 0 : 1;
+    q.frame_minmax = g.d_fmm64[slot];
+    q.out64 = g.d_rows64[slot];
+    q.out32 = g.d_pre32[slot];
+    CU(c, launch_rowprep64(q, st, &n64));
+    if (c->p.fft_multiplier <= 1) {
+      *launches = n + n64;
+      return ABCOCT_OK;
+    }
+  }
   PrepArgsHost h{};
+  h.pre = c->single ? g.d_pre32[slot] : nullptr;
   h.binned = src;  // without binning the row kernel reads the caller's (or the median's) frames through their strides
   h.row_stride = rs;
   h.frame_stride = fs;
@@ -536,7 +598,7 @@ int run_prep(abcoct_ctx* c, GpuState& g, int slot, const uint8_t* d_frames, size
   h.out = g.d_rows[slot];
   int nl = 0;
   CU(c, launch_rowprep(h, st, &nl));
-  *launches = n + nl;
+  *launches = n + nl + n64;
   return ABCOCT_OK;
 }
 
@@ -595,7 +657,7 @@ int enqueue_device(abcoct_ctx* c, GpuState& g, int slot, const uint8_t* d_frames
   float* d_outlin = static_cast<float*>(o.p[O_LIN]);
   size_t chunkB = std::min(nB, scratch_chunk_bscans(c));
   if (c->general) {  // the pre-processed f32 rows of a chunk stay below ~1 GiB
-    const size_t per_bscan = (size_t)c->A * c->oph * c->M * sizeof(float);
+    const size_t per_bscan = (size_t)c->A * c->oph * c->M * (c->single ? sizeof(double) : sizeof(float));
     chunkB = std::min(chunkB, std::max<size_t>(1, ((size_t)1 << 30) / per_bscan));
   }
   if (c->generic) chunkB = std::min<size_t>(chunkB, 65535);  // one grid row / plane per B-scan
@@ -631,6 +693,8 @@ int enqueue_device(abcoct_ctx* c, GpuState& g, int slot, const uint8_t* d_frames
     if (c->generic) {  // any transform length / row width / D up to N: two launches on the prepared rows
       GenericHost gh{};
       gh.rows = g.d_rows[slot];
+      gh.rows64 = (c->single && c->p.fft_multiplier <= 1) ? g.d_rows64[slot] : nullptr;
+      gh.wq64 = g.d_gwq64;
       gh.M = c->M; gh.N = c->N; gh.D = c->D; gh.Dp = a.Dp; gh.oph = c->oph; gh.A = c->A; gh.nB = (int)nb;
       gh.idx = g.d_gidx;
       gh.wq = g.d_gwq;
@@ -648,6 +712,7 @@ int enqueue_device(abcoct_ctx* c, GpuState& g, int slot, const uint8_t* d_frames
       gh.thr = (float)c->p.bscanthreshold - c->db_shift;
       gh.clamp_db = (float)c->p.clamp_db - c->db_shift;
       gh.clamp55 = c->p.clampupper ? 1 : 0;
+      gh.single_row = single_row_regime(c->p) ? 1 : 0;
       a.out8 = gh.out8;
       a.outdb = gh.outdb;
       a.dc01 = gh.dc01;
@@ -969,6 +1034,8 @@ int abcoct_create(const abcoct_params* params, const int* gpu_ids, int ngpu, abc
   // gather tables for the kernel: end points q = 0, N-1 are never written in the reference (BscanFFT.cpp:1164)
   std::vector<int> idx(c->N);
   std::vector<float> wq(c->N), winf(c->opw);
+  std::vector<double> wq64(c->N);
+  c->single = single_row_regime(*params);
   for (int q = 0; q < c->N; ++q) {
     int i = c->nk[q];
     double w = params->weight_mode == 0 ? c->frac[c->nk[q]] : c->frac[q];  // :1170 quirk vs corrected
@@ -981,6 +1048,7 @@ int abcoct_create(const abcoct_params* params, const int* gpu_ids, int ngpu, abc
     }
     idx[q] = i;
     wq[q] = (float)w;
+    wq64[q] = w;
   }
   for (int i = 0; i < c->opw; ++i) winf[i] = (float)c->win[i];
   c->gidx = idx;
@@ -1055,6 +1123,11 @@ int abcoct_create(const abcoct_params* params, const int* gpu_ids, int ngpu, abc
         ok = ok && cudaMemcpy(g.d_twW, twW.data(), twW.size() * 8, cudaMemcpyHostToDevice) == cudaSuccess;
         ok = ok && cudaMemcpy(g.d_twM, twM.data(), twM.size() * 8, cudaMemcpyHostToDevice) == cudaSuccess;
       }
+      if (c->single) {
+        ok = ok && cudaMalloc(&g.d_gwq64, wq64.size() * 8) == cudaSuccess && cudaMalloc(&g.d_win64, c->win.size() * 8) == cudaSuccess;
+        ok = ok && cudaMemcpy(g.d_gwq64, wq64.data(), wq64.size() * 8, cudaMemcpyHostToDevice) == cudaSuccess;
+        ok = ok && cudaMemcpy(g.d_win64, c->win.data(), c->win.size() * 8, cudaMemcpyHostToDevice) == cudaSuccess;
+      }
       if (c->generic) {
         ok = ok && cudaMalloc(&g.d_gidx, idx.size() * 4) == cudaSuccess && cudaMalloc(&g.d_gwq, wq.size() * 4) == cudaSuccess &&
              cudaMalloc(&g.d_twN, twN.size() * 8) == cudaSuccess;
@@ -1106,6 +1179,16 @@ void abcoct_destroy(abcoct_ctx* c) {
     cudaFree(g.d_win);
     cudaFree(g.d_twW);
     cudaFree(g.d_twM);
+    cudaFree(g.d_yb64);
+    cudaFree(g.d_yp64);
+    cudaFree(g.d_yd64);
+    cudaFree(g.d_win64);
+    cudaFree(g.d_gwq64);
+    for (int s2 = 0; s2 < kSlots; ++s2) {
+      cudaFree(g.d_rows64[s2]);
+      cudaFree(g.d_pre32[s2]);
+      cudaFree(g.d_fmm64[s2]);
+    }
     cudaFree(g.d_gidx);
     cudaFree(g.d_gwq);
     cudaFree(g.d_twN);
@@ -1564,7 +1647,10 @@ int abcoct_debug_linearised(abcoct_ctx* c, const void* frame, size_t stride_byte
   int nl = 0;
   rc = run_prep(c, g, 0, d_frame, 1, dense, dense * c->p.h, st, &nl);
   if (rc == ABCOCT_OK) {
-    e = launch_lerp_rows(g.d_rows[0], d_idx, d_wq, d_ylin, c->M, c->N, c->oph, st);
+    if (c->single)
+      e = launch_lerp_rows64(g.d_rows[0], c->p.fft_multiplier <= 1 ? g.d_rows64[0] : nullptr, d_idx, g.d_gwq64, d_ylin, c->M, c->N, c->oph, st);
+    else
+      e = launch_lerp_rows(g.d_rows[0], d_idx, d_wq, d_ylin, c->M, c->N, c->oph, st);
     if (e == cudaSuccess) e = cudaMemcpyAsync(ylin, d_ylin, (size_t)c->oph * c->N * sizeof(float), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) rc = fail(c, ABCOCT_ERR_CUDA, "debug tap: %s", cudaGetErrorString(e));

@@ -60,7 +60,21 @@ struct PrepArgsHost {
   int radW[12], radM[12];
   const float2 *twW, *twM;  // exp(-2 pi i k / opw), exp(+2 pi i k / M); needed when m > 1
   float* out;               // [nframes][oph][M]
+  const float* pre;         // nullable: rows already apodised in f64 (launch_rowprep64); only the Fourier upsample runs
 };
+// the same stages in f64, one row at a time (normalised-calibration regime, see prep_kernels.cu)
+struct PrepArgs64Host {
+  const void* binned;
+  size_t row_stride, frame_stride;
+  int bpp, opw, oph, nframes, movavgn;
+  double px_scale;
+  const double *yd, *yb, *yp, *win;
+  int rowwise, global_norm;
+  long long* frame_minmax;  // [nframes][2]
+  double* out64;            // [nframes][oph][opw], or NULL and
+  float* out32;             // the apodised rows as floats for the Fourier upsample
+};
+cudaError_t launch_rowprep64(const PrepArgs64Host& h, cudaStream_t st, int* launched);
 cudaError_t launch_median(const void* in, void* out, int bpp, int k, int w, int h, size_t row_stride_elems, size_t frame_stride_elems,
                           int nframes, cudaStream_t st);
 // BscanFFTwebcam.cpp:1021-1037: interleaved 8-bit BGR frames (strides in bytes) -> dense 16-bit frames of channel sums
@@ -73,12 +87,16 @@ cudaError_t launch_cal_accum(const void* px, int bpp, size_t row_stride_elems, s
                              int movavgn, double px_scale, double* acc, cudaStream_t st);
 cudaError_t launch_rowprep(const PrepArgsHost& h, cudaStream_t st, int* launched);
 size_t rowprep_smem_bytes(int opw, int M, int m, int movavgn);
+cudaError_t launch_lerp_rows64(const float* rows, const double* rows64, const int* idx, const double* wq, float* ylin, int M, int N, int oph,
+                               cudaStream_t st);
 cudaError_t launch_lerp_rows(const float* rows, const int* idx, const float* wq, float* ylin, int M, int N, int oph, cudaStream_t st);
 
 // ---- any transform length N = 2^a 3^b 5^c, any row width, D up to N (prep_kernels.cu): gather-lerp + Stockham DFT + magnitude +
 // accumulate + dB into the scratch, then normalise + transpose; runs on the rows prepared by launch_rowprep
 struct GenericHost {
   const float* rows;
+  const double* rows64;  // single_row without Fourier upsample: the prepared rows as doubles
+  const double* wq64;    // single_row: lerp weights in f64
   int M, N, D, Dp, oph, A, nB;
   const int* idx;
   const float* wq;
@@ -91,6 +109,7 @@ struct GenericHost {
   float* outdb;
   float out_scale, db_scale_ln, thr, clamp_db;
   int clamp55;
+  int single_row;  // one A-scan per transform instead of two packed ones (normalised-calibration regime)
 };
 size_t generic_smem_bytes(int N, int D);
 cudaError_t launch_generic(const GenericHost& h, cudaStream_t st, int* launched);

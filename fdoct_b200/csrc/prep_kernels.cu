@@ -164,6 +164,7 @@ struct PrepArgs {
   const float2* twW;    // exp(-2 pi i k / opw)
   const float2* twM;    // exp(+2 pi i k / M)
   float* out;           // [nframes][oph][M]
+  const float* pre;     // nullable: rows already apodised by rowprep64_kernel ([nframes][oph][opw]); only the Fourier upsample is left
 };
 
 __device__ __forceinline__ float block_reduce(float v, float* red, int op /*0 sum, 1 min, 2 max*/) {
@@ -357,7 +358,15 @@ __global__ void __launch_bounds__(256) rowprep_kernel(const PrepArgs a) {
   const unsigned char* s1 = static_cast<const unsigned char*>(a.binned) + ((size_t)f * a.frame_stride + (size_t)r1 * a.row_stride) * px;
   const bool fast = a.movavgn == 0 && !a.rowwise && !a.global_norm && (W & 7) == 0 &&
                     ((reinterpret_cast<uintptr_t>(s0) | reinterpret_cast<uintptr_t>(s1)) & (8 * px - 1)) == 0;
-  if (fast) {  // uniform over the CTA
+  if (a.pre) {
+    const float* p0 = a.pre + ((size_t)f * a.oph + r0) * W;
+    const float* p1 = a.pre + ((size_t)f * a.oph + r1) * W;
+    for (int j = threadIdx.x; j < W; j += blockDim.x) {
+      x0[j] = p0[j];
+      x1[j] = p1[j];
+    }
+    __syncthreads();
+  } else if (fast) {  // uniform over the CTA
     float sum0, sum1;
     if (a.bpp == 8)
       rowpair_fast<uint8_t>(a, s0, s1, r0, r1, x0, x1, sum0, sum1);
@@ -416,6 +425,139 @@ __global__ void __launch_bounds__(256) rowprep_kernel(const PrepArgs a) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------ row preparation in f64
+// The normalised-calibration regime (rowwisenormalize / !donotnormalize): data_yb is stretched to [1e-4, 1], 1 / data_yb spans four
+// decades, and the mean removal cancels several digits.  The reference does all of this in CV_64F and rounds to f32 once, at
+// Mat_<float>(data_ylin) (BscanFFT.cpp:1181); an f32 pipeline adds three to four roundings in front of the transform and ends up at
+// 1.9e-4 of the floor against the reference's 0.7e-4.  Here the same stages run in double, one CTA per row, same order as
+// rowprep_one; the rows go out as doubles (m == 1; generic_recon_kernel interpolates them in f64) or, in front of the Fourier
+// upsample, as floats exactly where zeropadrowwise converts (BscanFFT.cpp:209).
+struct PrepArgs64 {
+  const void* binned;
+  size_t row_stride, frame_stride;
+  int bpp, opw, oph, nframes, movavgn;
+  double px_scale;
+  const double *yd, *yb, *yp, *win;  // yd / yp nullable
+  int rowwise, global_norm;          // global_norm: 0 off, 1 reduce pass, 2 apply pass
+  long long* frame_minmax;           // [nframes][2] order-preserving integers of the doubles
+  double* out64;                     // m == 1: [nframes][oph][opw]
+  float* out32;                      // m > 1
+};
+__device__ __forceinline__ long long d2ord(double d) {
+  const long long i = __double_as_longlong(d);
+  return i >= 0 ? i : i ^ 0x7fffffffffffffffLL;
+}
+__device__ __forceinline__ double ord2d(long long i) { return __longlong_as_double(i >= 0 ? i : i ^ 0x7fffffffffffffffLL); }
+__device__ __forceinline__ double block_reduce64(double v, double* red, int op /*0 sum, 1 min, 2 max*/) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double u = __shfl_xor_sync(0xffffffffu, v, o);
+    v = op == 0 ? v + u : (op == 1 ? fmin(v, u) : fmax(v, u));
+  }
+  __syncthreads();
+  if (lane == 0) red[w] = v;
+  __syncthreads();
+  double r = red[0];
+  for (int i = 1; i < nw; ++i) r = op == 0 ? r + red[i] : (op == 1 ? fmin(r, red[i]) : fmax(r, red[i]));
+  return r;
+}
+__global__ void minmax64_reset_kernel(long long* mm, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    mm[2 * i] = d2ord(__longlong_as_double(0x7ff0000000000000LL));
+    mm[2 * i + 1] = d2ord(__longlong_as_double((long long)0xfff0000000000000ULL));
+  }
+}
+__global__ void __launch_bounds__(256) rowprep64_kernel(const PrepArgs64 a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ double red[8];
+  double* x = reinterpret_cast<double*>(smem_raw);
+  const int W = a.opw, row = blockIdx.x, f = blockIdx.y;
+  const size_t pix = (size_t)f * a.frame_stride + (size_t)row * a.row_stride;
+  if (a.bpp == 8) {  // convertTo(data_y, CV_64F), BscanFFT.cpp:987 (x 1 / 765 for the webcam channel sum)
+    const uint8_t* src = static_cast<const uint8_t*>(a.binned) + pix;
+    for (int j = threadIdx.x; j < W; j += blockDim.x) x[j] = (double)src[j] * a.px_scale;
+  } else {
+    const uint16_t* src = static_cast<const uint16_t*>(a.binned) + pix;
+    for (int j = threadIdx.x; j < W; j += blockDim.x) x[j] = (double)src[j] * a.px_scale;
+  }
+  __syncthreads();
+  if (a.movavgn > 0) {  // smoothmovavg, BscanFFT.cpp:247-304 (same summation order: taps -n .. n, then the centre once more)
+    const int n = a.movavgn;
+    double* y = x + W;
+    for (int j = threadIdx.x; j < W; j += blockDim.x) {
+      const double c = x[j];
+      double s = 0.0;
+      for (int k = -n; k <= n; ++k) {
+        const int jj = j + k;
+        s = s + ((jj > -1 && jj < W) ? x[jj] : c);
+      }
+      s = s + c;
+      y[j] = s / 2 / (n + 1);
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < W; j += blockDim.x) x[j] = y[j];
+    __syncthreads();
+  }
+  if (a.yd) {  // BscanDark.cpp:1269
+    const double* yd = a.yd + (size_t)row * W;
+    for (int j = threadIdx.x; j < W; j += blockDim.x) x[j] -= yd[j];
+    __syncthreads();
+  }
+  if (a.rowwise) {  // normalizerows(data_y, 0, 1): cv::normalize NORM_MINMAX = convertTo(scale, shift)
+    double mn = 1.7e308, mx = -1.7e308;
+    for (int j = threadIdx.x; j < W; j += blockDim.x) {
+      mn = fmin(mn, x[j]);
+      mx = fmax(mx, x[j]);
+    }
+    mn = block_reduce64(mn, red, 1);
+    mx = block_reduce64(mx, red, 2);
+    const double s = (mx - mn) > 2.220446049250313e-16 ? 1.0 / (mx - mn) : 0.0;
+    const double sh = 0.0 - mn * s;
+    for (int j = threadIdx.x; j < W; j += blockDim.x) x[j] = __dadd_rn(__dmul_rn(x[j], s), sh);
+    __syncthreads();
+  }
+  if (a.global_norm) {  // normalize(data_y, data_y, 0, 1, NORM_MINMAX) over the frame, BscanFFT.cpp:1128-1129
+    if (a.global_norm == 1) {
+      double mn = 1.7e308, mx = -1.7e308;
+      for (int j = threadIdx.x; j < W; j += blockDim.x) {
+        mn = fmin(mn, x[j]);
+        mx = fmax(mx, x[j]);
+      }
+      mn = block_reduce64(mn, red, 1);
+      mx = block_reduce64(mx, red, 2);
+      if (threadIdx.x == 0) {
+        atomicMin(a.frame_minmax + 2 * f, d2ord(mn));
+        atomicMax(a.frame_minmax + 2 * f + 1, d2ord(mx));
+      }
+      return;
+    }
+    const double mn = ord2d(a.frame_minmax[2 * f]), mx = ord2d(a.frame_minmax[2 * f + 1]);
+    const double s = (mx - mn) > 2.220446049250313e-16 ? 1.0 / (mx - mn) : 0.0;
+    const double sh = 0.0 - mn * s;
+    for (int j = threadIdx.x; j < W; j += blockDim.x) x[j] = __dadd_rn(__dmul_rn(x[j], s), sh);
+    __syncthreads();
+  }
+  const double* yb = a.yb + (size_t)row * W;
+  const double* yp = a.yp ? a.yp + (size_t)row * W : nullptr;
+  double sum = 0.0;
+  for (int j = threadIdx.x; j < W; j += blockDim.x) {  // (data_y - data_yp) / data_yb, BscanFFT.cpp:1132 (cv::divide: x / 0 = 0)
+    const double b = yb[j];
+    const double t = b != 0.0 ? (x[j] - (yp ? yp[j] : 0.0)) / b : 0.0;
+    x[j] = t;
+    sum += t;
+  }
+  const double mean = block_reduce64(sum, red, 0) / (double)W;  // BscanFFT.cpp:1135-1143
+  for (int j = threadIdx.x; j < W; j += blockDim.x) {
+    const double v = __dmul_rn(x[j] - mean, a.win[j]);
+    if (a.out64)
+      a.out64[((size_t)f * a.oph + row) * W + j] = v;
+    else
+      a.out32[((size_t)f * a.oph + row) * W + j] = (float)v;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ any transform length
 // cv::dft takes any N (BscanFFT.cpp:1185); the fused kernels are compiled for twelve lengths, rows that are multiples of 8 samples
 // and D <= N / 2.  Everything else (N = 2^a 3^b 5^c, any row width, D up to N) runs here, on the rows prepared by rowprep_kernel:
@@ -426,6 +568,8 @@ __global__ void __launch_bounds__(256) rowprep_kernel(const PrepArgs a) {
 // BASELINE configurations.
 struct GenericArgs {
   const float* rows;  // [nB * A][oph][M] prepared rows
+  const double* rows64;  // the same as doubles (single-row regime without Fourier upsample); rows is ignored then
+  const double* wq64;    // [N] lerp weights in f64 (single-row regime: the interpolation runs in f64 like the reference's)
   int M, N, D, Dp, oph, A, nB;
   const int* idx;     // [N] source sample (1 .. M - 1), M = never written (zero)
   const float* wq;    // [N] lerp weights (the reference's quirk already applied)
@@ -436,21 +580,35 @@ struct GenericArgs {
   float* dc01;        // nullable [nB][oph][2]
   float out_scale, db_scale_ln, thr;
   int clamp55;
+  int single;  // one A-scan per transform (imaginary part zero): every row has its own f32 noise floor, like cv::dft's rows
 };
 __global__ void __launch_bounds__(256) generic_recon_kernel(const GenericArgs a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   __shared__ float red[8];
-  const int N = a.N, b = blockIdx.y, r0 = 2 * blockIdx.x;
-  const bool has1 = r0 + 1 < a.oph;
+  const int N = a.N, b = blockIdx.y, r0 = a.single ? blockIdx.x : 2 * blockIdx.x;
+  const bool has1 = !a.single && r0 + 1 < a.oph;
   float2* bufa = reinterpret_cast<float2*>(smem_raw);
   float2* bufb = bufa + fft_buf_slots(N);
   float* acc0 = reinterpret_cast<float*>(bufb + fft_buf_slots(N));
   float* acc1 = acc0 + a.D;
   for (int k = threadIdx.x; k < a.D; k += blockDim.x) acc0[k] = acc1[k] = 0.f;
   for (int f = 0; f < a.A; ++f) {
-    const float* y0 = a.rows + (((size_t)b * a.A + f) * a.oph + r0) * a.M;
+    const size_t rowoff = (((size_t)b * a.A + f) * a.oph + r0) * a.M;
+    const float* y0 = a.rows + rowoff;
     const float* y1 = y0 + (has1 ? a.M : 0);
     __syncthreads();  // the buffers of the previous frame have been consumed
+    if (a.single) {  // data_ylin in f64, rounded to f32 once (Mat_<float>(data_ylin), BscanFFT.cpp:1181)
+      const double* z0 = a.rows64 ? a.rows64 + rowoff : nullptr;
+      for (int q = threadIdx.x; q < N; q += blockDim.x) {
+        const int i = a.idx[q];
+        float2 v = make_float2(0.f, 0.f);
+        if (i < a.M) {
+          const double yi = z0 ? z0[i] : (double)y0[i], ym = z0 ? z0[i - 1] : (double)y0[i - 1];
+          v.x = (float)__dadd_rn(yi, __dmul_rn(a.wq64[q], yi - ym));
+        }
+        bufa[fpad(q)] = v;
+      }
+    } else
     for (int q = threadIdx.x; q < N; q += blockDim.x) {
       const int i = a.idx[q];
       float2 v = make_float2(0.f, 0.f);
@@ -540,7 +698,7 @@ cudaError_t launch_generic(const GenericHost& h, cudaStream_t st, int* launched)
   GenericArgs a{};
   a.rows = h.rows; a.M = h.M; a.N = h.N; a.D = h.D; a.Dp = h.Dp; a.oph = h.oph; a.A = h.A; a.nB = h.nB; a.idx = h.idx; a.wq = h.wq;
   a.tw = h.tw; a.scratch = h.scratch; a.minv = h.minv; a.maxv = h.maxv; a.dc01 = h.dc01; a.out_scale = h.out_scale;
-  a.db_scale_ln = h.db_scale_ln; a.thr = h.thr; a.clamp55 = h.clamp55;
+  a.db_scale_ln = h.db_scale_ln; a.thr = h.thr; a.clamp55 = h.clamp55; a.single = h.single_row; a.rows64 = h.rows64; a.wq64 = h.wq64;
   a.rl.n = h.N; a.rl.count = h.nrad;
   int nc = h.N, stp = 1;
   for (int i = 0; i < h.nrad && i < 12; ++i) {
@@ -554,7 +712,7 @@ cudaError_t launch_generic(const GenericHost& h, cudaStream_t st, int* launched)
   cudaError_t e = cudaFuncSetAttribute(generic_recon_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
   generic_minmax_reset_kernel<<<(h.nB + 127) / 128, 128, 0, st>>>(h.minv, h.maxv, h.nB);
-  generic_recon_kernel<<<dim3((h.oph + 1) / 2, h.nB), 256, smem, st>>>(a);
+  generic_recon_kernel<<<dim3(h.single_row ? h.oph : (h.oph + 1) / 2, h.nB), 256, smem, st>>>(a);
   generic_norm_kernel<<<dim3((h.D + 31) / 32, (h.oph + 31) / 32, h.nB), dim3(32, 8), 0, st>>>(h.scratch, h.minv, h.maxv, h.out8, h.outdb, h.oph,
                                                                                                 h.D, h.Dp, h.thr, h.clamp55, h.clamp_db);
   if (launched) *launched = 3;
@@ -571,6 +729,25 @@ __global__ void lerp_rows_kernel(const float* __restrict__ rows, const int* __re
   const float* y = rows + (size_t)r * M;
   const int i = idx[q];
   ylin[(size_t)r * N + q] = i >= M ? 0.f : fmaf(wq[q], y[i] - y[i - 1], y[i]);
+}
+// the same in f64 (normalised-calibration regime): rows as doubles (rows64) or floats, weights as doubles, one rounding at the end
+__global__ void lerp_rows64_kernel(const float* __restrict__ rows, const double* __restrict__ rows64, const int* __restrict__ idx,
+                                   const double* __restrict__ wq, float* __restrict__ ylin, int M, int N, int oph) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
+  if (q >= N || r >= oph) return;
+  const int i = idx[q];
+  float v = 0.f;
+  if (i < M) {
+    const size_t o = (size_t)r * M + i;
+    const double yi = rows64 ? rows64[o] : (double)rows[o], ym = rows64 ? rows64[o - 1] : (double)rows[o - 1];
+    v = (float)__dadd_rn(yi, __dmul_rn(wq[q], yi - ym));
+  }
+  ylin[(size_t)r * N + q] = v;
+}
+cudaError_t launch_lerp_rows64(const float* rows, const double* rows64, const int* idx, const double* wq, float* ylin, int M, int N, int oph,
+                               cudaStream_t st) {
+  lerp_rows64_kernel<<<dim3((N + 255) / 256, oph), 256, 0, st>>>(rows, rows64, idx, wq, ylin, M, N, oph);
+  return cudaGetLastError();
 }
 cudaError_t launch_lerp_rows(const float* rows, const int* idx, const float* wq, float* ylin, int M, int N, int oph, cudaStream_t st) {
   lerp_rows_kernel<<<dim3((N + 255) / 256, oph), 256, 0, st>>>(rows, idx, wq, ylin, M, N, oph);
@@ -678,7 +855,7 @@ cudaError_t launch_rowprep(const PrepArgsHost& h, cudaStream_t st, int* launched
   PrepArgs a{};
   a.binned = h.binned; a.row_stride = h.row_stride; a.frame_stride = h.frame_stride; a.bpp = h.bpp; a.opw = h.opw; a.oph = h.oph; a.nframes = h.nframes; a.movavgn = h.movavgn; a.px_scale = h.px_scale;
   a.yd = h.yd; a.rowwise = h.rowwise; a.frame_minmax = h.frame_minmax; a.yb = h.yb; a.yp = h.yp; a.win = h.win;
-  a.m = h.m; a.M = h.M; a.bandpass = h.bandpass; a.twW = h.twW; a.twM = h.twM; a.out = h.out;
+  a.m = h.m; a.M = h.M; a.bandpass = h.bandpass; a.twW = h.twW; a.twM = h.twM; a.out = h.out; a.pre = h.pre;
   a.rlW.n = h.opw; a.rlW.count = h.nradW;
   a.rlM.n = h.M; a.rlM.count = h.nradM;
   for (int i = 0; i < 12; ++i) { a.rlW.r[i] = h.radW[i]; a.rlM.r[i] = h.radM[i]; }
@@ -700,7 +877,7 @@ cudaError_t launch_rowprep(const PrepArgsHost& h, cudaStream_t st, int* launched
   }
   dim3 grid((h.oph + 1) / 2, h.nframes);  // one CTA per row pair
   int n = 0;
-  if (h.global_norm) {
+  if (h.global_norm && !h.pre) {
     minmax_reset_kernel<<<(h.nframes + 127) / 128, 128, 0, st>>>(h.frame_minmax, h.nframes);
     a.global_norm = 1;
     rowprep_kernel<<<grid, 256, smem, st>>>(a);
@@ -708,6 +885,29 @@ cudaError_t launch_rowprep(const PrepArgsHost& h, cudaStream_t st, int* launched
     n += 2;
   }
   rowprep_kernel<<<grid, 256, smem, st>>>(a);
+  ++n;
+  if (launched) *launched = n;
+  return cudaGetLastError();
+}
+
+cudaError_t launch_rowprep64(const PrepArgs64Host& h, cudaStream_t st, int* launched) {
+  PrepArgs64 a{};
+  a.binned = h.binned; a.row_stride = h.row_stride; a.frame_stride = h.frame_stride; a.bpp = h.bpp; a.opw = h.opw; a.oph = h.oph;
+  a.nframes = h.nframes; a.movavgn = h.movavgn; a.px_scale = h.px_scale; a.yd = h.yd; a.yb = h.yb; a.yp = h.yp; a.win = h.win;
+  a.rowwise = h.rowwise; a.frame_minmax = h.frame_minmax; a.out64 = h.out64; a.out32 = h.out32;
+  const size_t smem = (size_t)h.opw * sizeof(double) * (h.movavgn > 0 ? 2 : 1);
+  cudaError_t e = cudaFuncSetAttribute(rowprep64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+  if (e != cudaSuccess) return e;
+  const dim3 grid(h.oph, h.nframes);
+  int n = 0;
+  if (h.global_norm) {
+    minmax64_reset_kernel<<<(h.nframes + 127) / 128, 128, 0, st>>>(h.frame_minmax, h.nframes);
+    a.global_norm = 1;
+    rowprep64_kernel<<<grid, 256, smem, st>>>(a);
+    a.global_norm = 2;
+    n += 2;
+  }
+  rowprep64_kernel<<<grid, 256, smem, st>>>(a);
   ++n;
   if (launched) *launched = n;
   return cudaGetLastError();

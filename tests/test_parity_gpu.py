@@ -1001,7 +1001,24 @@ def test_random_configurations_against_oracle(seed):
         assert err <= MAG_RTOL, f"{what}: magnitude error {err:.3g} > {MAG_RTOL}"
         return
     # Normalised captures (keys b / o / r with rowwisenormalize or !donotnormalize) stretch the calibration frames to [1e-4, 1]:
-    # 1 / data_yb spans four decades, a handful of edge samples dominate every row, the spectrum is flat and the bins of interest
-    # sit at the f32 noise floor of BOTH transforms (OpenCV's is 0.7e-4 from an exact evaluation here, the packed two-for-one
-    # transform up to 1.9e-4).  Documented bound for this regime: 3e-4, display image still +-1 LSB (asserted above).
-    assert err <= 3e-4, f"{what}: magnitude error {err:.3g} in the normalised-calibration regime"
+    # 1 / data_yb spans four decades and neighbouring rows differ by orders of magnitude.  Round 1 packed two rows into one
+    # transform there (noise floor of the larger row on the smaller one, 1.9e-4, asserted at 3e-4); since round 2 this regime runs
+    # one row per transform (generic kernel, single_row) and is held to the same 1e-4 with the floor of the row ITSELF.
+    err1 = mag_err(db_to_mag(outdb), db_to_mag(refdb))
+    print(f"{what}: normalised regime, per-row error {err1:.3g} (pairwise floor {err:.3g})")
+    if err1 > MAG_RTOL:
+        # two correct f32 transforms of a flat spectrum, each up to ~0.7e-4 from the truth, can be 1e-4 apart: then the CUDA path must
+        # be no further from an exact f64 evaluation of the block than the reference's own OpenCV f32 DFT is (the rule of
+        # test_accuracy_vs_exact_f64), and still within 1.5e-4 of it
+        A, D, N = op.averages, op.numdisplaypoints, op.numfftpoints
+        oe = Oracle(op)
+        oe.set_background(yb)
+        if variant == 1:
+            oe.set_dark(yd)
+        exact = np.stack([np.mean([np.abs(np.fft.ifft(oe.linearised(f), axis=1) * N)[:, :D].T for f in frames[b * A:(b + 1) * A]], axis=0)
+                          for b in range(frames.shape[0] // A)])
+        exact[:, 0] = exact[:, 4]
+        exact[:, 1] = exact[:, 4]
+        e_ours, e_ref = mag_err(db_to_mag(outdb), exact), mag_err(db_to_mag(refdb), exact)
+        print(f"{what}: from exact: CUDA {e_ours:.3g}, OpenCV f32 {e_ref:.3g}")
+        assert err1 <= 1.5e-4 and e_ours <= max(1.25 * e_ref, 5e-5), (err1, e_ours, e_ref)

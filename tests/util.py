@@ -10,11 +10,14 @@ Tolerances (BASELINE.json north_star):
                                        deviates from the exact result by 5.8e-5 .. 6.7e-5 of max(|x|, 1e-3 * A-scan max) for N = 1024 .. 4096, the
                                        CUDA path by 4.3e-5 .. 5.2e-5, so a 1e-3 floor would test the reference's rounding noise, not parity.
   * 8-bit display image .............. +-1 LSB; exact 0 / 255 present like the reference's min-max normalise
-  * noise scaling .................... the rounding noise of an f32 transform scales with the RMS of its spectrum, and the CUDA path packs two
-                                       A-scans into one complex transform, so its floor follows the larger row of the pair (mag_err_pairwise).
-                                       With normalised calibration captures (rowwisenormalize / !donotnormalize: 1 / data_yb spans four decades,
-                                       flat spectra) both transforms sit at their noise floor; documented bound there 3e-4
-                                       (test_random_configurations_against_oracle), display still +-1 LSB.
+  * noise scaling .................... the rounding noise of an f32 transform scales with the RMS of its spectrum, and the fused kernels pack
+                                       two A-scans into one complex transform, so their floor follows the larger row of the pair
+                                       (mag_err_pairwise).  With normalised calibration captures (rowwisenormalize / !donotnormalize: 1 / data_yb
+                                       spans four decades, neighbouring rows differ by orders of magnitude, the mean removal cancels digits) the
+                                       library therefore runs every stage up to data_ylin in f64 and one row per transform (round 2), and the
+                                       sweep holds that regime to the same 1e-4 with the row's OWN floor (measured 2e-6 .. 8e-5; one case where
+                                       two f32 transforms of a flat spectrum are 1.04e-4 apart is decided by their distances from the exact
+                                       result, like test_accuracy_vs_exact_f64).
 """
 from __future__ import annotations
 
