@@ -571,7 +571,8 @@ def run_ours(args, wl, rank, world, local_rank):
                          "secondary_roofs_ncu": ncu_summary(args.workload),
                          "kernel": ["recon_kernel (fused reconstruction + display normalisation, thread group per row pair, dB scratch in L2)",
                                     "wrow_kernel (fused reconstruction + display normalisation, one warp per A-scan, dB scratch in L2)",
-                                    "wres_kernel (fused reconstruction + display normalisation, one warp per A-scan, dB rows resident in shared memory)"][info.kernel_kind],
+                                    "wres_kernel (fused reconstruction + display normalisation, one warp per A-scan, dB rows resident in tensor memory)",
+                                    "generic_recon_kernel (any N = 2^a 3^b 5^c / row width / D <= N, shared-memory Stockham, run-time radices)"][info.kernel_kind],
                          "bytes_per_ascan": bytes_per_ascan,
                          "ascans_per_launch": ascans_per_launch, "launch_ms": recon_launch_ms, "peak_source": peak_src,
                          "whole_step_frac": bytes_per_ascan * value / world / 1e9 / peak},
