@@ -274,49 +274,6 @@ std::vector<int> factor_radices(int n) {  // greedy, largest first; every entry 
   return r;
 }
 
-// cv::normalize(src, dst, a, b, NORM_MINMAX) over [first, last): dst = src * scale + (a - min * scale)
-void host_normalize(double* first, double* last, double a, double b) {
-  const auto mm = std::minmax_element(first, last);
-  const double mn = *mm.first, mx = *mm.second;
-  const double scale = (b - a) * ((mx - mn) > 2.220446049250313e-16 ? 1.0 / (mx - mn) : 0.0);
-  const double shift = a - mn * scale;
-  for (double* p = first; p != last; ++p) *p = *p * scale + shift;
-}
-// lpfilter, BscanDark.cpp:119-167: f32 row DFT scaled by 1 / cols, keep the centre 20 % of the shifted spectrum, inverse
-// DFT with DFT_REAL_OUTPUT (which reads bins 0 .. cols/2 only): out[n] = Re X[0] + 2 Re sum_{0<k<cols/10} X[k] e^{2 pi i n k / cols}
-void host_lpfilter(std::vector<double>& m, int rows, int cols) {
-  const int keep = cols / 10;  // bins [0, floor(cols / 10))
-  const double tau = 6.283185307179586476925286766559;
-  std::vector<double> cs(cols), sn(cols), re(keep), im(keep), out(cols);
-  for (int k = 0; k < cols; ++k) {
-    cs[k] = std::cos(tau * k / cols);
-    sn[k] = std::sin(tau * k / cols);
-  }
-  for (int r = 0; r < rows; ++r) {
-    double* x = &m[(size_t)r * cols];
-    for (int k = 0; k < keep; ++k) {
-      double a = 0, b = 0;
-      for (int j = 0; j < cols; ++j) {
-        const double v = (double)(float)x[j];  // convertTo(CV_32F)
-        const int t = (int)(((long long)j * k) % cols);
-        a += v * cs[t];
-        b -= v * sn[t];
-      }
-      re[k] = a / cols;
-      im[k] = b / cols;
-    }
-    for (int n = 0; n < cols; ++n) {
-      double s = keep > 0 ? re[0] : 0.0;
-      for (int k = 1; k < keep; ++k) {
-        const int t = (int)(((long long)n * k) % cols);
-        s += 2.0 * (re[k] * cs[t] - im[k] * sn[t]);
-      }
-      out[n] = (double)(float)s;  // the inverse transform is f32
-    }
-    std::copy(out.begin(), out.end(), x);
-  }
-}
-
 int upload_calibration(abcoct_ctx* c) {
   if (!c->have_yb) return fail(c, ABCOCT_ERR_STATE, "no background set: data_yb is all zeros in the reference until key 'b' (BscanFFT.cpp:562)");
   const size_t n = (size_t)c->oph * c->opw;
@@ -1251,6 +1208,7 @@ int abcoct_set_calibration_from_frames(abcoct_ctx* c, int which, const void* fra
   const int pb = c->px_bytes, w = (int)c->p.w, h = (int)c->p.h;
   if (stride_bytes == 0) stride_bytes = (size_t)w * pb;
   if (stride_bytes % pb) return fail(c, ABCOCT_ERR_INVALID, "stride_bytes must be a multiple of the pixel size");
+  if (which == 1 && nframes != 1) return fail(c, ABCOCT_ERR_INVALID, "the pi-shifted frame is a copy of ONE frame (BscanFFT.cpp:1081)");
   const size_t n = (size_t)c->oph * c->opw;
   std::vector<double> acc(n, 0.0);
   {
@@ -1262,12 +1220,16 @@ int abcoct_set_calibration_from_frames(abcoct_ctx* c, int which, const void* fra
     const size_t in_bytes = nframes * (size_t)h * stride_bytes;
     const int ipb = c->bgr ? 2 : pb;  // bytes per pixel after the channel sum
     uint8_t *d_in = nullptr, *d_a = nullptr, *d_b = nullptr;
-    double* d_acc = nullptr;
+    double *d_acc = nullptr, *d_cs = nullptr, *d_sn = nullptr;
+    long long* d_mm = nullptr;
     auto cleanup = [&]() {
       cudaFree(d_in);
       cudaFree(d_a);
       cudaFree(d_b);
       cudaFree(d_acc);
+      cudaFree(d_cs);
+      cudaFree(d_sn);
+      cudaFree(d_mm);
     };
     cudaError_t e = cudaMalloc(&d_in, in_bytes);
     if (e == cudaSuccess) e = cudaMalloc(&d_acc, n * sizeof(double));
@@ -1298,29 +1260,43 @@ int abcoct_set_calibration_from_frames(abcoct_ctx* c, int which, const void* fra
     }
     if (e == cudaSuccess)  // convertTo + smoothmovavg (BscanFFT.cpp:987-991) + accumulate, f64
       e = launch_cal_accum(src, bpp, rs, fs, (int)nframes, c->opw, c->oph, c->p.movavgn, c->bgr ? 0.00130718954 : 1.0, d_acc, st);
+    // the once-per-capture tail, on the device too (cal_*_kernel, f64, the reference's operation order):
+    //   keys b / o / r / t, BscanFFT.cpp:1050-1057: if (rowwisenormalize) normalizerows(.., 0.0001, 1); if (!donotnormalize)
+    //     normalize(.., 0.0001, 1) else / n (Mat / double multiplies by the reciprocal); BscanDark.cpp:1070-1074, 1145-1149, 1218-1222:
+    //     lpfilter on the dark / reference / sample captures;
+    //   key p, BscanFFT.cpp:1092-1096: the copy is normalised to [0, 1] like data_y is (:1126-1129) - no 0.0001 floor, no division
+    CalTailHost t{};
+    t.x = d_acc;
+    t.rows = c->oph;
+    t.cols = c->opw;
+    t.rowwise = c->p.rowwisenormalize ? 1 : 0;
+    t.global_norm = c->p.donotnormalize ? 0 : 1;
+    t.lo = which == 1 ? 0.0 : 0.0001;
+    t.inv_n = which == 1 ? 1.0 : 1.0 / (double)nframes;
+    t.lowpass = (which >= 2 && c->p.lowpassfilter) ? 1 : 0;
+    if (e == cudaSuccess) e = cudaMalloc(&d_mm, 2 * sizeof(long long));
+    t.mm = d_mm;
+    if (e == cudaSuccess && t.lowpass) {
+      const double tau = 6.283185307179586476925286766559;
+      std::vector<double> cs(c->opw), sn(c->opw);
+      for (int k = 0; k < c->opw; ++k) {
+        cs[k] = std::cos(tau * k / c->opw);
+        sn[k] = std::sin(tau * k / c->opw);
+      }
+      e = cudaMalloc(&d_cs, cs.size() * 8);
+      if (e == cudaSuccess) e = cudaMalloc(&d_sn, sn.size() * 8);
+      if (e == cudaSuccess) e = cudaMemcpy(d_cs, cs.data(), cs.size() * 8, cudaMemcpyHostToDevice);
+      if (e == cudaSuccess) e = cudaMemcpy(d_sn, sn.data(), sn.size() * 8, cudaMemcpyHostToDevice);
+      t.cs = d_cs;
+      t.sn = d_sn;
+    }
+    int ntail = 0;
+    if (e == cudaSuccess) e = launch_cal_tail(t, st, &ntail);
     if (e == cudaSuccess) e = cudaMemcpyAsync(acc.data(), d_acc, n * sizeof(double), cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
     cleanup();
     if (e != cudaSuccess) return fail(c, ABCOCT_ERR_CUDA, "calibration capture: %s", cudaGetErrorString(e));
-    c->launches += 1 + (c->bgr ? 1 : 0) + (c->p.mediann > 0 ? 1 : 0) + ((c->p.binx > 1 || c->p.biny > 1) ? 1 : 0);
-  }
-  if (which != 1) {
-    // BscanFFT.cpp:1050-1057: if (rowwisenormalize) normalizerows(.., 0.0001, 1); if (!donotnormalize) normalize(.., 0.0001, 1); else / n
-    if (c->p.rowwisenormalize)
-      for (int r = 0; r < c->oph; ++r) host_normalize(&acc[(size_t)r * c->opw], &acc[(size_t)r * c->opw] + c->opw, 0.0001, 1.0);
-    if (!c->p.donotnormalize) {
-      host_normalize(acc.data(), acc.data() + n, 0.0001, 1.0);
-    } else {
-      const double s = 1.0 / (double)nframes;  // Mat / double multiplies by the reciprocal
-      for (double& v : acc) v *= s;
-    }
-    if (c->p.lowpassfilter && which >= 2) host_lpfilter(acc, c->oph, c->opw);  // BscanDark.cpp:1070-1074, 1145-1149, 1218-1222
-  } else {
-    if (nframes != 1) return fail(c, ABCOCT_ERR_INVALID, "the pi-shifted frame is a copy of ONE frame (BscanFFT.cpp:1081)");
-    // BscanFFT.cpp:1092-1096: the copy is normalised to [0, 1] like data_y is (:1126-1129) - no 0.0001 floor, no division by n
-    if (c->p.rowwisenormalize)
-      for (int r = 0; r < c->oph; ++r) host_normalize(&acc[(size_t)r * c->opw], &acc[(size_t)r * c->opw] + c->opw, 0.0, 1.0);
-    if (!c->p.donotnormalize) host_normalize(acc.data(), acc.data() + n, 0.0, 1.0);
+    c->launches += 1 + ntail + (c->bgr ? 1 : 0) + (c->p.mediann > 0 ? 1 : 0) + ((c->p.binx > 1 || c->p.biny > 1) ? 1 : 0);
   }
   std::vector<double>& dst = which == 0 ? c->yb : which == 1 ? c->yp : which == 2 ? c->yd : which == 3 ? c->yr : c->ys;
   bool& have = which == 0 ? c->have_yb : which == 1 ? c->have_yp : which == 2 ? c->have_yd : which == 3 ? c->have_yr : c->have_ys;

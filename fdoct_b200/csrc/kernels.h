@@ -85,6 +85,17 @@ cudaError_t launch_bin(const void* in, void* out, int bpp, int opw, int oph, int
 // calibration captures: sum over the frames of the binned pixels as f64 (+ smoothmovavg), BscanFFT.cpp:1041-1046
 cudaError_t launch_cal_accum(const void* px, int bpp, size_t row_stride_elems, size_t frame_stride_elems, int nframes, int opw, int oph,
                              int movavgn, double px_scale, double* acc, cudaStream_t st);
+// the once-per-capture tail on the accumulated frame x (rows x cols doubles, in place): row-wise / global min-max normalise to
+// [lo, 1] (BscanFFT.cpp:1050-1055, 1092-1096), else x *= inv_n (:1057), then lpfilter (BscanDark.cpp:119-167, 1070-1074)
+struct CalTailHost {
+  double* x;
+  int rows, cols;
+  int rowwise, global_norm, lowpass;
+  double lo, inv_n;
+  long long* mm;          // two words of scratch (global_norm)
+  const double *cs, *sn;  // cos / sin(2 pi k / cols), k < cols (lowpass)
+};
+cudaError_t launch_cal_tail(const CalTailHost& h, cudaStream_t st, int* launched);
 cudaError_t launch_rowprep(const PrepArgsHost& h, cudaStream_t st, int* launched);
 size_t rowprep_smem_bytes(int opw, int M, int m, int movavgn);
 cudaError_t launch_lerp_rows64(const float* rows, const double* rows64, const int* idx, const double* wq, float* ylin, int M, int N, int oph,

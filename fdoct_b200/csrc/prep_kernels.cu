@@ -11,6 +11,7 @@
 // The default configuration (16-bit frames, no binning / median / smoothing / normalisation, multiplier 1) never comes
 // here: it is handled entirely inside recon_kernel.  This path trades speed for coverage (it is still two orders of
 // magnitude above any camera's frame rate) and keeps the reference's integer rounding rules bit-exact.
+#include <algorithm>
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -805,6 +806,114 @@ cudaError_t launch_cal_accum(const void* px, int bpp, size_t row_stride_elems, s
     cal_accum_kernel<uint8_t><<<grid, block, 0, st>>>(static_cast<const uint8_t*>(px), row_stride_elems, frame_stride_elems, nframes, opw, oph, movavgn, px_scale, acc);
   else
     cal_accum_kernel<uint16_t><<<grid, block, 0, st>>>(static_cast<const uint16_t*>(px), row_stride_elems, frame_stride_elems, nframes, opw, oph, movavgn, px_scale, acc);
+  return cudaGetLastError();
+}
+
+// The once-per-capture tail on the accumulated frame (BscanFFT.cpp:1050-1057, 1092-1096; BscanDark.cpp:1070-1074), all f64 and in
+// the reference's operation order, so the captures stay exact to the last bit of cv::normalize / Mat-by-scalar arithmetic:
+//   normalizerows / normalize(., a, b, NORM_MINMAX): scale = (b - a) / (max - min) (0 for a flat image), shift = a - min * scale,
+//   dst = src * scale + shift (two roundings);  Mat / n: one multiplication by 1 / n.
+__global__ void __launch_bounds__(256) cal_rows_normalize_kernel(double* x, int cols, double a, double b) {
+  __shared__ double red[8];
+  double* row = x + (size_t)blockIdx.x * cols;
+  double mn = 1.7e308, mx = -1.7e308;
+  for (int j = threadIdx.x; j < cols; j += blockDim.x) {
+    mn = fmin(mn, row[j]);
+    mx = fmax(mx, row[j]);
+  }
+  mn = block_reduce64(mn, red, 1);
+  mx = block_reduce64(mx, red, 2);
+  const double scale = __dmul_rn(b - a, (mx - mn) > 2.220446049250313e-16 ? 1.0 / (mx - mn) : 0.0);
+  const double shift = a - __dmul_rn(mn, scale);
+  for (int j = threadIdx.x; j < cols; j += blockDim.x) row[j] = __dadd_rn(__dmul_rn(row[j], scale), shift);
+}
+__global__ void __launch_bounds__(256) cal_minmax_kernel(const double* __restrict__ x, size_t n, long long* mm) {
+  __shared__ double red[8];
+  double mn = 1.7e308, mx = -1.7e308;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    mn = fmin(mn, x[i]);
+    mx = fmax(mx, x[i]);
+  }
+  mn = block_reduce64(mn, red, 1);
+  mx = block_reduce64(mx, red, 2);
+  if (threadIdx.x == 0) {
+    atomicMin(mm, d2ord(mn));
+    atomicMax(mm + 1, d2ord(mx));
+  }
+}
+// mode 0: x = x * scale + shift with the min / max in mm (global normalise to [a, b]); mode 1: x *= a (Mat / n)
+__global__ void __launch_bounds__(256) cal_scale_kernel(double* x, size_t n, const long long* mm, double a, double b, int mode) {
+  double scale = a, shift = 0.0;
+  if (mode == 0) {
+    const double mn = ord2d(mm[0]), mx = ord2d(mm[1]);
+    scale = __dmul_rn(b - a, (mx - mn) > 2.220446049250313e-16 ? 1.0 / (mx - mn) : 0.0);
+    shift = a - __dmul_rn(mn, scale);
+  }
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    x[i] = mode == 0 ? __dadd_rn(__dmul_rn(x[i], scale), shift) : __dmul_rn(x[i], scale);
+}
+// lpfilter, BscanDark.cpp:119-167: the row as f32, DFT scaled by 1 / cols, keep the centre 20 % of the shifted spectrum (bins
+// |k| < floor(cols / 10)), inverse with DFT_REAL_OUTPUT (reads bins 0 .. cols / 2 only), back to f64 through f32:
+//   out[n] = Re X[0] + 2 Re sum_{0 < k < keep} X[k] e^{2 pi i n k / cols}.
+// Evaluated directly in f64 (keep * cols terms per row - a capture is ONE frame), one CTA per row; dynamic smem: cols + 2 keep doubles.
+__global__ void __launch_bounds__(256) cal_lpfilter_kernel(double* x, int cols, int keep, const double* __restrict__ cs, const double* __restrict__ sn) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* v = reinterpret_cast<double*>(smem_raw);
+  double* re = v + cols;
+  double* im = re + keep;
+  double* row = x + (size_t)blockIdx.x * cols;
+  for (int j = threadIdx.x; j < cols; j += blockDim.x) v[j] = (double)(float)row[j];  // convertTo(CV_32F)
+  __syncthreads();
+  for (int k = threadIdx.x; k < keep; k += blockDim.x) {
+    double a = 0.0, b = 0.0;
+    int t = 0;  // (j * k) mod cols, advanced incrementally
+    for (int j = 0; j < cols; ++j) {
+      a = __dadd_rn(a, __dmul_rn(v[j], cs[t]));
+      b = __dadd_rn(b, -__dmul_rn(v[j], sn[t]));
+      t += k;
+      if (t >= cols) t -= cols;
+    }
+    re[k] = a / cols;
+    im[k] = b / cols;
+  }
+  __syncthreads();
+  for (int n = threadIdx.x; n < cols; n += blockDim.x) {
+    double s = keep > 0 ? re[0] : 0.0;
+    int t = 0;
+    for (int k = 1; k < keep; ++k) {
+      t += n;
+      if (t >= cols) t -= cols;
+      s = __dadd_rn(s, __dmul_rn(2.0, __dadd_rn(__dmul_rn(re[k], cs[t]), -__dmul_rn(im[k], sn[t]))));
+    }
+    row[n] = (double)(float)s;  // the inverse transform is f32
+  }
+}
+cudaError_t launch_cal_tail(const CalTailHost& h, cudaStream_t st, int* launched) {
+  int nl = 0;
+  const size_t n = (size_t)h.rows * h.cols;
+  const unsigned gridn = (unsigned)std::min<size_t>((n + 255) / 256, 1184);
+  if (h.rowwise) {
+    cal_rows_normalize_kernel<<<h.rows, 256, 0, st>>>(h.x, h.cols, h.lo, 1.0);
+    ++nl;
+  }
+  if (h.global_norm) {
+    minmax64_reset_kernel<<<1, 32, 0, st>>>(h.mm, 1);
+    cal_minmax_kernel<<<gridn, 256, 0, st>>>(h.x, n, h.mm);
+    cal_scale_kernel<<<gridn, 256, 0, st>>>(h.x, n, h.mm, h.lo, 1.0, 0);
+    nl += 3;
+  } else if (h.inv_n != 1.0) {
+    cal_scale_kernel<<<gridn, 256, 0, st>>>(h.x, n, h.mm, h.inv_n, 0.0, 1);
+    ++nl;
+  }
+  if (h.lowpass) {
+    const int keep = h.cols / 10;
+    const size_t smem = ((size_t)h.cols + 2 * (size_t)keep) * sizeof(double);
+    cudaError_t e = cudaFuncSetAttribute(cal_lpfilter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) return e;
+    cal_lpfilter_kernel<<<h.rows, 256, smem, st>>>(h.x, h.cols, keep, h.cs, h.sn);
+    ++nl;
+  }
+  if (launched) *launched = nl;
   return cudaGetLastError();
 }
 
