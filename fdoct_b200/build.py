@@ -34,6 +34,8 @@ def _stale(target: str, deps: list[str]) -> bool:
 
 
 FLAGS = ["-std=c++17", "-O3", *ARCH, "-lineinfo", "-Xcompiler", "-fPIC,-ffp-contract=off"]
+if os.environ.get("ABCOCT_BUILD_RING") == "1":  # A/B build of the scratch-ring experiment (wrow_kernel.cuh, tools/r02_ring_ab.sh)
+    FLAGS.append("-DABC_WROW_RING")
 STAMP = LIB + ".stamp"
 
 
@@ -105,7 +107,7 @@ def build_native_test(name: str, out_dir: str | None = None) -> str:
     exe = os.path.join(out_dir, name)
     deps = [src] + [os.path.join(CSRC, h) for h in HEADERS + SOURCES]
     if _stale(exe, deps):
-        subprocess.run([_nvcc(), "-std=c++17", "-O2", *ARCH, "-o", exe, src, "-lpthread"], check=True)
+        subprocess.run([_nvcc(), "-std=c++17", "-O2", "-DABC_WROW_RING", *ARCH, "-o", exe, src, "-lpthread"], check=True)
     return exe
 
 

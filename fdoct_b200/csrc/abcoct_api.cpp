@@ -709,6 +709,17 @@ int enqueue_device(abcoct_ctx* c, GpuState& g, int slot, const uint8_t* d_frames
       a.nsplit = (int)std::max<long long>(1, std::min<long long>(ntiles, split));
       a.hints = 0;
       if (const char* e = getenv("ABCOCT_HINTS")) a.hints = atoi(e);
+      // EXPERIMENT, only in a build with -DABC_WROW_RING (ABCOCT_BUILD_RING=1): the dB scratch as a ring reused round-robin
+      a.ringB = 0;
+#ifdef ABC_WROW_RING
+      if (!c->wplan->resident) {
+        size_t ring_mb = 0;
+        if (const char* e = getenv("ABCOCT_RING_MB")) ring_mb = (size_t)std::max(0L, atol(e));
+        const size_t per = (size_t)c->oph * a.Dp * sizeof(float);
+        const size_t ring = std::max<size_t>(8, ring_mb * 1024 * 1024 / per);
+        if (ring_mb > 0 && ring < nb) a.ringB = (int)ring;
+      }
+#endif
     }
     a.gain = g.d_gain;
     a.subg = g.d_subg;

@@ -65,6 +65,7 @@ struct ReconArgs {
   // warp-per-A-scan kernel (wrow_kernel.cuh) only
   int calpitch;     // floats per calibration row in its permuted layout
   int nsplit;       // depth-tile ranges a normalisation part is split into (small launches: more, shorter jobs)
+  int ringB;        // wrow_kernel: the dB scratch holds this many B-scans and is reused round-robin (0: one region per B-scan)
   int hints;        // A/B switches (ABCOCT_HINTS).  L2 policies of the scratch kernel: 1 pixel-row prefetch evict_first, 2 scratch stores
                     // evict_last, 4 pixel loads evict_first (measured: no effect).  Resident-row kernel: 8 = every warp writes its own row's bytes
 };

@@ -163,6 +163,7 @@ struct WNormArgs {  // by value: the job runs as a real (non-inlined) device fun
   const int* maxv;
   int oph, D, Dp, nparts, nsplit, clamp55;
   float thr, clamp_db;
+  int ring;  // ABC_WROW_RING: B-scans the scratch holds (B-scan b lives in slot b mod ring)
 };
 #ifdef ABC_WROW_HOST_EMU
 #define WROW_NOINLINE static __host__ __device__
@@ -185,7 +186,11 @@ WROW_NOINLINE void wrow_normalise(const WNormArgs a, int job, int lane) {
 
   const float thr = a.thr;
   const int q = lane >> 2, cg = lane & 3;
+#ifdef ABC_WROW_RING
+  const float* src = a.scratch + ((size_t)(b % a.ring) * a.oph + r0) * a.Dp;
+#else
   const float* src = a.scratch + ((size_t)b * a.oph + r0) * a.Dp;
+#endif
   unsigned valid = 0;
   const float* rowp[4];
 #pragma unroll
@@ -378,6 +383,25 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
 
   auto njobs = [&]() { return a.nB * a.nparts * a.nsplit; };
   auto per_b = [&]() { return a.nparts * a.nsplit; };
+#ifdef ABC_WROW_RING
+  // EXPERIMENT (compiled in with -DABC_WROW_RING, off in the product build): the dB scratch as a ring of `ring`
+  // B-scans - B-scan b lives in slot b mod ring - so that the 4 KB per A-scan would be written and read back in L2 lines that stay
+  // resident instead of streaming through DRAM once each way.  A row of B-scan b >= ring may only be stored once every
+  // normalisation job of B-scan b - ring has finished: done_p(b) counts them (release by the job's warp, acquire by the writer).
+  // Measured: correct (emulation cases 9 / 10, GPU parity), DRAM traffic 15.8 -> 10.5 GB per launch at 64 MB, but the writers
+  // block (the write -> read distance of the scratch exceeds 16 B-scans) and even the dormant guard costs 2 % of the headline.
+  const int ring = a.ringB > 0 ? a.ringB : a.nB;
+  auto done_p = [&](int b) { return a.sched + kSchedHeader + 3 * a.nB + 32 * b; };  // one 128-byte line per B-scan, zeroed by sched_init
+  auto job_done = [&](int j) {  // all lanes
+    w_syncwarp();
+    if (lane == 0) {
+      w_fence_gpu();
+      w_atomic_add(done_p(j / per_b()), 1);  // result unused -> RED
+    }
+  };
+#else
+  auto job_done = [&](int) {};
+#endif
   auto norm_args = [&]() {  // built from the kernel parameters (constant bank) at the call, not kept in registers
     WNormArgs na;
     na.scratch = a.scratch;
@@ -393,6 +417,9 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
     na.clamp55 = a.clamp55;
     na.thr = a.thr;
     na.clamp_db = a.clamp_db;
+#ifdef ABC_WROW_RING
+    na.ring = ring;
+#endif
     return na;
   };
 
@@ -456,6 +483,7 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
       w_backoff();
     }
     wrow_normalise<3>(norm_args(), j, lane);
+    job_done(j);
   };
   // all lanes: hand out and run jobs until none is left (service warps when idle, worker warps after their last row)
   auto drain_jobs = [&](auto&& service) {
@@ -743,7 +771,33 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
           }
         }
         j = w_shfl_i(j, 0);
-        if (j >= 0) wrow_normalise<(WP::NW <= 12 ? 3 : 2)>(norm_args(), j, lane);
+        if (j >= 0) {
+          wrow_normalise<(WP::NW <= 12 ? 3 : 2)>(norm_args(), j, lane);
+          job_done(j);
+        }
+#ifdef ABC_WROW_RING
+        if (bscan >= ring) {  // ring guard: the slot this row goes to must have been consumed (normally it was, B-scans ago)
+          const unsigned long long t_start = w_now_ns();
+          for (;;) {
+            int ok = 0;
+            if (lane == 0) ok = w_ld_acquire(done_p(bscan - ring)) >= per_b() ? 1 : 0;
+            if (w_shfl_i(ok, 0)) break;
+            int jj = -1;  // a job this warp still owns may be one of those it is waiting for
+            if (lane == 0 && myjob >= 0 && advance_frontier() > myjob) {
+              jj = myjob;
+              myjob = -1;
+              w_acquire_fence();
+            }
+            jj = w_shfl_i(jj, 0);
+            if (jj >= 0) {
+              wrow_normalise<(WP::NW <= 12 ? 3 : 2)>(norm_args(), jj, lane);
+              job_done(jj);
+            }
+            if (w_now_ns() - t_start > kWrowWatchdogNs) w_trap();
+            w_backoff();
+          }
+        }
+#endif
         nx_raw = claim();  // the next ticket: issued here, far from the store burst at the end of a row
       }
       // ---------------------------------------------------------------- pass A: gather, radix-R, twiddle, exchange
@@ -787,7 +841,11 @@ WROW_HD void wrow_body(const ReconArgs& a, unsigned char* smem) {
       // The dB conversion and the scratch stores are fused into the split loop: every Z register dies as soon as its
       // pair has been formed, nothing but the running min / max is carried (no magnitude array).
       prefetch_step2(f, it2);
+#ifdef ABC_WROW_RING
+      float* const srow = a.scratch + ((size_t)(bscan % ring) * a.oph + row) * a.Dp;
+#else
       float* const srow = a.scratch + ((size_t)bscan * a.oph + row) * a.Dp;
+#endif
       float* const s1 = srow + lane;         // bin k1 = lane + R d
       float* const s2 = srow + (N2 - lane);  // bin k2 = N/2 - lane - R d
       float mn = w_inf(false), mx = w_inf(true);

@@ -121,6 +121,7 @@ struct is_resident : std::false_type {};
 template <class T>
 struct is_resident<T, std::void_t<decltype(T::TR)>> : std::true_type {};
 
+static int g_ring = 0;  // ReconArgs::ringB of the next case (scratch ring of the warp-per-A-scan kernel)
 template <class WP, bool HAS_SUB, bool A1, bool FULLD>
 static void run_grid(const ReconArgs& a, int ncta) {
   std::vector<wemu::Cta> ctas(ncta);
@@ -233,6 +234,7 @@ static double run_case(const Case& cs, unsigned seed) {
   a.subg = ps.data();
   a.idxT = reinterpret_cast<const uint32_t*>(blob.data());
   a.scratch = scratch.data();
+  a.ringB = g_ring;  // 0: one scratch region per B-scan
   a.sched = sched.data();
   uint8_t* o8 = out8.data();
   while (reinterpret_cast<uintptr_t>(o8) & 3) ++o8;
@@ -340,6 +342,12 @@ int main(int argc, char** argv) {
     worst = std::max(worst, run_case<WPlan<1280, 2>, false>(Case{1280, 64, 640, 1, 2, 5, 2, true, false, false}, 7));
     // three worker warps per service warp, more B-scans than CTAs: mailboxes, one fence for several workers, job order
     worst = std::max(worst, run_case<WPlan<1280, 4>, false>(Case{1280, 36, 640, 1, 5, 2, 2, false, false, false}, 8));
+  }
+  if (!quick) {  // the dB scratch as a ring of two B-scans: slot reuse, the writer's guard on the finished-job count of B-scan b - 2
+    g_ring = 2;
+    worst = std::max(worst, run_case<WPlan<1280, 4>, false>(Case{1280, 36, 640, 1, 7, 2, 2, false, true, false}, 9));
+    worst = std::max(worst, run_case<WPlan<2048, 2, 1>, true>(Case{2048, 8, 1024, 2, 5, 1, 1, true, true, true}, 10));
+    g_ring = 0;
   }
   // ---- resident-row kernel (wres_kernel.cuh): teams of 4 warps, dB rows parked in (emulated) tensor memory, static schedule
   //   one team, several rounds per team (slot reuse), partial last block (oph % 4 != 0), forced element, dB image, DC rows

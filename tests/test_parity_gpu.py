@@ -217,6 +217,35 @@ def test_spinjnt_multiplyfactor_shipped_shape(clamp):
     assert err <= MAG_RTOL, err
 
 
+def test_scratch_ring_reuse(monkeypatch):
+    """Many B-scans per launch through the warp-per-A-scan kernel (job queue, completion frontier over 96 B-scans).  In a build of
+    the scratch-ring experiment (ABCOCT_BUILD_RING=1: the dB scratch reused round-robin, writer's guard on the finished-job count
+    of B-scan b - ring; off in the product build, where ABCOCT_RING_MB is ignored) a ring much shorter than the batch must give the
+    very same bytes as no ring at all; both must match the oracle."""
+    from fdoct_b200 import api, synth
+    from oracle.abcoct_oracle import Oracle
+
+    w, h, N, D, nB = 1280, 16, 1280, 640, 96
+    op = oracle_params(w=w, h=h, numfftpoints=N, numdisplaypoints=D, lambdamin=840.5e-9, lambdamax=859.5e-9)
+    uniq = synth.make_frames(6, w, h, seed=99)
+    frames = np.ascontiguousarray(uniq[np.arange(nB) % 6])
+    yb = synth.make_background_frames(2, w, h, seed=98).mean(axis=0)
+    outs = {}
+    for ring_mb in ("0", "1"):  # 0: one region per B-scan; 1 MB: 25 B-scans of 40 KB each, reused almost four times
+        monkeypatch.setenv("ABCOCT_RING_MB", ring_mb)
+        with api.Context(abi_params(op)) as ctx:
+            ctx.set_background(yb)
+            outs[ring_mb] = ctx.process_bscans(frames, want_db=True)
+            assert ctx.info().kernel_kind == 1
+    assert np.array_equal(outs["0"][0], outs["1"][0]) and np.array_equal(outs["0"][1], outs["1"][1])
+    o = Oracle(op)
+    o.set_background(yb)
+    ref8, refdb = o.process_bscans(uniq)
+    for b in range(nB):
+        assert np.array_equal(outs["1"][0][b], outs["1"][0][b % 6])
+    _check(outs["1"][0][:6], outs["1"][1][:6], ref8, refdb, "scratch ring")
+
+
 GENERIC = [
     # any N = 2^a 3^b 5^c, any row width, D up to N (abcoct_info.kernel_kind 3): what cv::dft / colRange accept (BscanFFT.cpp:1185, 1193)
     (1000, 7, 2000, 1000, 1, 2, 0, {}),  # 2^4 5^3
