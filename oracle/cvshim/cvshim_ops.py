@@ -155,5 +155,9 @@ def threshold(a, thresh, maxval, ttype):
     return cv2.threshold(a, thresh, maxval, ttype)[1]
 
 
+def apply_color_map(a, colormap):
+    return cv2.applyColorMap(np.ascontiguousarray(a), colormap)
+
+
 def opencv_version():
     return cv2.__version__

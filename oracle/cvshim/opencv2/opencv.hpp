@@ -39,6 +39,7 @@ enum { INTER_NEAREST = 0, INTER_LINEAR = 1, INTER_CUBIC = 2, INTER_AREA = 3 };
 enum { BORDER_CONSTANT = 0 };
 enum { FONT_HERSHEY_SIMPLEX = 0 };
 enum { THRESH_BINARY = 0 };
+enum { COLORMAP_JET = 2 };
 
 inline py::module_& ops() {
   static py::module_* m = new py::module_(py::module_::import("cvshim_ops"));
@@ -294,6 +295,9 @@ inline void resize(const Mat& src, const OutputArray& dst, Size, double fx, doub
 inline double threshold(const Mat& src, const OutputArray& dst, double thresh, double maxval, int type) {
   dst.mat().put(ops().attr("threshold")(src.arr, thresh, maxval, type));
   return thresh;
+}
+inline void applyColorMap(const Mat& src, const OutputArray& dst, int colormap) {
+  dst.mat().put(ops().attr("apply_color_map")(src.arr, colormap));
 }
 // display calls of the camera loop: nothing to show here
 inline void putText(Mat&, const char*, Point, int, double, Scalar, int = 1, int = 8) {}

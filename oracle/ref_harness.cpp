@@ -8,8 +8,9 @@
 //   frag_window         BscanFFT.cpp:936-944    Bartlett-Hann window
 //   frag_ingest1        BscanFFT.cpp:953-958    medianBlur + INTER_AREA binning
 //   frag_ingest2        BscanFFT.cpp:987-991    convertTo(CV_64F) + smoothmovavg
-//   frag_block          BscanFFT.cpp:1125-1255  normalise, (y - yp) / yb, mean, window, upsample, gather-lerp, DFT, magnitude,
-//                                               accumulate, dB, DC mask, threshold, clamp, min-max, u8  (+ one closing brace)
+//   frag_block          BscanFFT.cpp:1125-1284  normalise, (y - yp) / yb, mean, window, upsample, gather-lerp, DFT, magnitude,
+//                                               accumulate, dB, DC mask, threshold, clamp, min-max, u8, the J0 lock-in display
+//                                               (:1225-1231, 1256-1268) and the JET colour images (:1267, 1284; the "^" marker of :1285 is not drawn)  (+ one closing brace)
 // and, compiled a second time with -DREF_DARK into abcoct_ref_dark, the same ranges of /root/reference/BscanDark.cpp
 // (82-91, 111-314 incl. lpfilter and the band-pass in zeropadrowwise, 614-697, 929-937, 946-951, 980-984,
 // 1268-1393: the block with the dark-frame subtraction `data_y = data_y - data_yd`).
@@ -23,9 +24,15 @@ using namespace cv;  // BscanFFT.cpp:86
 #include "_ref/frag_normalizerows.inc"
 #include "_ref/frag_helpers.inc"
 
+#ifndef REF_DARK
+// file output of the lock-in branch (BscanFFT.cpp:1276-1278): nothing is written here
+static void savematasdata(std::ofstream&, char*, Mat) {}
+static void savematasimage(char*, char*, char*, Mat) {}
+#endif
+
 namespace py = pybind11;
 
-static py::dict run_block(py::dict prm, py::array frames, py::object yb_in, py::object yp_in, py::object yd_in) {
+static py::dict run_block(py::dict prm, py::array frames, py::object yb_in, py::object yp_in, py::object yd_in, py::object jscan_in) {
   // ---- declarations, BscanFFT.cpp:357-613 (names and types as there; camera / file / GUI state left out)
   unsigned int w = prm["w"].cast<unsigned>(), h = prm["h"].cast<unsigned>(), opw, oph;
   uint indextemp;
@@ -72,6 +79,16 @@ static py::dict run_block(py::dict prm, py::array frames, py::object yb_in, py::
   Mat bscansave0[100];
   Mat bscansave1[100];
   Mat jscansave;
+#ifndef REF_DARK
+  Mat bscansublog, bscandispmanual, cmagI, cmagImanual, manualaccum;
+  uint manualindexi = 0;
+  char filename[20], filenamec[20], pathname[140] = "", dirname[80] = "";
+  std::ofstream outfile;
+  if (!jscan_in.is_none()) {  // key 'j' (BscanFFT.cpp:1292-1297): jscansave = a finished linear bscan, lock-in on
+    Mat(jscan_in).copyTo(jscansave);
+    jlockin = 1;
+  }
+#endif
   Mat positivediff;
   Mat magI;
   Scalar meanval;
@@ -90,7 +107,7 @@ static py::dict run_block(py::dict prm, py::array frames, py::object yb_in, py::
   if (!yb_in.is_none()) Mat(yb_in).copyTo(data_yb);
   if (!yp_in.is_none()) Mat(yp_in).copyTo(data_yp);
 
-  py::list disp, db;
+  py::list disp, db, jdisp, jbgr, bgr;
   py::object last_ylin = py::none();
   const py::ssize_t nframes = frames.shape(0);
   for (py::ssize_t fi = 0; fi < nframes; ++fi) {
@@ -104,17 +121,27 @@ static py::dict run_block(py::dict prm, py::array frames, py::object yb_in, py::
     if (indextemp == 0) {  // a B-scan was completed by this frame
       disp.append(ops().attr("copy")(bscandisp.arr));
       db.append(ops().attr("copy")(bscandb.arr));
+#ifndef REF_DARK
+      bgr.append(ops().attr("copy")(cmagI.arr));
+      if (jlockin) {
+        jdisp.append(ops().attr("copy")(bscandispmanual.arr));
+        jbgr.append(ops().attr("copy")(cmagImanual.arr));
+      }
+#endif
       bscantransposed = Mat::zeros(Size(numdisplaypoints, oph), CV_64F);  // :1482
     }
   }
   py::dict out;
   out["bscandisp"] = disp;
   out["bscandb"] = db;
+  out["cmagI"] = bgr;
+  out["bscandispmanual"] = jdisp;
+  out["cmagImanual"] = jbgr;
   out["nearestkindex"] = ops().attr("copy")(nearestkindex.arr);
   out["fractionalk"] = ops().attr("copy")(fractionalk.arr);
   out["barthannwin"] = ops().attr("copy")(barthannwin.arr);
   out["data_ylin"] = ops().attr("copy")(data_ylin.arr);
-  (void)kmin, (void)kmax, (void)zeroisactive, (void)saveframes, (void)jlockin, (void)textbuffer, (void)clampupper, (void)yd_in;
+  (void)kmin, (void)kmax, (void)zeroisactive, (void)saveframes, (void)jlockin, (void)textbuffer, (void)clampupper, (void)yd_in, (void)jscan_in;
   return out;
 }
 
@@ -131,6 +158,6 @@ PYBIND11_MODULE(abcoct_ref, mod) {
   mod.doc() = "the reference's processing block (BscanFFT.cpp), compiled verbatim against oracle/cvshim";
 #endif
   mod.def("run_block", &run_block, py::arg("params"), py::arg("frames"), py::arg("yb") = py::none(), py::arg("yp") = py::none(),
-          py::arg("yd") = py::none());
+          py::arg("yd") = py::none(), py::arg("jscan") = py::none());
   mod.def("opencv_version", []() { return ops().attr("opencv_version")().cast<std::string>(); });
 }

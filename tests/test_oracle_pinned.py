@@ -153,3 +153,30 @@ def test_reference_generated_golden_vectors():
 
         nk, fr, win = api.build_tables(abi_params(p))
         assert np.array_equal(nk, z["nearestkindex"]) and np.array_equal(fr, z["fractionalk"]) and np.array_equal(win, z["barthannwin"])
+
+
+def test_oracle_consumers_equal_compiled_block():
+    """The consumers of a finished B-scan inside the same block: the J0 lock-in display (BscanFFT.cpp:1225-1231, 1256-1268) and the
+    JET colour images (:1267, 1286) - oracle.jlockin_display / colormap_jet against the compiled reference, bit for bit."""
+    from fdoct_b200 import synth
+    from oracle.abcoct_oracle import Oracle, colormap_jet, jlockin_display
+
+    ref = _ref()
+    for kw in (dict(w=256, h=12, numfftpoints=256, numdisplaypoints=100), dict(w=1280, h=10, numfftpoints=1280, numdisplaypoints=640, averages=2)):
+        p = oracle_params(lambdamin=840.5e-9, lambdamax=859.5e-9, bscanthreshold=-20.0, **kw)
+        A = p.averages
+        scene1 = synth.make_frames(A, p.w, p.h, seed=31)
+        scene2 = synth.make_frames(2 * A, p.w, p.h, seed=32)
+        o = Oracle(p, strict=True)
+        yb = o.calib_mean_of_frames(synth.make_background_frames(2, p.w, p.h, seed=33))
+        o.set_background(yb)
+        _, _, lin1 = o.process_bscans(scene1, want_linear=True)
+        jscansave = np.ascontiguousarray(lin1[0])  # key 'j': bscan.copyTo(jscansave), BscanFFT.cpp:1294
+        o8, odb, olin = o.process_bscans(scene2, want_linear=True)
+        r = ref.run_block(ref_params(p), scene2, np.ascontiguousarray(yb), None, None, jscansave)
+        assert np.array_equal(np.stack(r["bscandisp"]), o8) and np.array_equal(np.stack(r["bscandb"]), odb)
+        for b in range(2):
+            jd = jlockin_display(olin[b], jscansave, p.bscanthreshold)
+            assert np.array_equal(r["bscandispmanual"][b], jd)
+            assert np.array_equal(r["cmagImanual"][b], colormap_jet(jd))
+            assert np.array_equal(r["cmagI"][b], colormap_jet(o8[b]))
