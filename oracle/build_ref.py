@@ -23,6 +23,7 @@ FRAGMENTS = {
     "frag_window": (936, 944, "for (uint p = 0; p<(opw); p++)", "}", ""),
     "frag_ingest1": (953, 958, "if (mediann>0)", "resize(m, opm, Size(), 1.0 / binvalue, 1.0 / binvalue, INTER_AREA);", ""),
     "frag_ingest2": (987, 991, "opm.convertTo(data_y, CV_64F);", "data_y = smoothmovavg(data_y, movavgn);", ""),
+    "frag_keys": (1000, 1099, "if (bkeypressed == 1)", "}", ""),
     "frag_block": (1125, 1284, "data_y.convertTo(data_y, CV_64F);", "applyColorMap(bscandisp, cmagI, COLORMAP_JET);", ""),
 }
 

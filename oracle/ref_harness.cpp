@@ -8,6 +8,8 @@
 //   frag_window         BscanFFT.cpp:936-944    Bartlett-Hann window
 //   frag_ingest1        BscanFFT.cpp:953-958    medianBlur + INTER_AREA binning
 //   frag_ingest2        BscanFFT.cpp:987-991    convertTo(CV_64F) + smoothmovavg
+//   frag_keys           BscanFFT.cpp:1000-1099  what keys 'b' (accumulate averagestoggle frames -> data_yb, normalise branches) and 'p'
+//                                               (copy of one frame -> data_yp, normalised like data_y) do inside the frame loop
 //   frag_block          BscanFFT.cpp:1125-1284  normalise, (y - yp) / yb, mean, window, upsample, gather-lerp, DFT, magnitude,
 //                                               accumulate, dB, DC mask, threshold, clamp, min-max, u8, the J0 lock-in display
 //                                               (:1225-1231, 1256-1268) and the JET colour images (:1267, 1284; the "^" marker of :1285 is not drawn)  (+ one closing brace)
@@ -84,6 +86,15 @@ static py::dict run_block(py::dict prm, py::array frames, py::object yb_in, py::
   uint manualindexi = 0;
   char filename[20], filenamec[20], pathname[140] = "", dirname[80] = "";
   std::ofstream outfile;
+  // key handler state (BscanFFT.cpp:365-377, 555-566); capture = 1: key 'b' was pressed before the first frame, 2: key 'p'
+  bool saveinterferograms = 0, manualaveraging = 0;
+  bool bkeypressed = prm.contains("capture") && prm["capture"].cast<int>() == 1;
+  bool pkeypressed = prm.contains("capture") && prm["capture"].cast<int>() == 2;
+  unsigned int indexi = 0;
+  Mat baccum = Mat::zeros(Size(opw, oph), CV_64F);  // :564
+  uint baccumcount = 0;                             // :565
+  Mat interferogramsave0[100], interferogramsave1[100], interferogrambsave0[100], interferogrambsave1[100];
+  Mat secrowofstatusimg = statusimg(Rect(0, 50, 600, 50));
   if (!jscan_in.is_none()) {  // key 'j' (BscanFFT.cpp:1292-1297): jscansave = a finished linear bscan, lock-in on
     Mat(jscan_in).copyTo(jscansave);
     jlockin = 1;
@@ -115,6 +126,9 @@ static py::dict run_block(py::dict prm, py::array frames, py::object yb_in, py::
     {
 #include "_ref/frag_ingest1.inc"
 #include "_ref/frag_ingest2.inc"
+#ifndef REF_DARK
+#include "_ref/frag_keys.inc"
+#endif
 #include "_ref/frag_block.inc"
       }  // closes `if (indextemp >= averagestoggle)` (the J0 lock-in display and the key handler follow in the reference)
     }
@@ -137,6 +151,11 @@ static py::dict run_block(py::dict prm, py::array frames, py::object yb_in, py::
   out["cmagI"] = bgr;
   out["bscandispmanual"] = jdisp;
   out["cmagImanual"] = jbgr;
+  out["data_yb"] = ops().attr("copy")(data_yb.arr);
+  out["data_yp"] = ops().attr("copy")(data_yp.arr);
+#ifndef REF_DARK
+  out["capture_pending"] = bkeypressed || pkeypressed;
+#endif
   out["nearestkindex"] = ops().attr("copy")(nearestkindex.arr);
   out["fractionalk"] = ops().attr("copy")(fractionalk.arr);
   out["barthannwin"] = ops().attr("copy")(barthannwin.arr);

@@ -180,3 +180,30 @@ def test_oracle_consumers_equal_compiled_block():
             assert np.array_equal(r["bscandispmanual"][b], jd)
             assert np.array_equal(r["cmagImanual"][b], colormap_jet(jd))
             assert np.array_equal(r["cmagI"][b], colormap_jet(o8[b]))
+
+
+@pytest.mark.parametrize("kw", [
+    dict(w=256, h=10, numfftpoints=256, numdisplaypoints=100),
+    dict(w=512, h=12, numfftpoints=256, numdisplaypoints=100, binx=2, biny=2, mediann=3, movavgn=2),
+    dict(w=320, h=9, numfftpoints=512, numdisplaypoints=200, rowwisenormalize=True),
+    dict(w=320, h=9, numfftpoints=512, numdisplaypoints=200, donotnormalize=False),
+    dict(w=320, h=9, numfftpoints=512, numdisplaypoints=200, rowwisenormalize=True, donotnormalize=False, movavgn=1),
+])
+def test_oracle_captures_equal_compiled_key_handler(kw):
+    """Keys 'b' and 'p' as the reference's frame loop handles them (BscanFFT.cpp:1000-1099, compiled verbatim): 'b' accumulates
+    averagestoggle frames and finishes on the next one (normalise branches or / n), 'p' copies one frame and normalises it like
+    data_y.  oracle.calib_capture / calib_capture_pishift must give the same doubles, bit for bit."""
+    from fdoct_b200 import synth
+    from oracle.abcoct_oracle import Oracle
+
+    ref = _ref()
+    nacc = 3
+    p = oracle_params(lambdamin=840.5e-9, lambdamax=859.5e-9, averages=nacc, **kw)
+    frames = synth.make_background_frames(nacc + 1, p.w, p.h, seed=71)  # the frame after the last accumulated one triggers the tail
+    o = Oracle(p, strict=True)
+    r = ref.run_block(dict(ref_params(p), capture=1), frames)
+    assert not r["capture_pending"]
+    assert np.array_equal(r["data_yb"], o.calib_capture(frames[:nacc]))
+    r = ref.run_block(dict(ref_params(p), capture=2), frames[:1])
+    assert not r["capture_pending"]
+    assert np.array_equal(r["data_yp"], o.calib_capture_pishift(frames[0]))
