@@ -35,6 +35,7 @@ FRAGMENTS_DARK = {
     "frag_window": (929, 937, "for (uint p = 0; p<(opw); p++)", "}", ""),
     "frag_ingest1": (946, 951, "if (mediann>0)", "resize(m, opm, Size(), 1.0 / binvalue, 1.0 / binvalue, INTER_AREA);", ""),
     "frag_ingest2": (980, 984, "opm.convertTo(data_y, CV_64F);", "data_y = smoothmovavg(data_y, movavgn);", ""),
+    "frag_keys": (993, 1249, "if (bkeypressed == 1)", "}", ""),
     "frag_block": (1268, 1393, "data_y.convertTo(data_y, CV_64F);", "bscandisp.convertTo(bscandisp, CV_8UC1, 255.0);", ""),
 }
 VARIANTS = {"abcoct_ref": (REF, FRAGMENTS, []), "abcoct_ref_dark": (REF_DARK, FRAGMENTS_DARK, ["-DREF_DARK"])}

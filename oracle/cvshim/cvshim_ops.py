@@ -71,6 +71,10 @@ def subtract(a, b):
     return cv2.subtract(a, b)
 
 
+def add(a, b):
+    return cv2.add(a, b)
+
+
 def add_scalar(a, s):
     return cv2.add(a, float(s))
 

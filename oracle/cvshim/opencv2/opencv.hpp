@@ -16,6 +16,7 @@
 #pragma once
 #include <pybind11/numpy.h>
 #include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
 
 #include <cmath>
 #include <cstdio>
@@ -201,6 +202,7 @@ struct MatExpr {
     }
     if (!b.empty()) {
       if (s == 0 && alpha == 1 && beta == -1) return ops().attr("subtract")(a.arr, b.arr);
+      if (s == 0 && alpha == 1 && beta == 1) return ops().attr("add")(a.arr, b.arr);
       throw std::runtime_error("cvshim: a MatExpr shape the reference block does not use");
     }
     // MatOp_AddEx::assign: a real scalar with |alpha| != 1 (or a destination of another buffer) is ONE convertTo(alpha, s);
@@ -220,6 +222,11 @@ inline Mat& Mat::operator=(const MatExpr& e) {
 inline MatExpr operator-(const Mat& a, const Mat& b) {
   MatExpr e;
   e.a = a, e.b = b, e.alpha = 1, e.beta = -1;
+  return e;
+}
+inline MatExpr operator+(const MatExpr& x, const MatExpr& y) {  // MatOp::add: operands with a second matrix are evaluated first
+  MatExpr e;
+  e.a = Mat(x), e.b = Mat(y), e.alpha = 1, e.beta = 1;
   return e;
 }
 inline MatExpr operator-(const Mat& a, double s) {  // operator-(const Mat&, const Scalar&): AddEx(a, 1, 0, -s)

@@ -14,7 +14,8 @@
 //                                               accumulate, dB, DC mask, threshold, clamp, min-max, u8, the J0 lock-in display
 //                                               (:1225-1231, 1256-1268) and the JET colour images (:1267, 1284; the "^" marker of :1285 is not drawn)  (+ one closing brace)
 // and, compiled a second time with -DREF_DARK into abcoct_ref_dark, the same ranges of /root/reference/BscanDark.cpp
-// (82-91, 111-314 incl. lpfilter and the band-pass in zeropadrowwise, 614-697, 929-937, 946-951, 980-984,
+// (82-91, 111-314 incl. lpfilter and the band-pass in zeropadrowwise, 614-697, 929-937, 946-951, 980-984, 993-1249: keys 'b'
+// (data_yb composed from the three captures), 'o' / 'r' / 't' (dark / reference-arm / sample-arm captures, lpfilter) and 'p',
 // 1268-1393: the block with the dark-frame subtraction `data_y = data_y - data_yd`).
 // Everything in THIS file is the scaffolding main() has around those ranges: the declarations (same names and types as
 // BscanFFT.cpp:349-613), the frame loop, and the state the key handler would set (data_yb / data_yp, BscanFFT.cpp:1027-1033, 1081).
@@ -26,11 +27,9 @@ using namespace cv;  // BscanFFT.cpp:86
 #include "_ref/frag_normalizerows.inc"
 #include "_ref/frag_helpers.inc"
 
-#ifndef REF_DARK
-// file output of the lock-in branch (BscanFFT.cpp:1276-1278): nothing is written here
+// file output of the lock-in branch and of saveinterferograms (BscanFFT.cpp:1023, 1276-1278): nothing is written here
 static void savematasdata(std::ofstream&, char*, Mat) {}
 static void savematasimage(char*, char*, char*, Mat) {}
-#endif
 
 namespace py = pybind11;
 
@@ -81,20 +80,28 @@ static py::dict run_block(py::dict prm, py::array frames, py::object yb_in, py::
   Mat bscansave0[100];
   Mat bscansave1[100];
   Mat jscansave;
-#ifndef REF_DARK
-  Mat bscansublog, bscandispmanual, cmagI, cmagImanual, manualaccum;
-  uint manualindexi = 0;
-  char filename[20], filenamec[20], pathname[140] = "", dirname[80] = "";
-  std::ofstream outfile;
-  // key handler state (BscanFFT.cpp:365-377, 555-566); capture = 1: key 'b' was pressed before the first frame, 2: key 'p'
+  // key handler state (BscanFFT.cpp:365-377, 555-566); prm["keys"][i] = the key pressed before frame i: 0 none, 1 'b', 2 'p',
+  // and in BscanDark 3 'o' (dark), 4 'r' (reference arm), 5 't' (sample arm)
   bool saveinterferograms = 0, manualaveraging = 0;
-  bool bkeypressed = prm.contains("capture") && prm["capture"].cast<int>() == 1;
-  bool pkeypressed = prm.contains("capture") && prm["capture"].cast<int>() == 2;
+  bool bkeypressed = 0, pkeypressed = 0;
   unsigned int indexi = 0;
   Mat baccum = Mat::zeros(Size(opw, oph), CV_64F);  // :564
   uint baccumcount = 0;                             // :565
   Mat interferogramsave0[100], interferogramsave1[100], interferogrambsave0[100], interferogrambsave1[100];
   Mat secrowofstatusimg = statusimg(Rect(0, 50, 600, 50));
+  std::vector<int> keys;
+  if (prm.contains("keys")) keys = prm["keys"].cast<std::vector<int>>();
+#ifdef REF_DARK
+  bool rkeypressed = 0, tkeypressed = 0, darkkeypressed = 0;
+  bool lowpassfilter = prm.contains("lowpassfilter") && prm["lowpassfilter"].cast<bool>();  // BscanDark.cpp:397
+  Mat data_yr = Mat::zeros(Size(opw, oph), CV_64F), data_ys = Mat::zeros(Size(opw, oph), CV_64F);
+  char filename[20], pathname[140] = "", dirname[80] = "";
+#endif
+#ifndef REF_DARK
+  Mat bscansublog, bscandispmanual, cmagI, cmagImanual, manualaccum;
+  uint manualindexi = 0;
+  char filename[20], filenamec[20], pathname[140] = "", dirname[80] = "";
+  std::ofstream outfile;
   if (!jscan_in.is_none()) {  // key 'j' (BscanFFT.cpp:1292-1297): jscansave = a finished linear bscan, lock-in on
     Mat(jscan_in).copyTo(jscansave);
     jlockin = 1;
@@ -123,12 +130,20 @@ static py::dict run_block(py::dict prm, py::array frames, py::object yb_in, py::
   const py::ssize_t nframes = frames.shape(0);
   for (py::ssize_t fi = 0; fi < nframes; ++fi) {
     mraw = Mat(py::reinterpret_borrow<py::object>(frames[py::int_(fi)]));  // GetQHYCCDLiveFrame(..., mraw.data), :949
+    switch ((size_t)fi < keys.size() ? keys[fi] : 0) {  // waitKey of the previous iteration
+      case 1: bkeypressed = 1; break;
+      case 2: pkeypressed = 1; break;
+#ifdef REF_DARK
+      case 3: darkkeypressed = 1; break;
+      case 4: rkeypressed = 1; break;
+      case 5: tkeypressed = 1; break;
+#endif
+      default: break;
+    }
     {
 #include "_ref/frag_ingest1.inc"
 #include "_ref/frag_ingest2.inc"
-#ifndef REF_DARK
 #include "_ref/frag_keys.inc"
-#endif
 #include "_ref/frag_block.inc"
       }  // closes `if (indextemp >= averagestoggle)` (the J0 lock-in display and the key handler follow in the reference)
     }
@@ -153,7 +168,13 @@ static py::dict run_block(py::dict prm, py::array frames, py::object yb_in, py::
   out["cmagImanual"] = jbgr;
   out["data_yb"] = ops().attr("copy")(data_yb.arr);
   out["data_yp"] = ops().attr("copy")(data_yp.arr);
-#ifndef REF_DARK
+#ifdef REF_DARK
+  // (BscanDark never clears bkeypressed: once 'b' was pressed, data_yb is recomposed on every frame, BscanDark.cpp:993-1003)
+  out["capture_pending"] = pkeypressed || darkkeypressed || rkeypressed || tkeypressed;
+  out["data_yd"] = ops().attr("copy")(data_yd.arr);
+  out["data_yr"] = ops().attr("copy")(data_yr.arr);
+  out["data_ys"] = ops().attr("copy")(data_ys.arr);
+#else
   out["capture_pending"] = bkeypressed || pkeypressed;
 #endif
   out["nearestkindex"] = ops().attr("copy")(nearestkindex.arr);

@@ -201,9 +201,59 @@ def test_oracle_captures_equal_compiled_key_handler(kw):
     p = oracle_params(lambdamin=840.5e-9, lambdamax=859.5e-9, averages=nacc, **kw)
     frames = synth.make_background_frames(nacc + 1, p.w, p.h, seed=71)  # the frame after the last accumulated one triggers the tail
     o = Oracle(p, strict=True)
-    r = ref.run_block(dict(ref_params(p), capture=1), frames)
+    r = ref.run_block(dict(ref_params(p), keys=[1]), frames)  # 'b' before the first frame
     assert not r["capture_pending"]
     assert np.array_equal(r["data_yb"], o.calib_capture(frames[:nacc]))
-    r = ref.run_block(dict(ref_params(p), capture=2), frames[:1])
+    r = ref.run_block(dict(ref_params(p), keys=[2]), frames[:1])  # 'p'
     assert not r["capture_pending"]
     assert np.array_equal(r["data_yp"], o.calib_capture_pishift(frames[0]))
+
+
+@pytest.mark.parametrize("kw", [
+    dict(w=256, h=10, numfftpoints=256, numdisplaypoints=100),
+    dict(w=640, h=8, numfftpoints=640, numdisplaypoints=200, lowpassfilter=True, movavgn=1),
+    dict(w=320, h=9, numfftpoints=512, numdisplaypoints=200, rowwisenormalize=True, lowpassfilter=True),
+    dict(w=320, h=9, numfftpoints=512, numdisplaypoints=200, donotnormalize=False, binx=2, biny=2),
+])
+def test_oracle_dark_calibration_flow_equals_compiled_key_handler(kw):
+    """BscanDark's key handler compiled verbatim (BscanDark.cpp:993-1249): keys 'o' / 'r' / 't' capture the dark, reference-arm and
+    sample-arm frames (accumulate, normalise branches or / n, lpfilter), 'b' composes data_yb = (yr - yd) + (ys - yd) (:996), 'p'
+    takes the pi-shift frame; then B-scans are processed with that state.  oracle.calib_capture(lowpass) / dark_background /
+    calib_capture_pishift and the processing must reproduce every array bit for bit."""
+    from fdoct_b200 import synth
+    from oracle.abcoct_oracle import Oracle, dark_background
+
+    ref = _ref("abcoct_ref_dark")
+    nacc = 2
+    p = oracle_params(variant=1, lambdamin=840.5e-9, lambdamax=859.5e-9, averages=nacc, **kw)
+    w, h = p.w, p.h
+    dark = synth.make_dark_frames(nacc + 1, w, h, seed=81)
+    refarm = synth.make_background_frames(nacc + 1, w, h, seed=82, dark=True)
+    sample = (0.1 * synth.make_background_frames(nacc + 1, w, h, seed=83, dark=True) + 0.9 * dark).astype(np.uint16)
+    scene = synth.make_frames(2 * nacc + 2, w, h, seed=84, dark=True)
+    # key presses: 'o' with the dark frames, 'r', 't', then 'b' (composition) and 'p' on the first scene frames, then plain processing
+    frames = np.concatenate([dark, refarm, sample, scene])
+    keys = [0] * len(frames)
+    keys[0], keys[nacc + 1], keys[2 * (nacc + 1)] = 3, 4, 5
+    keys[3 * (nacc + 1)] = 1
+    keys[3 * (nacc + 1) + 1] = 2
+    r = ref.run_block(dict(ref_params(p), lowpassfilter=p.lowpassfilter, keys=keys), frames)
+    assert not r["capture_pending"]
+    o = Oracle(p, strict=True)
+    yd = o.calib_capture(dark[:nacc], lowpass=p.lowpassfilter)
+    yr = o.calib_capture(refarm[:nacc], lowpass=p.lowpassfilter)
+    ys = o.calib_capture(sample[:nacc], lowpass=p.lowpassfilter)
+    assert np.array_equal(r["data_yd"], yd) and np.array_equal(r["data_yr"], yr) and np.array_equal(r["data_ys"], ys)
+    yb = dark_background(yr, yd, ys)
+    assert np.array_equal(r["data_yb"], yb)
+    yp = o.calib_capture_pishift(scene[1])
+    assert np.array_equal(r["data_yp"], yp)
+    # the B-scans made after the last key press: frames scene[2:], averaging restarts wherever indextemp stands - compare the last one
+    o.set_dark(yd)
+    o.set_background(yb)
+    o.set_pishift(yp)
+    nproc = len(frames)  # every frame went through the block; indextemp counts all of them
+    last_start = (nproc // nacc - 1) * nacc
+    assert last_start >= 3 * (nacc + 1) + 2  # the last B-scan was averaged entirely after the last key press
+    o8, odb = o.process_bscans(frames[last_start:last_start + nacc])
+    assert np.array_equal(r["bscandisp"][-1], o8[0]) and np.array_equal(r["bscandb"][-1], odb[0])
