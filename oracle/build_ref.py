@@ -38,6 +38,10 @@ FRAGMENTS_DARK = {
     "frag_keys": (993, 1249, "if (bkeypressed == 1)", "}", ""),
     "frag_block": (1268, 1393, "data_y.convertTo(data_y, CV_64F);", "bscandisp.convertTo(bscandisp, CV_8UC1, 255.0);", ""),
 }
+# one more range, from BscanFFTwebcam.cpp: the channel selection / channel sum in front of the same block (compiled into abcoct_ref)
+EXTRA_FRAGMENTS = {
+    "abcoct_ref": [("/root/reference/BscanFFTwebcam.cpp", "frag_webcam", 1018, 1038, "split(frame, rgbchannels);", "}")],
+}
 VARIANTS = {"abcoct_ref": (REF, FRAGMENTS, []), "abcoct_ref_dark": (REF_DARK, FRAGMENTS_DARK, ["-DREF_DARK"])}
 
 
@@ -63,6 +67,14 @@ def _build_one(name: str, force: bool) -> str | None:
             path = os.path.join(OUT, frag + ".inc")
             with open(path, "w") as f:
                 f.write("\n".join(lines[a - 1:b]) + "\n" + tail)
+            written.append(path)
+        for src, frag, a, b, first, last in EXTRA_FRAGMENTS.get(name, []):
+            xl = open(src, encoding="utf-8", errors="replace").read().split("\n")
+            if first not in xl[a - 1] or last not in xl[b - 1]:
+                raise RuntimeError(f"{src}:{a}-{b} is not the text this recipe was written for ({frag})")
+            path = os.path.join(OUT, frag + ".inc")
+            with open(path, "w") as f:
+                f.write("\n".join(xl[a - 1:b]) + "\n")
             written.append(path)
         import pybind11
 

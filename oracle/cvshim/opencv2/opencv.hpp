@@ -219,6 +219,11 @@ inline Mat& Mat::operator=(const MatExpr& e) {
   return *this;
 }
 
+inline MatExpr operator+(const Mat& a, const Mat& b) {  // AddEx(a, b, 1, 1) -> cv::add
+  MatExpr e;
+  e.a = a, e.b = b, e.alpha = 1, e.beta = 1;
+  return e;
+}
 inline MatExpr operator-(const Mat& a, const Mat& b) {
   MatExpr e;
   e.a = a, e.b = b, e.alpha = 1, e.beta = -1;

@@ -185,6 +185,18 @@ static py::dict run_block(py::dict prm, py::array frames, py::object yb_in, py::
   return out;
 }
 
+#ifndef REF_DARK
+// BscanFFTwebcam.cpp:1018-1038, compiled verbatim: the frame cap.read() returned -> mraw (one 8-bit plane for channelnum < 3, else the
+// CV_64F sum of the three planes * 0.00130718954).  Declarations as at BscanFFTwebcam.cpp:412, 578-580.
+static py::object webcam_mraw(py::object frame_in, int channelnum_in) {
+  int channelnum = channelnum_in;
+  Mat frame(frame_in), mraw;
+  Mat rgbchannels[3];
+#include "_ref/frag_webcam.inc"
+  return mraw.arr;
+}
+#endif
+
 #ifdef REF_DARK
 PYBIND11_MODULE(abcoct_ref_dark, mod) {
   mod.doc() = "the reference's processing block (BscanDark.cpp), compiled verbatim against oracle/cvshim";
@@ -196,6 +208,9 @@ PYBIND11_MODULE(abcoct_ref_dark, mod) {
 #else
 PYBIND11_MODULE(abcoct_ref, mod) {
   mod.doc() = "the reference's processing block (BscanFFT.cpp), compiled verbatim against oracle/cvshim";
+#endif
+#ifndef REF_DARK
+  mod.def("webcam_mraw", &webcam_mraw, py::arg("frame"), py::arg("channelnum"));
 #endif
   mod.def("run_block", &run_block, py::arg("params"), py::arg("frames"), py::arg("yb") = py::none(), py::arg("yp") = py::none(),
           py::arg("yd") = py::none(), py::arg("jscan") = py::none());

@@ -257,3 +257,18 @@ def test_oracle_dark_calibration_flow_equals_compiled_key_handler(kw):
     assert last_start >= 3 * (nacc + 1) + 2  # the last B-scan was averaged entirely after the last key press
     o8, odb = o.process_bscans(frames[last_start:last_start + nacc])
     assert np.array_equal(r["bscandisp"][-1], o8[0]) and np.array_equal(r["bscandb"][-1], odb[0])
+
+
+def test_oracle_webcam_channel_sum_equals_compiled():
+    """BscanFFTwebcam.cpp:1018-1038 compiled verbatim: channelnum < 3 copies one 8-bit plane, channelnum >= 3 sums the three planes
+    in CV_64F and scales by 0.00130718954 - oracle.bin_frame's restatement, bit for bit."""
+    from oracle.abcoct_oracle import bin_frame
+
+    ref = _ref()
+    rng = np.random.default_rng(12)
+    frame = rng.integers(0, 256, size=(24, 320, 3), dtype=np.uint8)
+    for c in range(3):
+        assert np.array_equal(ref.webcam_mraw(frame, c), frame[:, :, c])
+    p = oracle_params(w=320, h=24, bpp=8, numfftpoints=512, numdisplaypoints=100, channelnum=3)
+    got = ref.webcam_mraw(frame, 3)
+    assert got.dtype == np.float64 and np.array_equal(got, bin_frame(frame, p))
