@@ -387,13 +387,8 @@ class Oracle:
         p = self.p
         bscan = acc.T * (1.0 / averages)  # :1220-1221
         bscan = bscan + 0.00001  # :1222
-        if p.output_rebin and (p.bscanbinx > 1 or p.bscanbiny > 1 or p.binx > 1 or p.biny > 1):  # BscanFFTspinjnt.cpp:1856
-            multiplyfactor = p.bscanbinx * p.bscanbiny * p.binx * p.biny  # :835 (int)
-            bscanbinned = cv2.resize(np.ascontiguousarray(bscan), None, fx=1.0 / p.bscanbinx, fy=1.0 / p.bscanbiny,
-                                     interpolation=cv2.INTER_AREA)  # :1859
-            # :1860 - int * Mat is a MatExpr scaling (one multiplication per element); fx carries binvaluey, the reference's quirk
-            bscan = cv2.resize(bscanbinned * float(multiplyfactor), None, fx=p.bscanbinx * p.biny, fy=p.bscanbiny,
-                               interpolation=cv2.INTER_CUBIC)
+        if p.output_rebin:
+            bscan = spinjnt_rebin(bscan, p.bscanbinx, p.bscanbiny, p.binx, p.biny)
         bscanlog = cv2.log(bscan)  # :1235
         bscandb = bscanlog * (20.0 * (1.0 / 2.303))  # :1237
         bscandb[1] = bscandb[4]  # :1239
@@ -462,6 +457,16 @@ def colormap_jet(img8: np.ndarray) -> np.ndarray:
     """applyColorMap(., COLORMAP_JET), BscanFFT.cpp:1268, 1284: u8 (...) -> BGR u8 (..., 3)."""
     a = np.ascontiguousarray(img8, dtype=np.uint8)
     return cv2.applyColorMap(a.reshape(-1, 1), cv2.COLORMAP_JET).reshape(a.shape + (3,))
+
+
+def spinjnt_rebin(bscan: np.ndarray, bscanbinx: int, bscanbiny: int, binvaluex: int, binvaluey: int) -> np.ndarray:
+    """BscanFFTspinjnt.cpp:1856-1862: re-binning of the linear B-scan in front of the log, active whenever any factor exceeds 1."""
+    if not (bscanbinx > 1 or bscanbiny > 1 or binvaluex > 1 or binvaluey > 1):  # :1856
+        return bscan
+    multiplyfactor = bscanbinx * bscanbiny * binvaluex * binvaluey  # :835 (int)
+    bscanbinned = cv2.resize(np.ascontiguousarray(bscan), None, fx=1.0 / bscanbinx, fy=1.0 / bscanbiny, interpolation=cv2.INTER_AREA)  # :1859
+    # :1860 - int * Mat is a MatExpr scaling (one multiplication per element); fx carries binvaluey, the reference's quirk
+    return cv2.resize(bscanbinned * float(multiplyfactor), None, fx=bscanbinx * binvaluey, fy=bscanbiny, interpolation=cv2.INTER_CUBIC)
 
 
 def dark_background(yr, yd, ys):

@@ -40,7 +40,8 @@ FRAGMENTS_DARK = {
 }
 # one more range, from BscanFFTwebcam.cpp: the channel selection / channel sum in front of the same block (compiled into abcoct_ref)
 EXTRA_FRAGMENTS = {
-    "abcoct_ref": [("/root/reference/BscanFFTwebcam.cpp", "frag_webcam", 1018, 1038, "split(frame, rgbchannels);", "}")],
+    "abcoct_ref": [("/root/reference/BscanFFTwebcam.cpp", "frag_webcam", 1018, 1038, "split(frame, rgbchannels);", "}"),
+                   ("/root/reference/BscanFFTspinjnt.cpp", "frag_spinjnt_rebin", 1856, 1862, "if(bscanbinx > 1 || bscanbiny > 1 || binvaluex > 1", "}")],
 }
 VARIANTS = {"abcoct_ref": (REF, FRAGMENTS, []), "abcoct_ref_dark": (REF_DARK, FRAGMENTS_DARK, ["-DREF_DARK"])}
 

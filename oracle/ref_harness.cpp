@@ -197,6 +197,16 @@ static py::object webcam_mraw(py::object frame_in, int channelnum_in) {
 }
 #endif
 
+#ifndef REF_DARK
+// BscanFFTspinjnt.cpp:1856-1862, compiled verbatim: the re-binning of the linear B-scan in front of the log.  multiplyfactor as at :835.
+static py::object spinjnt_rebin(py::object bscan_in, int bscanbinx, int bscanbiny, int binvaluex, int binvaluey) {
+  int multiplyfactor = bscanbinx * bscanbiny * binvaluex * binvaluey;  // BscanFFTspinjnt.cpp:835
+  Mat bscan(ops().attr("copy")(bscan_in)), bscanbinned;
+#include "_ref/frag_spinjnt_rebin.inc"
+  return bscan.arr;
+}
+#endif
+
 #ifdef REF_DARK
 PYBIND11_MODULE(abcoct_ref_dark, mod) {
   mod.doc() = "the reference's processing block (BscanDark.cpp), compiled verbatim against oracle/cvshim";
@@ -211,6 +221,7 @@ PYBIND11_MODULE(abcoct_ref, mod) {
 #endif
 #ifndef REF_DARK
   mod.def("webcam_mraw", &webcam_mraw, py::arg("frame"), py::arg("channelnum"));
+  mod.def("spinjnt_rebin", &spinjnt_rebin, py::arg("bscan"), py::arg("bscanbinx"), py::arg("bscanbiny"), py::arg("binvaluex"), py::arg("binvaluey"));
 #endif
   mod.def("run_block", &run_block, py::arg("params"), py::arg("frames"), py::arg("yb") = py::none(), py::arg("yp") = py::none(),
           py::arg("yd") = py::none(), py::arg("jscan") = py::none());
