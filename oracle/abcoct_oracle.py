@@ -36,8 +36,9 @@ OpenCV C++ headers, no camera SDKs) - but its processing block can.  oracle/buil
 functions, the table precompute, the window loop and the frame ingest out of /root/reference/BscanFFT.cpp and
 BscanDark.cpp and compiles them verbatim against oracle/cvshim (a stand-in for the OpenCV headers that forwards every
 OpenCV call to the same kernels through cv2) into oracle/_ref/.  ``strict=True`` of this module equals those modules
-BIT FOR BIT (tables, display bytes, f64 dB image) on every configuration of tests/test_oracle_pinned.py, and reproduces
-the vectors they wrote (tests/golden/ref_*.npz).  Also kept: the physics known-answer test on the reference's own
+BIT FOR BIT (tables, display bytes, f64 dB image, calibration captures of both key handlers, the DARK composition, the
+J0 lock-in display, the JET images, the webcam channel sum, BscanFFTspinjnt's re-binning) on every configuration of
+tests/test_oracle_pinned.py, and reproduces the vectors they wrote (tests/golden/ref_*.npz).  Also kept: the physics known-answer test on the reference's own
 fixtures ``Matlab files/imgi.png`` / ``backg.png`` (tests/test_oracle.py).
 
 Two execution modes give the same f64 intermediates to <= 1e-12 relative (single f32 ulps can flip behind the f32 DFT):

@@ -1,4 +1,6 @@
-"""Builds oracle/_ref/abcoct_ref*.so: the reference's own processing block, cut out of /root/reference/BscanFFT.cpp at build time and
+"""Builds oracle/_ref/abcoct_ref*.so: the reference's own processing block - helpers, table precompute, window, frame ingest, key
+handler (calibration captures), the block itself with the J0 lock-in display and the JET mapping - cut out of
+/root/reference/BscanFFT.cpp and BscanDark.cpp (plus the webcam front end and BscanFFTspinjnt's output re-binning) at build time and
 compiled verbatim against oracle/cvshim (OpenCV calls forwarded to cv2).  TEST INFRASTRUCTURE ONLY.
 
 Only runs where /root/reference exists (this container); the built module travels to the GPU box, the fragments are deleted right
