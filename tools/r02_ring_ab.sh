@@ -1,5 +1,6 @@
 #!/bin/bash
-# A/B of the dB scratch ring of wrow_kernel (ABCOCT_RING_MB; 0 = one region per B-scan) on C5-2048: throughput, then DRAM traffic
+# A/B of the dB scratch ring of wrow_kernel (ABCOCT_RING_MB; 0 = one region per B-scan) on C5-2048: throughput, then DRAM traffic.
+# Needs a library built with ABCOCT_BUILD_RING=1 (-DABC_WROW_RING); the product build ignores ABCOCT_RING_MB.
 set -u
 mkdir -p gpurun_out
 timeout 300 python -m pytest tests/test_parity_gpu.py -m gpu -x -q -k "scratch_ring or test_against_oracle or full_size or golden" 2>&1 | tail -3

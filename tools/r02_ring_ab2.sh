@@ -1,5 +1,7 @@
 #!/bin/bash
-# scratch ring x eager job taking by the worker warps (ABCOCT_HINTS bit 8): throughput and DRAM traffic on C5-2048
+# scratch ring x eager job taking by the worker warps: throughput and DRAM traffic on C5-2048.  Needs a library built with
+# ABCOCT_BUILD_RING=1; ABCOCT_HINTS bit 8 (workers take any ready job, no backlog gate) existed only for this A/B and was removed
+# again after it showed no effect (profiles/r02_scratch_ring_experiments.txt, part 3).
 set -u
 mkdir -p gpurun_out
 : > gpurun_out/ring_ab2.txt
